@@ -1,0 +1,348 @@
+"""ctypes bindings used by the tests (and by bench.py / smoke() for the checker legs).
+
+Three libraries, all loaded lazily:
+  * oracle/_ref/libtetra_ref.so   - the reference's own lower MAC compiled in place
+                                    (oracle/Makefile `make ref`); prebuilt, travels
+                                    to the GPU box, never rebuilt there.
+  * oracle/libtetra_oracle.so     - the stand-alone CPU restatement (`make oracle`).
+  * osmo-tetra_b200/libtetra_b200.so - the product (CUDA + C-ABI), see include/tetra_b200.h.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_SO = os.path.join(ORACLE_DIR, "_ref", "libtetra_ref.so")
+ORACLE_SO = os.path.join(ORACLE_DIR, "libtetra_oracle.so")
+
+# enum tetra_train_seq, tetra_burst.h:27-33
+TS_NORM_1, TS_NORM_2, TS_NORM_3, TS_SYNC, TS_EXT = 0, 1, 2, 3, 4
+# enum tp_sap_data_type, tetra_burst.h:9-16
+T_SB1, T_SB2, T_NDB, T_BBK, T_SCH_HU, T_SCH_F = 0, 1, 2, 3, 4, 5
+# enum tetra_log_chan, tetra_common.h:22-39
+LC_UNKNOWN, LC_SCH_F, LC_AACH, LC_BSCH, LC_BNCH = 0, 1, 8, 10, 11
+
+BLK = {  # type345, type2, type1, a   (tetra_lower_mac.c:55-102)
+    T_SB1: (120, 80, 60, 11),
+    T_SB2: (216, 144, 124, 101),
+    T_NDB: (216, 144, 124, 101),
+    T_BBK: (30, 30, 14, 0),
+    T_SCH_HU: (168, 112, 92, 13),
+    T_SCH_F: (432, 288, 268, 103),
+}
+
+RECORD_DTYPE = np.dtype([
+    ("slot_bit", "<u4"), ("lchan", "u1"), ("crc_ok", "u1"), ("blk_num", "u1"),
+    ("tn", "u1"), ("fn", "u1"), ("mn", "u1"), ("type1_len", "<u2"),
+    ("scrambling_code", "<u4"), ("type1", "u1", (272,)),
+])
+assert RECORD_DTYPE.itemsize == 288
+
+EVENT_DTYPE = np.dtype([
+    ("call_index", "<u4"), ("buf_start_bit", "<u4"), ("window", "<u4"),
+    ("mask", "<u4"), ("rc", "<i4"), ("offset", "<u4"),
+])
+assert EVENT_DTYPE.itemsize == 24
+
+
+class GenCfg(C.Structure):
+    """struct orc_gen_cfg (oracle/tetra_oracle.c) == struct tb200_gen_cfg (include/tetra_b200.h)"""
+    _fields_ = [("seed", C.c_uint64), ("sb_period", C.c_uint32), ("lead_sb", C.c_uint32),
+                ("ndb2_per_256", C.c_uint32), ("ber_per_65536", C.c_uint32),
+                ("random_cell", C.c_uint32), ("lead_in_bits", C.c_uint32)]
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def bits_from_str(s):
+    return np.frombuffer(s.encode(), dtype=np.uint8) - ord("0")
+
+
+def bits_to_str(a):
+    return "".join(str(int(x)) for x in a)
+
+
+def ensure_oracle_built():
+    if not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < os.path.getmtime(
+            os.path.join(ORACLE_DIR, "tetra_oracle.c")):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "oracle"])
+    if os.path.isdir("/root/reference/src") and not os.path.exists(REF_SO):
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+
+
+class _Recorder:
+    """common record/event access for the two CPU libraries (prefix ref_ / orc_)"""
+
+    def __init__(self, lib, prefix):
+        self.lib, self.p = lib, prefix
+        f = lambda n: getattr(lib, prefix + n)
+        f("num_records").restype = C.c_size_t
+        f("records").restype = C.c_void_p
+        f("num_events").restype = C.c_size_t
+        f("events").restype = C.c_void_p
+        f("cell_scramb_init").restype = C.c_uint32
+        self._f = f
+
+    def reset(self):
+        self._f("reset")()
+
+    def records(self):
+        n = self._f("num_records")()
+        if n == 0:
+            return np.zeros(0, dtype=RECORD_DTYPE)
+        buf = C.string_at(self._f("records")(), n * RECORD_DTYPE.itemsize)
+        return np.frombuffer(buf, dtype=RECORD_DTYPE).copy()
+
+    def events(self):
+        n = self._f("num_events")()
+        if n == 0:
+            return np.zeros(0, dtype=EVENT_DTYPE)
+        buf = C.string_at(self._f("events")(), n * EVENT_DTYPE.itemsize)
+        return np.frombuffer(buf, dtype=EVENT_DTYPE).copy()
+
+    def rx_state(self):
+        return self._f("rx_state")()
+
+    def scramb_init(self):
+        return self._f("cell_scramb_init")()
+
+    def set_recording(self, on):
+        self._f("set_recording")(int(on))
+
+    def set_time(self, tn, fn, mn):
+        self._f("set_time")(C.c_uint32(tn), C.c_uint32(fn), C.c_uint32(mn))
+
+    def get_time(self):
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._f("get_time")(C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+
+class Ref(_Recorder):
+    """The reference's own code (oracle/_ref)."""
+
+    def __init__(self):
+        lib = C.CDLL(REF_SO)
+        super().__init__(lib, "ref_")
+        lib.tetra_scramb_get_init.restype = C.c_uint32
+        lib.tetra_rm3014_compute.restype = C.c_uint32
+        lib.crc16_ccitt_bits.restype = C.c_uint16
+        lib.ref_feed.restype = C.c_long
+        lib.ref_feed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_int]
+        lib.ref_rm3014_init()
+
+    def feed(self, bits, chunk=64):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        return self.lib.ref_feed(_ptr(bits), bits.size, chunk, 1)
+
+    def tp_sap(self, typ, blk_num, bits):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        self.lib.ref_tp_sap(typ, blk_num, _ptr(bits), bits.size, 1)
+
+    def find_train_seq(self, window, end, mask):
+        """window must have >= end+21 readable bytes"""
+        off = C.c_uint(0)
+        w = np.ascontiguousarray(window, dtype=np.uint8)
+        rc = self.lib.__real_tetra_find_train_seq(_ptr(w), C.c_uint(end), C.c_uint32(mask), C.byref(off)) \
+            if hasattr(self.lib, "__real_tetra_find_train_seq") else \
+            self.lib.tetra_find_train_seq(_ptr(w), C.c_uint(end), C.c_uint32(mask), C.byref(off))
+        return rc, off.value
+
+    def scramb_get_bits(self, init, n):
+        out = np.zeros(n, dtype=np.uint8)
+        self.lib.tetra_scramb_get_bits(C.c_uint32(init), _ptr(out), n)
+        return out
+
+    def scramb_bits(self, init, bits):
+        out = np.array(bits, dtype=np.uint8)
+        self.lib.tetra_scramb_bits(C.c_uint32(init), _ptr(out), out.size)
+        return out
+
+    def scramb_get_init(self, mcc, mnc, cc):
+        return self.lib.tetra_scramb_get_init(C.c_uint16(mcc), C.c_uint16(mnc), C.c_uint8(cc))
+
+    def deinterleave(self, K, a, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8); o = np.zeros(K, dtype=np.uint8)
+        self.lib.block_deinterleave(C.c_uint32(K), C.c_uint32(a), _ptr(i), _ptr(o))
+        return o
+
+    def interleave(self, K, a, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8); o = np.zeros(K, dtype=np.uint8)
+        self.lib.block_interleave(C.c_uint32(K), C.c_uint32(a), _ptr(i), _ptr(o))
+        return o
+
+    def depunct_2_3(self, type3, n_mother):
+        i = np.ascontiguousarray(type3, dtype=np.uint8); o = np.full(n_mother, 0xff, dtype=np.uint8)
+        self.lib.tetra_rcpc_depunct(0, _ptr(i), i.size, _ptr(o))
+        return o
+
+    def punct_2_3(self, mother, n_type3):
+        i = np.ascontiguousarray(mother, dtype=np.uint8); o = np.zeros(n_type3, dtype=np.uint8)
+        self.lib.get_punctured_rate(0, _ptr(i), n_type3, _ptr(o))
+        return o
+
+    def conv_encode(self, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8); o = np.zeros(4 * i.size, dtype=np.uint8)
+        st = (C.c_uint8 * 4)()
+        self.lib.conv_enc_init(st)
+        self.lib.conv_enc_input(st, _ptr(i), i.size, _ptr(o))
+        return o
+
+    def viterbi(self, mother, n):
+        i = np.ascontiguousarray(mother, dtype=np.uint8); o = np.zeros(n, dtype=np.uint8)
+        self.lib.viterbi_dec_sb1_wrapper(_ptr(i), _ptr(o), C.c_uint(n))
+        return o
+
+    def crc16(self, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8)
+        return self.lib.crc16_ccitt_bits(_ptr(i), C.c_uint(i.size))
+
+    def rm3014(self, info):
+        return self.lib.tetra_rm3014_compute(C.c_uint16(info))
+
+    def build_sync_burst(self, sb, bb, bkn):
+        out = np.zeros(510, dtype=np.uint8)
+        a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (sb, bb, bkn))
+        n = self.lib.ref_build_sync_burst(_ptr(out), _ptr(a), _ptr(b), _ptr(c))
+        assert n == 510
+        return out
+
+    def build_norm_burst(self, bkn1, bb, bkn2, two):
+        out = np.zeros(510, dtype=np.uint8)
+        a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (bkn1, bb, bkn2))
+        n = self.lib.ref_build_norm_burst(_ptr(out), _ptr(a), _ptr(b), _ptr(c), int(two))
+        assert n == 510
+        return out
+
+    def time_add_slot(self, tn, fn, mn):
+        class T(C.Structure):
+            _fields_ = [("hn", C.c_uint16), ("sn", C.c_uint32), ("tn", C.c_uint32),
+                        ("fn", C.c_uint32), ("mn", C.c_uint32)]
+        t = T(0, 0, tn, fn, mn)
+        self.lib.tetra_tdma_time_add_tn(C.byref(t), C.c_uint32(1))
+        return t.tn, t.fn, t.mn
+
+
+class Oracle(_Recorder):
+    """The stand-alone CPU restatement (oracle/tetra_oracle.c)."""
+
+    def __init__(self):
+        ensure_oracle_built()
+        lib = C.CDLL(ORACLE_SO)
+        super().__init__(lib, "orc_")
+        lib.orc_scramb_get_init.restype = C.c_uint32
+        lib.orc_rm3014_compute.restype = C.c_uint32
+        lib.orc_crc16.restype = C.c_uint16
+        lib.orc_feed.restype = C.c_long
+        lib.orc_feed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint]
+        lib.orc_records_digest.restype = C.c_uint64
+        lib.orc_records_digest.argtypes = [C.c_void_p, C.c_size_t]
+        lib.orc_gen_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
+        lib.orc_gen_burst.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+        lib.orc_gen_kind.argtypes = [C.c_void_p, C.c_uint64]
+
+    def feed(self, bits, chunk=64):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        return self.lib.orc_feed(_ptr(bits), bits.size, chunk)
+
+    def tp_sap(self, typ, blk_num, bits):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        self.lib.orc_tp_sap(typ, blk_num, _ptr(bits))
+
+    def set_cell(self, scramb_init):
+        self.lib.orc_set_cell(C.c_uint32(scramb_init))
+
+    def find_train_seq(self, window, end, mask):
+        off = C.c_uint(0)
+        w = np.ascontiguousarray(window, dtype=np.uint8)
+        rc = self.lib.orc_find_train_seq(_ptr(w), C.c_uint(end), C.c_uint32(mask), C.byref(off))
+        return rc, off.value
+
+    def scramb_get_bits(self, init, n):
+        out = np.zeros(n, dtype=np.uint8)
+        self.lib.orc_scramb_get_bits(C.c_uint32(init), _ptr(out), n)
+        return out
+
+    def scramb_bits(self, init, bits):
+        out = np.array(bits, dtype=np.uint8)
+        self.lib.orc_scramb_bits(C.c_uint32(init), _ptr(out), out.size)
+        return out
+
+    def scramb_get_init(self, mcc, mnc, cc):
+        return self.lib.orc_scramb_get_init(mcc, mnc, cc)
+
+    def deinterleave(self, K, a, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8); o = np.zeros(K, dtype=np.uint8)
+        self.lib.orc_deinterleave(K, a, _ptr(i), _ptr(o))
+        return o
+
+    def interleave(self, K, a, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8); o = np.zeros(K, dtype=np.uint8)
+        self.lib.orc_interleave(K, a, _ptr(i), _ptr(o))
+        return o
+
+    def depunct_2_3(self, type3, n_mother):
+        i = np.ascontiguousarray(type3, dtype=np.uint8); o = np.full(n_mother, 0xff, dtype=np.uint8)
+        self.lib.orc_depunct_2_3(_ptr(i), i.size, _ptr(o))
+        return o
+
+    def punct_2_3(self, mother, n_type3):
+        i = np.ascontiguousarray(mother, dtype=np.uint8); o = np.zeros(n_type3, dtype=np.uint8)
+        self.lib.orc_punct_2_3(_ptr(i), n_type3, _ptr(o))
+        return o
+
+    def conv_encode(self, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8); o = np.zeros(4 * i.size, dtype=np.uint8)
+        self.lib.orc_conv_encode(_ptr(i), i.size, _ptr(o))
+        return o
+
+    def viterbi(self, mother, n):
+        i = np.ascontiguousarray(mother, dtype=np.uint8); o = np.zeros(n, dtype=np.uint8)
+        self.lib.orc_viterbi(_ptr(i), _ptr(o), n)
+        return o
+
+    def crc16(self, bits):
+        i = np.ascontiguousarray(bits, dtype=np.uint8)
+        return self.lib.orc_crc16(_ptr(i), i.size)
+
+    def rm3014(self, info):
+        return self.lib.orc_rm3014_compute(C.c_uint16(info))
+
+    def time_add_slot(self, tn, fn, mn):
+        t = (C.c_uint32 * 3)(tn, fn, mn)
+        self.lib.orc_time_add_slot(t)
+        return t[0], t[1], t[2]
+
+    def digest(self, records):
+        r = np.ascontiguousarray(records)
+        return self.lib.orc_records_digest(_ptr(r), r.size)
+
+    # ---- generator
+    def gen_stream(self, cfg, k0, n, lead_in=True):
+        nbits = 510 * n + (cfg.lead_in_bits if lead_in else 0)
+        out = np.zeros(nbits, dtype=np.uint8)
+        self.lib.orc_gen_stream(C.byref(cfg), k0, n, _ptr(out), int(lead_in))
+        return out
+
+    def gen_kind(self, cfg, k):
+        return self.lib.orc_gen_kind(C.byref(cfg), k)
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+def records_equal(a, b):
+    """bit-exact comparison of two record arrays; returns (ok, message)"""
+    if a.size != b.size:
+        return False, f"record count {a.size} != {b.size}"
+    for name in RECORD_DTYPE.names:
+        if not np.array_equal(a[name], b[name]):
+            bad = np.nonzero(np.any(a[name] != b[name], axis=-1) if a[name].ndim > 1 else a[name] != b[name])[0]
+            return False, f"field {name} differs at records {bad[:5]} (of {bad.size})"
+    return True, ""
