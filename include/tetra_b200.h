@@ -1,0 +1,217 @@
+/*
+ * tetra_b200.h - C ABI of the B200-native TETRA lower-MAC receive chain
+ *                (type-5 bits -> type-1 bits), libtetra_b200.so.
+ *
+ * Every entry point states the reference interface it replaces (file:line relative
+ * to osmo-tetra/src).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Bit streams use the reference's ABI: one bit per byte, values 0/1
+ * (tetra-rx.c:82-95 reads such a file 64 bytes at a time).
+ */
+#ifndef TETRA_B200_H
+#define TETRA_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TB200_BITS_PER_SLOT   510     /* TETRA_BITS_PER_TS, tetra_common.h:19 */
+#define TB200_TYPE1_STRIDE    288     /* bytes of unpacked type-1 bits kept per slot (282 used max) */
+#define TB200_TYPE1_WORDS     9       /* 32-bit words of packed type-1 bits per slot */
+
+/* enum tetra_train_seq (phy/tetra_burst.h:27-33) */
+enum { TB200_TRAIN_NORM_1 = 0, TB200_TRAIN_NORM_2 = 1, TB200_TRAIN_NORM_3 = 2,
+       TB200_TRAIN_SYNC = 3, TB200_TRAIN_EXT = 4 };
+
+/* enum tp_sap_data_type (phy/tetra_burst.h:9-16) */
+enum { TB200_T_SB1 = 0, TB200_T_SB2 = 1, TB200_T_NDB = 2, TB200_T_BBK = 3,
+       TB200_T_SCH_HU = 4, TB200_T_SCH_F = 5 };
+
+/* enum rx_state (phy/tetra_burst_sync.h:6-10) */
+enum { TB200_RX_UNLOCKED = 0, TB200_RX_KNOW_FSTART = 1, TB200_RX_LOCKED = 2 };
+
+/* what a slot turned out to be (decides the layout of its type-1 bits) */
+enum { TB200_KIND_NONE = 0,    /* nothing delivered to the lower MAC (dropped / lock lost) */
+       TB200_KIND_SB = 1,      /* SYNC burst:   SB1[0,60)  BBK[60,74)  SB2[74,198)          tetra_burst.c:347-353 */
+       TB200_KIND_NDB_F = 2,   /* normal burst: BBK[0,14)  SCH/F[14,282)                    tetra_burst.c:363-373 */
+       TB200_KIND_NDB_2 = 3 }; /* normal burst: BBK[0,14)  BLK1[14,138)  BLK2[138,262)      tetra_burst.c:354-362 */
+
+/* tb200_slot.flags */
+#define TB200_F_KIND_MASK   0x03
+#define TB200_F_CRC_A       0x04   /* CRC of SB1 / SCH-F / BLK1 good (tetra_lower_mac.c:258-267) */
+#define TB200_F_CRC_B       0x08   /* CRC of SB2 / BLK2 good */
+#define TB200_F_BNCH        0x10   /* SB2 carries BNCH (is_bnch, tetra_lower_mac.c:122-127,170-173) */
+#define TB200_F_UNLOCK      0x20   /* this slot made the receiver lose lock (tetra_burst_sync.c:127,140) */
+
+/* One per slot the LOCKED receiver consumed (tetra_burst_sync.c:107-150), in stream order. */
+struct tb200_slot {
+	uint32_t slot_bit;         /* absolute bit number of the slot start (uint32, wraps like tetra_burst_sync.h:16) */
+	uint32_t scrambling_code;  /* cell scrambling code used for every block but SB1 (tetra_lower_mac.c:185) */
+	uint16_t find_off;         /* offset returned by the training-sequence search (valid if find_rc >= 0) */
+	uint16_t window;           /* bits the search was allowed to look at (bits_in_buf, tetra_burst_sync.c:117) */
+	uint16_t time;             /* tdma time on the slot's primitives: tn | fn << 3 | mn << 8 */
+	int8_t   find_rc;          /* enum tetra_train_seq or -1 (tetra_find_train_seq, tetra_burst.c:269-339) */
+	uint8_t  flags;            /* TB200_F_* */
+};
+
+/* Receiver state that survives from one call to the next: the reference keeps it in
+ * struct tetra_rx_state (tetra_burst_sync.h:12-20), t_phy_state (tetra_burst_sync.c:34)
+ * and the static _tcd (tetra_lower_mac.c:104-113). */
+struct tb200_rx_carry {
+	uint64_t stream_bits;      /* bits fed so far */
+	uint64_t buf_start_bit;    /* bitbuf_start_bitnum */
+	uint64_t next_frame_start; /* next_frame_start_bitnum */
+	uint64_t calls;            /* tetra_burst_sync_in() calls modelled so far */
+	uint32_t state;            /* TB200_RX_* */
+	uint32_t bits_in_buf;
+	uint32_t scramb_init;      /* tcd->scramb_init */
+	uint16_t mcc, mnc;
+	uint8_t  colour_code;
+	uint8_t  tn, fn, mn;       /* t_phy_state.time */
+};
+
+struct tb200_stats {
+	uint64_t slots;            /* slots consumed while LOCKED */
+	uint64_t bursts_decoded;   /* slots handed to the lower MAC (kind != NONE) */
+	uint64_t blocks;           /* TMV-SAP primitives produced */
+	uint64_t crc_ok_blocks;    /* of those with a CRC, how many were good */
+	uint64_t lock_losses;
+	uint64_t lock_acquisitions;
+	uint64_t kernel_launches;  /* CUDA kernels launched by the last call */
+};
+
+typedef struct tb200_ctx tb200_ctx;
+
+/* ---- life cycle ---------------------------------------------------------- */
+
+/* One context per GPU/process; `device` is the CUDA ordinal.  Returns 0 or a negative
+ * TB200_E_* code.  Fails (never falls back to the CPU) when no CUDA device is usable. */
+int  tb200_create(tb200_ctx **out, int device);
+void tb200_destroy(tb200_ctx *ctx);
+const char *tb200_last_error(const tb200_ctx *ctx);
+const char *tb200_version(void);
+
+#define TB200_E_CUDA     (-1)
+#define TB200_E_ARG      (-2)
+#define TB200_E_NOMEM    (-3)
+#define TB200_E_STATE    (-4)
+
+/* ---- options -------------------------------------------------------------- */
+
+#define TB200_OUT_UNPACKED  1   /* type-1 bits one per byte (reference ABI, msg->l1h) */
+#define TB200_OUT_PACKED    2   /* type-1 bits 32 per word, LSB first */
+
+#define TB200_VITERBI_WARP  0   /* one warp per burst, warp-shuffle ACS butterflies */
+#define TB200_VITERBI_LANE  1   /* one lane per coded block, registers-only ACS */
+
+struct tb200_options {
+	uint32_t chunk_bits;        /* read() size the caller models; tetra-rx.c:83 uses 64. 1..296 */
+	uint32_t output;            /* TB200_OUT_* bit mask */
+	uint32_t viterbi;           /* TB200_VITERBI_* */
+	uint32_t pipeline_slots;    /* slots per pipelined piece in the host-buffer path (0 = default) */
+};
+void tb200_default_options(struct tb200_options *opt);
+int  tb200_set_options(tb200_ctx *ctx, const struct tb200_options *opt);
+
+/* ---- batch receive: replaces the tetra-rx read loop + tetra_burst_sync_in -----
+ *
+ * Both calls behave like
+ *     for each chunk_bits-sized piece of bits[0..n_bits): tetra_burst_sync_in(trs, piece, len)
+ * (tetra-rx.c:82-95, phy/tetra_burst_sync.c:54-154) followed by the whole lower MAC
+ * (lower_mac/tetra_lower_mac.c:143-357) for every delivered block, except that results
+ * are returned as arrays instead of upper_mac_prim_recv() callbacks.
+ *
+ * flags: TB200_FRESH starts from a zeroed receiver (what tetra-rx.c:48-54 allocates),
+ * otherwise the call continues the stream where the previous call on this ctx stopped.
+ * TB200_FINAL says the stream ends with this call, so a trailing piece shorter than
+ * chunk_bits is fed as one last short read (read() at EOF, tetra-rx.c:85-94); without it
+ * the bits after the last full chunk boundary are kept for the next call.
+ */
+#define TB200_FRESH  1u
+#define TB200_FINAL  2u
+
+/* Device-resident: `d_bits` is a device pointer; results stay on the device.
+ * d_slots[max_slots], d_type1 (max_slots * TB200_TYPE1_STRIDE bytes, 16-byte aligned, may
+ * be NULL), d_type1_packed (max_slots * TB200_TYPE1_WORDS words, may be NULL) are device
+ * buffers owned by the caller.  Returns the number of slots written (>= 0) or TB200_E_*.
+ * All device work is complete when the call returns.  Needs TB200_FRESH | TB200_FINAL. */
+long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint32_t flags,
+                         struct tb200_slot *d_slots, uint8_t *d_type1, uint32_t *d_type1_packed,
+                         uint64_t max_slots);
+
+/* Host buffers in and out (pinned memory makes it faster, pageable works):
+ * H2D copies, kernels and D2H copies are pipelined over CUDA streams inside the call. */
+long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits, uint32_t flags,
+                          struct tb200_slot *slots, uint8_t *type1, uint32_t *type1_packed,
+                          uint64_t max_slots);
+
+/* Upper bound on the slots a stream of n_bits can yield. */
+uint64_t tb200_max_slots(uint64_t n_bits);
+
+int tb200_get_carry(const tb200_ctx *ctx, struct tb200_rx_carry *out);
+int tb200_get_stats(const tb200_ctx *ctx, struct tb200_stats *out);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
+void *tb200_host_alloc(size_t bytes);
+void  tb200_host_free(void *p);
+
+/* ---- records: what crosses TMV-SAP ------------------------------------------
+ * Expands slots + type-1 bits into one record per tp_sap_udata_ind() call, in the
+ * reference's call order (tetra_burst.c:347-373), with the fields of
+ * struct tmv_unitdata_param (tetra_prim.h:25-33).  Host-side helper. */
+struct tb200_record {
+	uint32_t slot_bit;
+	uint8_t  lchan;            /* enum tetra_log_chan, tetra_common.h:22-39 */
+	uint8_t  crc_ok;
+	uint8_t  blk_num;
+	uint8_t  tn, fn, mn;
+	uint16_t type1_len;
+	uint32_t scrambling_code;
+	uint8_t  type1[272];       /* one bit per byte */
+};
+/* returns records written; `records` may be NULL to count only */
+size_t tb200_expand_records(const struct tb200_slot *slots, const uint8_t *type1, size_t n_slots,
+                            struct tb200_record *records, size_t max_records);
+
+/* ---- leaf operators (batched, device side; used by the stage-parity tests) ----
+ * Each mirrors one reference function over `n` independent blocks laid out back to back. */
+
+/* tetra_scramb_bits + block_deinterleave (tetra_scramb.c:77, tetra_interleave.c:51):
+ * type-5 bytes -> type-3 bytes, n blocks of K bits each with interleaver constant a and
+ * per-block scrambling code d_codes[i].  Host or device pointers (is_device). */
+int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type5, uint8_t *type3,
+                                  const uint32_t *codes, uint64_t n, uint32_t K, uint32_t a,
+                                  int is_device);
+
+/* whole tp_sap_udata_ind arithmetic for n blocks of one type (tetra_lower_mac.c:143-280):
+ * type-5 bytes in; type-1 bytes (type1_bits each) and crc_ok flags out. Host pointers. */
+int tb200_decode_blocks(tb200_ctx *ctx, int blk_type, const uint8_t *type5, const uint32_t *codes,
+                        uint64_t n, uint8_t *type1, uint8_t *crc_ok);
+
+/* tetra_find_train_seq (tetra_burst.c:269-339) for n independent windows: window i is
+ * bits[starts[i] .. starts[i]+lens[i]); mask as in the reference. Host pointers. */
+int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits,
+                         const uint64_t *starts, const uint32_t *lens, uint64_t n, uint32_t mask,
+                         int32_t *rc, uint32_t *offset);
+
+/* ---- synthetic downlink generator (bench / test input, TX side) ----------------- */
+struct tb200_gen_cfg {
+	uint64_t seed;
+	uint32_t sb_period;      /* burst k is a SYNC burst iff k % sb_period == 0 (0: none) */
+	uint32_t lead_sb;        /* bursts [0, lead_sb) are SYNC bursts */
+	uint32_t ndb2_per_256;   /* share of the other bursts that carry two half-slot blocks */
+	uint32_t ber_per_65536;  /* i.i.d. payload bit-flip probability */
+	uint32_t random_cell;    /* per-SB random MCC/MNC/colour code */
+	uint32_t lead_in_bits;   /* random bits in front of burst 0 */
+};
+/* writes lead_in (if k0 == 0 and with_lead_in) + bursts [k0, k0+n) to a DEVICE buffer */
+int tb200_gen_stream_dev(tb200_ctx *ctx, const struct tb200_gen_cfg *cfg, uint64_t k0, uint64_t n,
+                         uint8_t *d_out, int with_lead_in);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TETRA_B200_H */

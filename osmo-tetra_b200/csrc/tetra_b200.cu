@@ -1,0 +1,1086 @@
+/*
+ * tetra_b200.cu - host side of libtetra_b200.so: tables, the lock state machine of
+ * tetra_burst_sync_in(), the batch driver and the C ABI declared in include/tetra_b200.h.
+ *
+ * The arithmetic (search, descramble, de-interleave, Viterbi, CRC) runs in the CUDA kernels
+ * of tetra_kernels.cuh; what stays on the host is control: which modelled read() call
+ * processes which slot, when the receiver is UNLOCKED / KNOW_FSTART / LOCKED
+ * (phy/tetra_burst_sync.c:54-154), and the stream plumbing.  There is no CPU decode path:
+ * without a CUDA device tb200_create() fails.
+ */
+#include "tetra_kernels.cuh"
+#include "tetra_gen.cuh"
+#include "../../include/tetra_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace tb;
+
+static_assert(sizeof(tb200_slot) == sizeof(SlotOut), "slot ABI");
+static_assert(sizeof(tb200_gen_cfg) == sizeof(GenCfg), "gen cfg ABI");
+static_assert(sizeof(tb200_record) == 288, "record ABI");
+
+/* ------------------------------------------------------------------ tables -- */
+
+static inline unsigned lfsr_step_host(uint32_t *st)   /* tetra_scramb.c:34-50 */
+{
+	unsigned fb = __builtin_parity(*st & 0xDB710641u);
+	*st = (*st >> 1) | ((uint32_t)fb << 31);
+	return fb;
+}
+
+static void lfsr_words_host(uint32_t init, uint32_t *w, int nwords)
+{
+	for (int i = 0; i < nwords; i++) {
+		uint32_t v = 0;
+		for (int b = 0; b < 32; b++)
+			v |= (uint32_t)lfsr_step_host(&init) << b;
+		w[i] = v;
+	}
+}
+
+static uint16_t crc16_host(const uint8_t *bits, int len, uint16_t crc)   /* crc_simple.c:65-82 */
+{
+	for (int i = 0; i < len; i++) {
+		unsigned top = ((crc >> 15) ^ bits[i]) & 1;
+		crc = (uint16_t)(crc << 1);
+		if (top) crc ^= 0x1021;
+	}
+	return crc;
+}
+
+static void build_tables(Tables *t)
+{
+	memset(t, 0, sizeof(*t));
+	for (int b = 0; b < 32; b++)
+		lfsr_words_host(1u << b, t->lfsr_col[b], 16);
+	lfsr_words_host(3, t->lfsr_sb1, 16);
+
+	std::vector<uint8_t> msg(300, 0);
+	for (int d = 0; d < 288; d++) {
+		std::fill(msg.begin(), msg.end(), 0);
+		msg[0] = 1;
+		t->crc_pow[d] = crc16_host(msg.data(), d + 1, 0);
+	}
+	std::fill(msg.begin(), msg.end(), 0);
+	const int Ls[3] = {76, 140, 284};
+	for (int i = 0; i < 3; i++)
+		t->crc_init[i] = crc16_host(msg.data(), Ls[i], 0xffff);
+
+	/* pre-filter blind spot, by running the filter of tetra_burst.c:286-303 on a buffer
+	 * that carries the sequence at offset k with the bit before it set to `prev` */
+	const uint64_t seqs[3] = {SEQ_Y, SEQ_N, SEQ_P};
+	const uint32_t pre[5] = {(uint32_t)(SEQ_Y & 0x3fffff), SEQ_N, SEQ_P, SEQ_Q, SEQ_X & 0x3fffff};
+	uint32_t pre_msb[5];
+	for (int i = 0; i < 5; i++) {          /* the filter shifts left: first bit ends up in bit 21 */
+		uint32_t v = 0;
+		for (int b = 0; b < 22; b++)
+			v = (v << 1) | ((pre[i] >> b) & 1);
+		pre_msb[i] = v;
+	}
+	for (int s = 0; s < 3; s++)
+		for (int prev = 0; prev < 2; prev++) {
+			uint32_t ok = 0;
+			for (int k = 0; k <= 20; k++) {
+				uint8_t in[96];
+				memset(in, 0, sizeof(in));
+				for (int b = 0; b < 38; b++)
+					in[k + b] = (seqs[s] >> b) & 1;     /* bits past the sequence do not reach the filter at k */
+				if (k > 0) in[k - 1] = prev;
+				uint32_t filt = 0;
+				for (int i = 0; i < 20; i++)
+					filt = (filt << 1) | in[i];
+				for (int c = 0; c <= k; c++)
+					filt = ((filt << 1) | in[c + 21]) & 0x3fffff;
+				for (int i = 0; i < 5; i++)
+					if (filt == pre_msb[i]) ok |= 1u << k;
+			}
+			t->blind_ok[s][prev] = ok;
+		}
+}
+
+/* --------------------------------------------------------------- context -- */
+
+#define NBUF 3
+
+struct RxHost {
+	uint32_t state = TB200_RX_UNLOCKED;
+	uint64_t calls = 0;          /* modelled tetra_burst_sync_in() calls done */
+	uint64_t buf_start = 0;      /* bitbuf_start_bitnum (64-bit here) */
+	uint32_t bits_in_buf = 0;
+	uint64_t next_frame_start = 0;
+};
+
+struct SyncHit { uint64_t pos; uint32_t prev; };
+
+struct tb200_ctx {
+	int device = 0;
+	int sm_count = 148;
+	char err[256] = {0};
+	tb200_options opt;
+	tb200_stats stats;
+	Tables h_tab;
+	Tables *d_tab = nullptr;
+	DevCarry *d_carry = nullptr;     /* chain of carries, one per piece (+1) */
+	size_t carry_cap = 0;
+	/* per-launch workspace, shared by all pieces (the compute stream serialises them) */
+	SlotWs *d_ws = nullptr;
+	uint32_t *d_slot_bits = nullptr;
+	int32_t *d_last_good = nullptr, *d_blk_last = nullptr, *d_blk_prev = nullptr;
+	size_t ws_slots = 0;
+	uint32_t *d_flags = nullptr;     /* first unlocking slot per piece */
+	uint32_t *h_flags = nullptr;     /* pinned mirror */
+	size_t flags_cap = 0;
+	/* host path staging */
+	uint8_t *d_in[NBUF] = {nullptr, nullptr, nullptr};
+	size_t in_cap = 0;
+	SlotOut *d_oslots[NBUF] = {nullptr, nullptr, nullptr};
+	uint8_t *d_otype1[NBUF] = {nullptr, nullptr, nullptr};
+	uint32_t *d_opacked[NBUF] = {nullptr, nullptr, nullptr};
+	size_t out_cap = 0;
+	/* UNLOCKED search */
+	uint32_t *d_hits = nullptr;      /* [0] = count, then (pos_lo, pos_hi|prev<<31) pairs */
+	uint32_t *h_hits = nullptr;
+	uint8_t *d_region = nullptr;
+	size_t region_cap = 0;
+	std::vector<SyncHit> hits;
+	uint64_t hits_lo = 0, hits_hi = 0;
+	cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+	cudaEvent_t ev_h2d[NBUF], ev_comp[NBUF], ev_d2h[NBUF];
+	/* stream state across calls */
+	RxHost rx;
+	std::vector<uint8_t> tail;       /* bits [tail_base, fed_end) kept from earlier calls (host path) */
+	uint64_t tail_base = 0;
+	uint64_t fed_end = 0;            /* absolute bits handed to the ctx so far */
+	DevCarry h_carry;
+};
+
+static int fail(tb200_ctx *c, int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(c->err, sizeof(c->err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+	return fail(ctx, TB200_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" const char *tb200_version(void)
+{
+#ifdef TB_SIMT_EMULATION
+	return "tetra_b200 0.1 (SIMT emulation build - tests only)";
+#else
+	return "tetra_b200 0.1 (sm_100a)";
+#endif
+}
+
+extern "C" void tb200_default_options(tb200_options *o)
+{
+	o->chunk_bits = 64;
+	o->output = TB200_OUT_UNPACKED | TB200_OUT_PACKED;
+	o->viterbi = TB200_VITERBI_WARP;
+	o->pipeline_slots = 0;
+}
+
+extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
+{
+	if (!ctx || !o) return TB200_E_ARG;
+	if (o->chunk_bits < 1 || o->chunk_bits > 296)
+		return fail(ctx, TB200_E_ARG, "chunk_bits must be 1..296");
+	if (o->viterbi > TB200_VITERBI_LANE)
+		return fail(ctx, TB200_E_ARG, "unknown viterbi variant");
+	ctx->opt = *o;
+	return 0;
+}
+
+extern "C" const char *tb200_last_error(const tb200_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" int tb200_create(tb200_ctx **out, int device)
+{
+	if (!out) return TB200_E_ARG;
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+		fprintf(stderr, "tetra_b200: no usable CUDA device (asked for %d of %d); there is no CPU path\n", device, ndev);
+		return TB200_E_CUDA;
+	}
+	tb200_ctx *ctx = new tb200_ctx();
+	ctx->device = device;
+	tb200_default_options(&ctx->opt);
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	memset(&ctx->h_carry, 0, sizeof(ctx->h_carry));
+	auto bail = [&](const char *what) { fprintf(stderr, "tetra_b200: %s failed\n", what); delete ctx; return TB200_E_CUDA; };
+	if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail("cudaGetDeviceProperties");
+	ctx->sm_count = prop.multiProcessorCount;
+	build_tables(&ctx->h_tab);
+	if (cudaMalloc((void **)&ctx->d_tab, sizeof(Tables)) != cudaSuccess) return bail("cudaMalloc");
+	if (cudaMemcpy(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy");
+	if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+	if (cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+	if (cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+	for (int i = 0; i < NBUF; i++) {
+		cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
+	}
+	if (cudaMalloc((void **)&ctx->d_hits, sizeof(uint32_t) * (2 * 8192 + 2)) != cudaSuccess) return bail("cudaMalloc");
+	if (cudaHostAlloc((void **)&ctx->h_hits, sizeof(uint32_t) * (2 * 8192 + 2), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
+	*out = ctx;
+	return 0;
+}
+
+extern "C" void tb200_destroy(tb200_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry); cudaFree(ctx->d_ws); cudaFree(ctx->d_slot_bits);
+	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev);
+	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags);
+	for (int i = 0; i < NBUF; i++) {
+		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]);
+		cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]);
+	}
+	cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_hits); cudaFree(ctx->d_region);
+	cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+	delete ctx;
+}
+
+extern "C" void *tb200_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+	return p;
+}
+extern "C" void tb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" uint64_t tb200_max_slots(uint64_t n_bits) { return n_bits / SLOT_BITS + 1; }
+
+/* ---------------------------------------------------------- small helpers -- */
+
+template <typename T>
+static int grow(tb200_ctx *ctx, T **p, size_t n)
+{
+	if (*p) cudaFree(*p);
+	*p = nullptr;
+	CU(cudaMalloc((void **)p, n * sizeof(T)));
+	return 0;
+}
+
+static int ensure_workspace(tb200_ctx *ctx, size_t slots)
+{
+	if (slots <= ctx->ws_slots) return 0;
+	CU(cudaDeviceSynchronize());
+	int rc;
+	if ((rc = grow(ctx, &ctx->d_ws, slots))) return rc;
+	if ((rc = grow(ctx, &ctx->d_slot_bits, slots * 16))) return rc;
+	if ((rc = grow(ctx, &ctx->d_last_good, slots))) return rc;
+	if ((rc = grow(ctx, &ctx->d_blk_last, slots / 1024 + 2))) return rc;
+	if ((rc = grow(ctx, &ctx->d_blk_prev, slots / 1024 + 2))) return rc;
+	ctx->ws_slots = slots;
+	return 0;
+}
+
+static int ensure_pieces(tb200_ctx *ctx, size_t npieces)
+{
+	if (npieces + 2 > ctx->carry_cap) {
+		CU(cudaDeviceSynchronize());
+		DevCarry keep = ctx->h_carry;
+		size_t cap = npieces + 64;
+		int rc;
+		if ((rc = grow(ctx, &ctx->d_carry, cap))) return rc;
+		ctx->carry_cap = cap;
+		CU(cudaMemcpy(ctx->d_carry, &keep, sizeof(keep), cudaMemcpyHostToDevice));
+	}
+	if (npieces + 2 > ctx->flags_cap) {
+		CU(cudaDeviceSynchronize());
+		size_t cap = npieces + 64;
+		int rc;
+		if ((rc = grow(ctx, &ctx->d_flags, cap))) return rc;
+		if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+		CU(cudaHostAlloc((void **)&ctx->h_flags, cap * sizeof(uint32_t), cudaHostAllocDefault));
+		ctx->flags_cap = cap;
+	}
+	return 0;
+}
+
+static int ensure_staging(tb200_ctx *ctx, size_t in_bytes, size_t slots)
+{
+	if (in_bytes > ctx->in_cap) {
+		CU(cudaDeviceSynchronize());
+		for (int i = 0; i < NBUF; i++) { int rc = grow(ctx, &ctx->d_in[i], in_bytes); if (rc) return rc; }
+		ctx->in_cap = in_bytes;
+	}
+	if (slots > ctx->out_cap) {
+		CU(cudaDeviceSynchronize());
+		for (int i = 0; i < NBUF; i++) {
+			int rc;
+			if ((rc = grow(ctx, &ctx->d_oslots[i], slots))) return rc;
+			if ((rc = grow(ctx, &ctx->d_otype1[i], slots * TYPE1_STRIDE))) return rc;
+			if ((rc = grow(ctx, &ctx->d_opacked[i], slots * TYPE1_WORDS))) return rc;
+		}
+		ctx->out_cap = slots;
+	}
+	return 0;
+}
+
+/* ------------------------------------------------------------ the source -- */
+
+/* Where the stream bits of this call live.  Absolute bit i of the stream is
+ *   tail[i - tail_base]            for tail_base <= i < new_base   (host path only)
+ *   data[i - new_base]             for new_base  <= i < end                          */
+struct Source {
+	bool on_device;
+	const uint8_t *data;
+	uint64_t new_base;
+	uint64_t end;
+};
+
+/* copy stream bits [lo, hi) to device memory `dst` (host path) */
+static int stage_bits(tb200_ctx *ctx, const Source &src, uint64_t lo, uint64_t hi, uint8_t *dst, cudaStream_t st)
+{
+	if (hi <= lo) return 0;
+	if (lo < src.new_base) {
+		uint64_t h = std::min(hi, src.new_base);
+		CU(cudaMemcpyAsync(dst, ctx->tail.data() + (lo - ctx->tail_base), h - lo, cudaMemcpyHostToDevice, st));
+		dst += h - lo;
+		lo = h;
+	}
+	if (hi > lo)
+		CU(cudaMemcpyAsync(dst, src.data + (lo - src.new_base), hi - lo, cudaMemcpyHostToDevice, st));
+	return 0;
+}
+
+/* -------------------------------------------------- UNLOCKED: SYNC search -- */
+
+/* every position p in [lo, hi) where the 38-bit SYNC training sequence starts; bits are
+ * readable up to `avail` bytes from `bits`; position p <-> bits[p - base] */
+__global__ void __launch_bounds__(256)
+k_scan_sync(const uint8_t *bits, uint64_t base, uint64_t avail, uint64_t lo, uint64_t hi,
+            const Tables *__restrict__ tab, uint32_t *hits, uint32_t cap)
+{
+	const unsigned lane = threadIdx.x & 31;
+	const uint64_t warp = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	const uint8_t *end = bits + avail;
+	for (uint64_t p0 = lo + warp * 1024; p0 < hi; p0 += nwarps * 1024) {
+		uint32_t x0, x1, x2;
+		load_window(bits + (p0 - base), end, lane, x0, x1, x2);
+		uint32_t My = 0xffffffffu;
+#pragma unroll
+		for (int b = 0; b < 32; ++b) {
+			uint32_t s = __funnelshift_r(x0, x1, b);
+			My &= ((SEQ_Y >> b) & 1) ? s : ~s;
+		}
+#pragma unroll
+		for (int b = 32; b < 38; ++b) {
+			uint32_t s = __funnelshift_r(x1, x2, b - 32);
+			My &= ((SEQ_Y >> b) & 1) ? s : ~s;
+		}
+		const uint64_t pl = p0 + 32 * lane;
+		/* keep positions < hi whose 38 bits are inside the available data */
+		const uint64_t data_end = base + avail;
+		const uint64_t conf = data_end >= 37 ? data_end - 37 : 0;
+		const long long lim = (long long)(hi < conf ? hi : conf) - (long long)pl - 1;
+		My &= low_mask(lim);
+		/* the bit before each position: bit i-1 of this lane's word, bit 31 of the previous lane's for i = 0 */
+		uint32_t prev_word = __shfl_up_sync(FULL, x0, 1);
+		uint32_t first_prev = 0;
+		if (lane == 0) {
+			if (p0 > base) first_prev = bits[p0 - base - 1] & 1;
+		} else {
+			first_prev = prev_word >> 31;
+		}
+		const uint32_t prevbits = (x0 << 1) | first_prev;
+		while (My) {
+			const int i = __ffs((int)My) - 1;
+			My &= My - 1;
+			const uint32_t slot = atomicAdd(&hits[0], 1u);
+			if (slot < cap) {
+				const uint64_t pos = pl + i;
+				hits[2 + 2 * slot] = (uint32_t)pos;
+				hits[3 + 2 * slot] = (uint32_t)(pos >> 32) | (((prevbits >> i) & 1) << 31);
+			}
+		}
+	}
+}
+
+#define REGION_BITS (1u << 18)
+#define HIT_CAP 8192u
+
+/* make sure the hit list covers [from, upto) as far as the data of this call allows */
+static int scan_more_hits(tb200_ctx *ctx, const Source &src, uint64_t from, uint64_t upto)
+{
+	if (from < ctx->hits_lo || from > ctx->hits_hi) {
+		ctx->hits.clear();
+		ctx->hits_lo = ctx->hits_hi = from;
+	}
+	/* a sequence starting in the last 37 bits of the data cannot be confirmed yet */
+	const uint64_t confirmable = src.end >= 37 ? src.end - 37 : 0;
+	const uint64_t first_bit = src.on_device ? src.new_base : ctx->tail_base;
+	while (ctx->hits_hi < upto && ctx->hits_hi < confirmable) {
+		const uint64_t lo = ctx->hits_hi;
+		const uint64_t hi = std::min<uint64_t>(lo + REGION_BITS, confirmable);
+		const uint8_t *dbits;
+		uint64_t dbase, davail;
+		if (src.on_device) {
+			dbits = src.data; dbase = src.new_base; davail = src.end - src.new_base;
+		} else {
+			const uint64_t rd_lo = (lo > first_bit) ? lo - 1 : lo;      /* one bit back for the blind-spot rule */
+			const uint64_t rd_hi = std::min<uint64_t>(hi + 64, src.end);
+			const size_t nb = (size_t)(rd_hi - rd_lo);
+			if (nb + 64 > ctx->region_cap) {
+				CU(cudaDeviceSynchronize());
+				int rc = grow(ctx, &ctx->d_region, (size_t)REGION_BITS + 256);
+				if (rc) return rc;
+				ctx->region_cap = (size_t)REGION_BITS + 256;
+			}
+			int rc = stage_bits(ctx, src, rd_lo, rd_hi, ctx->d_region, ctx->s_compute);
+			if (rc) return rc;
+			dbits = ctx->d_region; dbase = rd_lo; davail = nb;
+		}
+		CU(cudaMemsetAsync(ctx->d_hits, 0, sizeof(uint32_t) * 2, ctx->s_compute));
+		const unsigned blocks = (unsigned)std::min<uint64_t>((hi - lo + 8191) / 8192, (uint64_t)ctx->sm_count * 4);
+		TB_LAUNCH(k_scan_sync, blocks, 256, ctx->s_compute, dbits, dbase, davail, lo, hi, ctx->d_tab, ctx->d_hits, HIT_CAP);
+		ctx->stats.kernel_launches++;
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(uint32_t) * (2 + 2 * HIT_CAP), cudaMemcpyDeviceToHost, ctx->s_compute));
+		CU(cudaStreamSynchronize(ctx->s_compute));
+		const uint32_t n = ctx->h_hits[0];
+		if (n > HIT_CAP)
+			return fail(ctx, TB200_E_STATE, "SYNC hit list overflow (%u hits in %u bits)", n, REGION_BITS);
+		const size_t old = ctx->hits.size();
+		for (uint32_t i = 0; i < n; i++) {
+			SyncHit h;
+			h.pos = (uint64_t)ctx->h_hits[2 + 2 * i] | ((uint64_t)(ctx->h_hits[3 + 2 * i] & 0x7fffffffu) << 32);
+			h.prev = ctx->h_hits[3 + 2 * i] >> 31;
+			ctx->hits.push_back(h);
+		}
+		std::sort(ctx->hits.begin() + old, ctx->hits.end(), [](const SyncHit &x, const SyncHit &y) { return x.pos < y.pos; });
+		ctx->hits_hi = hi;
+	}
+	/* forget hits that no later search can reach */
+	if (ctx->hits.size() > 65536) {
+		auto it = std::lower_bound(ctx->hits.begin(), ctx->hits.end(), from,
+		                           [](const SyncHit &h, uint64_t v) { return h.pos < v; });
+		ctx->hits.erase(ctx->hits.begin(), it);
+		ctx->hits_lo = from;
+	}
+	return 0;
+}
+
+/* tetra_find_train_seq(bitbuf, bits_in_buf, SYNC only) as the UNLOCKED state calls it
+ * (tetra_burst_sync.c:75-76): first SYNC sequence fully inside the buffer, subject to the
+ * pre-filter blind spot relative to bitbuf[0] */
+static bool first_sync_in_buffer(tb200_ctx *ctx, uint64_t buf_start, uint32_t bits_in_buf, uint64_t *pos)
+{
+	auto it = std::lower_bound(ctx->hits.begin(), ctx->hits.end(), buf_start,
+	                           [](const SyncHit &h, uint64_t v) { return h.pos < v; });
+	for (; it != ctx->hits.end(); ++it) {
+		if (it->pos + 38 > buf_start + bits_in_buf) return false;
+		uint64_t k = it->pos - buf_start;
+		if (k <= 20 && !((ctx->h_tab.blind_ok[0][it->prev] >> k) & 1)) continue;
+		*pos = it->pos;
+		return true;
+	}
+	return false;
+}
+
+/* ----------------------------------------------------- LOCKED: the pieces -- */
+
+struct Outputs {
+	bool on_device;
+	tb200_slot *slots;
+	uint8_t *type1;
+	uint32_t *packed;
+	uint64_t max_slots;
+	uint64_t n;                  /* slots written so far */
+};
+
+struct Segment {
+	uint64_t a0;                 /* absolute bit of slot 0 */
+	uint64_t cmin;               /* first call that may process slot 0 */
+	uint64_t n_end;
+	uint32_t chunk;
+};
+
+static inline uint64_t slot_call(const Segment &s, uint64_t k)   /* call index that processes slot k */
+{
+	uint64_t need = (s.a0 + (uint64_t)SLOT_BITS * k + SLOT_BITS + s.chunk - 1) / s.chunk;
+	return std::max(need, s.cmin + k);
+}
+
+/* enqueue classify + scan + decode + carry for slots [k0, k0+nb) of the segment */
+static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32_t nb, const uint8_t *d_bits,
+                         uint64_t d_base, uint64_t d_avail, size_t piece_idx,
+                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base)
+{
+	cudaStream_t st = ctx->s_compute;
+	RxGeom g;
+	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base;
+	g.a0 = seg.a0 + (uint64_t)SLOT_BITS * k0; g.cmin = seg.cmin + k0; g.n_end = seg.n_end;
+	g.chunk = seg.chunk; g.n_slots = nb;
+	const unsigned wpb = 8;
+	const unsigned blocks = (unsigned)std::min<uint64_t>((nb + wpb - 1) / wpb, (uint64_t)ctx->sm_count * 16);
+	CU(cudaMemsetAsync(ctx->d_flags + piece_idx, 0xff, sizeof(uint32_t), st));
+	TB_LAUNCH(k_classify, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
+	const unsigned nblk = (nb + 1023) / 1024;
+	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, ctx->d_ws, nb, ctx->d_last_good, ctx->d_blk_last, ctx->d_flags + piece_idx);
+	TB_LAUNCH(k_scan_prefix, 1, 1024, st, ctx->d_blk_last, nblk, ctx->d_blk_prev);
+	DecodeArgs a;
+	a.ws = ctx->d_ws; a.slot_bits = ctx->d_slot_bits; a.last_good = ctx->d_last_good; a.blk_prev = ctx->d_blk_prev;
+	a.carry = ctx->d_carry + piece_idx; a.tab = ctx->d_tab;
+	a.slots = o_slots;
+	a.type1 = (ctx->opt.output & TB200_OUT_UNPACKED) ? o_type1 : nullptr;
+	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
+	a.a0 = g.a0; a.out_base = out_base; a.n_slots = nb;
+	TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
+	CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
+	TB_LAUNCH(k_finalize_carry, 1, 32, st, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, nb, ctx->d_carry + piece_idx + 1);
+	ctx->stats.kernel_launches += 5;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+/* Process slots [0, n_slots) of a LOCKED segment, optimistically assuming lock is kept;
+ * the first piece that reports a lock loss is redone up to and including the losing slot.
+ * *valid = slots consumed, *lost = whether the last one lost lock. */
+static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uint64_t n_slots,
+                      Outputs &out, uint64_t *valid, bool *lost)
+{
+	*valid = 0; *lost = false;
+	if (n_slots == 0) return 0;
+	if (out.n + n_slots > out.max_slots)
+		return fail(ctx, TB200_E_ARG, "output arrays too small: need %llu slots, have %llu",
+		            (unsigned long long)(out.n + n_slots), (unsigned long long)out.max_slots);
+	uint32_t P = ctx->opt.pipeline_slots ? ctx->opt.pipeline_slots : (src.on_device ? (1u << 20) : (1u << 15));
+	if (P > n_slots) P = (uint32_t)n_slots;
+	const size_t npieces = (size_t)((n_slots + P - 1) / P);
+	int rc;
+	if ((rc = ensure_workspace(ctx, P))) return rc;
+	if ((rc = ensure_pieces(ctx, npieces))) return rc;
+	/* bits a piece may touch: its slots plus the largest search window (<= 4096) */
+	const size_t piece_in = (size_t)P * SLOT_BITS + 4096 + 64;
+	if (!src.on_device && (rc = ensure_staging(ctx, piece_in, P))) return rc;
+	const bool host_out = !out.on_device;
+	if (src.on_device && host_out)
+		return fail(ctx, TB200_E_ARG, "device input with host output is not supported");
+
+	auto piece_range = [&](size_t i, uint64_t *k0, uint32_t *nb) {
+		*k0 = (uint64_t)i * P;
+		*nb = (uint32_t)std::min<uint64_t>(P, n_slots - *k0);
+	};
+	auto issue = [&](size_t i, uint32_t nb_override) -> int {
+		uint64_t k0; uint32_t nb;
+		piece_range(i, &k0, &nb);
+		if (nb_override) nb = nb_override;
+		const int b = (int)(i % NBUF);
+		const uint64_t lo = seg.a0 + (uint64_t)SLOT_BITS * k0;
+		const uint64_t hi = std::min<uint64_t>(seg.n_end, lo + (uint64_t)SLOT_BITS * nb + 4096);
+		const uint8_t *dbits; uint64_t dbase, davail;
+		if (src.on_device) {
+			dbits = src.data; dbase = src.new_base; davail = seg.n_end - src.new_base;
+		} else {
+			int r = stage_bits(ctx, src, lo, hi, ctx->d_in[b], ctx->s_h2d);
+			if (r) return r;
+			CU(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+			CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d[b], 0));
+			dbits = ctx->d_in[b]; dbase = lo; davail = hi - lo;
+		}
+		SlotOut *os; uint8_t *ot; uint32_t *op; uint64_t ob;
+		if (out.on_device) {
+			os = (SlotOut *)out.slots; ot = out.type1; op = out.packed; ob = out.n + k0;
+		} else {
+			os = ctx->d_oslots[b]; ot = ctx->d_otype1[b]; op = ctx->d_opacked[b]; ob = 0;
+		}
+		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, i, os, ot, op, ob);
+		if (r) return r;
+		CU(cudaEventRecord(ctx->ev_comp[b], ctx->s_compute));
+		cudaStream_t so = host_out ? ctx->s_d2h : ctx->s_compute;
+		if (host_out) {
+			CU(cudaStreamWaitEvent(so, ctx->ev_comp[b], 0));
+			const uint64_t o0 = out.n + k0;
+			CU(cudaMemcpyAsync(out.slots + o0, os, (size_t)nb * sizeof(SlotOut), cudaMemcpyDeviceToHost, so));
+			if (out.type1 && (ctx->opt.output & TB200_OUT_UNPACKED))
+				CU(cudaMemcpyAsync(out.type1 + o0 * TYPE1_STRIDE, ot, (size_t)nb * TYPE1_STRIDE, cudaMemcpyDeviceToHost, so));
+			if (out.packed && (ctx->opt.output & TB200_OUT_PACKED))
+				CU(cudaMemcpyAsync(out.packed + o0 * TYPE1_WORDS, op, (size_t)nb * TYPE1_WORDS * 4, cudaMemcpyDeviceToHost, so));
+		}
+		CU(cudaMemcpyAsync(ctx->h_flags + i, ctx->d_flags + i, sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
+		CU(cudaEventRecord(ctx->ev_d2h[b], so));
+		return 0;
+	};
+
+	size_t bad_piece = npieces;
+	for (size_t i = 0; i < npieces; i++) {
+		if (i >= NBUF) CU(cudaEventSynchronize(ctx->ev_d2h[i % NBUF]));
+		if ((rc = issue(i, 0))) return rc;
+		if (i >= 1) {
+			CU(cudaEventSynchronize(ctx->ev_d2h[(i - 1) % NBUF]));
+			if (ctx->h_flags[i - 1] != 0xffffffffu) { bad_piece = i - 1; break; }
+		}
+	}
+	CU(cudaStreamSynchronize(ctx->s_h2d));
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	CU(cudaStreamSynchronize(ctx->s_d2h));
+	if (bad_piece == npieces && ctx->h_flags[npieces - 1] != 0xffffffffu) bad_piece = npieces - 1;
+
+	size_t last_piece;
+	if (bad_piece < npieces) {
+		/* redo the piece that lost lock, cut right after the losing slot, so that outputs and
+		 * the carried cell state stop exactly where the reference's LOCKED state stops */
+		const uint32_t u = ctx->h_flags[bad_piece];
+		uint64_t k0; uint32_t nb;
+		piece_range(bad_piece, &k0, &nb);
+		if ((rc = issue(bad_piece, u + 1))) return rc;
+		CU(cudaStreamSynchronize(ctx->s_h2d));
+		CU(cudaStreamSynchronize(ctx->s_compute));
+		CU(cudaStreamSynchronize(ctx->s_d2h));
+		*valid = k0 + u + 1;
+		*lost = true;
+		last_piece = bad_piece;
+	} else {
+		*valid = n_slots;
+		last_piece = npieces - 1;
+	}
+	/* the state after the last valid slot becomes the start of the chain again */
+	CU(cudaMemcpy(&ctx->h_carry, ctx->d_carry + last_piece + 1, sizeof(DevCarry), cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(ctx->d_carry, &ctx->h_carry, sizeof(DevCarry), cudaMemcpyHostToDevice));
+	out.n += *valid;
+	return 0;
+}
+
+/* ------------------------------------------------------- the state machine -- */
+
+static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
+{
+	const uint32_t C = ctx->opt.chunk_bits;
+	const uint64_t total = src.end;
+	const uint64_t c_max = final ? (total + C - 1) / C : total / C;
+	const uint64_t n_end = final ? total : c_max * C;
+	RxHost &rx = ctx->rx;
+	auto T = [&](uint64_t c) { return std::min<uint64_t>(c * C, n_end); };
+	int rc;
+
+	while (rx.calls < c_max) {
+		if (rx.state == TB200_RX_LOCKED) {
+			Segment seg;
+			seg.a0 = rx.buf_start; seg.cmin = rx.calls + 1; seg.n_end = n_end; seg.chunk = C;
+			uint64_t n_slots = 0;
+			if (n_end >= seg.a0 + SLOT_BITS) {
+				uint64_t by_bits = (n_end - SLOT_BITS - seg.a0) / SLOT_BITS + 1;
+				uint64_t by_calls = c_max - seg.cmin + 1;
+				n_slots = std::min(by_bits, by_calls);
+			}
+			if (n_slots == 0) {
+				rx.calls = c_max;
+				rx.bits_in_buf = (uint32_t)(T(c_max) - rx.buf_start);
+				break;
+			}
+			uint64_t valid = 0; bool lost = false;
+			if ((rc = run_locked(ctx, src, seg, n_slots, out, &valid, &lost))) return rc;
+			ctx->stats.slots += valid;
+			const uint64_t c_last = slot_call(seg, valid - 1);
+			rx.calls = c_last;
+			rx.buf_start = seg.a0 + (uint64_t)SLOT_BITS * valid;
+			rx.bits_in_buf = (uint32_t)(T(c_last) - rx.buf_start);
+			rx.next_frame_start += (uint64_t)SLOT_BITS * valid;
+			if (lost) {
+				rx.state = TB200_RX_UNLOCKED;
+				ctx->stats.lock_losses++;
+			}
+			continue;
+		}
+		/* UNLOCKED / KNOW_FSTART: one modelled call at a time (tetra_burst_sync.c:60-106) */
+		const uint64_t c = rx.calls + 1;
+		const uint64_t t_prev = T(rx.calls), t_now = T(c);
+		uint64_t bib = (uint64_t)rx.bits_in_buf + (t_now - t_prev);
+		if (bib > 4096) { rx.buf_start += bib - 4096; bib = 4096; }   /* make_bitbuf_space, :38-51 */
+		rx.bits_in_buf = (uint32_t)bib;
+		rx.calls = c;
+		if (rx.state == TB200_RX_UNLOCKED) {
+			if (bib < 2 * SLOT_BITS) continue;
+			if ((rc = scan_more_hits(ctx, src, rx.buf_start, rx.buf_start + bib))) return rc;
+			uint64_t pos;
+			if (!first_sync_in_buffer(ctx, rx.buf_start, rx.bits_in_buf, &pos)) continue;
+			rx.state = TB200_RX_KNOW_FSTART;
+			rx.next_frame_start = pos + 296;
+			ctx->stats.lock_acquisitions++;
+			continue;
+		}
+		/* KNOW_FSTART */
+		if (rx.buf_start + rx.bits_in_buf < rx.next_frame_start) continue;
+		const uint64_t shift = rx.next_frame_start - rx.buf_start;
+		rx.bits_in_buf -= (uint32_t)shift;
+		rx.buf_start = rx.next_frame_start;
+		rx.next_frame_start += SLOT_BITS;
+		rx.state = TB200_RX_LOCKED;
+		rx.calls = c - 1;            /* the LOCKED arm runs in this same call (fall-through, :105-107) */
+	}
+	return 0;
+}
+
+static void reset_stream(tb200_ctx *ctx)
+{
+	ctx->rx = RxHost();
+	ctx->tail.clear();
+	ctx->tail_base = 0;
+	ctx->fed_end = 0;
+	ctx->hits.clear();
+	ctx->hits_lo = ctx->hits_hi = 0;
+	memset(&ctx->h_carry, 0, sizeof(ctx->h_carry));
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+}
+
+static int push_carry(tb200_ctx *ctx)
+{
+	int rc = ensure_pieces(ctx, 1);
+	if (rc) return rc;
+	CU(cudaMemcpy(ctx->d_carry, &ctx->h_carry, sizeof(DevCarry), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint32_t flags,
+                                    tb200_slot *d_slots, uint8_t *d_type1, uint32_t *d_type1_packed, uint64_t max_slots)
+{
+	if (!ctx) return TB200_E_ARG;
+	if ((flags & (TB200_FRESH | TB200_FINAL)) != (TB200_FRESH | TB200_FINAL))
+		return fail(ctx, TB200_E_ARG, "the device-resident call needs TB200_FRESH | TB200_FINAL");
+	if (!d_bits || !d_slots) return fail(ctx, TB200_E_ARG, "null buffer");
+	if (d_type1 && ((uintptr_t)d_type1 & 15)) return fail(ctx, TB200_E_ARG, "d_type1 must be 16-byte aligned");
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	reset_stream(ctx);
+	int rc = push_carry(ctx);
+	if (rc) return rc;
+	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits;
+	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
+	out.max_slots = max_slots; out.n = 0;
+	ctx->fed_end = n_bits;
+	rc = rx_run(ctx, src, true, out);
+	if (rc) return rc;
+	return (long)out.n;
+}
+
+extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits, uint32_t flags,
+                                     tb200_slot *slots, uint8_t *type1, uint32_t *type1_packed, uint64_t max_slots)
+{
+	if (!ctx) return TB200_E_ARG;
+	if ((!bits && n_bits) || !slots) return fail(ctx, TB200_E_ARG, "null buffer");
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	if (flags & TB200_FRESH) reset_stream(ctx);
+	int rc = push_carry(ctx);
+	if (rc) return rc;
+	const uint64_t kernels_before = ctx->stats.kernel_launches;
+	(void)kernels_before;
+	Source src; src.on_device = false; src.data = bits; src.new_base = ctx->fed_end; src.end = ctx->fed_end + n_bits;
+	Outputs out; out.on_device = false; out.slots = slots; out.type1 = type1; out.packed = type1_packed;
+	out.max_slots = max_slots; out.n = 0;
+	ctx->fed_end += n_bits;
+	rc = rx_run(ctx, src, (flags & TB200_FINAL) != 0, out);
+	if (rc) return rc;
+	/* keep what a later call may still look at: everything from bitbuf[0] on */
+	const uint64_t keep_from = std::min<uint64_t>(ctx->rx.buf_start, ctx->fed_end);
+	std::vector<uint8_t> nt;
+	nt.reserve(ctx->fed_end - keep_from);
+	for (uint64_t i = keep_from; i < ctx->fed_end; i++)
+		nt.push_back(i < src.new_base ? ctx->tail[i - ctx->tail_base] : bits[i - src.new_base]);
+	ctx->tail.swap(nt);
+	ctx->tail_base = keep_from;
+	/* hits before the kept range are of no further use */
+	return (long)out.n;
+}
+
+extern "C" int tb200_get_carry(const tb200_ctx *ctx, tb200_rx_carry *o)
+{
+	if (!ctx || !o) return TB200_E_ARG;
+	memset(o, 0, sizeof(*o));
+	o->stream_bits = ctx->fed_end;
+	o->buf_start_bit = ctx->rx.buf_start;
+	o->next_frame_start = ctx->rx.next_frame_start;
+	o->calls = ctx->rx.calls;
+	o->state = ctx->rx.state;
+	o->bits_in_buf = ctx->rx.bits_in_buf;
+	o->scramb_init = ctx->h_carry.scramb_init;
+	o->mcc = (uint16_t)ctx->h_carry.mcc; o->mnc = (uint16_t)ctx->h_carry.mnc; o->colour_code = (uint8_t)ctx->h_carry.cc;
+	o->tn = (uint8_t)ctx->h_carry.tn; o->fn = (uint8_t)ctx->h_carry.fn; o->mn = (uint8_t)ctx->h_carry.mn;
+	return 0;
+}
+
+extern "C" int tb200_get_stats(const tb200_ctx *ctx, tb200_stats *o)
+{
+	if (!ctx || !o) return TB200_E_ARG;
+	*o = ctx->stats;
+	return 0;
+}
+
+/* ------------------------------------------------------------- records -- */
+
+extern "C" size_t tb200_expand_records(const tb200_slot *slots, const uint8_t *type1, size_t n_slots,
+                                       tb200_record *rec, size_t max_records)
+{
+	/* enum tetra_log_chan values, tetra_common.h:22-39 */
+	enum { LC_UNKNOWN = 0, LC_SCH_F = 1, LC_AACH = 8, LC_BSCH = 10, LC_BNCH = 11 };
+	size_t n = 0;
+	auto emit = [&](const tb200_slot &s, const uint8_t *t1, int off, int len, int lchan, int crc_ok, int blk, uint32_t code) {
+		if (rec && n < max_records) {
+			tb200_record &r = rec[n];
+			memset(&r, 0, sizeof(r));
+			r.slot_bit = s.slot_bit;
+			r.lchan = (uint8_t)lchan; r.crc_ok = (uint8_t)crc_ok; r.blk_num = (uint8_t)blk;
+			r.tn = s.time & 7; r.fn = (s.time >> 3) & 31; r.mn = (s.time >> 8) & 63;
+			r.type1_len = (uint16_t)len;
+			r.scrambling_code = code;
+			if (t1) memcpy(r.type1, t1 + off, len);
+		}
+		n++;
+	};
+	for (size_t i = 0; i < n_slots; i++) {
+		const tb200_slot &s = slots[i];
+		const uint8_t *t1 = type1 ? type1 + i * TB200_TYPE1_STRIDE : nullptr;
+		const int a = (s.flags & TB200_F_CRC_A) != 0, b = (s.flags & TB200_F_CRC_B) != 0;
+		switch (s.flags & TB200_F_KIND_MASK) {
+		case TB200_KIND_SB:       /* tetra_burst.c:350-352 */
+			emit(s, t1, 0, 60, LC_BSCH, a, 1, 3);
+			emit(s, t1, 60, 14, LC_AACH, 1, 0, s.scrambling_code);
+			emit(s, t1, 74, 124, (s.flags & TB200_F_BNCH) ? LC_BNCH : LC_UNKNOWN, b, 2, s.scrambling_code);
+			break;
+		case TB200_KIND_NDB_F:    /* tetra_burst.c:371-372 */
+			emit(s, t1, 0, 14, LC_AACH, 1, 0, s.scrambling_code);
+			emit(s, t1, 14, 268, LC_SCH_F, a, 0, s.scrambling_code);
+			break;
+		case TB200_KIND_NDB_2:    /* tetra_burst.c:359-361 */
+			emit(s, t1, 0, 14, LC_AACH, 1, 0, s.scrambling_code);
+			emit(s, t1, 14, 124, LC_UNKNOWN, a, 1, s.scrambling_code);
+			emit(s, t1, 138, 124, LC_UNKNOWN, b, 2, s.scrambling_code);
+			break;
+		default:
+			break;
+		}
+	}
+	return n;
+}
+
+/* -------------------------------------------------------- leaf operators -- */
+
+/* one warp per window */
+__global__ void __launch_bounds__(256)
+k_leaf_find(const uint8_t *bits, uint64_t n_bytes, const uint64_t *starts, const uint32_t *lens, uint64_t n,
+            uint32_t mask, const Tables *__restrict__ tab, int32_t *rc, uint32_t *offs)
+{
+	const unsigned lane = threadIdx.x & 31;
+	const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += nwarps) {
+		unsigned off = 0;
+		int r = find_train_seq_warp(bits + starts[i], bits + n_bytes, lens[i], mask, tab, &off, nullptr);
+		if (lane == 0) { rc[i] = r; offs[i] = off; }
+	}
+}
+
+template <int BT>
+__device__ __forceinline__ void leaf_decode_one(WarpSmem &S, const uint8_t *type5, uint32_t code, const Tables *tab,
+                                                uint8_t *type1, uint8_t *crc_ok, unsigned lane, int variant)
+{
+	constexpr int K = Blk<BT>::K, N = Blk<BT>::N, T1 = Blk<BT>::T1;
+	uint32_t x0, x1, x2;
+	load_window(type5, type5 + K, lane, x0, x1, x2);
+	if (lane < 16) S.bw[lane] = x0;
+	if (lane < 4) S.bw[16 + lane] = 0;
+	const uint32_t lw = lfsr_word(code, lane, tab);
+	if (lane < 16) S.lf[lane] = lw;
+	if (lane < 12) S.outw[lane] = 0;
+	__syncwarp();
+	gather_type3<BT, PL_RAW>(S.bw, S.lf, S.t3[0], lane);
+	uint32_t crc;
+	if (variant == TB200_VITERBI_LANE) {
+		if (lane == 0) viterbi_lane<N>(S.t3[0], S.dec, S.t2[0]);
+		__syncwarp();
+		crc = crc16_serial(S.t2[0], T1 + 16);
+	} else {
+		viterbi_warp<N>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
+		crc = crc16_half(S.t2[0], T1 + 16, Blk<BT>::CRCI, tab);
+	}
+	put_bits(S.outw, 0, S.t2[0], T1, lane);
+	__syncwarp();
+	for (int i = lane; i < T1; i += 32)
+		type1[i] = (S.outw[i >> 5] >> (i & 31)) & 1;
+	if (lane == 0) *crc_ok = (crc == 0x1d0f);
+	__syncwarp();
+}
+
+__global__ void __launch_bounds__(256)
+k_leaf_decode(int blk_type, const uint8_t *type5, const uint32_t *codes, uint64_t n, const Tables *__restrict__ tab,
+              uint8_t *type1, uint8_t *crc_ok, int variant)
+{
+	__shared__ WarpSmem sm[8];
+	const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib; i < n; i += nwarps) {
+		if (blk_type == TB200_T_SB1)
+			leaf_decode_one<0>(sm[wib], type5 + i * 120, codes[i], tab, type1 + i * 60, crc_ok + i, lane, variant);
+		else if (blk_type == TB200_T_SCH_F)
+			leaf_decode_one<5>(sm[wib], type5 + i * 432, codes[i], tab, type1 + i * 268, crc_ok + i, lane, variant);
+		else
+			leaf_decode_one<1>(sm[wib], type5 + i * 216, codes[i], tab, type1 + i * 124, crc_ok + i, lane, variant);
+	}
+}
+
+/* The fused descramble + de-interleave stage on its own (type-5 bytes -> type-3 bytes):
+ * a CTA stages 8 blocks, each warp permutes one.  Memory-bound by construction:
+ * K bytes read + K bytes written per block. */
+__global__ void __launch_bounds__(256)
+k_descramble_deinterleave(const uint8_t *__restrict__ type5, uint8_t *__restrict__ type3,
+                          const uint32_t *__restrict__ codes, uint64_t n, uint32_t K, uint32_t a,
+                          const Tables *__restrict__ tab)
+{
+	__shared__ uint32_t s_bits[8][16];
+	__shared__ uint32_t s_lf[8][16];
+	const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+	for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib; i < n; i += nwarps) {
+		const uint8_t *src = type5 + i * K;
+		uint32_t x0, x1, x2;
+		load_window(src, src + K, lane, x0, x1, x2);
+		const uint32_t lw = lfsr_word(codes[i], lane, tab);
+		if (lane < 16) { s_bits[wib][lane] = x0 ^ lw; }
+		(void)s_lf;
+		__syncwarp();
+		uint8_t *dst = type3 + i * K;
+		/* each lane produces 4 consecutive output bytes per round -> coalesced 128-byte stores */
+		for (uint32_t j0 = 4 * lane; j0 < K; j0 += 128) {
+			uint32_t word = 0;
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const uint32_t j = j0 + q;
+				if (j < K) {
+					const uint32_t m = (a * (j + 1)) % K;
+					word |= ((s_bits[wib][m >> 5] >> (m & 31)) & 1) << (8 * q);
+				}
+			}
+			if (j0 + 4 <= K && (((uintptr_t)(dst + j0)) & 3) == 0) {
+				*reinterpret_cast<uint32_t *>(dst + j0) = word;
+			} else {
+				for (int q = 0; q < 4 && j0 + q < K; ++q)
+					dst[j0 + q] = (word >> (8 * q)) & 0xff;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+static int leaf_common(tb200_ctx *ctx)
+{
+	if (!ctx) return TB200_E_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	return 0;
+}
+
+extern "C" int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits, const uint64_t *starts,
+                                    const uint32_t *lens, uint64_t n, uint32_t mask, int32_t *rc, uint32_t *offset)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (n == 0) return 0;
+	uint8_t *d_bits = nullptr; uint64_t *d_st = nullptr; uint32_t *d_len = nullptr, *d_off = nullptr; int32_t *d_rc = nullptr;
+	CU(cudaMalloc((void **)&d_bits, n_bits + 64));
+	CU(cudaMalloc((void **)&d_st, n * 8)); CU(cudaMalloc((void **)&d_len, n * 4));
+	CU(cudaMalloc((void **)&d_off, n * 4)); CU(cudaMalloc((void **)&d_rc, n * 4));
+	CU(cudaMemcpy(d_bits, bits, n_bits, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d_st, starts, n * 8, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(d_len, lens, n * 4, cudaMemcpyHostToDevice));
+	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, 4096);
+	TB_LAUNCH(k_leaf_find, blocks, 256, ctx->s_compute, d_bits, n_bits, d_st, d_len, n, mask, ctx->d_tab, d_rc, d_off);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	CU(cudaMemcpy(rc, d_rc, n * 4, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(offset, d_off, n * 4, cudaMemcpyDeviceToHost));
+	cudaFree(d_bits); cudaFree(d_st); cudaFree(d_len); cudaFree(d_off); cudaFree(d_rc);
+	return 0;
+}
+
+extern "C" int tb200_decode_blocks(tb200_ctx *ctx, int blk_type, const uint8_t *type5, const uint32_t *codes,
+                                   uint64_t n, uint8_t *type1, uint8_t *crc_ok)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	int K, T1;
+	switch (blk_type) {
+	case TB200_T_SB1: K = 120; T1 = 60; break;
+	case TB200_T_SB2: case TB200_T_NDB: K = 216; T1 = 124; break;
+	case TB200_T_SCH_F: K = 432; T1 = 268; break;
+	default: return fail(ctx, TB200_E_ARG, "block type %d is not decoded by the receive path", blk_type);
+	}
+	if (n == 0) return 0;
+	uint8_t *d5 = nullptr, *d1 = nullptr, *dc = nullptr; uint32_t *dcode = nullptr;
+	CU(cudaMalloc((void **)&d5, n * K + 64)); CU(cudaMalloc((void **)&d1, n * T1)); CU(cudaMalloc((void **)&dc, n));
+	CU(cudaMalloc((void **)&dcode, n * 4));
+	CU(cudaMemcpy(d5, type5, n * K, cudaMemcpyHostToDevice));
+	CU(cudaMemcpy(dcode, codes, n * 4, cudaMemcpyHostToDevice));
+	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, 4096);
+	TB_LAUNCH(k_leaf_decode, blocks, 256, ctx->s_compute, blk_type, d5, dcode, n, ctx->d_tab, d1, dc, (int)ctx->opt.viterbi);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	CU(cudaMemcpy(type1, d1, n * T1, cudaMemcpyDeviceToHost));
+	CU(cudaMemcpy(crc_ok, dc, n, cudaMemcpyDeviceToHost));
+	cudaFree(d5); cudaFree(d1); cudaFree(dc); cudaFree(dcode);
+	return 0;
+}
+
+extern "C" int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type5, uint8_t *type3, const uint32_t *codes,
+                                             uint64_t n, uint32_t K, uint32_t a, int is_device)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (K == 0 || K > 432 || a == 0) return fail(ctx, TB200_E_ARG, "K must be 1..432");
+	if (n == 0) return 0;
+	const uint8_t *d5 = type5; uint8_t *d3 = type3; const uint32_t *dcode = codes;
+	uint8_t *a5 = nullptr, *a3 = nullptr; uint32_t *ac = nullptr;
+	if (!is_device) {
+		CU(cudaMalloc((void **)&a5, n * K + 64)); CU(cudaMalloc((void **)&a3, n * K)); CU(cudaMalloc((void **)&ac, n * 4));
+		CU(cudaMemcpy(a5, type5, n * K, cudaMemcpyHostToDevice));
+		CU(cudaMemcpy(ac, codes, n * 4, cudaMemcpyHostToDevice));
+		d5 = a5; d3 = a3; dcode = ac;
+	}
+	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8);
+	TB_LAUNCH(k_descramble_deinterleave, blocks, 256, ctx->s_compute, d5, d3, dcode, n, K, a, ctx->d_tab);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	if (!is_device) {
+		CU(cudaMemcpy(type3, a3, n * K, cudaMemcpyDeviceToHost));
+		cudaFree(a5); cudaFree(a3); cudaFree(ac);
+	}
+	return 0;
+}
+
+/* -------------------------------------------------------------- generator -- */
+
+extern "C" int tb200_gen_stream_dev(tb200_ctx *ctx, const tb200_gen_cfg *cfg, uint64_t k0, uint64_t n,
+                                    uint8_t *d_out, int with_lead_in)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (!cfg || !d_out) return fail(ctx, TB200_E_ARG, "null argument");
+	GenCfg g;
+	memcpy(&g, cfg, sizeof(g));
+	uint8_t *bursts = d_out;
+	if (with_lead_in && g.lead_in_bits) {
+		const unsigned blocks = (g.lead_in_bits + 255) / 256;
+		TB_LAUNCH(k_gen_lead_in, blocks, 256, ctx->s_compute, g, d_out);
+		bursts += g.lead_in_bits;
+	}
+	if (n) {
+		const unsigned blocks = (unsigned)std::min<uint64_t>((n + 63) / 64, 1u << 20);
+		TB_LAUNCH(k_gen_bursts, blocks, 64, ctx->s_compute, g, k0, n, bursts);
+	}
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	return 0;
+}

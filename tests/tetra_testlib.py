@@ -346,3 +346,177 @@ def records_equal(a, b):
             bad = np.nonzero(np.any(a[name] != b[name], axis=-1) if a[name].ndim > 1 else a[name] != b[name])[0]
             return False, f"field {name} differs at records {bad[:5]} (of {bad.size})"
     return True, ""
+
+
+# --------------------------------------------------------------------------- product
+
+PRODUCT_SO = os.path.join(ROOT, "osmo-tetra_b200", "libtetra_b200.so")
+SIMT_SO = os.path.join(ROOT, "tests", "simt", "_build", "libtetra_b200_simt.so")
+
+SLOT_DTYPE = np.dtype([("slot_bit", "<u4"), ("scrambling_code", "<u4"), ("find_off", "<u2"),
+                       ("window", "<u2"), ("time", "<u2"), ("find_rc", "i1"), ("flags", "u1")])
+assert SLOT_DTYPE.itemsize == 16
+
+TB200_FRESH, TB200_FINAL = 1, 2
+OUT_UNPACKED, OUT_PACKED = 1, 2
+VITERBI_WARP, VITERBI_LANE = 0, 1
+
+
+class Options(C.Structure):
+    _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
+                ("pipeline_slots", C.c_uint32)]
+
+
+class Carry(C.Structure):
+    _fields_ = [("stream_bits", C.c_uint64), ("buf_start_bit", C.c_uint64), ("next_frame_start", C.c_uint64),
+                ("calls", C.c_uint64), ("state", C.c_uint32), ("bits_in_buf", C.c_uint32),
+                ("scramb_init", C.c_uint32), ("mcc", C.c_uint16), ("mnc", C.c_uint16),
+                ("colour_code", C.c_uint8), ("tn", C.c_uint8), ("fn", C.c_uint8), ("mn", C.c_uint8)]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("slots", "bursts_decoded", "blocks", "crc_ok_blocks",
+                                           "lock_losses", "lock_acquisitions", "kernel_launches")]
+
+
+def build_simt():
+    """(re)build the CPU SIMT-emulation flavour of the library - test infrastructure only"""
+    srcs = [os.path.join(ROOT, "osmo-tetra_b200", "csrc", f) for f in
+            ("tetra_b200.cu", "tetra_kernels.cuh", "tetra_gen.cuh")] + \
+           [os.path.join(ROOT, "tests", "simt", f) for f in ("cpu_simt.h", "cpu_simt.cpp")] + \
+           [os.path.join(ROOT, "include", "tetra_b200.h")]
+    if os.path.exists(SIMT_SO) and all(os.path.getmtime(SIMT_SO) >= os.path.getmtime(s) for s in srcs):
+        return SIMT_SO
+    os.makedirs(os.path.dirname(SIMT_SO), exist_ok=True)
+    subprocess.check_call([
+        "g++", "-std=c++17", "-O2", "-g", "-fPIC", "-shared", "-x", "c++",
+        "-include", os.path.join(ROOT, "tests", "simt", "cpu_simt.h"),
+        "-I" + os.path.join(ROOT, "osmo-tetra_b200", "csrc"),
+        os.path.join(ROOT, "osmo-tetra_b200", "csrc", "tetra_b200.cu"),
+        os.path.join(ROOT, "tests", "simt", "cpu_simt.cpp"), "-o", SIMT_SO])
+    return SIMT_SO
+
+
+class B200:
+    """ctypes view of include/tetra_b200.h.  emulate=True loads the SIMT-emulation build (CPU tests)."""
+
+    def __init__(self, emulate=False, device=0):
+        path = build_simt() if emulate else PRODUCT_SO
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} is missing - run __graft_entry__.build() first")
+        lib = self.lib = C.CDLL(path)
+        lib.tb200_version.restype = C.c_char_p
+        lib.tb200_last_error.restype = C.c_char_p
+        lib.tb200_last_error.argtypes = [C.c_void_p]
+        lib.tb200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        lib.tb200_destroy.argtypes = [C.c_void_p]
+        lib.tb200_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
+        for f in (lib.tb200_rx_stream_host, lib.tb200_rx_stream_dev):
+            f.restype = C.c_long
+            f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        lib.tb200_max_slots.restype = C.c_uint64
+        lib.tb200_max_slots.argtypes = [C.c_uint64]
+        lib.tb200_expand_records.restype = C.c_size_t
+        lib.tb200_expand_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        lib.tb200_get_carry.argtypes = [C.c_void_p, C.POINTER(Carry)]
+        lib.tb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        lib.tb200_find_train_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
+                                             C.c_uint32, C.c_void_p, C.c_void_p]
+        lib.tb200_decode_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
+        lib.tb200_descramble_deinterleave.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                      C.c_uint32, C.c_uint32, C.c_int]
+        lib.tb200_gen_stream_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
+        lib.tb200_host_alloc.restype = C.c_void_p
+        lib.tb200_host_alloc.argtypes = [C.c_size_t]
+        lib.tb200_host_free.argtypes = [C.c_void_p]
+        self.emulate = emulate
+        h = C.c_void_p()
+        rc = lib.tb200_create(C.byref(h), device)
+        if rc != 0:
+            raise RuntimeError(f"tb200_create failed ({rc}): no CUDA device and no CPU path")
+        self.h = h
+        self.opt = Options()
+        lib.tb200_default_options(C.byref(self.opt))
+
+    def close(self):
+        if self.h:
+            self.lib.tb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def err(self):
+        return self.lib.tb200_last_error(self.h).decode()
+
+    def set_options(self, **kw):
+        for k, v in kw.items():
+            setattr(self.opt, k, v)
+        rc = self.lib.tb200_set_options(self.h, C.byref(self.opt))
+        if rc:
+            raise ValueError(self.err())
+
+    def rx_stream_host(self, bits, flags=TB200_FRESH | TB200_FINAL, max_slots=None):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        if max_slots is None:
+            max_slots = int(self.lib.tb200_max_slots(bits.size)) + 16
+        slots = np.zeros(max_slots, dtype=SLOT_DTYPE)
+        type1 = np.zeros((max_slots, 288), dtype=np.uint8)
+        packed = np.zeros((max_slots, 9), dtype=np.uint32)
+        n = self.lib.tb200_rx_stream_host(self.h, _ptr(bits), bits.size, flags, _ptr(slots), _ptr(type1), _ptr(packed), max_slots)
+        if n < 0:
+            raise RuntimeError(f"tb200_rx_stream_host: {n}: {self.err()}")
+        return slots[:n], type1[:n], packed[:n]
+
+    def expand_records(self, slots, type1):
+        slots = np.ascontiguousarray(slots); type1 = np.ascontiguousarray(type1)
+        n = self.lib.tb200_expand_records(_ptr(slots), _ptr(type1), slots.size, None, 0)
+        rec = np.zeros(n, dtype=RECORD_DTYPE)
+        self.lib.tb200_expand_records(_ptr(slots), _ptr(type1), slots.size, _ptr(rec), n)
+        return rec
+
+    def records_host(self, bits, flags=TB200_FRESH | TB200_FINAL):
+        slots, type1, _ = self.rx_stream_host(bits, flags)
+        return self.expand_records(slots, type1)
+
+    def carry(self):
+        c = Carry()
+        self.lib.tb200_get_carry(self.h, C.byref(c))
+        return c
+
+    def stats(self):
+        s = Stats()
+        self.lib.tb200_get_stats(self.h, C.byref(s))
+        return s
+
+    def find_train_seq(self, bits, starts, lens, mask):
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        starts = np.ascontiguousarray(starts, dtype=np.uint64); lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        rc = np.zeros(starts.size, dtype=np.int32); off = np.zeros(starts.size, dtype=np.uint32)
+        r = self.lib.tb200_find_train_seq(self.h, _ptr(bits), bits.size, _ptr(starts), _ptr(lens), starts.size, mask, _ptr(rc), _ptr(off))
+        if r:
+            raise RuntimeError(self.err())
+        return rc, off
+
+    def decode_blocks(self, blk_type, type5, codes):
+        k, _, t1, _ = BLK[blk_type]
+        type5 = np.ascontiguousarray(type5, dtype=np.uint8).reshape(-1, k)
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        n = type5.shape[0]
+        out = np.zeros((n, t1), dtype=np.uint8); ok = np.zeros(n, dtype=np.uint8)
+        r = self.lib.tb200_decode_blocks(self.h, blk_type, _ptr(type5), _ptr(codes), n, _ptr(out), _ptr(ok))
+        if r:
+            raise RuntimeError(self.err())
+        return out, ok
+
+    def descramble_deinterleave(self, type5, codes, K, a):
+        type5 = np.ascontiguousarray(type5, dtype=np.uint8).reshape(-1, K)
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        out = np.zeros_like(type5)
+        r = self.lib.tb200_descramble_deinterleave(self.h, _ptr(type5), _ptr(out), _ptr(codes), type5.shape[0], K, a, 0)
+        if r:
+            raise RuntimeError(self.err())
+        return out
