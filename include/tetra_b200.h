@@ -211,6 +211,11 @@ struct tb200_gen_cfg {
 int tb200_gen_stream_dev(tb200_ctx *ctx, const struct tb200_gen_cfg *cfg, uint64_t k0, uint64_t n,
                          uint8_t *d_out, int with_lead_in);
 
+/* ---- introspection used by the tests ------------------------------------------------ */
+
+/* n x tetra_tdma_time_add_tn(tm, 1) (tetra_tdma.c:75-79) in closed form, as the kernels do it */
+void tb200_debug_time_advance(uint32_t *tn, uint32_t *fn, uint32_t *mn, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

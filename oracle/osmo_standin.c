@@ -247,3 +247,22 @@ int bitvec_set_uint(struct bitvec *bv, unsigned int in, unsigned int count)
 			return -1;
 	return 0;
 }
+
+/* test hook: decode with an explicit variant (0 = acc, 1 = generic) and the TETRA mother
+ * code tables rebuilt from the generator polynomials (viterbi_cch.c:28-48) */
+int oracle_tetra_cch_decode(int variant, const sbit_t *in, int n, ubit_t *out)
+{
+	static uint8_t nout[16][2], nst[16][2];
+	for (unsigned s = 0; s < 16; s++)
+		for (unsigned b = 0; b < 2; b++) {
+			unsigned d1 = s & 1, d2 = (s >> 1) & 1, d3 = (s >> 2) & 1, d4 = (s >> 3) & 1;
+			unsigned g1 = b ^ d1 ^ d4, g2 = b ^ d2 ^ d3 ^ d4, g3 = b ^ d1 ^ d2 ^ d4, g4 = b ^ d1 ^ d3 ^ d4;
+			nout[s][b] = (g1 << 3) | (g2 << 2) | (g3 << 1) | g4;
+			nst[s][b] = ((s << 1) | b) & 15;
+		}
+	struct osmo_conv_code code;
+	memset(&code, 0, sizeof(code));
+	code.N = 4; code.K = 5; code.len = n;
+	code.next_output = nout; code.next_state = nst;
+	return variant ? oracle_conv_decode_gen(&code, in, out) : oracle_conv_decode_acc(&code, in, out);
+}

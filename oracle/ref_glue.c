@@ -25,6 +25,7 @@
 #include <unistd.h>
 #include <fcntl.h>
 
+#include <osmocom/core/bits.h>
 #include <lower_mac/tetra_lower_mac.c>   /* compiled in place, see header comment */
 
 #include "oracle_records.h"
@@ -214,4 +215,68 @@ void ref_rm3014_init(void)
 	silence();
 	tetra_rm3014_init();
 	unsilence();
+}
+
+/* ---- config 1: the reference's own conv_enc_test generator -------------------
+ * build_sb() (conv_enc_test.c:198-305) prints the 510-bit SYNC burst as ASCII at :302;
+ * capture that line.  `r` plays the role of rand() at conv_enc_test.c:337-339. */
+extern uint8_t pdu_sync[8];
+void testpdu_init(void);
+int build_sb(void);
+int build_ndb_schf(void);
+
+static int capture_burst(int (*fn)(void), const char *tag, uint8_t *out510)
+{
+	char path[] = "/tmp/tetra_ref_capXXXXXX";
+	int fd = mkstemp(path);
+	if (fd < 0)
+		return -1;
+	fflush(stdout);
+	int saved = dup(1);
+	dup2(fd, 1);
+	fn();
+	fflush(stdout);
+	dup2(saved, 1);
+	close(saved);
+	off_t sz = lseek(fd, 0, SEEK_END);
+	if (sz <= 0 || sz > (1 << 24)) { close(fd); unlink(path); return -1; }
+	char *buf = malloc((size_t)sz + 1);
+	lseek(fd, 0, SEEK_SET);
+	ssize_t got = read(fd, buf, (size_t)sz);
+	close(fd);
+	unlink(path);
+	int rc = -1;
+	if (got > 0) {
+		buf[got] = 0;
+		char *p = strstr(buf, tag);
+		if (p) {
+			p += strlen(tag);
+			rc = 0;
+			for (int i = 0; i < 510; i++) {
+				if (p[i] != '0' && p[i] != '1') { rc = -1; break; }
+				out510[i] = p[i] - '0';
+			}
+		}
+	}
+	free(buf);
+	return rc;
+}
+
+int ref_conv_enc_test_sb(uint32_t r, uint8_t *out510)
+{
+	static int inited;
+	if (!inited) { silence(); testpdu_init(); unsilence(); inited = 1; }
+	osmo_store32le(r, pdu_sync);
+	osmo_store32le(r, pdu_sync + 4);
+	return capture_burst(build_sb, "cont sync DL burst: ", out510);
+}
+
+extern uint8_t pdu_schf[268];
+int ref_conv_enc_test_ndb(uint32_t r, uint8_t *out510)
+{
+	static int inited;
+	if (!inited) { silence(); testpdu_init(); unsilence(); inited = 1; }
+	osmo_store32le(r, pdu_schf);
+	osmo_store32le(r, pdu_schf + 4);
+	return capture_burst(build_ndb_schf, "cont norm DL burst: ", out510);
 }

@@ -1084,3 +1084,10 @@ extern "C" int tb200_gen_stream_dev(tb200_ctx *ctx, const tb200_gen_cfg *cfg, ui
 	CU(cudaStreamSynchronize(ctx->s_compute));
 	return 0;
 }
+
+extern "C" void tb200_debug_time_advance(uint32_t *tn, uint32_t *fn, uint32_t *mn, uint64_t n)
+{
+	Tm t = { *tn, *fn, *mn };
+	t = tm_advance(t, n);
+	*tn = t.tn; *fn = t.fn; *mn = t.mn;
+}

@@ -1,0 +1,159 @@
+"""Kernel logic and host-side lock state machine, checked on the CPU by compiling the CUDA
+sources against the SIMT emulator in tests/simt (test infrastructure, not a product path).
+The same scenarios run on the real GPU in test_gpu.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import tetra_testlib as T
+from tetra_testlib import bits_from_str as B
+from test_oracle import SEQS, _stream
+
+
+def test_time_advance_closed_form(emu, orc):
+    lib = emu.lib
+    lib.tb200_debug_time_advance.argtypes = [C.POINTER(C.c_uint32)] * 3 + [C.c_uint64]
+    rng = np.random.default_rng(0)
+    for tn in range(0, 5):
+        for fn in (0, 1, 17, 18, 19, 25, 31):
+            for mn in (0, 1, 59, 60, 61, 63):
+                t = (tn, fn, mn)
+                want = {}
+                cur = t
+                for n in range(0, 6000):
+                    if n in (0, 1, 2, 3, 4, 5, 71, 72, 73, 4319, 4320, 4321, 5999) or n % 997 == 0:
+                        want[n] = cur
+                    cur = orc.time_add_slot(*cur)
+                for n, w in want.items():
+                    a, b, c = C.c_uint32(tn), C.c_uint32(fn), C.c_uint32(mn)
+                    lib.tb200_debug_time_advance(C.byref(a), C.byref(b), C.byref(c), n)
+                    assert (a.value, b.value, c.value) == w, (t, n)
+
+
+def test_find_blind_spot(emu, orc):
+    rng = np.random.default_rng(7)
+    wins, exp = [], []
+    for ts in (T.TS_SYNC, T.TS_NORM_1, T.TS_NORM_2, T.TS_NORM_3):
+        sb = B(SEQS[ts])
+        for k in range(0, 44):
+            for prev in (0, 1):
+                for bg in ("zeros", "random"):
+                    w = np.zeros(700, np.uint8) if bg == "zeros" else rng.integers(0, 2, 700).astype(np.uint8)
+                    w[k:k + sb.size] = sb
+                    if k:
+                        w[k - 1] = prev
+                    wins.append(w)
+                    exp.append(orc.find_train_seq(w, 600, 0b1011))
+    bits = np.concatenate(wins)
+    starts = np.arange(len(wins), dtype=np.uint64) * 700
+    rc, off = emu.find_train_seq(bits, starts, np.full(len(wins), 600, np.uint32), 0b1011)
+    for i, (r, o) in enumerate(exp):
+        assert rc[i] == r and (r < 0 or off[i] == o), (i, (r, o), (rc[i], off[i]))
+
+
+def test_find_windows(emu, orc):
+    """random windows of every length class, including > 1024 (catch-up after a re-lock) and misaligned starts"""
+    rng = np.random.default_rng(9)
+    bits = rng.integers(0, 2, 60000).astype(np.uint8)
+    starts, lens = [], []
+    for i in range(150):
+        st = int(rng.integers(0, 50000)); ln = int(rng.choice([30, 37, 38, 100, 510, 573, 1023, 1024, 1025, 2100, 4096]))
+        ts = int(rng.choice([T.TS_SYNC, T.TS_NORM_1, T.TS_NORM_2])); sb = B(SEQS[ts])
+        k = int(rng.integers(0, ln + 10))
+        if i % 5:
+            bits[st + k:st + k + sb.size] = sb
+        starts.append(st); lens.append(ln)
+    pad = np.concatenate([bits, np.zeros(64, np.uint8)])
+    for mask in (0b1011, 0b1000):
+        rc, off = emu.find_train_seq(bits, np.array(starts, np.uint64), np.array(lens, np.uint32), mask)
+        for i, (st, ln) in enumerate(zip(starts, lens)):
+            ln_eff = min(ln, bits.size - st)
+            r, o = orc.find_train_seq(pad[st:], ln, mask) if st + ln <= bits.size else (None, None)
+            if r is None:
+                continue
+            assert rc[i] == r and (r < 0 or off[i] == o), (i, st, ln, mask, (r, o), (rc[i], off[i]))
+
+
+def test_descramble_deinterleave(emu, orc):
+    rng = np.random.default_rng(4)
+    for K, a in ((120, 11), (216, 101), (432, 103), (168, 13)):
+        t5 = rng.integers(0, 2, (9, K)).astype(np.uint8)
+        codes = rng.integers(0, 2 ** 32, 9).astype(np.uint32); codes[0] = 3; codes[1] = 0
+        got = emu.descramble_deinterleave(t5, codes, K, a)
+        for i in range(9):
+            want = orc.deinterleave(K, a, orc.scramb_bits(int(codes[i]), t5[i]))
+            assert np.array_equal(got[i], want), (K, i)
+
+
+def _check(emu, orc, bits, chunk=64, **opts):
+    orc.reset(); orc.feed(bits, chunk)
+    emu.set_options(chunk_bits=chunk, **opts)
+    slots, t1, packed = emu.rx_stream_host(bits)
+    got = emu.expand_records(slots, t1)
+    T.check_stream_against(orc.records(), orc.events(), slots, got)
+    # packed output carries the same bits
+    unp = ((packed[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(packed.shape[0], 288).astype(np.uint8)
+    assert np.array_equal(unp[:, :282], t1[:, :282])
+    c = emu.carry()
+    assert c.state == orc.rx_state() and c.scramb_init == orc.scramb_init()
+    if slots.size:
+        assert (c.tn, c.fn, c.mn) == orc.get_time()
+    return slots
+
+
+@pytest.mark.parametrize("variant", [T.VITERBI_WARP, T.VITERBI_LANE])
+def test_stream_mixed(emu, orc, variant):
+    bits, _ = _stream(orc, n=120, random_cell=1)
+    slots = _check(emu, orc, bits, viterbi=variant, pipeline_slots=0)
+    assert slots.size == 119
+
+
+@pytest.mark.parametrize("chunk", [1, 7, 64, 100, 296])
+def test_stream_chunks(emu, orc, chunk):
+    bits, _ = _stream(orc, n=40)
+    _check(emu, orc, bits, chunk=chunk, viterbi=T.VITERBI_WARP, pipeline_slots=0)
+
+
+def test_stream_lock_loss_and_pieces(emu, orc):
+    """lock loss inside a pipelined piece: the optimistic pieces are rolled back"""
+    bits, _ = _stream(orc, n=150, random_cell=1)
+    o = lambda k: 333 + 510 * k
+    b2 = bits.copy(); b2[o(60) + 244:o(60) + 266] = 0
+    for pieces in (0, 16, 25):
+        _check(emu, orc, b2, viterbi=T.VITERBI_WARP, pipeline_slots=pieces)
+    assert emu.stats().lock_losses == 1
+    b3 = bits.copy(); b3[o(50) + 100:o(50) + 138] = B(SEQS[T.TS_SYNC])
+    _check(emu, orc, b3, viterbi=T.VITERBI_WARP, pipeline_slots=16)
+    b4 = bits.copy(); b4[o(51) + 30:o(51) + 52] = B(SEQS[T.TS_NORM_2])
+    _check(emu, orc, b4, viterbi=T.VITERBI_WARP, pipeline_slots=16)
+
+
+def test_stream_edge_inputs(emu, orc):
+    bits, _ = _stream(orc, n=12)
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 63, 509, 1019, 1020, 1021, 1531, 333 + 510 * 7 + 123):
+        _check(emu, orc, bits[:n], viterbi=T.VITERBI_WARP, pipeline_slots=0)
+    _check(emu, orc, rng.integers(0, 2, 9000).astype(np.uint8), viterbi=T.VITERBI_WARP, pipeline_slots=0)
+    sb_only, _ = _stream(orc, n=30, sb_period=1, random_cell=1, lead_in_bits=17)
+    _check(emu, orc, sb_only, viterbi=T.VITERBI_WARP, pipeline_slots=0)
+
+
+def test_stream_continuation(emu, orc):
+    """feeding the stream in arbitrary pieces gives what one call gives"""
+    bits, _ = _stream(orc, n=60, random_cell=1)
+    bits[333 + 510 * 20 + 244:333 + 510 * 20 + 266] = 0
+    orc.reset(); orc.feed(bits, 64)
+    want = orc.records()
+    emu.set_options(chunk_bits=64, viterbi=T.VITERBI_WARP, pipeline_slots=0)
+    rng = np.random.default_rng(5)
+    cuts = sorted(set(int(x) for x in rng.integers(1, bits.size, 7))) + [bits.size]
+    got = []
+    pos = 0
+    for i, c in enumerate(cuts):
+        flags = (T.TB200_FRESH if i == 0 else 0) | (T.TB200_FINAL if c == bits.size else 0)
+        slots, t1, _ = emu.rx_stream_host(bits[pos:c], flags=flags)
+        got.append(emu.expand_records(slots, t1))
+        pos = c
+    ok, msg = T.records_equal(want, np.concatenate(got))
+    assert ok, msg

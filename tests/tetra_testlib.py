@@ -520,3 +520,46 @@ class B200:
         if r:
             raise RuntimeError(self.err())
         return out
+
+
+# --------------------------------------------------------------------------- golden fixtures
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def load_golden_stream(name):
+    """-> (bits, records, events) of a fixture written by tests/golden/make_golden.py"""
+    z = np.load(os.path.join(GOLDEN_DIR, name))
+    bits = np.unpackbits(z["bits"])[:int(z["n_bits"])]
+    n = z["slot_bit"].size
+    rec = np.zeros(n, dtype=RECORD_DTYPE)
+    for f in ("slot_bit", "lchan", "crc_ok", "blk_num", "tn", "fn", "mn", "type1_len", "scrambling_code"):
+        rec[f] = z[f]
+    rec["type1"] = np.unpackbits(z["type1"], axis=1)[:, :272]
+    return bits, rec, z["events"]
+
+
+def load_golden_blocks(name):
+    z = np.load(os.path.join(GOLDEN_DIR, "blocks_noisy.npz"))
+    bt = {"sb1": T_SB1, "ndb": T_NDB, "schf": T_SCH_F}[name]
+    K, _, T1, _ = BLK[bt]
+    return (bt, np.unpackbits(z[name + "_type5"], axis=1)[:, :K], z[name + "_code"],
+            np.unpackbits(z[name + "_type1"], axis=1)[:, :T1], z[name + "_crc_ok"])
+
+
+def locked_events(events):
+    """the searches the LOCKED state made (mask NORM_1|NORM_2|SYNC, tetra_burst_sync.c:117-120)"""
+    return events[events["mask"] == 0b1011]
+
+
+def check_stream_against(records, events, slots, got_records):
+    """compare a product result (slots + expanded records) with reference records + search log"""
+    ok, msg = records_equal(records, got_records)
+    assert ok, msg
+    lev = locked_events(events)
+    assert lev.size == slots.size, (lev.size, slots.size)
+    assert np.array_equal(lev["rc"], slots["find_rc"])
+    assert np.array_equal(lev["window"], slots["window"])
+    assert np.array_equal(lev["buf_start_bit"], slots["slot_bit"])
+    found = lev["rc"] >= 0
+    assert np.array_equal(lev["offset"][found], slots["find_off"][found])
