@@ -112,6 +112,7 @@ struct tb200_options {
 	uint32_t output;            /* TB200_OUT_* bit mask */
 	uint32_t viterbi;           /* TB200_VITERBI_* */
 	uint32_t pipeline_slots;    /* slots per pipelined piece in the host-buffer path (0 = default) */
+	uint32_t profile;           /* 1: bracket every kernel with CUDA events on its stream (tb200_get_timing) */
 };
 void tb200_default_options(struct tb200_options *opt);
 int  tb200_set_options(tb200_ctx *ctx, const struct tb200_options *opt);
@@ -153,6 +154,24 @@ uint64_t tb200_max_slots(uint64_t n_bits);
 
 int tb200_get_carry(const tb200_ctx *ctx, struct tb200_rx_carry *out);
 int tb200_get_stats(const tb200_ctx *ctx, struct tb200_stats *out);
+
+/* Device time of the kernels of the last rx call, measured with CUDA events recorded on the
+ * stream the kernels were launched on (needs options.profile = 1, which serialises nothing
+ * but adds event records).  *_ms are sums over all launches of that kernel in the call. */
+struct tb200_timing {
+	float total_ms;             /* first launch to last launch of the call, compute stream */
+	float classify_ms;          /* k_classify: load + pack + training-sequence search + SB1 */
+	float scan_ms;              /* k_scan_blocks + k_scan_prefix + k_finalize_carry */
+	float decode_ms;            /* k_decode_*: descramble + de-interleave + Viterbi + CRC + output */
+	uint32_t launches_classify, launches_scan, launches_decode;
+	uint32_t pieces;
+	uint64_t slots;             /* slots those launches covered */
+};
+int tb200_get_timing(const tb200_ctx *ctx, struct tb200_timing *out);
+
+/* Integer-ALU peak of this GPU (32-bit add / min / compare results per second), measured with a
+ * register-only kernel; the denominator for the Viterbi add-compare-select roofline. */
+double tb200_measure_int_peak(tb200_ctx *ctx);
 
 /* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) */
 void *tb200_host_alloc(size_t bytes);

@@ -158,6 +158,10 @@ struct tb200_ctx {
 	uint64_t tail_base = 0;
 	uint64_t fed_end = 0;            /* absolute bits handed to the ctx so far */
 	DevCarry h_carry;
+	/* profiling (options.profile) */
+	std::vector<cudaEvent_t> prof_ev;    /* 5 per piece: start, after classify, after scan, after decode, after carry */
+	size_t prof_used = 0;
+	tb200_timing timing;
 };
 
 static int fail(tb200_ctx *c, int code, const char *fmt, ...)
@@ -187,6 +191,7 @@ extern "C" void tb200_default_options(tb200_options *o)
 	o->output = TB200_OUT_UNPACKED | TB200_OUT_PACKED;
 	o->viterbi = TB200_VITERBI_WARP;
 	o->pipeline_slots = 0;
+	o->profile = 0;
 }
 
 extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
@@ -532,10 +537,25 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	const unsigned wpb = 8;
 	const unsigned blocks = (unsigned)std::min<uint64_t>((nb + wpb - 1) / wpb, (uint64_t)ctx->sm_count * 16);
 	CU(cudaMemsetAsync(ctx->d_flags + piece_idx, 0xff, sizeof(uint32_t), st));
+	cudaEvent_t *pe = nullptr;
+	if (ctx->opt.profile) {
+		while (ctx->prof_ev.size() < ctx->prof_used + 5) {
+			cudaEvent_t e;
+			CU(cudaEventCreateWithFlags(&e, 0));
+			ctx->prof_ev.push_back(e);
+		}
+		pe = &ctx->prof_ev[ctx->prof_used];
+		ctx->prof_used += 5;
+		ctx->timing.pieces++;
+		ctx->timing.slots += nb;
+		CU(cudaEventRecord(pe[0], st));
+	}
 	TB_LAUNCH(k_classify, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
+	if (pe) CU(cudaEventRecord(pe[1], st));
 	const unsigned nblk = (nb + 1023) / 1024;
 	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, ctx->d_ws, nb, ctx->d_last_good, ctx->d_blk_last, ctx->d_flags + piece_idx);
 	TB_LAUNCH(k_scan_prefix, 1, 1024, st, ctx->d_blk_last, nblk, ctx->d_blk_prev);
+	if (pe) CU(cudaEventRecord(pe[2], st));
 	DecodeArgs a;
 	a.ws = ctx->d_ws; a.slot_bits = ctx->d_slot_bits; a.last_good = ctx->d_last_good; a.blk_prev = ctx->d_blk_prev;
 	a.carry = ctx->d_carry + piece_idx; a.tab = ctx->d_tab;
@@ -544,8 +564,10 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
 	a.a0 = g.a0; a.out_base = out_base; a.n_slots = nb;
 	TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
+	if (pe) CU(cudaEventRecord(pe[3], st));
 	CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
 	TB_LAUNCH(k_finalize_carry, 1, 32, st, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, nb, ctx->d_carry + piece_idx + 1);
+	if (pe) CU(cudaEventRecord(pe[4], st));
 	ctx->stats.kernel_launches += 5;
 	CU(cudaGetLastError());
 	return 0;
@@ -729,6 +751,33 @@ static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
 	return 0;
 }
 
+#ifdef TB_SIMT_EMULATION
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return 0; }
+#endif
+
+static void profile_begin(tb200_ctx *ctx)
+{
+	ctx->prof_used = 0;
+	memset(&ctx->timing, 0, sizeof(ctx->timing));
+}
+
+static int profile_end(tb200_ctx *ctx)
+{
+	if (!ctx->opt.profile || ctx->prof_used == 0) return 0;
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	float ms = 0.f;
+	for (size_t i = 0; i + 5 <= ctx->prof_used; i += 5) {
+		cudaEvent_t *e = &ctx->prof_ev[i];
+		CU(cudaEventElapsedTime(&ms, e[0], e[1])); ctx->timing.classify_ms += ms; ctx->timing.launches_classify++;
+		CU(cudaEventElapsedTime(&ms, e[1], e[2])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan += 2;
+		CU(cudaEventElapsedTime(&ms, e[2], e[3])); ctx->timing.decode_ms += ms; ctx->timing.launches_decode++;
+		CU(cudaEventElapsedTime(&ms, e[3], e[4])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan++;
+	}
+	CU(cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[ctx->prof_used - 1]));
+	ctx->timing.total_ms = ms;
+	return 0;
+}
+
 static void reset_stream(tb200_ctx *ctx)
 {
 	ctx->rx = RxHost();
@@ -765,8 +814,10 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
 	out.max_slots = max_slots; out.n = 0;
 	ctx->fed_end = n_bits;
+	profile_begin(ctx);
 	rc = rx_run(ctx, src, true, out);
 	if (rc) return rc;
+	if ((rc = profile_end(ctx))) return rc;
 	return (long)out.n;
 }
 
@@ -785,8 +836,10 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	Outputs out; out.on_device = false; out.slots = slots; out.type1 = type1; out.packed = type1_packed;
 	out.max_slots = max_slots; out.n = 0;
 	ctx->fed_end += n_bits;
+	profile_begin(ctx);
 	rc = rx_run(ctx, src, (flags & TB200_FINAL) != 0, out);
 	if (rc) return rc;
+	if ((rc = profile_end(ctx))) return rc;
 	/* keep what a later call may still look at: everything from bitbuf[0] on */
 	const uint64_t keep_from = std::min<uint64_t>(ctx->rx.buf_start, ctx->fed_end);
 	std::vector<uint8_t> nt;
@@ -813,6 +866,56 @@ extern "C" int tb200_get_carry(const tb200_ctx *ctx, tb200_rx_carry *o)
 	o->mcc = (uint16_t)ctx->h_carry.mcc; o->mnc = (uint16_t)ctx->h_carry.mnc; o->colour_code = (uint8_t)ctx->h_carry.cc;
 	o->tn = (uint8_t)ctx->h_carry.tn; o->fn = (uint8_t)ctx->h_carry.fn; o->mn = (uint8_t)ctx->h_carry.mn;
 	return 0;
+}
+
+extern "C" int tb200_get_timing(const tb200_ctx *ctx, tb200_timing *o)
+{
+	if (!ctx || !o) return TB200_E_ARG;
+	*o = ctx->timing;
+	return 0;
+}
+
+/* register-only integer kernel: 8 independent add/min chains per thread */
+__global__ void __launch_bounds__(256)
+k_int_peak(uint32_t *out, int iters, uint32_t seed)
+{
+	uint32_t a0 = seed + threadIdx.x, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+	const uint32_t k = seed | 1;
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll 8
+		for (int u = 0; u < 8; ++u) {
+			a0 = umin(a0 + k, a1); a1 = umin(a1 + k, a2); a2 = umin(a2 + k, a3); a3 = umin(a3 + k, a4);
+			a4 = umin(a4 + k, a5); a5 = umin(a5 + k, a6); a6 = umin(a6 + k, a7); a7 = umin(a7 + k, a0);
+		}
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+
+extern "C" double tb200_measure_int_peak(tb200_ctx *ctx)
+{
+	if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return 0.0;
+	const int blocks = ctx->sm_count * 8, iters = 4096;
+	uint32_t *d = nullptr;
+	if (cudaMalloc((void **)&d, sizeof(uint32_t) * blocks * 256) != cudaSuccess) return 0.0;
+	double best = 0.0;
+#ifndef TB_SIMT_EMULATION
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	for (int rep = 0; rep < 5; rep++) {
+		cudaEventRecord(e0, ctx->s_compute);
+		k_int_peak<<<blocks, 256, 0, ctx->s_compute>>>(d, iters, 12345u + rep);
+		cudaEventRecord(e1, ctx->s_compute);
+		cudaEventSynchronize(e1);
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		/* 8 x 8 (add + min) pairs per iteration per thread = 128 integer results */
+		const double ops = (double)blocks * 256 * iters * 128.0;
+		if (rep > 0 && ms > 0.f) best = std::max(best, ops / (ms * 1e-3));
+	}
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+#endif
+	cudaFree(d);
+	return best;
 }
 
 extern "C" int tb200_get_stats(const tb200_ctx *ctx, tb200_stats *o)

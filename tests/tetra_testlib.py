@@ -364,7 +364,13 @@ VITERBI_WARP, VITERBI_LANE = 0, 1
 
 class Options(C.Structure):
     _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
-                ("pipeline_slots", C.c_uint32)]
+                ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("classify_ms", C.c_float), ("scan_ms", C.c_float), ("decode_ms", C.c_float),
+                ("launches_classify", C.c_uint32), ("launches_scan", C.c_uint32), ("launches_decode", C.c_uint32),
+                ("pieces", C.c_uint32), ("slots", C.c_uint64)]
 
 
 class Carry(C.Structure):
@@ -420,6 +426,9 @@ class B200:
         lib.tb200_expand_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         lib.tb200_get_carry.argtypes = [C.c_void_p, C.POINTER(Carry)]
         lib.tb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        lib.tb200_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
+        lib.tb200_measure_int_peak.restype = C.c_double
+        lib.tb200_measure_int_peak.argtypes = [C.c_void_p]
         lib.tb200_find_train_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
                                              C.c_uint32, C.c_void_p, C.c_void_p]
         lib.tb200_decode_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
@@ -491,6 +500,11 @@ class B200:
         s = Stats()
         self.lib.tb200_get_stats(self.h, C.byref(s))
         return s
+
+    def timing(self):
+        t = Timing()
+        self.lib.tb200_get_timing(self.h, C.byref(t))
+        return t
 
     def find_train_seq(self, bits, starts, lens, mask):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
