@@ -280,7 +280,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bursts_per_gpu_per_step": n, "viterbi": "warp-shuffle" if args.viterbi == 0 else "lane-per-block",
+            "config": {"workload": WORKLOAD, "bursts_per_gpu_per_step": n, "viterbi": "warp-shuffle, one warp per burst" if args.viterbi == 0 else "lane: two packed trellises per thread",
                        "l2": "inputs larger than L2 (510 MB stream per step)", "parallelism": f"independent streams x{world}",
                        "e2e_output": "slot records + unpacked type-1 bits (1 bit/byte)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nbits * world,
@@ -298,10 +298,10 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--viterbi", type=int, default=0, help="0 warp-shuffle, 1 lane-per-block")
+    ap.add_argument("--viterbi", type=int, default=1, help="0 warp-shuffle (one warp per burst), 1 lane (two trellises per thread)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
     args = ap.parse_args()

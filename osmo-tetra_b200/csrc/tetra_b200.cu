@@ -9,6 +9,7 @@
  * without a CUDA device tb200_create() fails.
  */
 #include "tetra_kernels.cuh"
+#include "tetra_lane.cuh"
 #include "tetra_gen.cuh"
 #include "../../include/tetra_b200.h"
 
@@ -71,6 +72,18 @@ static void build_tables(Tables *t)
 	const int Ls[3] = {76, 140, 284};
 	for (int i = 0; i < 3; i++)
 		t->crc_init[i] = crc16_host(msg.data(), Ls[i], 0xffff);
+
+	/* reflected CRC tables: register bit-reversed, polynomial 0x1021 -> 0x8408 */
+	for (int x = 0; x < 256; x++) {
+		uint32_t r = x;
+		for (int i = 0; i < 8; i++) r = (r & 1) ? (r >> 1) ^ 0x8408 : (r >> 1);
+		t->crc_tab_r[x] = r;
+	}
+	for (int x = 0; x < 16; x++) {
+		uint32_t r = x;
+		for (int i = 0; i < 4; i++) r = (r & 1) ? (r >> 1) ^ 0x8408 : (r >> 1);
+		t->crc_tab_r[256 + x] = r;
+	}
 
 	/* pre-filter blind spot, by running the filter of tetra_burst.c:286-303 on a buffer
 	 * that carries the sequence at offset k with the bit before it set to `prev` */
@@ -189,7 +202,7 @@ extern "C" void tb200_default_options(tb200_options *o)
 {
 	o->chunk_bits = 64;
 	o->output = TB200_OUT_UNPACKED | TB200_OUT_PACKED;
-	o->viterbi = TB200_VITERBI_WARP;
+	o->viterbi = TB200_VITERBI_LANE;
 	o->pipeline_slots = 0;
 	o->profile = 0;
 }
@@ -550,7 +563,18 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 		ctx->timing.slots += nb;
 		CU(cudaEventRecord(pe[0], st));
 	}
-	TB_LAUNCH(k_classify, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
+	const bool lane = ctx->opt.viterbi == TB200_VITERBI_LANE;
+	const unsigned lane_nt = 32;
+	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
+	const uint64_t npairs = ((uint64_t)nb + 1) / 2;
+	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->sm_count * 5);
+	if (lane) {
+		TB_LAUNCH(k_classify<false>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
+		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, nb, ctx->d_tab);
+		ctx->stats.kernel_launches++;
+	} else {
+		TB_LAUNCH(k_classify<true>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
+	}
 	if (pe) CU(cudaEventRecord(pe[1], st));
 	const unsigned nblk = (nb + 1023) / 1024;
 	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, ctx->d_ws, nb, ctx->d_last_good, ctx->d_blk_last, ctx->d_flags + piece_idx);
@@ -563,7 +587,8 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	a.type1 = (ctx->opt.output & TB200_OUT_UNPACKED) ? o_type1 : nullptr;
 	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
 	a.a0 = g.a0; a.out_base = out_base; a.n_slots = nb;
-	TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
+	if (lane) TB_LAUNCH_SMEM(k_decode_lane, lane_blocks, lane_nt, lane_smem, st, a);
+	else      TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
 	if (pe) CU(cudaEventRecord(pe[3], st));
 	CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
 	TB_LAUNCH(k_finalize_carry, 1, 32, st, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, nb, ctx->d_carry + piece_idx + 1);

@@ -20,6 +20,9 @@
 #ifndef TB_SIMT_EMULATION
 #include <cuda_runtime.h>
 #define TB_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#define TB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+extern __shared__ __align__(16) uint8_t tb_dyn_smem_[];
+#define TB_DYN_SMEM() (tb_dyn_smem_)
 #endif
 
 #define TB_HD __host__ __device__
@@ -47,6 +50,9 @@ struct Tables {
 	 * prev = stream bit k-1 (ignored for k = 0). */
 	uint32_t blind_ok[3][2];
 	uint32_t pad[2];
+	/* the same CRC with the register bit-reversed: byte table [0,256) and nibble table [256,272),
+	 * so that LSB-first packed bytes feed it directly (lane kernels) */
+	uint32_t crc_tab_r[272];
 };
 
 /* training sequences, LSB = first bit on air (values checked against the reference's
@@ -612,6 +618,7 @@ __device__ __forceinline__ unsigned slot_window(const RxGeom &g, uint64_t k, uin
 /* Pass 1, one warp per slot: load + pack the slot, search the training sequence with the
  * reference's first-match semantics, classify, and decode SB1 of SYNC bursts (its scrambling
  * code is fixed, so it needs no cell state).  Leaves SlotWs + the packed slot for pass 2. */
+template <bool DO_SB1>
 __global__ void __launch_bounds__(256)
 k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, uint32_t *__restrict__ slot_bits)
 {
@@ -646,7 +653,7 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
 		}
 		uint32_t good = 0, t1lo = 0, t1hi = 0, code = 0;
 		uint32_t tn = 0, fn = 0, mn = 0, cc = 0, mcc = 0, mnc = 0;
-		if (kind == KIND_SB) {
+		if (DO_SB1 && kind == KIND_SB) {
 			if (lane < 16) S.lf[lane] = tab->lfsr_sb1[lane];
 			if (lane < 4) S.bw[16 + lane] = 0;
 			__syncwarp();

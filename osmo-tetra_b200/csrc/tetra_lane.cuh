@@ -1,0 +1,531 @@
+/*
+ * tetra_lane.cuh - the throughput form of the decode pass: one THREAD owns two slots.
+ *
+ * The warp-per-slot kernels of tetra_kernels.cuh spend ~20k warp instructions per SCH/F burst,
+ * almost all of it shuffles and lane-redundant work around a 16-state trellis that cannot use
+ * 32 lanes.  Here the trellis lives entirely in one thread's registers and two independent
+ * trellises are packed into the 16-bit halves of each register, so every add-compare-select
+ * is one VIADD + one VIADDMNMX.U16x2 for two blocks at once; survivor decisions are taken from
+ * the sign of a packed difference and stored bit-packed (16 bits per trellis per step) in
+ * shared memory for the trace back.  Descrambling is a handful of word XORs in the burst
+ * domain and de-interleaving + de-puncturing is a fully unrolled constant-index bit gather.
+ *
+ * Semantics are those of the reference chain (tetra_lower_mac.c:143-357, viterbi.c:6-25,
+ * libosmocore osmo_conv_decode): see viterbi_warp() in tetra_kernels.cuh for the rules.
+ */
+#pragma once
+#include "tetra_kernels.cuh"
+
+namespace tb {
+
+constexpr int LANE_DEC_ROWS = 296;     /* 292 trellis steps max, padded */
+constexpr int LANE_T3_ROWS = 14;
+constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: one warp, 5 CTAs fit an SM's shared memory */
+
+/* dynamic shared memory of a lane kernel with NT threads, in 32-bit words */
+__host__ __device__ constexpr size_t lane_smem_words(int nt)
+{
+	return (size_t)LANE_DEC_ROWS * nt + 2 * LANE_T3_ROWS * nt + 256 + 16 + (nt / 32) * 16;
+}
+
+struct LaneSmem {
+	uint32_t *dec;       /* [LANE_DEC_ROWS][NT]  bit s: trellis X state s, bit 16+s: trellis Y */
+	uint32_t *t3;        /* [2][LANE_T3_ROWS][NT] type-3 bits, later the decoded type-2 bits */
+	uint32_t *crc_tab;   /* [256] reflected CRC-CCITT byte table, then [16] nibble table */
+	uint32_t *lfb;       /* [NT/32][16] per-warp scrambling sequence broadcast */
+	static constexpr int nt = LANE_NT;
+	__device__ __forceinline__ LaneSmem(uint8_t *base, int)
+	{
+		uint32_t *p = reinterpret_cast<uint32_t *>(base);
+		dec = p; p += (size_t)LANE_DEC_ROWS * nt;
+		t3 = p; p += 2 * LANE_T3_ROWS * nt;
+		crc_tab = p; p += 256 + 16;
+		lfb = p;
+	}
+	__device__ __forceinline__ uint32_t *t3col(int tr, int tid) const { return t3 + (size_t)tr * LANE_T3_ROWS * nt + tid; }
+};
+
+/* class of the (G1,G2) outputs of branch (state j, input 0): idx = 2*G1 + G2 */
+__host__ __device__ constexpr unsigned branch_class(unsigned j)
+{
+	return ((((j >> 0) & 1) ^ ((j >> 3) & 1)) << 1) | (((j >> 1) & 1) ^ ((j >> 2) & 1) ^ ((j >> 3) & 1));
+}
+
+__device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b)
+{
+#ifdef TB_SIMT_EMULATION
+	return a - b;
+#else
+	uint32_t r;
+	asm("sub.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+	return r;
+#endif
+}
+
+/* One trellis step for two packed trellises.  Path metrics are kept doubled (even numbers);
+ * the candidate coming from the older-bit-1 predecessor carries a 1 in its LSB, so a single
+ * packed add-min both selects the survivor (ties go to the even candidate = predecessor s>>1,
+ * the reference rule) and leaves the decision in bit 0 / bit 16 of the result.
+ * M0[c] = 2 * mismatches of output class c, M1[c] = M0[c] + 1 per half; the complementary
+ * branch has class c ^ 3.  Returns the decisions: bit s = trellis X state s, bit 16+s = Y. */
+__device__ __forceinline__ uint32_t acs2_step(uint32_t (&pm)[16], const uint32_t (&M0)[4], const uint32_t (&M1)[4])
+{
+	uint32_t nm[16];
+	uint32_t dhi = 0, dlo = 0;
+#pragma unroll
+	for (int s = 15; s >= 0; --s) {
+		const unsigned c = branch_class(s >> 1) ^ ((s & 1) ? 3u : 0u);
+		const uint32_t c1 = pm[(s >> 1) | 8] + M1[c ^ 3];
+		const uint32_t r = __viaddmin_u16x2(pm[s >> 1], M0[c], c1);
+		const uint32_t tag = r & 0x00010001u;
+		nm[s] = sub_opaque(r, tag);                 /* clears the tag; an add, so it can go to either pipe */
+		if (s >= 8) dhi = dhi * 2 + tag;
+		else        dlo = dlo * 2 + tag;
+	}
+#pragma unroll
+	for (int s = 0; s < 16; ++s) pm[s] = nm[s];
+	return dhi * 256 + dlo;
+}
+
+/* Forward pass + trace back for the two blocks whose type-3 bits sit in sm.t3[0] / sm.t3[1]
+ * (columns of this thread).  nx, ny: type-2 lengths (0 = no block); nmax: warp-wide maximum so
+ * the loop is uniform.  Leaves the decoded type-2 bits in the same columns. */
+template <bool MASKED>
+__device__ __forceinline__ void viterbi_pair_t(const LaneSmem &sm, int tid, int nx, int ny, int nmax)
+{
+	uint32_t pm[16];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x20002000u : 0u;
+	const uint32_t *cx = sm.t3col(0, tid), *cy = sm.t3col(1, tid);
+	uint32_t *dec = sm.dec + tid;
+	constexpr int nt = LANE_NT;
+	const int groups = nmax / 8;                       /* 4 step pairs = 12 type-3 bits per group */
+	for (int g = 0; g < groups; ++g) {
+		const unsigned bp = 12 * g, w = bp >> 5, sh = bp & 31;
+		const uint32_t vx = __funnelshift_r(cx[w * nt], cx[(w + 1) * nt], sh) & 0xfffu;
+		const uint32_t vy = __funnelshift_r(cy[w * nt], cy[(w + 1) * nt], sh) & 0xfffu;
+		const uint32_t z = (vx | (vy << 16)) << 1;          /* bits pre-doubled: value 2 where a 1 was received */
+		uint32_t live = 0xffffffffu;
+		if (MASKED) live = ((8 * g < nx) ? 0xffffu : 0u) | ((8 * g < ny) ? 0xffff0000u : 0u);
+#pragma unroll
+		for (int p = 0; p < 4; ++p) {
+			const uint32_t r1 = (z >> (3 * p)) & 0x00020002u;
+			const uint32_t r2 = (z >> (3 * p + 1)) & 0x00020002u;
+			const uint32_t r3 = (z >> (3 * p + 2)) & 0x00020002u;
+			uint32_t M0[4], M1[4];
+			M0[0] = r1 + r2;                                  /* expected 00 */
+			M0[3] = 0x00040004u - M0[0];                      /* expected 11 */
+			M0[2] = 0x00020002u - r1 + r2;                    /* expected G1=1, G2=0 */
+			M0[1] = 0x00040004u - M0[2];                      /* expected G1=0, G2=1 */
+			if (MASKED) { M0[0] &= live; M0[1] &= live; M0[2] &= live; M0[3] &= live; }
+#pragma unroll
+			for (int c = 0; c < 4; ++c) M1[c] = M0[c] + 0x00010001u;
+			dec[(8 * g + 2 * p) * nt] = acs2_step(pm, M0, M1);
+			M0[0] = r3; M0[2] = 0x00020002u - r3;             /* odd step: only G1 was sent */
+			if (MASKED) { M0[0] &= live; M0[2] &= live; }
+			M0[1] = M0[0]; M0[3] = M0[2];
+#pragma unroll
+			for (int c = 0; c < 4; ++c) M1[c] = M0[c] + 0x00010001u;
+			dec[(8 * g + 2 * p + 1) * nt] = acs2_step(pm, M0, M1);
+		}
+	}
+	{
+		const uint32_t Z0[4] = { 0, 0, 0, 0 }, Z1[4] = { 0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u };
+#pragma unroll
+		for (int t = 0; t < 4; ++t) dec[(nmax + t) * nt] = acs2_step(pm, Z0, Z1);
+	}
+	/* Trace back.  The state after step t is the last four decoded bits, and the decision looked up
+	 * at step t is decoded bit t-4, so one shift register per path is both the state (its top four
+	 * bits) and the output: h = (h >> 1) | (decision << 31). */
+	uint32_t *ox = sm.t3col(0, tid), *oy = sm.t3col(1, tid);
+	uint32_t hx = 0, hy = 0;
+	/* output word wi holds decoded bits [32wi, 32wi+32): they come from steps t = 32wi+35 .. 32wi+4 */
+	for (int wi = (nmax - 1) >> 5; wi >= 0; --wi) {
+		const int thi = 32 * wi + 35 < nmax + 3 ? 32 * wi + 35 : nmax + 3;
+		const uint32_t *dp = dec + thi * nt;
+		const int cnt = thi - (32 * wi + 4) + 1;
+		for (int i = 0; i < cnt; ++i) {
+			const uint32_t w = *dp;
+			dp -= nt;
+			if (MASKED) {
+				const int t = thi - i;
+				if (t <= nx + 3) hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
+				if (t <= ny + 3) hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
+			} else {
+				hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
+				hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
+			}
+		}
+		ox[wi * nt] = __brev(hx);
+		oy[wi * nt] = __brev(hy);
+	}
+}
+
+__device__ inline void viterbi_pair(const LaneSmem &sm, int tid, int nx, int ny, int nmax)
+{
+	/* warp-uniform choice: no masking work when every lane carries two full-length blocks */
+	const bool uniform = __all_sync(FULL, nx == nmax && ny == nmax);
+	if (uniform) viterbi_pair_t<false>(sm, tid, nx, ny, nmax);
+	else         viterbi_pair_t<true>(sm, tid, nx, ny, nmax);
+}
+
+/* CRC-16-CCITT of the first L type-2 bits of a column, reflected byte-table form of
+ * crc_simple.c:65-82 (register bit-reversed, so packed LSB-first bytes feed it directly);
+ * returns true when the residue is TETRA_CRC_OK (0x1d0f, tetra_common.h:69). L % 8 == 4. */
+__device__ __forceinline__ bool crc_ok_col(const LaneSmem &sm, const uint32_t *col, int L)
+{
+	uint32_t r = 0xffff;
+	constexpr int nt = LANE_NT;
+	const int nbytes = L >> 3;
+	for (int i = 0; i < nbytes; ++i) {
+		const uint32_t b = (col[(i >> 2) * nt] >> (8 * (i & 3))) & 0xff;
+		r = (r >> 8) ^ sm.crc_tab[(r ^ b) & 0xff];
+	}
+	const int bp = L & ~7;
+	const uint32_t nib = (col[(bp >> 5) * nt] >> (bp & 31)) & 0xf;
+	r = (r >> 4) ^ sm.crc_tab[256 + ((r ^ nib) & 0xf)];
+	return r == 0xf0b8;               /* bit-reversed 0x1d0f */
+}
+
+/* ---- descrambling in the burst domain ------------------------------------------- */
+
+template <int S>
+__device__ __forceinline__ uint32_t lf_window(const uint32_t (&lf)[LANE_T3_ROWS])   /* bits [S, S+32) of the sequence */
+{
+	if constexpr (S <= -32 || S >= 32 * LANE_T3_ROWS) {
+		return 0;
+	} else if constexpr (S < 0) {
+		return lf[0] << (-S);
+	} else {
+		constexpr int w = S >> 5, sh = S & 31;
+		const uint32_t lo = lf[w];
+		if constexpr (sh == 0) {
+			return lo;
+		} else if constexpr (w + 1 < LANE_T3_ROWS) {
+			return __funnelshift_r(lo, lf[w + 1], sh);
+		} else {
+			return lo >> sh;
+		}
+	}
+}
+
+/* burst bits [DST, DST+LEN) ^= sequence bits [SRC, SRC+LEN)  (tetra_scramb.c:77-85 per block) */
+template <int DST, int SRC, int LEN>
+__device__ __forceinline__ void xor_region(uint32_t (&bw)[16], const uint32_t (&lf)[LANE_T3_ROWS])
+{
+#pragma unroll
+	for (int w = 0; w < 16; ++w) {
+		const int lo = 32 * w, hi = 32 * w + 32;
+		if (hi <= DST || lo >= DST + LEN) continue;
+		uint32_t mask = 0xffffffffu;
+		if (DST > lo) mask &= 0xffffffffu << (DST - lo);
+		if (DST + LEN < hi) mask &= 0xffffffffu >> (hi - (DST + LEN));
+		uint32_t v = 0;
+		switch (w) {   /* compile-time window selection */
+#define TB_CASE(W) case W: v = lf_window<SRC + 32 * W - DST>(lf); break;
+		TB_CASE(0) TB_CASE(1) TB_CASE(2) TB_CASE(3) TB_CASE(4) TB_CASE(5) TB_CASE(6) TB_CASE(7)
+		TB_CASE(8) TB_CASE(9) TB_CASE(10) TB_CASE(11) TB_CASE(12) TB_CASE(13) TB_CASE(14) TB_CASE(15)
+#undef TB_CASE
+		}
+		bw[w] ^= v & mask;
+	}
+}
+
+/* ---- de-interleave + de-puncture addressing, constant indices ---------------------- */
+
+/* type-3 bit j = (descrambled) burst bit place(A(j+1) mod K)  (tetra_interleave.c:51-60);
+ * K bits written as words to the thread's column */
+template <int BT, int PL>
+__device__ __forceinline__ void gather_lane(const uint32_t (&bw)[16], uint32_t *col, int nt)
+{
+	constexpr int K = Blk<BT>::K, A = Blk<BT>::A, NW = (K + 31) / 32;
+#pragma unroll
+	for (int w = 0; w < NW; ++w) {
+		uint32_t acc = 0;
+#pragma unroll
+		for (int i = 0; i < 32; ++i) {
+			const int j = 32 * w + i;
+			if (j < K) {
+				const unsigned m = (unsigned)(A * (j + 1)) % K;
+				const unsigned pos = place<PL>(m);
+				const int sh = (int)(pos & 31) - i;
+				const uint32_t src = bw[pos >> 5];
+				const uint32_t v = sh >= 0 ? (src >> sh) : (src << (-sh));
+				acc |= v & (1u << i);
+			}
+		}
+		col[w * nt] = acc;
+	}
+}
+
+/* OR `len` bits into the slot's type-1 string at bit `dst`; get(i) returns source word i */
+template <typename F>
+__device__ __forceinline__ void put_lane(uint32_t (&outw)[9], int dst, int len, F get)
+{
+#pragma unroll
+	for (int w = 0; w < 9; ++w) {
+		const int sidx = 32 * w - dst;
+		uint32_t val = 0;
+		if (sidx >= 0) {
+			if (sidx < len) {
+				const uint32_t lo = get(sidx >> 5), hi = get((sidx >> 5) + 1);
+				val = __funnelshift_r(lo, hi, sidx & 31);
+			}
+		} else if (sidx > -32) {
+			val = get(0) << (-sidx);
+		}
+		const int hi_ = len - sidx;
+		if (hi_ <= 0) val = 0;
+		else if (hi_ < 32) val &= (1u << hi_) - 1;
+		outw[w] |= val;
+	}
+}
+
+/* scrambling sequence words for `code`, for every lane of the warp: cooperative when the warp
+ * shares one code (the normal case: one cell), per distinct code otherwise */
+__device__ inline void lane_lfsr(uint32_t code, bool need, uint32_t (&lf)[LANE_T3_ROWS], uint32_t *bcast,
+                                 const Tables *__restrict__ tab)
+{
+	const unsigned lane = threadIdx.x & 31;
+	unsigned pending = __ballot_sync(FULL, need);
+	while (pending) {
+		const int leader = __ffs((int)pending) - 1;
+		const uint32_t c = __shfl_sync(FULL, code, leader);
+		const uint32_t wv = lfsr_word(c, lane, tab);
+		if (lane < 16) bcast[lane] = wv;
+		__syncwarp();
+		const bool mine = need && code == c;
+		if (mine) {
+#pragma unroll
+			for (int i = 0; i < LANE_T3_ROWS; ++i) lf[i] = bcast[i];
+		}
+		pending &= ~__ballot_sync(FULL, mine);
+		__syncwarp();
+	}
+}
+
+__device__ __forceinline__ void lane_load_tables(const LaneSmem &sm, const Tables *__restrict__ tab)
+{
+	for (int i = threadIdx.x; i < 256 + 16; i += blockDim.x)
+		sm.crc_tab[i] = tab->crc_tab_r[i];
+	__syncthreads();
+}
+
+__device__ __forceinline__ void load_slot_bits(const uint32_t *__restrict__ slot_bits, uint64_t k, uint32_t (&bw)[16])
+{
+	const uint4 *p = reinterpret_cast<const uint4 *>(slot_bits + k * 16);
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		const uint4 v = p[i];
+		bw[4 * i] = v.x; bw[4 * i + 1] = v.y; bw[4 * i + 2] = v.z; bw[4 * i + 3] = v.w;
+	}
+}
+
+/* =============================================================== SB1 pass ==
+ * SYNC bursts only: SB1 always uses scrambling code 3 (tetra_lower_mac.c:181-183), so it can be
+ * decoded before the cell state is known.  Fills the SYNC-PDU part of SlotWs. */
+__global__ void __launch_bounds__(32)
+k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits, uint32_t n_slots,
+           const Tables *__restrict__ tab)
+{
+	LaneSmem sm(TB_DYN_SMEM(), blockDim.x);
+	lane_load_tables(sm, tab);
+	const int tid = threadIdx.x;
+	const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+	const uint64_t npairs = ((uint64_t)n_slots + 1) / 2;
+	const uint64_t rounds = (npairs + nthreads - 1) / nthreads;
+	uint32_t lf[LANE_T3_ROWS];
+#pragma unroll
+	for (int i = 0; i < LANE_T3_ROWS; ++i) lf[i] = tab->lfsr_sb1[i];
+
+	for (uint64_t r = 0; r < rounds; ++r) {
+		const uint64_t pair = r * nthreads + (uint64_t)blockIdx.x * blockDim.x + tid;
+		const uint64_t k[2] = { 2 * pair, 2 * pair + 1 };
+		int n[2] = { 0, 0 };
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			if (k[h] < n_slots && ws[k[h]].kind == KIND_SB) {
+				uint32_t bw[16];
+				load_slot_bits(slot_bits, k[h], bw);
+				xor_region<94, 0, 120>(bw, lf);
+				gather_lane<0, PL_SB1>(bw, sm.t3col(h, tid), sm.nt);
+				n[h] = 80;
+			}
+		}
+		int nmax = n[0] > n[1] ? n[0] : n[1];
+		nmax = __shfl_sync(FULL, __ballot_sync(FULL, nmax != 0) ? 80 : 0, 0);
+		if (nmax == 0) continue;
+		viterbi_pair(sm, tid, n[0], n[1], nmax);
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			if (n[h]) {
+				const uint32_t *col = sm.t3col(h, tid);
+				constexpr int nt = LANE_NT;
+				const bool good = crc_ok_col(sm, col, 76);
+				const uint32_t w0 = col[0], w1 = col[nt], w2 = col[2 * nt];
+				const uint32_t t2[4] = { w0, w1, w2, 0 };
+				SlotWs w = ws[k[h]];
+				w.sb1_t1[0] = w0; w.sb1_t1[1] = w1 & 0x0fffffffu;
+				w.good_sb = good;
+				w.cc = (uint8_t)field_msb_first(t2, 4, 6);
+				w.tn = (uint8_t)(field_msb_first(t2, 10, 2) + 1);
+				w.fn = (uint8_t)field_msb_first(t2, 12, 5);
+				w.mn = (uint8_t)field_msb_first(t2, 17, 6);
+				w.mcc = (uint16_t)field_msb_first(t2, 31, 10);
+				w.mnc = (uint16_t)field_msb_first(t2, 41, 14);
+				w.sb_code = scramb_init_from(w.mcc, w.mnc, w.cc);
+				ws[k[h]] = w;
+			}
+		}
+		__syncwarp();
+	}
+}
+
+/* ============================================================= decode pass ==
+ * Everything of tp_sap_udata_ind that needs the cell state, two slots per thread. */
+__global__ void __launch_bounds__(32)
+k_decode_lane(DecodeArgs a)
+{
+	LaneSmem sm(TB_DYN_SMEM(), blockDim.x);
+	const Tables *__restrict__ tab = a.tab;
+	lane_load_tables(sm, tab);
+	const int tid = threadIdx.x;
+	constexpr int nt = LANE_NT;
+	uint32_t *bcast = sm.lfb + (tid >> 5) * 16;
+	const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+	const uint64_t npairs = ((uint64_t)a.n_slots + 1) / 2;
+	const uint64_t rounds = (npairs + nthreads - 1) / nthreads;
+
+	for (uint64_t r = 0; r < rounds; ++r) {
+		const uint64_t pair = r * nthreads + (uint64_t)blockIdx.x * blockDim.x + tid;
+		const uint64_t k[2] = { 2 * pair, 2 * pair + 1 };
+		uint32_t bw[2][16];
+		uint32_t outw[2][9];
+		uint32_t code[2] = { 0, 0 }, flags[2] = { 0, 0 };
+		int kind[2] = { KIND_NONE, KIND_NONE };
+		bool have[2] = { false, false };
+		Tm tm[2];
+		SlotWs w[2];
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			have[h] = k[h] < a.n_slots;
+			tm[h].tn = tm[h].fn = tm[h].mn = 0;
+#pragma unroll
+			for (int i = 0; i < 9; ++i) outw[h][i] = 0;
+			if (have[h]) {
+				w[h] = a.ws[k[h]];
+				kind[h] = w[h].kind;
+				cell_state(k[h], a.ws, a.last_good, a.blk_prev, a.carry, &tm[h], &code[h]);
+				flags[h] = (uint32_t)kind[h] | (w[h].unlock ? F_UNLOCK : 0);
+				if (kind[h] != KIND_NONE) load_slot_bits(a.slot_bits, k[h], bw[h]);
+			}
+		}
+		/* scrambling sequence(s) and descrambling of every block the slot carries */
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			uint32_t lf[LANE_T3_ROWS];
+			lane_lfsr(code[h], kind[h] != KIND_NONE, lf, bcast, tab);
+			if (kind[h] == KIND_SB) {
+				xor_region<252, 0, 30>(bw[h], lf);
+				xor_region<282, 0, 216>(bw[h], lf);
+			} else if (kind[h] == KIND_NDB_F) {
+				xor_region<14, 0, 216>(bw[h], lf);
+				xor_region<282, 216, 216>(bw[h], lf);
+				xor_region<230, 0, 14>(bw[h], lf);
+				xor_region<266, 14, 16>(bw[h], lf);
+			} else if (kind[h] == KIND_NDB_2) {
+				xor_region<14, 0, 216>(bw[h], lf);
+				xor_region<282, 0, 216>(bw[h], lf);
+				xor_region<230, 0, 14>(bw[h], lf);
+				xor_region<266, 14, 16>(bw[h], lf);
+			}
+		}
+		/* round 1: SB2 / SCH-F / BLK1 */
+		int n[2] = { 0, 0 };
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			uint32_t *col = sm.t3col(h, tid);
+			if (kind[h] == KIND_SB) { gather_lane<1, PL_BLK2>(bw[h], col, nt); n[h] = 144; }
+			else if (kind[h] == KIND_NDB_F) { gather_lane<5, PL_SCHF>(bw[h], col, nt); n[h] = 288; }
+			else if (kind[h] == KIND_NDB_2) { gather_lane<1, PL_BLK1>(bw[h], col, nt); n[h] = 144; }
+		}
+		int nmax = n[0] > n[1] ? n[0] : n[1];
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) {
+			const int o = __shfl_xor_sync(FULL, nmax, d);
+			nmax = o > nmax ? o : nmax;
+		}
+		if (nmax) viterbi_pair(sm, tid, n[0], n[1], nmax);
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			const uint32_t *col = sm.t3col(h, tid);
+			auto src = [&](int i) { return col[i * nt]; };
+			if (kind[h] == KIND_SB) {
+				if (w[h].good_sb) flags[h] |= F_CRC_A;
+				if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_B;
+				if (tm_is_bnch(tm[h])) flags[h] |= F_BNCH;
+				const uint32_t s0 = w[h].sb1_t1[0], s1 = w[h].sb1_t1[1];
+				put_lane(outw[h], 0, 60, [&](int i) { return i == 0 ? s0 : (i == 1 ? s1 : 0u); });
+				const uint32_t bbk = extract_bits(bw[h], 252, 14);
+				put_lane(outw[h], 60, 14, [&](int i) { return i == 0 ? bbk : 0u; });
+				put_lane(outw[h], 74, 124, src);
+			} else if (kind[h] == KIND_NDB_F) {
+				if (crc_ok_col(sm, col, 284)) flags[h] |= F_CRC_A;
+				const uint32_t bbk = extract_bits(bw[h], 230, 14);
+				put_lane(outw[h], 0, 14, [&](int i) { return i == 0 ? bbk : 0u; });
+				put_lane(outw[h], 14, 268, src);
+			} else if (kind[h] == KIND_NDB_2) {
+				if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_A;
+				const uint32_t bbk = extract_bits(bw[h], 230, 14);
+				put_lane(outw[h], 0, 14, [&](int i) { return i == 0 ? bbk : 0u; });
+				put_lane(outw[h], 14, 124, src);
+			}
+		}
+		/* round 2: BLK2 of two-block bursts */
+		const bool any2 = __ballot_sync(FULL, kind[0] == KIND_NDB_2 || kind[1] == KIND_NDB_2) != 0;
+		if (any2) {
+			__syncwarp();
+			int m[2] = { 0, 0 };
+#pragma unroll
+			for (int h = 0; h < 2; ++h)
+				if (kind[h] == KIND_NDB_2) { gather_lane<1, PL_BLK2>(bw[h], sm.t3col(h, tid), nt); m[h] = 144; }
+			viterbi_pair(sm, tid, m[0], m[1], 144);
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				if (kind[h] == KIND_NDB_2) {
+					const uint32_t *col = sm.t3col(h, tid);
+					if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_B;
+					put_lane(outw[h], 138, 124, [&](int i) { return col[i * nt]; });
+				}
+			}
+		}
+		/* results */
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			if (!have[h]) continue;
+			const uint64_t ko = a.out_base + k[h];
+			if (a.type1) {
+				uint4 *dst = reinterpret_cast<uint4 *>(a.type1 + ko * TYPE1_STRIDE);
+#pragma unroll
+				for (int c = 0; c < 18; ++c) {
+					const uint32_t hbits = (outw[h][c >> 1] >> (16 * (c & 1))) & 0xffff;
+					dst[c] = make_uint4(unpack4(hbits), unpack4(hbits >> 4), unpack4(hbits >> 8), unpack4(hbits >> 12));
+				}
+			}
+			if (a.type1_packed) {
+#pragma unroll
+				for (int i = 0; i < 9; ++i) a.type1_packed[ko * TYPE1_WORDS + i] = outw[h][i];
+			}
+			SlotOut o;
+			o.slot_bit = (uint32_t)(a.a0 + (uint64_t)SLOT_BITS * k[h]);
+			o.scrambling_code = code[h];
+			o.find_off = w[h].find_off; o.window = w[h].window;
+			o.time = (uint16_t)(tm[h].tn | (tm[h].fn << 3) | (tm[h].mn << 8));
+			o.find_rc = w[h].find_rc; o.flags = (uint8_t)flags[h];
+			a.slots[ko] = o;
+		}
+		__syncwarp();
+	}
+}
+
+}  // namespace tb

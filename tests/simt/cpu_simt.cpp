@@ -131,6 +131,10 @@ void run_block(Block &b)
 	g_blk = nullptr;
 }
 
+static thread_local std::vector<uint8_t> g_dyn;
+void set_dyn_smem(size_t bytes) { if (g_dyn.size() < bytes + 64) g_dyn.resize(bytes + 64); }
+uint8_t *dyn_smem() { return (uint8_t *)(((uintptr_t)g_dyn.data() + 15) & ~(uintptr_t)15); }
+
 void launch(dim3 grid, dim3 block, const std::function<void()> &body)
 {
 	static thread_local Block blk;

@@ -72,6 +72,8 @@ static inline unsigned warp_id() { return g_threadIdx.x >> 5; }
 
 void warp_barrier();
 void block_barrier();
+void set_dyn_smem(size_t bytes);
+uint8_t *dyn_smem();
 
 template <typename T>
 static inline T warp_exchange(T v, unsigned src)
@@ -202,3 +204,21 @@ static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { mems
 
 #define TB_LAUNCH(kernel, grid, block, stream, ...) \
 	simt::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); })
+#define TB_LAUNCH_SMEM(kernel, grid, block, smem, stream, ...) \
+	(simt::set_dyn_smem(smem), simt::launch(dim3(grid), dim3(block), [&]() { kernel(__VA_ARGS__); }))
+#define TB_DYN_SMEM() (simt::dyn_smem())
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
+
+/* packed 16x2 SIMD intrinsics used by the lane Viterbi */
+static inline uint32_t __vadd2(uint32_t a, uint32_t b)
+{
+	return ((a + b) & 0xffffu) | (((a >> 16) + (b >> 16)) << 16);
+}
+static inline uint32_t __vminu2(uint32_t a, uint32_t b)
+{
+	uint32_t lo = (a & 0xffff) < (b & 0xffff) ? (a & 0xffff) : (b & 0xffff);
+	uint32_t hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+	return lo | (hi << 16);
+}
+static inline uint32_t __viaddmin_u16x2(uint32_t a, uint32_t b, uint32_t c) { return __vminu2(__vadd2(a, b), c); }

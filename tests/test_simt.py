@@ -109,6 +109,13 @@ def test_stream_mixed(emu, orc, variant):
     assert slots.size == 119
 
 
+def test_stream_uniform_schf(emu, orc):
+    """only SCH/F bursts after the two leading SBs: whole warps of the lane kernel take the unmasked path"""
+    bits, _ = _stream(orc, n=200, sb_period=0, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=5)
+    for variant in (T.VITERBI_WARP, T.VITERBI_LANE):
+        _check(emu, orc, bits, viterbi=variant, pipeline_slots=0)
+
+
 @pytest.mark.parametrize("chunk", [1, 7, 64, 100, 296])
 def test_stream_chunks(emu, orc, chunk):
     bits, _ = _stream(orc, n=40)

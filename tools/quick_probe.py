@@ -17,14 +17,15 @@ def main():
     d_slots = torch.empty(ms * 16, dtype=torch.uint8, device="cuda")
     d_t1 = torch.empty(ms * 288, dtype=torch.uint8, device="cuda")
     d_pk = torch.empty(ms * 9, dtype=torch.int32, device="cuda")
-    for variant in (T.VITERBI_WARP,):
-        g.set_options(viterbi=variant)
+    for variant in (T.VITERBI_WARP, T.VITERBI_LANE):
+        g.set_options(viterbi=variant, profile=1)
         for it in range(4):
             torch.cuda.synchronize(); t = time.time()
             ns = g.lib.tb200_rx_stream_dev(g.h, C.c_void_p(d_bits.data_ptr()), nbits, 3, C.c_void_p(d_slots.data_ptr()),
                                            C.c_void_p(d_t1.data_ptr()), C.c_void_p(d_pk.data_ptr()), ms)
             torch.cuda.synchronize(); dt = time.time() - t
-            print(f"variant {variant} iter {it}: slots {ns} in {dt*1e3:.2f} ms -> {ns/dt/1e6:.2f} M bursts/s", g.err() if ns < 0 else "")
+            tm = g.timing()
+            print(f"variant {variant} iter {it}: slots {ns} in {dt*1e3:.2f} ms -> {ns/dt/1e6:.2f} M bursts/s | dev total {tm.total_ms:.2f} classify {tm.classify_ms:.2f} scan {tm.scan_ms:.2f} decode {tm.decode_ms:.2f}", g.err() if ns < 0 else "")
         slots = np.frombuffer(d_slots.cpu().numpy().tobytes(), dtype=T.SLOT_DTYPE)[:ns]
         print(" kinds", np.unique(slots['flags'] & 3, return_counts=True), "crcA frac", ((slots['flags'] & 4) != 0).mean())
 
