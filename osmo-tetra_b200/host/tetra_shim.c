@@ -1,0 +1,171 @@
+/*
+ * tetra_shim.c - drop-in for the reference's PHY + lower MAC objects.
+ *
+ * Link this file and libtetra_b200.so INSTEAD of libosmo-tetra-phy.a (phy/tetra_burst_sync.o,
+ * phy/tetra_burst.o) and lower_mac/tetra_lower_mac.o (src/Makefile:13-26); tetra-rx.c and the
+ * whole upper MAC stay untouched.  It exports the symbols tetra-rx links against
+ *     int tetra_burst_sync_in(struct tetra_rx_state *, uint8_t *, unsigned int)   tetra_burst_sync.h:24
+ *     struct tetra_phy_state t_phy_state                                          tetra_common.h:44-47
+ * and delivers, per decoded block and in stream order on the calling thread, the same
+ * TMV-SAP primitive the reference builds (tetra_lower_mac.c:129-140,162-167,276-352) to
+ *     int upper_mac_prim_recv(struct osmo_prim_hdr *op, void *priv)              tetra_upper_mac.h:22
+ *
+ * Bits are queued and decoded on the GPU in batches (TETRA_B200_BATCH_BITS, default 8 Mi bits);
+ * tetra-rx has no end-of-stream call, so the tail is flushed from an atexit() handler, or
+ * explicitly with tetra_b200_shim_flush().  Compiled against the reference's own headers.
+ *
+ * Not reproduced: the stdout text of the PHY / lower MAC (SURVEY 8b "text side-channel") and the
+ * is_traffic dump path (tetra_lower_mac.c:194-241).  read() sizes must be constant (64 in
+ * tetra-rx.c:83) except for the last one; other call patterns are rejected loudly.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <osmocom/core/msgb.h>
+#include <osmocom/core/talloc.h>
+
+#include <tetra_common.h>
+#include <tetra_tdma.h>
+#include <tetra_prim.h>
+#include <tetra_upper_mac.h>
+#include <phy/tetra_burst.h>
+#include <phy/tetra_burst_sync.h>
+
+#include "tetra_b200.h"
+
+struct tetra_phy_state t_phy_state;
+
+static struct {
+	tb200_ctx *ctx;
+	uint8_t *bits;
+	size_t n_bits, cap_bits, batch_bits;
+	unsigned int chunk;
+	int short_read_seen;
+	int started;
+	struct tetra_rx_state *trs;
+	struct tb200_slot *slots;
+	uint8_t *type1;
+	struct tb200_record *rec;
+	size_t max_slots;
+} S;
+
+static void shim_die(const char *msg)
+{
+	fprintf(stderr, "tetra_b200 shim: %s\n", msg);
+	exit(1);
+}
+
+/* what tp_sap_udata_ind does after the arithmetic: allocate the primitive, fill it, hand it up,
+ * re-invoke while the upper MAC consumed only part of the block (tetra_lower_mac.c:326-352) */
+static void deliver(const struct tb200_record *r, void *priv)
+{
+	struct tetra_tmvsap_prim *ttp = talloc_zero(NULL, struct tetra_tmvsap_prim);
+	struct tmv_unitdata_param *tup = &ttp->u.unitdata;
+	struct msgb *msg = ttp->oph.msg = msgb_alloc(412, "tmvsap_prim");
+	ttp->oph.sap = TETRA_SAP_TMV;
+	ttp->oph.primitive = PRIM_TMV_UNITDATA;
+	ttp->oph.operation = PRIM_OP_INDICATION;
+	tup->lchan = r->lchan;
+	tup->crc_ok = r->crc_ok;
+	tup->scrambling_code = r->scrambling_code;
+	tup->blk_num = r->blk_num;
+	tup->tdma_time.tn = r->tn;
+	tup->tdma_time.fn = r->fn;
+	tup->tdma_time.mn = r->mn;
+	msg->l1h = msgb_put(msg, r->type1_len);
+	memcpy(msg->l1h, r->type1, r->type1_len);
+
+	uint32_t offset = 0;
+	uint8_t *orig_head = msg->head, *orig_tail = msg->tail;
+	while (offset < (uint32_t)(r->type1_len - 16)) {
+		int pdu_bits = upper_mac_prim_recv(&ttp->oph, priv);
+		if (pdu_bits < 0)
+			break;
+		offset += pdu_bits;
+		msg->head = orig_head + offset;
+		msg->tail = orig_tail;
+		msg->len = msg->tail - msg->head;
+		msg->l1h = msg->head;
+		msg->l2h = msg->l3h = msg->l4h = 0;
+	}
+	talloc_free(msg);
+	talloc_free(ttp);
+}
+
+static void shim_run(int final)
+{
+	if (!S.ctx || (!S.n_bits && !final))
+		return;
+	uint32_t flags = (S.started ? 0 : TB200_FRESH) | (final ? TB200_FINAL : 0);
+	long n = tb200_rx_stream_host(S.ctx, S.bits, S.n_bits, flags, S.slots, S.type1, NULL, S.max_slots);
+	if (n < 0) {
+		fprintf(stderr, "tetra_b200 shim: %s\n", tb200_last_error(S.ctx));
+		exit(1);
+	}
+	S.started = 1;
+	S.n_bits = 0;
+	size_t nrec = tb200_expand_records(S.slots, S.type1, (size_t)n, S.rec, 3 * S.max_slots);
+	void *priv = S.trs ? S.trs->burst_cb_priv : NULL;
+	for (size_t i = 0; i < nrec; i++)
+		deliver(&S.rec[i], priv);
+	struct tb200_rx_carry c;
+	tb200_get_carry(S.ctx, &c);
+	if (S.trs) {                      /* mirror what callers could look at */
+		S.trs->state = (enum rx_state)c.state;
+		S.trs->bits_in_buf = c.bits_in_buf;
+		S.trs->bitbuf_start_bitnum = (unsigned int)c.buf_start_bit;
+		S.trs->next_frame_start_bitnum = (unsigned int)c.next_frame_start;
+	}
+	t_phy_state.time.tn = c.tn; t_phy_state.time.fn = c.fn; t_phy_state.time.mn = c.mn;
+}
+
+void tetra_b200_shim_flush(void)
+{
+	shim_run(1);
+}
+
+static void shim_init(unsigned int first_len)
+{
+	const char *e = getenv("TETRA_B200_BATCH_BITS");
+	const char *d = getenv("TETRA_B200_DEVICE");
+	S.batch_bits = e ? strtoull(e, NULL, 0) : (8u << 20);
+	if (S.batch_bits < 4096) S.batch_bits = 4096;
+	if (tb200_create(&S.ctx, d ? atoi(d) : 0) != 0)
+		shim_die("no usable CUDA device - this build has no CPU lower MAC");
+	struct tb200_options opt;
+	tb200_default_options(&opt);
+	opt.chunk_bits = first_len;
+	opt.output = TB200_OUT_UNPACKED;
+	if (tb200_set_options(S.ctx, &opt) != 0)
+		shim_die(tb200_last_error(S.ctx));
+	S.chunk = first_len;
+	S.cap_bits = S.batch_bits + 4096;
+	S.bits = tb200_host_alloc(S.cap_bits);
+	S.max_slots = tb200_max_slots(S.cap_bits) + 16;
+	S.slots = tb200_host_alloc(S.max_slots * sizeof(*S.slots));
+	S.type1 = tb200_host_alloc(S.max_slots * TB200_TYPE1_STRIDE);
+	S.rec = malloc(3 * S.max_slots * sizeof(*S.rec));
+	if (!S.bits || !S.slots || !S.type1 || !S.rec)
+		shim_die("out of memory");
+	atexit(tetra_b200_shim_flush);
+}
+
+int tetra_burst_sync_in(struct tetra_rx_state *trs, uint8_t *bits, unsigned int len)
+{
+	if (!S.ctx)
+		shim_init(len);
+	S.trs = trs;
+	if (S.short_read_seen && len)
+		shim_die("a short read() was followed by more data: only constant read sizes are modelled");
+	if (len != S.chunk)
+		S.short_read_seen = 1;
+	if (len > S.cap_bits - S.n_bits)
+		shim_run(0);
+	memcpy(S.bits + S.n_bits, bits, len);
+	S.n_bits += len;
+	if (S.n_bits >= S.batch_bits && S.n_bits % S.chunk == 0)
+		shim_run(0);
+	return len;
+}
