@@ -10,6 +10,7 @@
  */
 #include "tetra_kernels.cuh"
 #include "tetra_lane.cuh"
+#include "tetra_classify_tma.cuh"
 #include "tetra_gen.cuh"
 #include "../../include/tetra_b200.h"
 
@@ -250,6 +251,10 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 		cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
 	}
+#ifndef TB_SIMT_EMULATION
+	if (cudaFuncSetAttribute(k_classify_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_SMEM) != cudaSuccess)
+		return bail("cudaFuncSetAttribute");
+#endif
 	if (cudaMalloc((void **)&ctx->d_hits, sizeof(uint32_t) * (2 * 8192 + 2)) != cudaSuccess) return bail("cudaMalloc");
 	if (cudaHostAlloc((void **)&ctx->h_hits, sizeof(uint32_t) * (2 * 8192 + 2), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
 	*out = ctx;
@@ -569,7 +574,12 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	const uint64_t npairs = ((uint64_t)nb + 1) / 2;
 	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->sm_count * 5);
 	if (lane) {
-		TB_LAUNCH(k_classify<false>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
+		WinGeom wg;
+		wg.chunk = g.chunk; wg.rel0 = (uint32_t)(g.a0 % g.chunk); wg.c00 = g.a0 / g.chunk;
+		wg.cmin = g.cmin; wg.n_end = g.n_end; wg.a0 = g.a0;
+		const unsigned cls_groups = (nb + 31) / 32;
+		const unsigned cls_blocks = std::min<unsigned>((cls_groups + CLS_WARPS - 1) / CLS_WARPS, (unsigned)ctx->sm_count * 3);
+		TB_LAUNCH_SMEM(k_classify_tma, cls_blocks, CLS_WARPS * 32, CLS_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
 		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, nb, ctx->d_tab);
 		ctx->stats.kernel_launches++;
 	} else {
