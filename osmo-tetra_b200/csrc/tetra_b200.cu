@@ -147,6 +147,8 @@ struct tb200_ctx {
 	uint32_t *d_slot_bits = nullptr;
 	int32_t *d_last_good = nullptr, *d_blk_last = nullptr, *d_blk_prev = nullptr;
 	size_t ws_slots = 0;
+	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the lane kernels, one area per resident CTA */
+	unsigned lane_ctas = 0;               /* resident CTAs of the lane kernels (grid size) */
 	uint32_t *d_flags = nullptr;     /* first unlocking slot per piece */
 	uint32_t *h_flags = nullptr;     /* pinned mirror */
 	size_t flags_cap = 0;
@@ -251,6 +253,17 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 		cudaEventCreateWithFlags(&ctx->ev_comp[i], cudaEventDisableTiming);
 		cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming);
 	}
+	{
+		int per_sm = 8;
+#ifndef TB_SIMT_EMULATION
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_lane, LANE_NT,
+		                                                   lane_smem_words(LANE_NT) * sizeof(uint32_t)) != cudaSuccess || per_sm < 1)
+			return bail("cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+#endif
+		ctx->lane_ctas = (unsigned)(ctx->sm_count * per_sm);
+		if (cudaMalloc((void **)&ctx->d_lane_scratch, (size_t)ctx->lane_ctas * lane_scratch_words_per_cta(LANE_NT) * sizeof(uint32_t)) != cudaSuccess)
+			return bail("cudaMalloc");
+	}
 #ifndef TB_SIMT_EMULATION
 	if (cudaFuncSetAttribute(k_classify_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_SMEM) != cudaSuccess)
 		return bail("cudaFuncSetAttribute");
@@ -268,7 +281,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	cudaDeviceSynchronize();
 	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry); cudaFree(ctx->d_ws); cudaFree(ctx->d_slot_bits);
 	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev);
-	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags);
+	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch);
 	for (int i = 0; i < NBUF; i++) {
 		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]);
 		cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]);
@@ -572,7 +585,7 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	const unsigned lane_nt = 32;
 	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
 	const uint64_t npairs = ((uint64_t)nb + 1) / 2;
-	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->sm_count * 5);
+	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->lane_ctas);
 	if (lane) {
 		WinGeom wg;
 		wg.chunk = g.chunk; wg.rel0 = (uint32_t)(g.a0 % g.chunk); wg.c00 = g.a0 / g.chunk;
@@ -580,7 +593,7 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 		const unsigned cls_groups = (nb + 31) / 32;
 		const unsigned cls_blocks = std::min<unsigned>((cls_groups + CLS_WARPS - 1) / CLS_WARPS, (unsigned)ctx->sm_count * 3);
 		TB_LAUNCH_SMEM(k_classify_tma, cls_blocks, CLS_WARPS * 32, CLS_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
-		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, nb, ctx->d_tab);
+		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, nb, ctx->d_tab, ctx->d_lane_scratch);
 		ctx->stats.kernel_launches++;
 	} else {
 		TB_LAUNCH(k_classify<true>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
@@ -597,7 +610,7 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	a.type1 = (ctx->opt.output & TB200_OUT_UNPACKED) ? o_type1 : nullptr;
 	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
 	a.a0 = g.a0; a.out_base = out_base; a.n_slots = nb;
-	if (lane) TB_LAUNCH_SMEM(k_decode_lane, lane_blocks, lane_nt, lane_smem, st, a);
+	if (lane) TB_LAUNCH_SMEM(k_decode_lane, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else      TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
 	if (pe) CU(cudaEventRecord(pe[3], st));
 	CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));

@@ -22,22 +22,26 @@ constexpr int LANE_DEC_ROWS = 296;     /* 292 trellis steps max, padded */
 constexpr int LANE_T3_ROWS = 14;
 constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: one warp, 5 CTAs fit an SM's shared memory */
 
-/* dynamic shared memory of a lane kernel with NT threads, in 32-bit words */
+/* dynamic shared memory of a lane kernel with NT threads, in 32-bit words.  The survivor
+ * decisions (296 x 4 B per thread) do NOT live here: at 37.9 KB per warp they would cap an SM at
+ * five warps; they go to a per-CTA scratch area in global memory that stays L2 resident
+ * (written once, read once a few microseconds later, 128-byte coalesced rows). */
 __host__ __device__ constexpr size_t lane_smem_words(int nt)
 {
-	return (size_t)LANE_DEC_ROWS * nt + 2 * LANE_T3_ROWS * nt + 256 + 16 + (nt / 32) * 16;
+	return (size_t)2 * LANE_T3_ROWS * nt + 256 + 16 + (nt / 32) * 16;
 }
+__host__ __device__ constexpr size_t lane_scratch_words_per_cta(int nt) { return (size_t)LANE_DEC_ROWS * nt; }
 
 struct LaneSmem {
-	uint32_t *dec;       /* [LANE_DEC_ROWS][NT]  bit s: trellis X state s, bit 16+s: trellis Y */
+	uint32_t *dec;       /* [LANE_DEC_ROWS][NT] in GLOBAL scratch; bit s: trellis X state s, bit 16+s: trellis Y */
 	uint32_t *t3;        /* [2][LANE_T3_ROWS][NT] type-3 bits, later the decoded type-2 bits */
 	uint32_t *crc_tab;   /* [256] reflected CRC-CCITT byte table, then [16] nibble table */
 	uint32_t *lfb;       /* [NT/32][16] per-warp scrambling sequence broadcast */
 	static constexpr int nt = LANE_NT;
-	__device__ __forceinline__ LaneSmem(uint8_t *base, int)
+	__device__ __forceinline__ LaneSmem(uint8_t *base, uint32_t *scratch)
 	{
 		uint32_t *p = reinterpret_cast<uint32_t *>(base);
-		dec = p; p += (size_t)LANE_DEC_ROWS * nt;
+		dec = scratch + (size_t)blockIdx.x * lane_scratch_words_per_cta(nt);
 		t3 = p; p += 2 * LANE_T3_ROWS * nt;
 		crc_tab = p; p += 256 + 16;
 		lfb = p;
@@ -143,17 +147,23 @@ __device__ __forceinline__ void viterbi_pair_t(const LaneSmem &sm, int tid, int 
 	for (int wi = (nmax - 1) >> 5; wi >= 0; --wi) {
 		const int thi = 32 * wi + 35 < nmax + 3 ? 32 * wi + 35 : nmax + 3;
 		const uint32_t *dp = dec + thi * nt;
-		const int cnt = thi - (32 * wi + 4) + 1;
-		for (int i = 0; i < cnt; ++i) {
-			const uint32_t w = *dp;
-			dp -= nt;
-			if (MASKED) {
-				const int t = thi - i;
-				if (t <= nx + 3) hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
-				if (t <= ny + 3) hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
-			} else {
-				hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
-				hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
+		const int cnt = thi - (32 * wi + 4) + 1;           /* 16 or 32 */
+		for (int i = 0; i < cnt; i += 8) {
+			uint32_t w8[8];
+#pragma unroll
+			for (int u = 0; u < 8; ++u) w8[u] = dp[-u * nt];     /* loads first: L2 latency overlaps */
+			dp -= 8 * nt;
+#pragma unroll
+			for (int u = 0; u < 8; ++u) {
+				const uint32_t w = w8[u];
+				if (MASKED) {
+					const int t = thi - i - u;
+					if (t <= nx + 3) hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
+					if (t <= ny + 3) hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
+				} else {
+					hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
+					hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
+				}
 			}
 		}
 		ox[wi * nt] = __brev(hx);
@@ -326,9 +336,9 @@ __device__ __forceinline__ void load_slot_bits(const uint32_t *__restrict__ slot
  * decoded before the cell state is known.  Fills the SYNC-PDU part of SlotWs. */
 __global__ void __launch_bounds__(32)
 k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits, uint32_t n_slots,
-           const Tables *__restrict__ tab)
+           const Tables *__restrict__ tab, uint32_t *__restrict__ scratch)
 {
-	LaneSmem sm(TB_DYN_SMEM(), blockDim.x);
+	LaneSmem sm(TB_DYN_SMEM(), scratch);
 	lane_load_tables(sm, tab);
 	const int tid = threadIdx.x;
 	const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
@@ -384,9 +394,9 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits, uint
 /* ============================================================= decode pass ==
  * Everything of tp_sap_udata_ind that needs the cell state, two slots per thread. */
 __global__ void __launch_bounds__(32)
-k_decode_lane(DecodeArgs a)
+k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 {
-	LaneSmem sm(TB_DYN_SMEM(), blockDim.x);
+	LaneSmem sm(TB_DYN_SMEM(), scratch);
 	const Tables *__restrict__ tab = a.tab;
 	lane_load_tables(sm, tab);
 	const int tid = threadIdx.x;
