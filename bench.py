@@ -55,7 +55,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -154,11 +154,27 @@ def run_reference(args, rank, world):
 
 # ------------------------------------------------------------------------------ our arm
 
+def rank_seed(rank):
+    """every rank decodes its own self-contained stream: shards are independent"""
+    return SEED + rank
+
+
+def reduce_max(dist, values, device):
+    """max over ranks of a list of floats (device timings are reported as the slowest rank's)"""
+    import torch
+    t = torch.tensor(values, dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.cpu()]
+
+
 def run_ours(args, rank, world, local_rank):
     import numpy as np
     import torch
     import tetra_testlib as T
     import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build()
     G.load_package().load_library()          # fails loudly if the CUDA library is missing
     torch.cuda.set_device(local_rank)
     dist = None
@@ -174,29 +190,48 @@ def run_ours(args, rank, world, local_rank):
     g = T.B200(device=local_rank)
     n = N_BURSTS
     nbits = 510 * n
-    cfg = gen_cfg(T, SEED + rank)             # every rank decodes its own stream: shards are independent
+    cfg = gen_cfg(T, rank_seed(rank))
     d_bits = torch.zeros(nbits + 64, dtype=torch.uint8, device="cuda")
     rc = g.lib.tb200_gen_stream_dev(g.h, C.byref(cfg), 0, n, C.c_void_p(d_bits.data_ptr()), 0)
     assert rc == 0, g.err()
     ms = n + 16
     d_slots = torch.zeros(ms * 16, dtype=torch.uint8, device="cuda")
     d_t1 = torch.zeros(ms * 288, dtype=torch.uint8, device="cuda")
-    d_pk = torch.zeros(ms * 9, dtype=torch.int32, device="cuda")
-    g.set_options(chunk_bits=64, viterbi=args.viterbi, output=T.OUT_UNPACKED | T.OUT_PACKED, pipeline_slots=0, profile=1)
+    g.set_options(chunk_bits=64, viterbi=args.viterbi, output=T.OUT_UNPACKED, pipeline_slots=0, profile=1)
 
     def step_dev():
         ns = g.lib.tb200_rx_stream_dev(g.h, C.c_void_p(d_bits.data_ptr()), nbits, 3, C.c_void_p(d_slots.data_ptr()),
-                                       C.c_void_p(d_t1.data_ptr()), C.c_void_p(d_pk.data_ptr()), ms)
+                                       C.c_void_p(d_t1.data_ptr()), None, ms)
         assert ns == n - 1, (ns, g.err())
         return ns
 
-    # ---- device-resident: value + per-kernel device times
+    h_bits_p = g.lib.tb200_host_alloc(nbits)
+    h_slots_p = g.lib.tb200_host_alloc(ms * 16)
+    h_t1_p = g.lib.tb200_host_alloc(ms * 288)
+    h_pk_p = g.lib.tb200_host_alloc(ms * 36)
+    assert h_bits_p and h_slots_p and h_t1_p and h_pk_p
+    h_bits = np.ctypeslib.as_array(C.cast(h_bits_p, C.POINTER(C.c_uint8)), shape=(nbits,))
+    h_bits[:] = d_bits[:nbits].cpu().numpy()
+
+    def step_host(packed=False):
+        ns = g.lib.tb200_rx_stream_host(g.h, h_bits_p, nbits, 3, h_slots_p, None if packed else h_t1_p,
+                                        h_pk_p if packed else None, ms)
+        assert ns == n - 1, (ns, g.err())
+
+    # ---- warm-up of both legs, then the clock sampler runs across both timed regions
     for _ in range(max(args.warmup, 3)):
         step_dev()
+    g.set_options(profile=0)
+    for _ in range(3):
+        step_host()
+    g.set_options(profile=1)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
+
+    # ---- device-resident: value + per-kernel device times (CUDA events on the launching stream)
+    barrier()
     t0 = time.perf_counter()
     tim = {"total": 0.0, "classify": 0.0, "scan": 0.0, "decode": 0.0}
     for _ in range(args.steps):
@@ -205,43 +240,53 @@ def run_ours(args, rank, world, local_rank):
         tim["total"] += t.total_ms; tim["classify"] += t.classify_ms; tim["scan"] += t.scan_ms; tim["decode"] += t.decode_ms
     barrier()
     wall = time.perf_counter() - t0
-    clocks = sampler.stop() if rank == 0 else None
     launches = g.stats().kernel_launches * args.steps     # stats restart with every TB200_FRESH call
 
-    # ---- end to end: pinned host buffers, copies inside the timed region
+    # ---- end to end: pinned host buffers, H2D + D2H inside the timed region
     g.set_options(profile=0, output=T.OUT_UNPACKED)
-    h_bits_p = g.lib.tb200_host_alloc(nbits)
-    h_slots_p = g.lib.tb200_host_alloc(ms * 16)
-    h_t1_p = g.lib.tb200_host_alloc(ms * 288)
-    assert h_bits_p and h_slots_p and h_t1_p
-    h_bits = np.ctypeslib.as_array(C.cast(h_bits_p, C.POINTER(C.c_uint8)), shape=(nbits,))
-    h_bits[:] = d_bits[:nbits].cpu().numpy()
-
-    def step_host():
-        ns = g.lib.tb200_rx_stream_host(g.h, h_bits_p, nbits, 3, h_slots_p, h_t1_p, None, ms)
-        assert ns == n - 1, (ns, g.err())
-
+    wall_e2e = wall_e2e_packed = float("nan")
     if args.no_e2e:
         step_host()
-        wall_e2e = float("nan")
     else:
-        for _ in range(3):
-            step_host()
         barrier()
         t1 = time.perf_counter()
         for _ in range(args.steps):
             step_host()
         barrier()
         wall_e2e = time.perf_counter() - t1
-
-    # quick self-check inside the bench: host path == device path on the slot records
     hs = np.ctypeslib.as_array(C.cast(h_slots_p, C.POINTER(C.c_uint8)), shape=((n - 1) * 16,))
-    same = bool(np.array_equal(hs, d_slots[:(n - 1) * 16].cpu().numpy()))
+    ht = np.ctypeslib.as_array(C.cast(h_t1_p, C.POINTER(C.c_uint8)), shape=((n - 1) * 288,))
+    same = bool(np.array_equal(hs, d_slots[:(n - 1) * 16].cpu().numpy())) and \
+        bool(np.array_equal(ht[:288 * 4096], d_t1[:288 * 4096].cpu().numpy()))
+    if not args.no_e2e:
+        g.set_options(output=T.OUT_PACKED)
+        for _ in range(2):
+            step_host(packed=True)
+        barrier()
+        t2 = time.perf_counter()
+        for _ in range(args.steps):
+            step_host(packed=True)
+        barrier()
+        wall_e2e_packed = time.perf_counter() - t2
+    clocks = sampler.stop() if rank == 0 else None
 
-    times = torch.tensor([wall, wall_e2e, tim["total"], tim["classify"], tim["scan"], tim["decode"]], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    wall, wall_e2e, t_total, t_cls, t_scan, t_dec = [float(x) for x in times.cpu()]
+    # ---- the fused descramble + de-interleave stage on its own (north star: >= 70 % of the HBM roofline)
+    g.set_options(profile=1)
+    nblk = 4_000_000
+    d5 = torch.randint(0, 2, (nblk * 432,), dtype=torch.uint8, device="cuda")
+    d3 = torch.empty_like(d5)
+    dcodes = torch.randint(0, 2 ** 31 - 1, (nblk,), dtype=torch.int32, device="cuda")
+    stage_ms = []
+    for _ in range(6):
+        rc = g.lib.tb200_descramble_deinterleave(g.h, C.c_void_p(d5.data_ptr()), C.c_void_p(d3.data_ptr()),
+                                                 C.c_void_p(dcodes.data_ptr()), nblk, 432, 103, 1)
+        assert rc == 0, g.err()
+        stage_ms.append(g.timing().leaf_ms)
+    stage_ms = min(stage_ms[1:])
+    del d5, d3
+
+    wall, wall_e2e, wall_e2e_packed, t_total, t_cls, t_scan, t_dec = reduce_max(
+        dist, [wall, wall_e2e, wall_e2e_packed, tim["total"], tim["classify"], tim["scan"], tim["decode"]], "cuda")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -262,30 +307,39 @@ def run_ours(args, rank, world, local_rank):
     alg_bytes = (BYTES_PER_BURST_IN + BYTES_PER_BURST_OUT) * (n - 1)
     dec_gbs = alg_bytes / (per_launch_dec_ms * 1e-3) / 1e9
     cls_gbs = BYTES_PER_BURST_IN * (n - 1) / (per_launch_cls_ms * 1e-3) / 1e9
+    stage_gbs = 2 * 432 * nblk / (stage_ms * 1e-3) / 1e9
     int_peak = g.lib.tb200_measure_int_peak(g.h)
     acs_rate = ACS_PER_BURST * (n - 1) / (per_launch_dec_ms * 1e-3)
-    roofline = {"kernel": "k_decode_warp" if args.viterbi == 0 else "k_decode_lane", "bound": "hbm",
+    dec_name = "k_decode_warp" if args.viterbi == 0 else "k_decode_lane"
+    roofline = {"kernel": dec_name, "bound": "hbm",
                 "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "traffic": None,
                 "peak_source": peak_src, "ms_per_launch": per_launch_dec_ms,
                 "algorithmic_bytes_per_burst": BYTES_PER_BURST_IN + BYTES_PER_BURST_OUT,
-                "note": "the decode kernel is integer-ALU bound (add-compare-select), not HBM bound: see int_alu",
+                "note": "the decode kernel is integer-ALU bound (16-state add-compare-select), not HBM bound: int_alu is its real roofline",
                 "int_alu": {"acs_per_s": acs_rate, "int_ops_per_s": acs_rate * 4, "measured_int_peak_ops_per_s": int_peak,
-                            "frac": (acs_rate * 4 / int_peak) if int_peak else None},
-                "sync_search": {"kernel": "k_classify", "bound": "hbm", "achieved": cls_gbs, "peak": hbm_peak, "unit": "GB/s",
-                                "frac": cls_gbs / hbm_peak, "ms_per_launch": per_launch_cls_ms,
+                            "frac": (acs_rate * 4 / int_peak) if int_peak else None,
+                            "how": "4672 ACS x 4 integer results per SCH/F burst / kernel time, against a register-only add+min kernel (both integer pipes)"},
+                "sync_search": {"kernel": "k_classify_tma (+k_sb1_lane)" if args.viterbi else "k_classify", "bound": "hbm", "achieved": cls_gbs,
+                                "peak": hbm_peak, "unit": "GB/s", "frac": cls_gbs / hbm_peak, "ms_per_launch": per_launch_cls_ms,
                                 "algorithmic_bytes_per_burst": BYTES_PER_BURST_IN},
+                "descramble_deinterleave_stage": {"kernel": "k_descramble_deinterleave", "bound": "hbm", "achieved": stage_gbs,
+                                                  "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak, "ms_per_launch": stage_ms,
+                                                  "algorithmic_bytes_per_block": 864, "blocks": nblk},
                 "step_share": {"classify": t_cls / t_total, "scan": t_scan / t_total, "decode": t_dec / t_total}}
     cores = os.cpu_count() or 1
     cpu = cpu_reference_rate(20000, cores) if (world == 1 and not args.no_cpu) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "bursts_per_gpu_per_step": n, "viterbi": "warp-shuffle, one warp per burst" if args.viterbi == 0 else "lane: two packed trellises per thread",
+            "config": {"workload": WORKLOAD, "bursts_per_gpu_per_step": n,
+                       "viterbi": "warp-shuffle, one warp per burst" if args.viterbi == 0 else "lane: two packed trellises per thread",
                        "l2": "inputs larger than L2 (510 MB stream per step)", "parallelism": f"independent streams x{world}",
-                       "e2e_output": "slot records + unpacked type-1 bits (1 bit/byte)"},
+                       "output": "slot records + unpacked type-1 bits (1 bit/byte)"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": nbits * world,
                     "d2h_bytes_per_step": (n - 1) * (16 + 288) * world, "ms_per_step": wall_e2e / args.steps * 1e3,
-                    "matches_device_path": same},
+                    "matches_device_path": same,
+                    "packed_output": {"value": bursts / wall_e2e_packed, "d2h_bytes_per_step": (n - 1) * (16 + 36) * world,
+                                      "ms_per_step": wall_e2e_packed / args.steps * 1e3}},
             "gpu_launches": int(launches), "device_ms_per_step": t_total / args.steps,
             "roofline": roofline, "clocks": clocks}
     if cpu is not None:
@@ -298,7 +352,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--viterbi", type=int, default=1, help="0 warp-shuffle (one warp per burst), 1 lane (two trellises per thread)")

@@ -166,6 +166,7 @@ struct tb200_timing {
 	uint32_t launches_classify, launches_scan, launches_decode;
 	uint32_t pieces;
 	uint64_t slots;             /* slots those launches covered */
+	float leaf_ms;              /* last tb200_descramble_deinterleave kernel (device pointers) */
 };
 int tb200_get_timing(const tb200_ctx *ctx, struct tb200_timing *out);
 

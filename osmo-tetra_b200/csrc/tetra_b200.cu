@@ -632,9 +632,22 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 	if (out.n + n_slots > out.max_slots)
 		return fail(ctx, TB200_E_ARG, "output arrays too small: need %llu slots, have %llu",
 		            (unsigned long long)(out.n + n_slots), (unsigned long long)out.max_slots);
-	uint32_t P = ctx->opt.pipeline_slots ? ctx->opt.pipeline_slots : (src.on_device ? (1u << 20) : (1u << 15));
+	uint32_t P = ctx->opt.pipeline_slots ? ctx->opt.pipeline_slots : (src.on_device ? (1u << 20) : (1u << 17));
 	if (P > n_slots) P = (uint32_t)n_slots;
-	const size_t npieces = (size_t)((n_slots + P - 1) / P);
+	/* piece boundaries; the host path ramps the first pieces up (P/16, P/8, ...) so that the first
+	 * copy is short and compute / copy-back start early */
+	std::vector<uint64_t> pstart;
+	{
+		uint64_t k = 0;
+		uint32_t cur = (!src.on_device && !ctx->opt.pipeline_slots && P >= 16384) ? P / 16 : P;
+		while (k < n_slots) {
+			pstart.push_back(k);
+			k += cur;
+			if (cur < P) cur = std::min<uint32_t>(P, cur * 2);
+		}
+		pstart.push_back(n_slots);
+	}
+	const size_t npieces = pstart.size() - 1;
 	int rc;
 	if ((rc = ensure_workspace(ctx, P))) return rc;
 	if ((rc = ensure_pieces(ctx, npieces))) return rc;
@@ -646,8 +659,8 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		return fail(ctx, TB200_E_ARG, "device input with host output is not supported");
 
 	auto piece_range = [&](size_t i, uint64_t *k0, uint32_t *nb) {
-		*k0 = (uint64_t)i * P;
-		*nb = (uint32_t)std::min<uint64_t>(P, n_slots - *k0);
+		*k0 = pstart[i];
+		*nb = (uint32_t)(pstart[i + 1] - pstart[i]);
 	};
 	auto issue = [&](size_t i, uint32_t nb_override) -> int {
 		uint64_t k0; uint32_t nb;
@@ -1201,9 +1214,19 @@ extern "C" int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type
 		d5 = a5; d3 = a3; dcode = ac;
 	}
 	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8);
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (ctx->opt.profile) {
+		CU(cudaEventCreateWithFlags(&e0, 0)); CU(cudaEventCreateWithFlags(&e1, 0));
+		CU(cudaEventRecord(e0, ctx->s_compute));
+	}
 	TB_LAUNCH(k_descramble_deinterleave, blocks, 256, ctx->s_compute, d5, d3, dcode, n, K, a, ctx->d_tab);
+	if (ctx->opt.profile) CU(cudaEventRecord(e1, ctx->s_compute));
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(ctx->s_compute));
+	if (ctx->opt.profile) {
+		CU(cudaEventElapsedTime(&ctx->timing.leaf_ms, e0, e1));
+		cudaEventDestroy(e0); cudaEventDestroy(e1);
+	}
 	if (!is_device) {
 		CU(cudaMemcpy(type3, a3, n * K, cudaMemcpyDeviceToHost));
 		cudaFree(a5); cudaFree(a3); cudaFree(ac);
