@@ -146,6 +146,7 @@ struct tb200_ctx {
 	SlotWs *d_ws = nullptr;
 	uint32_t *d_slot_bits = nullptr;
 	int32_t *d_last_good = nullptr, *d_blk_last = nullptr, *d_blk_prev = nullptr;
+	uint32_t *d_sb_list = nullptr;   /* slots classified as SYNC bursts; [ws_slots] + counter at the end */
 	size_t ws_slots = 0;
 	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the lane kernels, one area per resident CTA */
 	unsigned lane_ctas = 0;               /* resident CTAs of the lane kernels (grid size) */
@@ -280,7 +281,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry); cudaFree(ctx->d_ws); cudaFree(ctx->d_slot_bits);
-	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev);
+	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev); cudaFree(ctx->d_sb_list);
 	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch);
 	for (int i = 0; i < NBUF; i++) {
 		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]);
@@ -322,6 +323,7 @@ static int ensure_workspace(tb200_ctx *ctx, size_t slots)
 	if ((rc = grow(ctx, &ctx->d_last_good, slots))) return rc;
 	if ((rc = grow(ctx, &ctx->d_blk_last, slots / 1024 + 2))) return rc;
 	if ((rc = grow(ctx, &ctx->d_blk_prev, slots / 1024 + 2))) return rc;
+	if ((rc = grow(ctx, &ctx->d_sb_list, slots + 4))) return rc;
 	ctx->ws_slots = slots;
 	return 0;
 }
@@ -592,8 +594,12 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 		wg.cmin = g.cmin; wg.n_end = g.n_end; wg.a0 = g.a0;
 		const unsigned cls_groups = (nb + 31) / 32;
 		const unsigned cls_blocks = std::min<unsigned>((cls_groups + CLS_WARPS - 1) / CLS_WARPS, (unsigned)ctx->sm_count * 3);
-		TB_LAUNCH_SMEM(k_classify_tma, cls_blocks, CLS_WARPS * 32, CLS_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
-		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, nb, ctx->d_tab, ctx->d_lane_scratch);
+		uint32_t *sb_count = ctx->d_sb_list + ctx->ws_slots;
+		CU(cudaMemsetAsync(sb_count, 0, sizeof(uint32_t), st));
+		TB_LAUNCH_SMEM(k_classify_tma, cls_blocks, CLS_WARPS * 32, CLS_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits,
+		               ctx->d_sb_list, sb_count);
+		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
+		               ctx->d_tab, ctx->d_lane_scratch);
 		ctx->stats.kernel_launches++;
 	} else {
 		TB_LAUNCH(k_classify<true>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);

@@ -22,7 +22,7 @@
 namespace tb {
 
 constexpr int CLS_ROW = 528;                 /* bytes staged per slot */
-constexpr int CLS_WARPS = 4;                 /* warps per CTA */
+constexpr int CLS_WARPS = 6;                 /* warps per CTA (6 x 2 x 16.5 KB of rows = 203 KB: one CTA per SM) */
 constexpr int CLS_STAGES = 2;
 constexpr size_t CLS_SMEM = (size_t)CLS_WARPS * CLS_STAGES * 32 * CLS_ROW + CLS_WARPS * CLS_STAGES * 8 + 16;
 
@@ -121,7 +121,7 @@ __device__ __forceinline__ void match32(uint32_t x0, uint32_t x1, uint32_t x2, u
 
 __global__ void __launch_bounds__(CLS_WARPS * 32)
 k_classify_tma(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__restrict__ ws,
-               uint32_t *__restrict__ slot_bits)
+               uint32_t *__restrict__ slot_bits, uint32_t *__restrict__ sb_list, uint32_t *__restrict__ sb_count)
 {
 	uint8_t *smem = TB_DYN_SMEM();
 	const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -230,13 +230,25 @@ k_classify_tma(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__r
 			}
 			if ((int)lane == src) { rc = r2; off = o2; X[15] &= 0x3fffffffu; }
 		}
+		int kind = KIND_NONE;
+		bool unlock = false;
 		if (have) {
-			int kind = KIND_NONE;
-			bool unlock = false;
 			if (rc == TS_SYNC) { if (off == 214) kind = KIND_SB; else unlock = true; }
 			else if (rc == TS_NORM_1) { if (off == 244) kind = KIND_NDB_F; }
 			else if (rc == TS_NORM_2) { if (off == 244) kind = KIND_NDB_2; }
 			else unlock = true;
+		}
+		/* SYNC bursts are listed so that the SB1 pass only touches them (one atomic per warp) */
+		{
+			const unsigned m = __ballot_sync(FULL, kind == KIND_SB);
+			if (m) {
+				uint32_t base = 0;
+				if (lane == (unsigned)(__ffs((int)m) - 1)) base = atomicAdd(sb_count, (uint32_t)__popc(m));
+				base = __shfl_sync(FULL, base, __ffs((int)m) - 1);
+				if (kind == KIND_SB) sb_list[base + __popc(m & ((1u << lane) - 1))] = k;
+			}
+		}
+		if (have) {
 			uint4 *sb = reinterpret_cast<uint4 *>(slot_bits + (size_t)k * 16);
 #pragma unroll
 			for (int j = 0; j < 4; ++j) sb[j] = make_uint4(X[4 * j], X[4 * j + 1], X[4 * j + 2], X[4 * j + 3]);

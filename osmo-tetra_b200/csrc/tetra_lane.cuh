@@ -20,6 +20,7 @@ namespace tb {
 
 constexpr int LANE_DEC_ROWS = 296;     /* 292 trellis steps max, padded */
 constexpr int LANE_T3_ROWS = 14;
+constexpr int LANE_T3B_ROWS = 8;       /* second block of two-block bursts: 216 bits + one readable row */
 constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: one warp, 5 CTAs fit an SM's shared memory */
 
 /* dynamic shared memory of a lane kernel with NT threads, in 32-bit words.  The survivor
@@ -28,13 +29,14 @@ constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: on
  * (written once, read once a few microseconds later, 128-byte coalesced rows). */
 __host__ __device__ constexpr size_t lane_smem_words(int nt)
 {
-	return (size_t)2 * LANE_T3_ROWS * nt + 256 + 16 + (nt / 32) * 16;
+	return (size_t)2 * LANE_T3_ROWS * nt + (size_t)2 * LANE_T3B_ROWS * nt + 256 + 16 + (nt / 32) * 16;
 }
 __host__ __device__ constexpr size_t lane_scratch_words_per_cta(int nt) { return (size_t)LANE_DEC_ROWS * nt; }
 
 struct LaneSmem {
 	uint32_t *dec;       /* [LANE_DEC_ROWS][NT] in GLOBAL scratch; bit s: trellis X state s, bit 16+s: trellis Y */
 	uint32_t *t3;        /* [2][LANE_T3_ROWS][NT] type-3 bits, later the decoded type-2 bits */
+	uint32_t *t3b;       /* [2][LANE_T3B_ROWS][NT] the same for BLK2 of two-block bursts */
 	uint32_t *crc_tab;   /* [256] reflected CRC-CCITT byte table, then [16] nibble table */
 	uint32_t *lfb;       /* [NT/32][16] per-warp scrambling sequence broadcast */
 	static constexpr int nt = LANE_NT;
@@ -43,10 +45,12 @@ struct LaneSmem {
 		uint32_t *p = reinterpret_cast<uint32_t *>(base);
 		dec = scratch + (size_t)blockIdx.x * lane_scratch_words_per_cta(nt);
 		t3 = p; p += 2 * LANE_T3_ROWS * nt;
+		t3b = p; p += 2 * LANE_T3B_ROWS * nt;
 		crc_tab = p; p += 256 + 16;
 		lfb = p;
 	}
 	__device__ __forceinline__ uint32_t *t3col(int tr, int tid) const { return t3 + (size_t)tr * LANE_T3_ROWS * nt + tid; }
+	__device__ __forceinline__ uint32_t *t3bcol(int tr, int tid) const { return t3b + (size_t)tr * LANE_T3B_ROWS * nt + tid; }
 };
 
 /* class of the (G1,G2) outputs of branch (state j, input 0): idx = 2*G1 + G2 */
@@ -95,13 +99,11 @@ __device__ __forceinline__ uint32_t acs2_step(uint32_t (&pm)[16], const uint32_t
  * (columns of this thread).  nx, ny: type-2 lengths (0 = no block); nmax: warp-wide maximum so
  * the loop is uniform.  Leaves the decoded type-2 bits in the same columns. */
 template <bool MASKED>
-__device__ __forceinline__ void viterbi_pair_t(const LaneSmem &sm, int tid, int nx, int ny, int nmax)
+__device__ __noinline__ void viterbi_pair_t(uint32_t *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	uint32_t pm[16];
 #pragma unroll
 	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x20002000u : 0u;
-	const uint32_t *cx = sm.t3col(0, tid), *cy = sm.t3col(1, tid);
-	uint32_t *dec = sm.dec + tid;
 	constexpr int nt = LANE_NT;
 	const int groups = nmax / 8;                       /* 4 step pairs = 12 type-3 bits per group */
 	for (int g = 0; g < groups; ++g) {
@@ -141,7 +143,7 @@ __device__ __forceinline__ void viterbi_pair_t(const LaneSmem &sm, int tid, int 
 	/* Trace back.  The state after step t is the last four decoded bits, and the decision looked up
 	 * at step t is decoded bit t-4, so one shift register per path is both the state (its top four
 	 * bits) and the output: h = (h >> 1) | (decision << 31). */
-	uint32_t *ox = sm.t3col(0, tid), *oy = sm.t3col(1, tid);
+	uint32_t *ox = cx, *oy = cy;
 	uint32_t hx = 0, hy = 0;
 	/* output word wi holds decoded bits [32wi, 32wi+32): they come from steps t = 32wi+35 .. 32wi+4 */
 	for (int wi = (nmax - 1) >> 5; wi >= 0; --wi) {
@@ -171,12 +173,12 @@ __device__ __forceinline__ void viterbi_pair_t(const LaneSmem &sm, int tid, int 
 	}
 }
 
-__device__ inline void viterbi_pair(const LaneSmem &sm, int tid, int nx, int ny, int nmax)
+__device__ __forceinline__ void viterbi_pair(uint32_t *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	/* warp-uniform choice: no masking work when every lane carries two full-length blocks */
 	const bool uniform = __all_sync(FULL, nx == nmax && ny == nmax);
-	if (uniform) viterbi_pair_t<false>(sm, tid, nx, ny, nmax);
-	else         viterbi_pair_t<true>(sm, tid, nx, ny, nmax);
+	if (uniform) viterbi_pair_t<false>(dec, cx, cy, nx, ny, nmax);
+	else         viterbi_pair_t<true>(dec, cx, cy, nx, ny, nmax);
 }
 
 /* CRC-16-CCITT of the first L type-2 bits of a column, reflected byte-table form of
@@ -335,26 +337,29 @@ __device__ __forceinline__ void load_slot_bits(const uint32_t *__restrict__ slot
  * SYNC bursts only: SB1 always uses scrambling code 3 (tetra_lower_mac.c:181-183), so it can be
  * decoded before the cell state is known.  Fills the SYNC-PDU part of SlotWs. */
 __global__ void __launch_bounds__(32)
-k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits, uint32_t n_slots,
+k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
+           const uint32_t *__restrict__ sb_list, const uint32_t *__restrict__ sb_count,
            const Tables *__restrict__ tab, uint32_t *__restrict__ scratch)
 {
 	LaneSmem sm(TB_DYN_SMEM(), scratch);
 	lane_load_tables(sm, tab);
 	const int tid = threadIdx.x;
-	const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-	const uint64_t npairs = ((uint64_t)n_slots + 1) / 2;
-	const uint64_t rounds = (npairs + nthreads - 1) / nthreads;
+	const uint32_t n_sb = *sb_count;                 /* SYNC bursts the classify pass listed */
+	const uint32_t nthreads = gridDim.x * blockDim.x;
+	const uint32_t npairs = (n_sb + 1) / 2;
+	const uint32_t rounds = (npairs + nthreads - 1) / nthreads;
 	uint32_t lf[LANE_T3_ROWS];
 #pragma unroll
 	for (int i = 0; i < LANE_T3_ROWS; ++i) lf[i] = tab->lfsr_sb1[i];
 
-	for (uint64_t r = 0; r < rounds; ++r) {
-		const uint64_t pair = r * nthreads + (uint64_t)blockIdx.x * blockDim.x + tid;
-		const uint64_t k[2] = { 2 * pair, 2 * pair + 1 };
+	for (uint32_t r = 0; r < rounds; ++r) {
+		const uint32_t pair = r * nthreads + blockIdx.x * blockDim.x + tid;
+		uint32_t k[2] = { 0, 0 };
 		int n[2] = { 0, 0 };
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
-			if (k[h] < n_slots && ws[k[h]].kind == KIND_SB) {
+			if (2 * pair + h < n_sb) {
+				k[h] = sb_list[2 * pair + h];
 				uint32_t bw[16];
 				load_slot_bits(slot_bits, k[h], bw);
 				xor_region<94, 0, 120>(bw, lf);
@@ -362,10 +367,8 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits, uint
 				n[h] = 80;
 			}
 		}
-		int nmax = n[0] > n[1] ? n[0] : n[1];
-		nmax = __shfl_sync(FULL, __ballot_sync(FULL, nmax != 0) ? 80 : 0, 0);
-		if (nmax == 0) continue;
-		viterbi_pair(sm, tid, n[0], n[1], nmax);
+		if (!__ballot_sync(FULL, n[0] != 0)) continue;
+		viterbi_pair(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], 80);
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
 			if (n[h]) {
@@ -409,129 +412,122 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 	for (uint64_t r = 0; r < rounds; ++r) {
 		const uint64_t pair = r * nthreads + (uint64_t)blockIdx.x * blockDim.x + tid;
 		const uint64_t k[2] = { 2 * pair, 2 * pair + 1 };
-		uint32_t bw[2][16];
-		uint32_t outw[2][9];
-		uint32_t code[2] = { 0, 0 }, flags[2] = { 0, 0 };
+		uint32_t code[2] = { 0, 0 }, flags[2] = { 0, 0 }, bbk[2] = { 0, 0 };
 		int kind[2] = { KIND_NONE, KIND_NONE };
-		bool have[2] = { false, false };
+		int n[2] = { 0, 0 };
 		Tm tm[2];
-		SlotWs w[2];
+		/* load, descramble and de-interleave every block of the two slots; the packed slot words
+		 * only live inside this loop body, so the ACS loop below runs with a small register set */
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
-			have[h] = k[h] < a.n_slots;
+			const bool have = k[h] < a.n_slots;
 			tm[h].tn = tm[h].fn = tm[h].mn = 0;
-#pragma unroll
-			for (int i = 0; i < 9; ++i) outw[h][i] = 0;
-			if (have[h]) {
-				w[h] = a.ws[k[h]];
-				kind[h] = w[h].kind;
+			bool good_sb = false, unlock = false;
+			if (have) {
+				const SlotWs w = a.ws[k[h]];
+				kind[h] = w.kind; good_sb = w.good_sb; unlock = w.unlock;
 				cell_state(k[h], a.ws, a.last_good, a.blk_prev, a.carry, &tm[h], &code[h]);
-				flags[h] = (uint32_t)kind[h] | (w[h].unlock ? F_UNLOCK : 0);
-				if (kind[h] != KIND_NONE) load_slot_bits(a.slot_bits, k[h], bw[h]);
 			}
-		}
-		/* scrambling sequence(s) and descrambling of every block the slot carries */
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
+			flags[h] = (uint32_t)kind[h] | (unlock ? F_UNLOCK : 0) | ((kind[h] == KIND_SB && good_sb) ? F_CRC_A : 0);
 			uint32_t lf[LANE_T3_ROWS];
 			lane_lfsr(code[h], kind[h] != KIND_NONE, lf, bcast, tab);
-			if (kind[h] == KIND_SB) {
-				xor_region<252, 0, 30>(bw[h], lf);
-				xor_region<282, 0, 216>(bw[h], lf);
-			} else if (kind[h] == KIND_NDB_F) {
-				xor_region<14, 0, 216>(bw[h], lf);
-				xor_region<282, 216, 216>(bw[h], lf);
-				xor_region<230, 0, 14>(bw[h], lf);
-				xor_region<266, 14, 16>(bw[h], lf);
-			} else if (kind[h] == KIND_NDB_2) {
-				xor_region<14, 0, 216>(bw[h], lf);
-				xor_region<282, 0, 216>(bw[h], lf);
-				xor_region<230, 0, 14>(bw[h], lf);
-				xor_region<266, 14, 16>(bw[h], lf);
+			if (kind[h] != KIND_NONE) {
+				uint32_t bw[16];
+				load_slot_bits(a.slot_bits, k[h], bw);
+				uint32_t *col = sm.t3col(h, tid);
+				if (kind[h] == KIND_SB) {
+					xor_region<252, 0, 30>(bw, lf);
+					xor_region<282, 0, 216>(bw, lf);
+					bbk[h] = extract_bits(bw, 252, 14);
+					gather_lane<1, PL_BLK2>(bw, col, nt); n[h] = 144;
+				} else if (kind[h] == KIND_NDB_F) {
+					xor_region<14, 0, 216>(bw, lf);
+					xor_region<282, 216, 216>(bw, lf);
+					xor_region<230, 0, 14>(bw, lf);
+					bbk[h] = extract_bits(bw, 230, 14);
+					gather_lane<5, PL_SCHF>(bw, col, nt); n[h] = 288;
+				} else {
+					xor_region<14, 0, 216>(bw, lf);
+					xor_region<282, 0, 216>(bw, lf);
+					xor_region<230, 0, 14>(bw, lf);
+					bbk[h] = extract_bits(bw, 230, 14);
+					gather_lane<1, PL_BLK1>(bw, col, nt); n[h] = 144;
+					gather_lane<1, PL_BLK2>(bw, sm.t3bcol(h, tid), nt);
+				}
 			}
 		}
 		/* round 1: SB2 / SCH-F / BLK1 */
-		int n[2] = { 0, 0 };
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			uint32_t *col = sm.t3col(h, tid);
-			if (kind[h] == KIND_SB) { gather_lane<1, PL_BLK2>(bw[h], col, nt); n[h] = 144; }
-			else if (kind[h] == KIND_NDB_F) { gather_lane<5, PL_SCHF>(bw[h], col, nt); n[h] = 288; }
-			else if (kind[h] == KIND_NDB_2) { gather_lane<1, PL_BLK1>(bw[h], col, nt); n[h] = 144; }
-		}
 		int nmax = n[0] > n[1] ? n[0] : n[1];
 #pragma unroll
 		for (int d = 16; d > 0; d >>= 1) {
 			const int o = __shfl_xor_sync(FULL, nmax, d);
 			nmax = o > nmax ? o : nmax;
 		}
-		if (nmax) viterbi_pair(sm, tid, n[0], n[1], nmax);
+		if (nmax) viterbi_pair(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], nmax);
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
 			const uint32_t *col = sm.t3col(h, tid);
-			auto src = [&](int i) { return col[i * nt]; };
 			if (kind[h] == KIND_SB) {
-				if (w[h].good_sb) flags[h] |= F_CRC_A;
 				if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_B;
 				if (tm_is_bnch(tm[h])) flags[h] |= F_BNCH;
-				const uint32_t s0 = w[h].sb1_t1[0], s1 = w[h].sb1_t1[1];
-				put_lane(outw[h], 0, 60, [&](int i) { return i == 0 ? s0 : (i == 1 ? s1 : 0u); });
-				const uint32_t bbk = extract_bits(bw[h], 252, 14);
-				put_lane(outw[h], 60, 14, [&](int i) { return i == 0 ? bbk : 0u; });
-				put_lane(outw[h], 74, 124, src);
 			} else if (kind[h] == KIND_NDB_F) {
 				if (crc_ok_col(sm, col, 284)) flags[h] |= F_CRC_A;
-				const uint32_t bbk = extract_bits(bw[h], 230, 14);
-				put_lane(outw[h], 0, 14, [&](int i) { return i == 0 ? bbk : 0u; });
-				put_lane(outw[h], 14, 268, src);
 			} else if (kind[h] == KIND_NDB_2) {
 				if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_A;
-				const uint32_t bbk = extract_bits(bw[h], 230, 14);
-				put_lane(outw[h], 0, 14, [&](int i) { return i == 0 ? bbk : 0u; });
-				put_lane(outw[h], 14, 124, src);
 			}
 		}
 		/* round 2: BLK2 of two-block bursts */
 		const bool any2 = __ballot_sync(FULL, kind[0] == KIND_NDB_2 || kind[1] == KIND_NDB_2) != 0;
 		if (any2) {
 			__syncwarp();
-			int m[2] = { 0, 0 };
+			const int m0 = kind[0] == KIND_NDB_2 ? 144 : 0, m1 = kind[1] == KIND_NDB_2 ? 144 : 0;
+			viterbi_pair(sm.dec + tid, sm.t3bcol(0, tid), sm.t3bcol(1, tid), m0, m1, 144);
 #pragma unroll
 			for (int h = 0; h < 2; ++h)
-				if (kind[h] == KIND_NDB_2) { gather_lane<1, PL_BLK2>(bw[h], sm.t3col(h, tid), nt); m[h] = 144; }
-			viterbi_pair(sm, tid, m[0], m[1], 144);
-#pragma unroll
-			for (int h = 0; h < 2; ++h) {
-				if (kind[h] == KIND_NDB_2) {
-					const uint32_t *col = sm.t3col(h, tid);
-					if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_B;
-					put_lane(outw[h], 138, 124, [&](int i) { return col[i * nt]; });
-				}
-			}
+				if (kind[h] == KIND_NDB_2 && crc_ok_col(sm, sm.t3bcol(h, tid), 140)) flags[h] |= F_CRC_B;
 		}
-		/* results */
+		/* assemble the slot's type-1 string in the reference's delivery order and store */
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
-			if (!have[h]) continue;
+			if (k[h] >= a.n_slots) continue;
+			uint32_t outw[9];
+#pragma unroll
+			for (int i = 0; i < 9; ++i) outw[i] = 0;
+			const uint32_t *col = sm.t3col(h, tid), *colb = sm.t3bcol(h, tid);
+			const uint32_t bb = bbk[h];
+			const SlotWs w = a.ws[k[h]];
+			if (kind[h] == KIND_SB) {
+				const uint32_t s0 = w.sb1_t1[0], s1 = w.sb1_t1[1];
+				put_lane(outw, 0, 60, [&](int i) { return i == 0 ? s0 : (i == 1 ? s1 : 0u); });
+				put_lane(outw, 60, 14, [&](int i) { return i == 0 ? bb : 0u; });
+				put_lane(outw, 74, 124, [&](int i) { return col[i * nt]; });
+			} else if (kind[h] == KIND_NDB_F) {
+				put_lane(outw, 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
+				put_lane(outw, 14, 268, [&](int i) { return col[i * nt]; });
+			} else if (kind[h] == KIND_NDB_2) {
+				put_lane(outw, 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
+				put_lane(outw, 14, 124, [&](int i) { return col[i * nt]; });
+				put_lane(outw, 138, 124, [&](int i) { return colb[i * nt]; });
+			}
 			const uint64_t ko = a.out_base + k[h];
 			if (a.type1) {
 				uint4 *dst = reinterpret_cast<uint4 *>(a.type1 + ko * TYPE1_STRIDE);
 #pragma unroll
 				for (int c = 0; c < 18; ++c) {
-					const uint32_t hbits = (outw[h][c >> 1] >> (16 * (c & 1))) & 0xffff;
+					const uint32_t hbits = (outw[c >> 1] >> (16 * (c & 1))) & 0xffff;
 					dst[c] = make_uint4(unpack4(hbits), unpack4(hbits >> 4), unpack4(hbits >> 8), unpack4(hbits >> 12));
 				}
 			}
 			if (a.type1_packed) {
 #pragma unroll
-				for (int i = 0; i < 9; ++i) a.type1_packed[ko * TYPE1_WORDS + i] = outw[h][i];
+				for (int i = 0; i < 9; ++i) a.type1_packed[ko * TYPE1_WORDS + i] = outw[i];
 			}
 			SlotOut o;
 			o.slot_bit = (uint32_t)(a.a0 + (uint64_t)SLOT_BITS * k[h]);
 			o.scrambling_code = code[h];
-			o.find_off = w[h].find_off; o.window = w[h].window;
+			o.find_off = w.find_off; o.window = w.window;
 			o.time = (uint16_t)(tm[h].tn | (tm[h].fn << 3) | (tm[h].mn << 8));
-			o.find_rc = w[h].find_rc; o.flags = (uint8_t)flags[h];
+			o.find_rc = w.find_rc; o.flags = (uint8_t)flags[h];
 			a.slots[ko] = o;
 		}
 		__syncwarp();

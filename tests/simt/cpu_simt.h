@@ -27,6 +27,7 @@
 #define __forceinline__ inline __attribute__((always_inline))
 #define __restrict__
 #define __launch_bounds__(...)
+#define __noinline__ __attribute__((noinline))
 #define __shared__ static
 #define __constant__ static
 
