@@ -11,6 +11,7 @@
 #include "tetra_kernels.cuh"
 #include "tetra_lane.cuh"
 #include "tetra_classify_tma.cuh"
+#include "tetra_stage_tma.cuh"
 #include "tetra_gen.cuh"
 #include "../../include/tetra_b200.h"
 
@@ -266,6 +267,8 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 			return bail("cudaMalloc");
 	}
 #ifndef TB_SIMT_EMULATION
+	if (cudaFuncSetAttribute(k_stage_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM) != cudaSuccess)
+		return bail("cudaFuncSetAttribute");
 	if (cudaFuncSetAttribute(k_classify_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_SMEM) != cudaSuccess)
 		return bail("cudaFuncSetAttribute");
 #endif
@@ -1225,7 +1228,13 @@ extern "C" int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type
 		CU(cudaEventCreateWithFlags(&e0, 0)); CU(cudaEventCreateWithFlags(&e1, 0));
 		CU(cudaEventRecord(e0, ctx->s_compute));
 	}
-	TB_LAUNCH(k_descramble_deinterleave, blocks, 256, ctx->s_compute, d5, d3, dcode, n, K, a, ctx->d_tab);
+	if (K == ST_K && a == ST_A && (((uintptr_t)d5 | (uintptr_t)d3) & 15) == 0) {
+		const uint64_t groups = (n + 31) / 32;
+		const unsigned sb = (unsigned)std::min<uint64_t>((groups + ST_WARPS - 1) / ST_WARPS, (uint64_t)ctx->sm_count);
+		TB_LAUNCH_SMEM(k_stage_tma, sb, ST_WARPS * 32, ST_SMEM, ctx->s_compute, d5, d3, dcode, n, ctx->d_tab);
+	} else {
+		TB_LAUNCH(k_descramble_deinterleave, blocks, 256, ctx->s_compute, d5, d3, dcode, n, K, a, ctx->d_tab);
+	}
 	if (ctx->opt.profile) CU(cudaEventRecord(e1, ctx->s_compute));
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(ctx->s_compute));

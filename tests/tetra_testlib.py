@@ -387,8 +387,8 @@ class Stats(C.Structure):
 
 def build_simt():
     """(re)build the CPU SIMT-emulation flavour of the library - test infrastructure only"""
-    srcs = [os.path.join(ROOT, "osmo-tetra_b200", "csrc", f) for f in
-            ("tetra_b200.cu", "tetra_kernels.cuh", "tetra_gen.cuh")] + \
+    csrc = os.path.join(ROOT, "osmo-tetra_b200", "csrc")
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + \
            [os.path.join(ROOT, "tests", "simt", f) for f in ("cpu_simt.h", "cpu_simt.cpp")] + \
            [os.path.join(ROOT, "include", "tetra_b200.h")]
     if os.path.exists(SIMT_SO) and all(os.path.getmtime(SIMT_SO) >= os.path.getmtime(s) for s in srcs):
