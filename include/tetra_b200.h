@@ -231,6 +231,35 @@ struct tb200_gen_cfg {
 int tb200_gen_stream_dev(tb200_ctx *ctx, const struct tb200_gen_cfg *cfg, uint64_t k0, uint64_t n,
                          uint8_t *d_out, int with_lead_in);
 
+/* ---- one stream sharded over several GPUs --------------------------------------
+ * Slots of a LOCKED stream sit at fixed positions, so contiguous slot ranges decode independently
+ * except for the cell state (scrambling code + TDMA time of the latest CRC-good SB1).  Pass 1
+ * (search, classification, SB1) needs no cell state; the ranks then exchange one 32-byte summary
+ * each (an all-gather), derive their carry-in with tb200_shard_carry_in() and run pass 2.
+ * All pointers are device pointers except `summary` / `carry`. */
+struct tb200_shard_summary {
+	uint32_t n_slots;          /* slots this rank classified */
+	uint32_t first_unlock;     /* first rank-local slot that lost lock, 0xffffffff if none */
+	uint32_t has_good_sb;      /* the shard contains a CRC-good SB1 ... */
+	uint32_t scramb_init;      /* ... announcing this cell code */
+	uint32_t slots_after;      /* slots of the shard after that SB1 (n_slots if none) */
+	uint16_t mcc, mnc;
+	uint8_t  tn, fn, mn, cc;   /* its raw SYNC-PDU time and colour code */
+	uint32_t pad;
+};
+/* lock acquisition on the head of the stream (UNLOCKED / KNOW_FSTART of tetra_burst_sync.c:67-106):
+ * returns 1 and the absolute bit of the first LOCKED slot + the call that may process it, 0 if no lock */
+int  tb200_find_lock(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint64_t *a0, uint64_t *cmin);
+/* d_bits holds stream bits [base_bit, base_bit + n_bytes); the shard's slots start at absolute bit a0
+ * (= lock a0 + 510 * first slot index), cmin = lock cmin + first slot index, n_end = stream length */
+int  tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t base_bit, uint64_t n_bytes,
+                       uint64_t a0, uint64_t cmin, uint64_t n_end, uint32_t n_slots,
+                       struct tb200_shard_summary *summary);
+void tb200_shard_carry_in(const struct tb200_shard_summary *all, int rank, const struct tb200_rx_carry *initial,
+                          struct tb200_rx_carry *out);
+long tb200_shard_pass2(tb200_ctx *ctx, const struct tb200_rx_carry *carry_in, struct tb200_slot *d_slots,
+                       uint8_t *d_type1, uint32_t *d_type1_packed);
+
 /* ---- introspection used by the tests ------------------------------------------------ */
 
 /* n x tetra_tdma_time_add_tn(tm, 1) (tetra_tdma.c:75-79) in closed form, as the kernels do it */

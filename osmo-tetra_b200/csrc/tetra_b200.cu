@@ -176,6 +176,10 @@ struct tb200_ctx {
 	uint64_t tail_base = 0;
 	uint64_t fed_end = 0;            /* absolute bits handed to the ctx so far */
 	DevCarry h_carry;
+	bool stop_at_lock = false;       /* tb200_find_lock: return from rx_run as soon as LOCKED is reached */
+	/* sharded decode: what pass 1 left for pass 2 */
+	uint64_t shard_a0 = 0;
+	uint32_t shard_slots = 0;
 	/* profiling (options.profile) */
 	std::vector<cudaEvent_t> prof_ev;    /* 5 per piece: start, after classify, after scan, after decode, after carry */
 	size_t prof_used = 0;
@@ -560,34 +564,17 @@ static inline uint64_t slot_call(const Segment &s, uint64_t k)   /* call index t
 	return std::max(need, s.cmin + k);
 }
 
-/* enqueue classify + scan + decode + carry for slots [k0, k0+nb) of the segment */
-static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32_t nb, const uint8_t *d_bits,
-                         uint64_t d_base, uint64_t d_avail, size_t piece_idx,
-                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base)
+/* pass 1 of a piece: classify (+ SB1) and the scan over "last CRC-good SB1"; needs no cell state */
+static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cudaEvent_t *pe)
 {
 	cudaStream_t st = ctx->s_compute;
-	RxGeom g;
-	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base;
-	g.a0 = seg.a0 + (uint64_t)SLOT_BITS * k0; g.cmin = seg.cmin + k0; g.n_end = seg.n_end;
-	g.chunk = seg.chunk; g.n_slots = nb;
+	const uint32_t nb = g.n_slots;
 	const unsigned wpb = 8;
 	const unsigned blocks = (unsigned)std::min<uint64_t>((nb + wpb - 1) / wpb, (uint64_t)ctx->sm_count * 16);
 	CU(cudaMemsetAsync(ctx->d_flags + piece_idx, 0xff, sizeof(uint32_t), st));
-	cudaEvent_t *pe = nullptr;
-	if (ctx->opt.profile) {
-		while (ctx->prof_ev.size() < ctx->prof_used + 5) {
-			cudaEvent_t e;
-			CU(cudaEventCreateWithFlags(&e, 0));
-			ctx->prof_ev.push_back(e);
-		}
-		pe = &ctx->prof_ev[ctx->prof_used];
-		ctx->prof_used += 5;
-		ctx->timing.pieces++;
-		ctx->timing.slots += nb;
-		CU(cudaEventRecord(pe[0], st));
-	}
+	if (pe) CU(cudaEventRecord(pe[0], st));
 	const bool lane = ctx->opt.viterbi == TB200_VITERBI_LANE;
-	const unsigned lane_nt = 32;
+	const unsigned lane_nt = LANE_NT;
 	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
 	const uint64_t npairs = ((uint64_t)nb + 1) / 2;
 	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->lane_ctas);
@@ -612,22 +599,64 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, ctx->d_ws, nb, ctx->d_last_good, ctx->d_blk_last, ctx->d_flags + piece_idx);
 	TB_LAUNCH(k_scan_prefix, 1, 1024, st, ctx->d_blk_last, nblk, ctx->d_blk_prev);
 	if (pe) CU(cudaEventRecord(pe[2], st));
+	ctx->stats.kernel_launches += 3;
+	CU(cudaGetLastError());
+	return 0;
+}
+
+/* pass 2 of a piece: everything that needs the cell state carried in d_carry[piece_idx] */
+static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_idx, cudaEvent_t *pe,
+                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base)
+{
+	cudaStream_t st = ctx->s_compute;
+	const bool lane = ctx->opt.viterbi == TB200_VITERBI_LANE;
+	const unsigned lane_nt = LANE_NT;
+	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
+	const uint64_t npairs = ((uint64_t)nb + 1) / 2;
+	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->lane_ctas);
+	const unsigned blocks = (unsigned)std::min<uint64_t>((nb + 7) / 8, (uint64_t)ctx->sm_count * 16);
 	DecodeArgs a;
 	a.ws = ctx->d_ws; a.slot_bits = ctx->d_slot_bits; a.last_good = ctx->d_last_good; a.blk_prev = ctx->d_blk_prev;
 	a.carry = ctx->d_carry + piece_idx; a.tab = ctx->d_tab;
 	a.slots = o_slots;
 	a.type1 = (ctx->opt.output & TB200_OUT_UNPACKED) ? o_type1 : nullptr;
 	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
-	a.a0 = g.a0; a.out_base = out_base; a.n_slots = nb;
+	a.a0 = a0; a.out_base = out_base; a.n_slots = nb;
 	if (lane) TB_LAUNCH_SMEM(k_decode_lane, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else      TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
 	if (pe) CU(cudaEventRecord(pe[3], st));
 	CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
 	TB_LAUNCH(k_finalize_carry, 1, 32, st, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, nb, ctx->d_carry + piece_idx + 1);
 	if (pe) CU(cudaEventRecord(pe[4], st));
-	ctx->stats.kernel_launches += 5;
+	ctx->stats.kernel_launches += 2;
 	CU(cudaGetLastError());
 	return 0;
+}
+
+/* enqueue classify + scan + decode + carry for slots [k0, k0+nb) of the segment */
+static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32_t nb, const uint8_t *d_bits,
+                         uint64_t d_base, uint64_t d_avail, size_t piece_idx,
+                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base)
+{
+	RxGeom g;
+	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base;
+	g.a0 = seg.a0 + (uint64_t)SLOT_BITS * k0; g.cmin = seg.cmin + k0; g.n_end = seg.n_end;
+	g.chunk = seg.chunk; g.n_slots = nb;
+	cudaEvent_t *pe = nullptr;
+	if (ctx->opt.profile) {
+		while (ctx->prof_ev.size() < ctx->prof_used + 5) {
+			cudaEvent_t e;
+			CU(cudaEventCreateWithFlags(&e, 0));
+			ctx->prof_ev.push_back(e);
+		}
+		pe = &ctx->prof_ev[ctx->prof_used];
+		ctx->prof_used += 5;
+		ctx->timing.pieces++;
+		ctx->timing.slots += nb;
+	}
+	int rc = enqueue_pass1(ctx, g, piece_idx, pe);
+	if (rc) return rc;
+	return enqueue_pass2(ctx, g.a0, nb, piece_idx, pe, o_slots, o_type1, o_packed, out_base);
 }
 
 /* Process slots [0, n_slots) of a LOCKED segment, optimistically assuming lock is kept;
@@ -765,6 +794,7 @@ static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
 
 	while (rx.calls < c_max) {
 		if (rx.state == TB200_RX_LOCKED) {
+			if (ctx->stop_at_lock) return 0;
 			Segment seg;
 			seg.a0 = rx.buf_start; seg.cmin = rx.calls + 1; seg.n_end = n_end; seg.chunk = C;
 			uint64_t n_slots = 0;
@@ -1279,4 +1309,115 @@ extern "C" void tb200_debug_time_advance(uint32_t *tn, uint32_t *fn, uint32_t *m
 	Tm t = { *tn, *fn, *mn };
 	t = tm_advance(t, n);
 	*tn = t.tn; *fn = t.fn; *mn = t.mn;
+}
+
+/* ------------------------------------------------- sharded decode (multi-GPU) -- */
+
+static_assert(sizeof(tb200_shard_summary) == 32, "shard summary ABI");
+
+/* what a rank tells the others about its shard: last CRC-good SB1 and first lock loss */
+__global__ void k_shard_summary(const SlotWs *__restrict__ ws, const int32_t *__restrict__ last_good,
+                                const int32_t *__restrict__ blk_prev, const uint32_t *__restrict__ first_unlock,
+                                uint32_t n, tb200_shard_summary *out)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	tb200_shard_summary s;
+	memset(&s, 0, sizeof(s));
+	s.n_slots = n;
+	s.first_unlock = *first_unlock;
+	s.slots_after = n;
+	if (n) {
+		int32_t j = last_good[n - 1];
+		if (j < 0) j = blk_prev[(n - 1) >> 10];
+		if (j >= 0) {
+			const SlotWs w = ws[j];
+			s.has_good_sb = 1; s.scramb_init = w.sb_code; s.slots_after = n - 1 - (uint32_t)j;
+			s.mcc = w.mcc; s.mnc = w.mnc; s.tn = w.tn; s.fn = w.fn; s.mn = w.mn; s.cc = w.cc;
+		}
+	}
+	*out = s;
+}
+
+extern "C" int tb200_find_lock(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint64_t *a0, uint64_t *cmin)
+{
+	if (!ctx || !d_bits || !a0 || !cmin) return TB200_E_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	reset_stream(ctx);
+	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits;
+	Outputs out; out.on_device = true; out.slots = nullptr; out.type1 = nullptr; out.packed = nullptr; out.max_slots = 0; out.n = 0;
+	ctx->fed_end = n_bits;
+	ctx->stop_at_lock = true;
+	int rc = rx_run(ctx, src, true, out);
+	ctx->stop_at_lock = false;
+	if (rc) return rc;
+	if (ctx->rx.state != TB200_RX_LOCKED) return 0;
+	*a0 = ctx->rx.buf_start;
+	*cmin = ctx->rx.calls + 1;
+	return 1;
+}
+
+extern "C" int tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t base_bit, uint64_t n_bytes,
+                                 uint64_t a0, uint64_t cmin, uint64_t n_end, uint32_t n_slots,
+                                 tb200_shard_summary *summary)
+{
+	if (!ctx || !d_bits || !summary) return TB200_E_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	if (a0 < base_bit) return fail(ctx, TB200_E_ARG, "shard bits start after the first slot");
+	int rc;
+	if ((rc = ensure_workspace(ctx, n_slots ? n_slots : 1))) return rc;
+	if ((rc = ensure_pieces(ctx, 1))) return rc;
+	RxGeom g;
+	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.n_end = n_end;
+	g.chunk = ctx->opt.chunk_bits; g.n_slots = n_slots;
+	memset(&ctx->stats, 0, sizeof(ctx->stats));
+	if (n_slots && (rc = enqueue_pass1(ctx, g, 0, nullptr))) return rc;
+	tb200_shard_summary *d_sum = reinterpret_cast<tb200_shard_summary *>(ctx->d_hits);    /* small scratch */
+	if (!n_slots) CU(cudaMemsetAsync(ctx->d_flags, 0xff, sizeof(uint32_t), ctx->s_compute));
+	TB_LAUNCH(k_shard_summary, 1, 32, ctx->s_compute, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, ctx->d_flags, n_slots, d_sum);
+	ctx->stats.kernel_launches++;
+	CU(cudaMemcpyAsync(summary, d_sum, sizeof(*summary), cudaMemcpyDeviceToHost, ctx->s_compute));
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	ctx->shard_a0 = a0;
+	ctx->shard_slots = n_slots;
+	return 0;
+}
+
+/* receiver state in front of rank `rank`'s shard, from the initial state and the summaries of ranks 0..rank-1 */
+extern "C" void tb200_shard_carry_in(const tb200_shard_summary *all, int rank, const tb200_rx_carry *initial, tb200_rx_carry *out)
+{
+	tb200_rx_carry c = *initial;
+	for (int r = 0; r < rank; r++) {
+		const tb200_shard_summary &s = all[r];
+		Tm t;
+		if (s.has_good_sb) {
+			t.tn = s.tn; t.fn = s.fn; t.mn = s.mn;
+			t = tm_advance(t, s.slots_after);
+			c.scramb_init = s.scramb_init; c.mcc = s.mcc; c.mnc = s.mnc; c.colour_code = s.cc;
+		} else {
+			t.tn = c.tn; t.fn = c.fn; t.mn = c.mn;
+			t = tm_advance(t, s.n_slots);
+		}
+		c.tn = (uint8_t)t.tn; c.fn = (uint8_t)t.fn; c.mn = (uint8_t)t.mn;
+	}
+	*out = c;
+}
+
+extern "C" long tb200_shard_pass2(tb200_ctx *ctx, const tb200_rx_carry *carry_in, tb200_slot *d_slots, uint8_t *d_type1,
+                                  uint32_t *d_type1_packed)
+{
+	if (!ctx || !carry_in || !d_slots) return TB200_E_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	if (d_type1 && ((uintptr_t)d_type1 & 15)) return fail(ctx, TB200_E_ARG, "d_type1 must be 16-byte aligned");
+	DevCarry dc;
+	memset(&dc, 0, sizeof(dc));
+	dc.scramb_init = carry_in->scramb_init; dc.tn = carry_in->tn; dc.fn = carry_in->fn; dc.mn = carry_in->mn;
+	dc.mcc = carry_in->mcc; dc.mnc = carry_in->mnc; dc.cc = carry_in->colour_code;
+	CU(cudaMemcpyAsync(ctx->d_carry, &dc, sizeof(dc), cudaMemcpyHostToDevice, ctx->s_compute));
+	if (ctx->shard_slots) {
+		int rc = enqueue_pass2(ctx, ctx->shard_a0, ctx->shard_slots, 0, nullptr, (SlotOut *)d_slots, d_type1, d_type1_packed, 0);
+		if (rc) return rc;
+	}
+	CU(cudaMemcpyAsync(&ctx->h_carry, ctx->d_carry + (ctx->shard_slots ? 1 : 0), sizeof(DevCarry), cudaMemcpyDeviceToHost, ctx->s_compute));
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	return (long)ctx->shard_slots;
 }

@@ -380,6 +380,15 @@ class Carry(C.Structure):
                 ("colour_code", C.c_uint8), ("tn", C.c_uint8), ("fn", C.c_uint8), ("mn", C.c_uint8)]
 
 
+class ShardSummary(C.Structure):
+    _fields_ = [("n_slots", C.c_uint32), ("first_unlock", C.c_uint32), ("has_good_sb", C.c_uint32),
+                ("scramb_init", C.c_uint32), ("slots_after", C.c_uint32), ("mcc", C.c_uint16), ("mnc", C.c_uint16),
+                ("tn", C.c_uint8), ("fn", C.c_uint8), ("mn", C.c_uint8), ("cc", C.c_uint8), ("pad", C.c_uint32)]
+
+
+assert C.sizeof(ShardSummary) == 32
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("slots", "bursts_decoded", "blocks", "crc_ok_blocks",
                                            "lock_losses", "lock_acquisitions", "kernel_launches")]
@@ -435,6 +444,13 @@ class B200:
         lib.tb200_descramble_deinterleave.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                       C.c_uint32, C.c_uint32, C.c_int]
         lib.tb200_gen_stream_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
+        lib.tb200_find_lock.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        lib.tb200_shard_pass1.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.c_uint32, C.POINTER(ShardSummary)]
+        lib.tb200_shard_carry_in.argtypes = [C.c_void_p, C.c_int, C.POINTER(Carry), C.POINTER(Carry)]
+        lib.tb200_shard_carry_in.restype = None
+        lib.tb200_shard_pass2.restype = C.c_long
+        lib.tb200_shard_pass2.argtypes = [C.c_void_p, C.POINTER(Carry), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.tb200_host_alloc.restype = C.c_void_p
         lib.tb200_host_alloc.argtypes = [C.c_size_t]
         lib.tb200_host_free.argtypes = [C.c_void_p]
@@ -505,6 +521,35 @@ class B200:
         t = Timing()
         self.lib.tb200_get_timing(self.h, C.byref(t))
         return t
+
+    # ---- sharded decode (pointers are raw device addresses; host addresses under emulation)
+    def find_lock(self, d_bits_ptr, n_bits):
+        a0, cmin = C.c_uint64(0), C.c_uint64(0)
+        rc = self.lib.tb200_find_lock(self.h, C.c_void_p(d_bits_ptr), n_bits, C.byref(a0), C.byref(cmin))
+        if rc < 0:
+            raise RuntimeError(self.err())
+        return rc == 1, a0.value, cmin.value
+
+    def shard_pass1(self, d_bits_ptr, base_bit, n_bytes, a0, cmin, n_end, n_slots):
+        s = ShardSummary()
+        rc = self.lib.tb200_shard_pass1(self.h, C.c_void_p(d_bits_ptr), base_bit, n_bytes, a0, cmin, n_end, n_slots, C.byref(s))
+        if rc:
+            raise RuntimeError(self.err())
+        return s
+
+    def shard_carry_in(self, summaries, rank, initial=None):
+        arr = (ShardSummary * len(summaries))(*summaries)
+        init = initial or Carry()
+        out = Carry()
+        self.lib.tb200_shard_carry_in(arr, rank, C.byref(init), C.byref(out))
+        return out
+
+    def shard_pass2(self, carry, d_slots_ptr, d_type1_ptr, d_packed_ptr=None):
+        n = self.lib.tb200_shard_pass2(self.h, C.byref(carry), C.c_void_p(d_slots_ptr), C.c_void_p(d_type1_ptr),
+                                       C.c_void_p(d_packed_ptr) if d_packed_ptr else None)
+        if n < 0:
+            raise RuntimeError(self.err())
+        return n
 
     def find_train_seq(self, bits, starts, lens, mask):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
