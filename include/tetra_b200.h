@@ -138,7 +138,8 @@ int  tb200_set_options(tb200_ctx *ctx, const struct tb200_options *opt);
  * d_slots[max_slots], d_type1 (max_slots * TB200_TYPE1_STRIDE bytes, 16-byte aligned, may
  * be NULL), d_type1_packed (max_slots * TB200_TYPE1_WORDS words, may be NULL) are device
  * buffers owned by the caller.  Returns the number of slots written (>= 0) or TB200_E_*.
- * All device work is complete when the call returns.  Needs TB200_FRESH | TB200_FINAL. */
+ * The call waits for the device on entry (the caller's buffers may still be in flight on other
+ * streams) and all its device work is complete when it returns.  Needs TB200_FRESH | TB200_FINAL. */
 long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint32_t flags,
                          struct tb200_slot *d_slots, uint8_t *d_type1, uint32_t *d_type1_packed,
                          uint64_t max_slots);

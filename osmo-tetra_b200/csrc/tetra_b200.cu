@@ -907,6 +907,7 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 	if (!d_bits || !d_slots) return fail(ctx, TB200_E_ARG, "null buffer");
 	if (d_type1 && ((uintptr_t)d_type1 & 15)) return fail(ctx, TB200_E_ARG, "d_type1 must be 16-byte aligned");
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	CU(cudaDeviceSynchronize());        /* the caller's buffers may still be in flight on its own streams */
 	reset_stream(ctx);
 	int rc = push_carry(ctx);
 	if (rc) return rc;
@@ -1183,6 +1184,9 @@ static int leaf_common(tb200_ctx *ctx)
 {
 	if (!ctx) return TB200_E_ARG;
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	/* callers hand in device buffers they may have just produced on THEIR streams (e.g. a torch.zeros
+	 * still running); our streams are non-blocking, so wait for the device before touching them */
+	CU(cudaDeviceSynchronize());
 	return 0;
 }
 
@@ -1342,6 +1346,7 @@ extern "C" int tb200_find_lock(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n
 {
 	if (!ctx || !d_bits || !a0 || !cmin) return TB200_E_ARG;
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	CU(cudaDeviceSynchronize());
 	reset_stream(ctx);
 	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits;
 	Outputs out; out.on_device = true; out.slots = nullptr; out.type1 = nullptr; out.packed = nullptr; out.max_slots = 0; out.n = 0;
@@ -1363,6 +1368,7 @@ extern "C" int tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t
 	if (!ctx || !d_bits || !summary) return TB200_E_ARG;
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	if (a0 < base_bit) return fail(ctx, TB200_E_ARG, "shard bits start after the first slot");
+	CU(cudaDeviceSynchronize());
 	int rc;
 	if ((rc = ensure_workspace(ctx, n_slots ? n_slots : 1))) return rc;
 	if ((rc = ensure_pieces(ctx, 1))) return rc;
@@ -1408,6 +1414,7 @@ extern "C" long tb200_shard_pass2(tb200_ctx *ctx, const tb200_rx_carry *carry_in
 	if (!ctx || !carry_in || !d_slots) return TB200_E_ARG;
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	if (d_type1 && ((uintptr_t)d_type1 & 15)) return fail(ctx, TB200_E_ARG, "d_type1 must be 16-byte aligned");
+	CU(cudaDeviceSynchronize());
 	DevCarry dc;
 	memset(&dc, 0, sizeof(dc));
 	dc.scramb_init = carry_in->scramb_init; dc.tn = carry_in->tn; dc.fn = carry_in->fn; dc.mn = carry_in->mn;
