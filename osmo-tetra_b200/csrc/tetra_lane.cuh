@@ -18,7 +18,7 @@
 
 namespace tb {
 
-constexpr int LANE_DEC_ROWS = 296;     /* 292 trellis steps max, padded */
+constexpr int LANE_DEC_ROWS = 296;     /* words per thread: 73 groups of 4 trellis steps x uint4, padded */
 constexpr int LANE_T3_ROWS = 14;
 constexpr int LANE_T3B_ROWS = 8;       /* second block of two-block bursts: 216 bits + one readable row */
 constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: one warp, 5 CTAs fit an SM's shared memory */
@@ -34,7 +34,7 @@ __host__ __device__ constexpr size_t lane_smem_words(int nt)
 __host__ __device__ constexpr size_t lane_scratch_words_per_cta(int nt) { return (size_t)LANE_DEC_ROWS * nt; }
 
 struct LaneSmem {
-	uint32_t *dec;       /* [LANE_DEC_ROWS][NT] in GLOBAL scratch; bit s: trellis X state s, bit 16+s: trellis Y */
+	uint4 *dec;          /* [LANE_DEC_ROWS / 4][NT] in GLOBAL scratch: survivor histories, one uint4 per thread and group of 4 steps */
 	uint32_t *t3;        /* [2][LANE_T3_ROWS][NT] type-3 bits, later the decoded type-2 bits */
 	uint32_t *t3b;       /* [2][LANE_T3B_ROWS][NT] the same for BLK2 of two-block bursts */
 	uint32_t *crc_tab;   /* [256] reflected CRC-CCITT byte table, then [16] nibble table */
@@ -43,7 +43,7 @@ struct LaneSmem {
 	__device__ __forceinline__ LaneSmem(uint8_t *base, uint32_t *scratch)
 	{
 		uint32_t *p = reinterpret_cast<uint32_t *>(base);
-		dec = scratch + (size_t)blockIdx.x * lane_scratch_words_per_cta(nt);
+		dec = reinterpret_cast<uint4 *>(scratch + (size_t)blockIdx.x * lane_scratch_words_per_cta(nt));
 		t3 = p; p += 2 * LANE_T3_ROWS * nt;
 		t3b = p; p += 2 * LANE_T3B_ROWS * nt;
 		crc_tab = p; p += 256 + 16;
@@ -59,6 +59,11 @@ __host__ __device__ constexpr unsigned branch_class(unsigned j)
 	return ((((j >> 0) & 1) ^ ((j >> 3) & 1)) << 1) | (((j >> 1) & 1) ^ ((j >> 2) & 1) ^ ((j >> 3) & 1));
 }
 
+__host__ __device__ constexpr unsigned rev4(unsigned v)
+{
+	return ((v & 1) << 3) | ((v & 2) << 1) | ((v & 4) >> 1) | ((v & 8) >> 3);
+}
+
 __device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b)
 {
 #ifdef TB_SIMT_EMULATION
@@ -70,110 +75,150 @@ __device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b)
 #endif
 }
 
-/* One trellis step for two packed trellises.  Path metrics are kept doubled (even numbers);
- * the candidate coming from the older-bit-1 predecessor carries a 1 in its LSB, so a single
- * packed add-min both selects the survivor (ties go to the even candidate = predecessor s>>1,
- * the reference rule) and leaves the decision in bit 0 / bit 16 of the result.
- * M0[c] = 2 * mismatches of output class c, M1[c] = M0[c] + 1 per half; the complementary
- * branch has class c ^ 3.  Returns the decisions: bit s = trellis X state s, bit 16+s = Y. */
-__device__ __forceinline__ uint32_t acs2_step(uint32_t (&pm)[16], const uint32_t (&M0)[4], const uint32_t (&M1)[4])
+/* One trellis step for two packed trellises (16-bit halves of every register).
+ *
+ * Path metrics are kept in units of 16 (one mismatching symbol costs 16), which leaves the low
+ * four bits of every metric free.  Step q = t mod 4 of a group of four adds 2^q to the candidate
+ * that comes from the older-bit-1 predecessor (s>>1)|8.  The bits below 2^q of any metric only
+ * hold tags of earlier steps of the group, i.e. they are < 2^q, so a single packed add-min
+ *   - compares the true metrics exactly,
+ *   - gives ties to the predecessor s>>1 (the reference rule: libosmocore keeps the first/lower
+ *     predecessor on equal cost), and
+ *   - leaves in bit q of the winner "which predecessor won", while bits < q are inherited from
+ *     the winner: after four steps the low nibble of a state's metric is the decision history of
+ *     its survivor path through the group (register exchange for free, no per-step extraction).
+ * The trellis has 4 bits of memory, so that nibble IS the state the survivor had four steps
+ * earlier (bit-reversed), and also the four decoded bits of the previous group.
+ * M0[c] = 16 * mismatches of output class c (per half); the complementary branch has class c ^ 3.
+ * Cost: one add + one VIADDMNMX.U16x2 per state and step for two trellises. */
+template <int Q>
+__device__ __forceinline__ void acs2_step(uint32_t (&pm)[16], const uint32_t (&M0)[4])
 {
-	uint32_t nm[16];
-	uint32_t dhi = 0, dlo = 0;
+	uint32_t M1[4], nm[16];
 #pragma unroll
-	for (int s = 15; s >= 0; --s) {
+	for (int c = 0; c < 4; ++c) M1[c] = M0[c] + (0x00010001u << Q);
+#pragma unroll
+	for (int s = 0; s < 16; ++s) {
 		const unsigned c = branch_class(s >> 1) ^ ((s & 1) ? 3u : 0u);
 		const uint32_t c1 = pm[(s >> 1) | 8] + M1[c ^ 3];
-		const uint32_t r = __viaddmin_u16x2(pm[s >> 1], M0[c], c1);
-		const uint32_t tag = r & 0x00010001u;
-		nm[s] = sub_opaque(r, tag);                 /* clears the tag; an add, so it can go to either pipe */
-		if (s >= 8) dhi = dhi * 2 + tag;
-		else        dlo = dlo * 2 + tag;
+		nm[s] = __viaddmin_u16x2(pm[s >> 1], M0[c], c1);
 	}
 #pragma unroll
 	for (int s = 0; s < 16; ++s) pm[s] = nm[s];
-	return dhi * 256 + dlo;
+}
+
+/* After the fourth step of a group: strip the history nibbles off the 16 metrics and pack them.
+ * The nibble of state s goes to position rev4(s), so that the trace back can index it with the
+ * previous group's decoded nibble directly.  Result: x,y = trellis X positions 0-7, 8-15; z,w = Y. */
+__device__ __forceinline__ uint4 take_history(uint32_t (&pm)[16])
+{
+	uint32_t W[4];
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		uint32_t acc = 0;
+#pragma unroll
+		for (int i = 3; i >= 0; --i) {
+			const unsigned s = rev4(4 * j + i);
+			const uint32_t h = pm[s] & 0x000f000fu;
+			pm[s] = sub_opaque(pm[s], h);
+			acc = acc * 16 + h;
+		}
+		W[j] = acc;
+	}
+	return make_uint4(__byte_perm(W[0], W[1], 0x5410), __byte_perm(W[2], W[3], 0x5410),
+	                  __byte_perm(W[0], W[1], 0x7632), __byte_perm(W[2], W[3], 0x7632));
+}
+
+/* nibble f (0..15) of the 64-bit value hi:lo */
+__device__ __forceinline__ uint32_t nibble64(uint32_t lo, uint32_t hi, uint32_t f)
+{
+	const uint32_t src = (f & 8) ? hi : lo;
+	return (src >> ((f & 7) * 4)) & 15u;
 }
 
 /* Forward pass + trace back for the two blocks whose type-3 bits sit in sm.t3[0] / sm.t3[1]
  * (columns of this thread).  nx, ny: type-2 lengths (0 = no block); nmax: warp-wide maximum so
- * the loop is uniform.  Leaves the decoded type-2 bits in the same columns. */
+ * the loop is uniform.  Leaves the decoded type-2 bits in the same columns.
+ * dec: this thread's column of the history scratch, one uint4 per group of four steps. */
 template <bool MASKED>
-__device__ __noinline__ void viterbi_pair_t(uint32_t *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
+__device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	uint32_t pm[16];
 #pragma unroll
-	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x20002000u : 0u;
+	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x40004000u : 0u;     /* start in state 0 (osmo_conv_decode) */
 	constexpr int nt = LANE_NT;
 	const int groups = nmax / 8;                       /* 4 step pairs = 12 type-3 bits per group */
 	for (int g = 0; g < groups; ++g) {
 		const unsigned bp = 12 * g, w = bp >> 5, sh = bp & 31;
 		const uint32_t vx = __funnelshift_r(cx[w * nt], cx[(w + 1) * nt], sh) & 0xfffu;
 		const uint32_t vy = __funnelshift_r(cy[w * nt], cy[(w + 1) * nt], sh) & 0xfffu;
-		const uint32_t z = (vx | (vy << 16)) << 1;          /* bits pre-doubled: value 2 where a 1 was received */
+		const uint32_t z = (vx | (vy << 16)) << 4;          /* bits pre-scaled: value 16 where a 1 was received */
 		uint32_t live = 0xffffffffu;
 		if (MASKED) live = ((8 * g < nx) ? 0xffffu : 0u) | ((8 * g < ny) ? 0xffff0000u : 0u);
 #pragma unroll
 		for (int p = 0; p < 4; ++p) {
-			const uint32_t r1 = (z >> (3 * p)) & 0x00020002u;
-			const uint32_t r2 = (z >> (3 * p + 1)) & 0x00020002u;
-			const uint32_t r3 = (z >> (3 * p + 2)) & 0x00020002u;
-			uint32_t M0[4], M1[4];
+			const uint32_t r1 = (z >> (3 * p)) & 0x00100010u;
+			const uint32_t r2 = (z >> (3 * p + 1)) & 0x00100010u;
+			const uint32_t r3 = (z >> (3 * p + 2)) & 0x00100010u;
+			uint32_t M0[4];
 			M0[0] = r1 + r2;                                  /* expected 00 */
-			M0[3] = 0x00040004u - M0[0];                      /* expected 11 */
-			M0[2] = 0x00020002u - r1 + r2;                    /* expected G1=1, G2=0 */
-			M0[1] = 0x00040004u - M0[2];                      /* expected G1=0, G2=1 */
+			M0[3] = 0x00200020u - M0[0];                      /* expected 11 */
+			M0[2] = 0x00100010u - r1 + r2;                    /* expected G1=1, G2=0 */
+			M0[1] = 0x00200020u - M0[2];                      /* expected G1=0, G2=1 */
 			if (MASKED) { M0[0] &= live; M0[1] &= live; M0[2] &= live; M0[3] &= live; }
-#pragma unroll
-			for (int c = 0; c < 4; ++c) M1[c] = M0[c] + 0x00010001u;
-			dec[(8 * g + 2 * p) * nt] = acs2_step(pm, M0, M1);
-			M0[0] = r3; M0[2] = 0x00020002u - r3;             /* odd step: only G1 was sent */
+			if (p & 1) acs2_step<2>(pm, M0); else acs2_step<0>(pm, M0);
+			M0[0] = r3; M0[2] = 0x00100010u - r3;             /* odd step: only G1 was sent */
 			if (MASKED) { M0[0] &= live; M0[2] &= live; }
 			M0[1] = M0[0]; M0[3] = M0[2];
-#pragma unroll
-			for (int c = 0; c < 4; ++c) M1[c] = M0[c] + 0x00010001u;
-			dec[(8 * g + 2 * p + 1) * nt] = acs2_step(pm, M0, M1);
+			if (p & 1) {
+				acs2_step<3>(pm, M0);
+				dec[(2 * g + (p >> 1)) * nt] = take_history(pm);
+			} else {
+				acs2_step<1>(pm, M0);
+			}
 		}
 	}
 	{
-		const uint32_t Z0[4] = { 0, 0, 0, 0 }, Z1[4] = { 0x00010001u, 0x00010001u, 0x00010001u, 0x00010001u };
-#pragma unroll
-		for (int t = 0; t < 4; ++t) dec[(nmax + t) * nt] = acs2_step(pm, Z0, Z1);
+		/* four flush steps: no received symbols, so no cost; both inputs stay allowed, the trace back
+		 * starts in state 0, which only the all-zero tail can reach */
+		const uint32_t Z0[4] = { 0, 0, 0, 0 };
+		acs2_step<0>(pm, Z0); acs2_step<1>(pm, Z0); acs2_step<2>(pm, Z0); acs2_step<3>(pm, Z0);
+		dec[(nmax >> 2) * nt] = take_history(pm);
 	}
-	/* Trace back.  The state after step t is the last four decoded bits, and the decision looked up
-	 * at step t is decoded bit t-4, so one shift register per path is both the state (its top four
-	 * bits) and the output: h = (h >> 1) | (decision << 31). */
-	uint32_t *ox = cx, *oy = cy;
-	uint32_t hx = 0, hy = 0;
-	/* output word wi holds decoded bits [32wi, 32wi+32): they come from steps t = 32wi+35 .. 32wi+4 */
+	/* Trace back, one group (= one decoded nibble) per step.  f = decoded nibble of group g = bit-reversed
+	 * state after the group; the history nibble at position f of group g is the decoded nibble of group
+	 * g-1.  The block with n type-2 bits ends (after its flush group n/4) in state 0. */
+	uint32_t fx = 0, fy = 0, hx = 0, hy = 0;
+	/* output word wi holds the nibbles of groups 8wi .. 8wi+7, read from the histories of groups 8wi+1 .. 8wi+8 */
+	const int gtop = nmax >> 2;                         /* index of the flush group of a full-length block */
 	for (int wi = (nmax - 1) >> 5; wi >= 0; --wi) {
-		const int thi = 32 * wi + 35 < nmax + 3 ? 32 * wi + 35 : nmax + 3;
-		const uint32_t *dp = dec + thi * nt;
-		const int cnt = thi - (32 * wi + 4) + 1;           /* 16 or 32 */
-		for (int i = 0; i < cnt; i += 8) {
-			uint32_t w8[8];
+		const int ghi = 8 * wi + 8 < gtop ? 8 * wi + 8 : gtop;
+		const uint4 *dp = dec + ghi * nt;
+		const int cnt = ghi - 8 * wi;                      /* 4 or 8 */
+		for (int i = 0; i < cnt; i += 4) {
+			uint4 h4[4];
 #pragma unroll
-			for (int u = 0; u < 8; ++u) w8[u] = dp[-u * nt];     /* loads first: L2 latency overlaps */
-			dp -= 8 * nt;
+			for (int u = 0; u < 4; ++u) h4[u] = dp[-u * nt];     /* loads first: L2 latency overlaps */
+			dp -= 4 * nt;
 #pragma unroll
-			for (int u = 0; u < 8; ++u) {
-				const uint32_t w = w8[u];
+			for (int u = 0; u < 4; ++u) {
+				const uint4 h = h4[u];
 				if (MASKED) {
-					const int t = thi - i - u;
-					if (t <= nx + 3) hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
-					if (t <= ny + 3) hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
+					const int g = ghi - i - u;
+					if (4 * g <= nx) { fx = nibble64(h.x, h.y, fx); hx = hx * 16 + fx; }
+					if (4 * g <= ny) { fy = nibble64(h.z, h.w, fy); hy = hy * 16 + fy; }
 				} else {
-					hx = __funnelshift_r(hx, w >> (hx >> 28), 1);
-					hy = __funnelshift_r(hy, (w >> 16) >> (hy >> 28), 1);
+					fx = nibble64(h.x, h.y, fx); hx = hx * 16 + fx;
+					fy = nibble64(h.z, h.w, fy); hy = hy * 16 + fy;
 				}
 			}
 		}
-		ox[wi * nt] = __brev(hx);
-		oy[wi * nt] = __brev(hy);
+		cx[wi * nt] = hx;
+		cy[wi * nt] = hy;
 	}
 }
 
-__device__ __forceinline__ void viterbi_pair(uint32_t *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
+__device__ __forceinline__ void viterbi_pair(uint4 *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	/* warp-uniform choice: no masking work when every lane carries two full-length blocks */
 	const bool uniform = __all_sync(FULL, nx == nmax && ny == nmax);
