@@ -161,13 +161,14 @@ int tb200_get_stats(const tb200_ctx *ctx, struct tb200_stats *out);
  * but adds event records).  *_ms are sums over all launches of that kernel in the call. */
 struct tb200_timing {
 	float total_ms;             /* first launch to last launch of the call, compute stream */
-	float classify_ms;          /* k_classify: load + pack + training-sequence search + SB1 */
+	float classify_ms;          /* search kernel (load + pack + training-sequence search + slot records) + SB1 pass */
 	float scan_ms;              /* k_scan_blocks + k_scan_prefix + k_finalize_carry */
 	float decode_ms;            /* k_decode_*: descramble + de-interleave + Viterbi + CRC + output */
 	uint32_t launches_classify, launches_scan, launches_decode;
 	uint32_t pieces;
 	uint64_t slots;             /* slots those launches covered */
 	float leaf_ms;              /* last tb200_descramble_deinterleave kernel (device pointers) */
+	float search_ms;            /* the training-sequence search kernel alone (classify_ms minus the SB1 pass) */
 };
 int tb200_get_timing(const tb200_ctx *ctx, struct tb200_timing *out);
 

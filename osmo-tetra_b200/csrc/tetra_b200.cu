@@ -11,6 +11,7 @@
 #include "tetra_kernels.cuh"
 #include "tetra_lane.cuh"
 #include "tetra_classify_tma.cuh"
+#include "tetra_classify_tile.cuh"
 #include "tetra_stage_tma.cuh"
 #include "tetra_gen.cuh"
 #include "../../include/tetra_b200.h"
@@ -151,6 +152,7 @@ struct tb200_ctx {
 	size_t ws_slots = 0;
 	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the lane kernels, one area per resident CTA */
 	unsigned lane_ctas = 0;               /* resident CTAs of the lane kernels (grid size) */
+	int classify_form = 0;                /* 0: CTA per tile of 64 slots (default), 1: thread per slot (env TB200_CLASSIFY=1) */
 	uint32_t *d_flags = nullptr;     /* first unlocking slot per piece */
 	uint32_t *h_flags = nullptr;     /* pinned mirror */
 	size_t flags_cap = 0;
@@ -181,7 +183,7 @@ struct tb200_ctx {
 	uint64_t shard_a0 = 0;
 	uint32_t shard_slots = 0;
 	/* profiling (options.profile) */
-	std::vector<cudaEvent_t> prof_ev;    /* 5 per piece: start, after classify, after scan, after decode, after carry */
+	std::vector<cudaEvent_t> prof_ev;    /* 6 per piece: start, after classify, after scan, after decode, after carry, after the search kernel */
 	size_t prof_used = 0;
 	tb200_timing timing;
 };
@@ -275,7 +277,10 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 		return bail("cudaFuncSetAttribute");
 	if (cudaFuncSetAttribute(k_classify_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_SMEM) != cudaSuccess)
 		return bail("cudaFuncSetAttribute");
+	if (cudaFuncSetAttribute(k_classify_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM) != cudaSuccess)
+		return bail("cudaFuncSetAttribute");
 #endif
+	if (const char *e = getenv("TB200_CLASSIFY")) ctx->classify_form = atoi(e);
 	if (cudaMalloc((void **)&ctx->d_hits, sizeof(uint32_t) * (2 * 8192 + 2)) != cudaSuccess) return bail("cudaMalloc");
 	if (cudaHostAlloc((void **)&ctx->h_hits, sizeof(uint32_t) * (2 * 8192 + 2), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
 	*out = ctx;
@@ -582,17 +587,26 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cuda
 		WinGeom wg;
 		wg.chunk = g.chunk; wg.rel0 = (uint32_t)(g.a0 % g.chunk); wg.c00 = g.a0 / g.chunk;
 		wg.cmin = g.cmin; wg.n_end = g.n_end; wg.a0 = g.a0;
-		const unsigned cls_groups = (nb + 31) / 32;
-		const unsigned cls_blocks = std::min<unsigned>((cls_groups + CLS_WARPS - 1) / CLS_WARPS, (unsigned)ctx->sm_count * 3);
 		uint32_t *sb_count = ctx->d_sb_list + ctx->ws_slots;
 		CU(cudaMemsetAsync(sb_count, 0, sizeof(uint32_t), st));
-		TB_LAUNCH_SMEM(k_classify_tma, cls_blocks, CLS_WARPS * 32, CLS_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits,
-		               ctx->d_sb_list, sb_count);
+		if (ctx->classify_form == 0) {
+			const unsigned tiles = (nb + CT_SLOTS - 1) / CT_SLOTS;
+			const unsigned cls_blocks = std::min<unsigned>(tiles, (unsigned)ctx->sm_count * 3);
+			TB_LAUNCH_SMEM(k_classify_tile, cls_blocks, CT_THREADS, CT_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits,
+			               ctx->d_sb_list, sb_count);
+		} else {
+			const unsigned cls_groups = (nb + 31) / 32;
+			const unsigned cls_blocks = std::min<unsigned>((cls_groups + CLS_WARPS - 1) / CLS_WARPS, (unsigned)ctx->sm_count * 3);
+			TB_LAUNCH_SMEM(k_classify_tma, cls_blocks, CLS_WARPS * 32, CLS_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits,
+			               ctx->d_sb_list, sb_count);
+		}
+		if (pe) CU(cudaEventRecord(pe[5], st));
 		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
 		               ctx->d_tab, ctx->d_lane_scratch);
 		ctx->stats.kernel_launches++;
 	} else {
 		TB_LAUNCH(k_classify<true>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
+		if (pe) CU(cudaEventRecord(pe[5], st));
 	}
 	if (pe) CU(cudaEventRecord(pe[1], st));
 	const unsigned nblk = (nb + 1023) / 1024;
@@ -644,13 +658,13 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	g.chunk = seg.chunk; g.n_slots = nb;
 	cudaEvent_t *pe = nullptr;
 	if (ctx->opt.profile) {
-		while (ctx->prof_ev.size() < ctx->prof_used + 5) {
+		while (ctx->prof_ev.size() < ctx->prof_used + 6) {
 			cudaEvent_t e;
 			CU(cudaEventCreateWithFlags(&e, 0));
 			ctx->prof_ev.push_back(e);
 		}
 		pe = &ctx->prof_ev[ctx->prof_used];
-		ctx->prof_used += 5;
+		ctx->prof_used += 6;
 		ctx->timing.pieces++;
 		ctx->timing.slots += nb;
 	}
@@ -866,14 +880,15 @@ static int profile_end(tb200_ctx *ctx)
 	if (!ctx->opt.profile || ctx->prof_used == 0) return 0;
 	CU(cudaStreamSynchronize(ctx->s_compute));
 	float ms = 0.f;
-	for (size_t i = 0; i + 5 <= ctx->prof_used; i += 5) {
+	for (size_t i = 0; i + 6 <= ctx->prof_used; i += 6) {
 		cudaEvent_t *e = &ctx->prof_ev[i];
 		CU(cudaEventElapsedTime(&ms, e[0], e[1])); ctx->timing.classify_ms += ms; ctx->timing.launches_classify++;
+		CU(cudaEventElapsedTime(&ms, e[0], e[5])); ctx->timing.search_ms += ms;
 		CU(cudaEventElapsedTime(&ms, e[1], e[2])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan += 2;
 		CU(cudaEventElapsedTime(&ms, e[2], e[3])); ctx->timing.decode_ms += ms; ctx->timing.launches_decode++;
 		CU(cudaEventElapsedTime(&ms, e[3], e[4])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan++;
 	}
-	CU(cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[ctx->prof_used - 1]));
+	CU(cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[ctx->prof_used - 2]));
 	ctx->timing.total_ms = ms;
 	return 0;
 }

@@ -1,0 +1,248 @@
+/*
+ * tetra_classify_tile.cuh - pass 1 (training-sequence search + slot packing), one CTA per TILE of slots.
+ *
+ * The thread-per-slot form (tetra_classify_tma.cuh) stages 528 bytes per slot and can keep only six
+ * warps on an SM; it is latency bound at 65 % of the HBM roofline.  Slots of a LOCKED stream are back to
+ * back, so here a CTA takes 64 consecutive slots = one contiguous 32 640-byte piece of the stream:
+ *
+ *   copy   one cp.async.bulk (TMA bulk copy) brings the 16-byte aligned superset of the tile into shared
+ *          memory; two tile buffers per CTA, the copy of the CTA's next tile is in flight while the
+ *          current one is searched (3 CTAs per SM -> ~96 KB in flight per SM, every byte read once);
+ *   pack   all threads turn the 0/1 bytes into a dense bit string (16 bytes -> 16 bits with IDP.4A);
+ *   emit   the slot's 510 bits, re-aligned to a 64-byte record (funnel shifts of the bit string), written
+ *          coalesced for the decode pass and kept transposed in shared memory for the search;
+ *   search position-parallel: warp j tests the 32 positions of word j of a slot against the three downlink
+ *          sequences, two pattern bits per LOP3; offsets 0..255 are covered (the expected offsets 214 /
+ *          244 are inside; a hit there is the first hit whatever the search window).  Words 0..5 almost
+ *          never hold a match, so six of the eight warps leave after 12 pattern bits.  Hits (about one
+ *          per slot) go through the reference's pre-filter blind spot rule and an atomicMin per slot
+ *          keeps the first;
+ *   decide one thread per slot: search window, kind, lock loss; slots without a hit in the tested range go
+ *          through the exact warp-cooperative search over their whole window (rare).
+ *
+ * Semantics: tetra_find_train_seq (tetra_burst.c:269-339) + LOCKED arm of tetra_burst_sync_in
+ * (tetra_burst_sync.c:107-143).
+ */
+#pragma once
+#include "tetra_kernels.cuh"
+#include "tetra_classify_tma.cuh"
+
+namespace tb {
+
+constexpr int CT_SLOTS = 64;                                  /* slots per tile */
+constexpr int CT_THREADS = 256;
+constexpr int CT_RAW = ((15 + 510 * CT_SLOTS + 15) / 16) * 16;     /* bytes of one raw tile buffer (32 672) */
+constexpr int CT_BITW = CT_RAW / 32 + 4;                       /* words of the packed tile (+ read-ahead) */
+constexpr int CT_AROW = CT_SLOTS + 1;                          /* row pitch of the aligned slot words (odd: no bank conflicts on the transposed write) */
+constexpr size_t CT_SMEM = (size_t)2 * CT_RAW + (size_t)CT_BITW * 4 + (size_t)16 * CT_AROW * 4 + CT_SLOTS * 4 + 2 * 8;
+
+/* two pattern bits (B, B+1) of the three downlink sequences against the 32 positions of word x0 */
+template <int B>
+__device__ __forceinline__ void match_pair(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t &My, uint32_t &Mn, uint32_t &Mp)
+{
+	uint32_t s0, s1;
+	if constexpr (B < 32) s0 = __funnelshift_r(x0, x1, B); else s0 = __funnelshift_r(x1, x2, B - 32);
+	if constexpr (B + 1 < 32) s1 = __funnelshift_r(x0, x1, B + 1); else s1 = __funnelshift_r(x1, x2, B + 1 - 32);
+	My &= (((SEQ_Y >> B) & 1) ? s0 : ~s0) & (((SEQ_Y >> (B + 1)) & 1) ? s1 : ~s1);
+	if constexpr (B < 22) {
+		Mn &= (((SEQ_N >> B) & 1) ? s0 : ~s0) & (((SEQ_N >> (B + 1)) & 1) ? s1 : ~s1);
+		Mp &= (((SEQ_P >> B) & 1) ? s0 : ~s0) & (((SEQ_P >> (B + 1)) & 1) ? s1 : ~s1);
+	}
+}
+#define TB_MATCH_PAIR(b) match_pair<(b)>(x0, x1, x2, My, Mn, Mp)
+
+struct TileGeom {
+	const uint8_t *src;      /* 16-byte aligned start of the copy */
+	uint32_t lead;           /* bytes between src and the first slot of the tile (0..15) */
+	uint32_t bytes;          /* copy size, multiple of 16 */
+	uint32_t k0, ns;         /* first slot, slots in the tile */
+	bool staged;             /* the aligned superset lies inside the caller's buffer: TMA copy */
+};
+
+__device__ __forceinline__ TileGeom tile_geom(const RxGeom &g, uint32_t tile, uintptr_t buf_lo, uintptr_t buf_hi)
+{
+	TileGeom t;
+	t.k0 = tile * CT_SLOTS;
+	t.ns = g.n_slots - t.k0 < (uint32_t)CT_SLOTS ? g.n_slots - t.k0 : (uint32_t)CT_SLOTS;
+	const uintptr_t p = reinterpret_cast<uintptr_t>(g.bits) + (size_t)((g.a0 - g.base_bit) + 510ull * t.k0);
+	const uintptr_t a = p & ~(uintptr_t)15;
+	t.src = reinterpret_cast<const uint8_t *>(a);
+	t.lead = (uint32_t)(p - a);
+	t.bytes = (t.lead + 510u * t.ns + 15u) & ~15u;
+	t.staged = a >= buf_lo && a + t.bytes <= buf_hi;
+	return t;
+}
+
+__global__ void __launch_bounds__(CT_THREADS, 3)
+k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__restrict__ ws,
+                uint32_t *__restrict__ slot_bits, uint32_t *__restrict__ sb_list, uint32_t *__restrict__ sb_count)
+{
+	uint8_t *smem = TB_DYN_SMEM();
+	uint8_t *raw = smem;                                                 /* [2][CT_RAW] */
+	uint32_t *bitw = reinterpret_cast<uint32_t *>(smem + 2 * CT_RAW);     /* [CT_BITW] the tile as a dense bit string */
+	uint32_t *al = bitw + CT_BITW;                                       /* [16][CT_AROW] word j of slot s, slot-aligned */
+	uint32_t *first = al + 16 * CT_AROW;                                 /* [CT_SLOTS] (offset << 3 | type), ~0 = none */
+	uint64_t *bars = reinterpret_cast<uint64_t *>(first + CT_SLOTS);     /* [2] */
+	const unsigned tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+
+	const uintptr_t buf_lo = (reinterpret_cast<uintptr_t>(g.bits) + 15) & ~(uintptr_t)15;
+	const uintptr_t buf_hi = (reinterpret_cast<uintptr_t>(g.bits) + g.n_bytes) & ~(uintptr_t)15;
+	const uint8_t *end = g.bits + g.n_bytes;
+	const uint32_t ntiles = (g.n_slots + CT_SLOTS - 1) / CT_SLOTS;
+
+	if (tid == 0) {
+		mbar_init(&bars[0], 1);
+		mbar_init(&bars[1], 1);
+	}
+	__syncthreads();
+	auto issue = [&](uint32_t tile, int b) {            /* thread 0 only */
+		if (tile >= ntiles) return;
+		const TileGeom t = tile_geom(g, tile, buf_lo, buf_hi);
+		if (!t.staged) return;
+		mbar_expect_tx(&bars[b], t.bytes);
+		bulk_g2s(raw + (size_t)b * CT_RAW, t.src, t.bytes, &bars[b]);
+	};
+	if (tid == 0) issue(blockIdx.x, 0);
+	__syncthreads();
+
+	unsigned phase_bits = 0;                     /* bit b = parity the next wait on buffer b expects */
+	int b = 0;
+	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, b ^= 1) {
+		const TileGeom t = tile_geom(g, tile, buf_lo, buf_hi);
+		uint8_t *rb = raw + (size_t)b * CT_RAW;
+		if (tid == 0) issue(tile + gridDim.x, b ^ 1);         /* prefetch this CTA's next tile */
+		if (t.staged) {
+			mbar_wait(&bars[b], (phase_bits >> b) & 1u);
+			phase_bits ^= 1u << b;
+		} else {
+			/* tile touches the ends of the caller's buffer (or the buffer is not 16-byte aligned there) */
+			for (uint32_t i = tid; i < t.bytes; i += CT_THREADS) {
+				const uint8_t *a = t.src + i;
+				rb[i] = (a >= g.bits && a < end) ? *a : 0;
+			}
+			__syncthreads();
+		}
+		/* ---- pack: 16 bytes -> 16 bits, two quads per thread and round */
+		{
+			const uint32_t nq = t.bytes >> 4;
+			const uint4 *q4 = reinterpret_cast<const uint4 *>(rb);
+			uint16_t *bh = reinterpret_cast<uint16_t *>(bitw);
+			for (uint32_t q = tid; q < nq + 8; q += 2 * CT_THREADS) {
+				const uint32_t q1 = q + CT_THREADS;
+				const uint4 v0 = q < nq ? q4[q] : make_uint4(0, 0, 0, 0);
+				const uint4 v1 = q1 < nq ? q4[q1] : make_uint4(0, 0, 0, 0);
+				bh[q] = (uint16_t)pack16_dp4a(v0);
+				if (q1 < nq + 8) bh[q1] = (uint16_t)pack16_dp4a(v1);
+			}
+			if (tid < CT_SLOTS) first[tid] = 0xffffffffu;
+		}
+		__syncthreads();
+		/* ---- align + emit: word j of slot s (bit i of the slot -> word i>>5 bit i&31); thread = (j, 4 slots).
+		 * 16 slots further on the stream is 255 words further on and equally aligned. */
+		{
+			const uint32_t j = tid & 15, s0 = tid >> 4;
+			const uint32_t dt = t.lead + 510u * s0, sh = dt & 31;
+			const uint32_t *src = bitw + (dt >> 5) + j;
+			uint32_t *dst = slot_bits + (size_t)t.k0 * 16 + tid;
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				const uint32_t s = s0 + 16 * r;
+				uint32_t v = __funnelshift_r(src[255 * r], src[255 * r + 1], sh);
+				if (j == 15) v &= 0x3fffffffu;
+				al[j * CT_AROW + s] = v;
+				if (s < t.ns) dst[256 * r] = v;
+			}
+		}
+		__syncthreads();
+		/* ---- search offsets 0..255 of every slot: warp j tests the 32 positions of word j of the slots
+		 * lane and lane + 32.  The expected offsets 214 (SYNC) and 244 (normal) sit in words 6 and 7, so
+		 * the other warps leave after 12 pattern bits almost always. */
+#pragma unroll 1
+		for (int r = 0; r < 2; ++r) {
+			const uint32_t s = lane + 32 * r, j = wib;
+			const uint32_t x0 = al[j * CT_AROW + s], x1 = al[(j + 1) * CT_AROW + s];
+			uint32_t x2 = 0;
+			uint32_t My = 0xffffffffu, Mn = 0xffffffffu, Mp = 0xffffffffu;
+			TB_MATCH_PAIR(0); TB_MATCH_PAIR(2); TB_MATCH_PAIR(4); TB_MATCH_PAIR(6); TB_MATCH_PAIR(8); TB_MATCH_PAIR(10);
+			if (s >= t.ns) My = Mn = Mp = 0;
+			if (__any_sync(FULL, (My | Mn | Mp) != 0)) {
+				TB_MATCH_PAIR(12); TB_MATCH_PAIR(14); TB_MATCH_PAIR(16); TB_MATCH_PAIR(18); TB_MATCH_PAIR(20);
+				if (My) {            /* the 16 remaining bits of the SYNC sequence, only where its prefix matched */
+					x2 = al[(j + 2) * CT_AROW + s];
+					TB_MATCH_PAIR(22); TB_MATCH_PAIR(24); TB_MATCH_PAIR(26); TB_MATCH_PAIR(28);
+					TB_MATCH_PAIR(30); TB_MATCH_PAIR(32); TB_MATCH_PAIR(34); TB_MATCH_PAIR(36);
+				}
+				uint32_t Mall = My | Mn | Mp;
+				while (Mall) {
+					const int i0 = __ffs((int)Mall) - 1;
+					Mall &= Mall - 1;
+					const uint32_t rel = 32u * j + (uint32_t)i0;
+					const int seq = ((My >> i0) & 1) ? 0 : ((Mn >> i0) & 1) ? 1 : 2;
+					bool ok = true;
+					if (rel <= 20) {      /* pre-filter blind spot, offsets 0..20 (tetra_burst.c:288-294); only word 0 */
+						const uint32_t prev = rel > 0 ? (x0 >> (rel - 1)) & 1u : 0u;
+						ok = (tab->blind_ok[seq][prev] >> rel) & 1u;
+					}
+					if (ok) {
+						const uint32_t ty = seq == 0 ? (uint32_t)TS_SYNC : seq == 1 ? (uint32_t)TS_NORM_1 : (uint32_t)TS_NORM_2;
+						atomicMin(&first[s], (rel << 3) | ty);
+					}
+				}
+			}
+		}
+		__syncthreads();
+		/* ---- decide: one thread per slot (warps 0 and 1) */
+		if (tid < CT_SLOTS) {
+			const bool have = tid < t.ns;
+			const uint32_t k = t.k0 + tid;
+			const uint64_t ak = g.a0 + 510ull * k;
+			const unsigned W = have ? slot_window32(wg, k) : 0;
+			const uint32_t f = first[tid];
+			int rc = -1;
+			unsigned off = 0;
+			if (have && f != 0xffffffffu) { rc = (int)(f & 7u); off = f >> 3; }
+			/* exact warp-cooperative search for the slots the fast path could not settle */
+			unsigned todo = __ballot_sync(FULL, have && rc < 0);
+			while (todo) {
+				const int src = __ffs((int)todo) - 1;
+				todo &= todo - 1;
+				const uint64_t off_b = __shfl_sync(FULL, (uint64_t)(ak - g.base_bit), src);
+				const unsigned Ws = __shfl_sync(FULL, W, src);
+				unsigned o2 = 0;
+				const uint32_t mask = (1u << TS_SYNC) | (1u << TS_NORM_1) | (1u << TS_NORM_2);
+				const int r2 = find_train_seq_warp(g.bits + off_b, end, Ws, mask, tab, &o2, nullptr);
+				if ((int)lane == src) { rc = r2; off = o2; }
+			}
+			int kind = KIND_NONE;
+			bool unlock = false;
+			if (have) {
+				if (rc == TS_SYNC) { if (off == 214) kind = KIND_SB; else unlock = true; }
+				else if (rc == TS_NORM_1) { if (off == 244) kind = KIND_NDB_F; }
+				else if (rc == TS_NORM_2) { if (off == 244) kind = KIND_NDB_2; }
+				else unlock = true;
+			}
+			/* SYNC bursts are listed so that the SB1 pass only touches them (one atomic per warp) */
+			{
+				const unsigned m = __ballot_sync(FULL, kind == KIND_SB);
+				if (m) {
+					uint32_t base = 0;
+					if (lane == (unsigned)(__ffs((int)m) - 1)) base = atomicAdd(sb_count, (uint32_t)__popc(m));
+					base = __shfl_sync(FULL, base, __ffs((int)m) - 1);
+					if (kind == KIND_SB) sb_list[base + __popc(m & ((1u << lane) - 1))] = k;
+				}
+			}
+			if (have) {
+				SlotWs w;
+				w.sb1_t1[0] = 0; w.sb1_t1[1] = 0; w.sb_code = 0;
+				w.find_off = (uint16_t)off; w.window = (uint16_t)W;
+				w.find_rc = (int8_t)rc; w.good_sb = 0; w.kind = (uint8_t)kind; w.unlock = unlock;
+				w.tn = w.fn = w.mn = w.cc = 0; w.mcc = w.mnc = 0; w.pad = 0;
+				ws[k] = w;
+			}
+		}
+		__syncthreads();
+	}
+}
+#undef TB_MATCH_PAIR
+
+}  // namespace tb
