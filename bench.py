@@ -233,11 +233,11 @@ def run_ours(args, rank, world, local_rank):
     # ---- device-resident: value + per-kernel device times (CUDA events on the launching stream)
     barrier()
     t0 = time.perf_counter()
-    tim = {"total": 0.0, "classify": 0.0, "scan": 0.0, "decode": 0.0}
+    tim = {"total": 0.0, "classify": 0.0, "scan": 0.0, "decode": 0.0, "search": 0.0}
     for _ in range(args.steps):
         step_dev()
         t = g.timing()
-        tim["total"] += t.total_ms; tim["classify"] += t.classify_ms; tim["scan"] += t.scan_ms; tim["decode"] += t.decode_ms
+        tim["total"] += t.total_ms; tim["classify"] += t.classify_ms; tim["scan"] += t.scan_ms; tim["decode"] += t.decode_ms; tim["search"] += t.search_ms
     barrier()
     wall = time.perf_counter() - t0
     launches = g.stats().kernel_launches * args.steps     # stats restart with every TB200_FRESH call
@@ -285,8 +285,8 @@ def run_ours(args, rank, world, local_rank):
     stage_ms = min(stage_ms[1:])
     del d5, d3
 
-    wall, wall_e2e, wall_e2e_packed, t_total, t_cls, t_scan, t_dec = reduce_max(
-        dist, [wall, wall_e2e, wall_e2e_packed, tim["total"], tim["classify"], tim["scan"], tim["decode"]], "cuda")
+    wall, wall_e2e, wall_e2e_packed, t_total, t_cls, t_scan, t_dec, t_search = reduce_max(
+        dist, [wall, wall_e2e, wall_e2e_packed, tim["total"], tim["classify"], tim["scan"], tim["decode"], tim["search"]], "cuda")
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -304,28 +304,44 @@ def run_ours(args, rank, world, local_rank):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     per_launch_dec_ms = t_dec / args.steps
     per_launch_cls_ms = t_cls / args.steps
+    per_launch_search_ms = t_search / args.steps
     alg_bytes = (BYTES_PER_BURST_IN + BYTES_PER_BURST_OUT) * (n - 1)
     dec_gbs = alg_bytes / (per_launch_dec_ms * 1e-3) / 1e9
-    cls_gbs = BYTES_PER_BURST_IN * (n - 1) / (per_launch_cls_ms * 1e-3) / 1e9
+    search_gbs = BYTES_PER_BURST_IN * (n - 1) / (per_launch_search_ms * 1e-3) / 1e9
     stage_gbs = 2 * 432 * nblk / (stage_ms * 1e-3) / 1e9
     int_peak = g.lib.tb200_measure_int_peak(g.h)
     acs_rate = ACS_PER_BURST * (n - 1) / (per_launch_dec_ms * 1e-3)
     dec_name = "k_decode_warp" if args.viterbi == 0 else "k_decode_lane"
+    # per-launch constants read from the committed ncu capture of this same workload (profiles/kernel_constants.json)
+    kc = {}
+    try:
+        kc = json.load(open(os.path.join(ROOT, "profiles", "kernel_constants.json")))
+    except Exception:
+        pass
+    kdec, kcls = kc.get(dec_name, {}), kc.get("k_classify_tile", {})
+    inst_per_acs = (kdec["thread_inst_per_launch"] / (ACS_PER_BURST * (n - 1))) if "thread_inst_per_launch" in kdec else None
     roofline = {"kernel": dec_name, "bound": "hbm",
-                "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak, "traffic": None,
+                "achieved": dec_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": dec_gbs / hbm_peak,
+                "traffic": kdec.get("dram_bytes_per_launch"),
                 "peak_source": peak_src, "ms_per_launch": per_launch_dec_ms,
                 "algorithmic_bytes_per_burst": BYTES_PER_BURST_IN + BYTES_PER_BURST_OUT,
-                "note": "the decode kernel is integer-ALU bound (16-state add-compare-select), not HBM bound: int_alu is its real roofline",
-                "int_alu": {"acs_per_s": acs_rate, "int_ops_per_s": acs_rate * 4, "measured_int_peak_ops_per_s": int_peak,
-                            "frac": (acs_rate * 4 / int_peak) if int_peak else None,
-                            "how": "4672 ACS x 4 integer results per SCH/F burst / kernel time, against a register-only add+min kernel (both integer pipes)"},
-                "sync_search": {"kernel": "k_classify_tma (+k_sb1_lane)" if args.viterbi else "k_classify", "bound": "hbm", "achieved": cls_gbs,
-                                "peak": hbm_peak, "unit": "GB/s", "frac": cls_gbs / hbm_peak, "ms_per_launch": per_launch_cls_ms,
-                                "algorithmic_bytes_per_burst": BYTES_PER_BURST_IN},
-                "descramble_deinterleave_stage": {"kernel": "k_descramble_deinterleave", "bound": "hbm", "achieved": stage_gbs,
+                "note": "the decode kernel is integer-issue bound (16-state add-compare-select), not HBM bound: int_alu is its real roofline",
+                "int_alu": {"acs_per_s": acs_rate, "thread_inst_per_acs": inst_per_acs,
+                            "int_inst_per_s": (acs_rate * inst_per_acs) if inst_per_acs else None,
+                            "measured_int_peak_inst_per_s": int_peak,
+                            "frac": (acs_rate * inst_per_acs / int_peak) if (inst_per_acs and int_peak) else None,
+                            "how": "thread instructions the kernel executes per launch (ncu smsp__inst_executed x 32, profiles/kernel_constants.json) / kernel time, "
+                                   "against a register-only add+min kernel that keeps both integer pipes busy (tb200_measure_int_peak); "
+                                   "4672 add-compare-select per SCH/F burst, each a packed add + VIADDMNMX.U16x2 shared by two trellises"},
+                "sync_search": {"kernel": "k_classify_tile" if args.viterbi else "k_classify", "bound": "hbm", "achieved": search_gbs,
+                                "peak": hbm_peak, "unit": "GB/s", "frac": search_gbs / hbm_peak, "ms_per_launch": per_launch_search_ms,
+                                "algorithmic_bytes_per_burst": BYTES_PER_BURST_IN, "traffic": kcls.get("dram_bytes_per_launch"),
+                                "with_sb1_pass_ms": per_launch_cls_ms},
+                "descramble_deinterleave_stage": {"kernel": "k_stage_tma", "bound": "hbm", "achieved": stage_gbs,
                                                   "peak": hbm_peak, "unit": "GB/s", "frac": stage_gbs / hbm_peak, "ms_per_launch": stage_ms,
                                                   "algorithmic_bytes_per_block": 864, "blocks": nblk},
-                "step_share": {"classify": t_cls / t_total, "scan": t_scan / t_total, "decode": t_dec / t_total}}
+                "step_share": {"classify": t_cls / t_total, "scan": t_scan / t_total, "decode": t_dec / t_total},
+                "constants_from": kc.get("source")}
     cores = os.cpu_count() or 1
     cpu = cpu_reference_rate(20000, cores) if (world == 1 and not args.no_cpu) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

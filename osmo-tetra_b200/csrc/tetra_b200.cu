@@ -269,8 +269,27 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 			return bail("cudaOccupancyMaxActiveBlocksPerMultiprocessor");
 #endif
 		ctx->lane_ctas = (unsigned)(ctx->sm_count * per_sm);
-		if (cudaMalloc((void **)&ctx->d_lane_scratch, (size_t)ctx->lane_ctas * lane_scratch_words_per_cta(LANE_NT) * sizeof(uint32_t)) != cudaSuccess)
+		const size_t scratch_bytes = (size_t)ctx->lane_ctas * lane_scratch_words_per_cta(LANE_NT) * sizeof(uint32_t);
+		if (cudaMalloc((void **)&ctx->d_lane_scratch, scratch_bytes) != cudaSuccess)
 			return bail("cudaMalloc");
+#ifndef TB_SIMT_EMULATION
+		/* The survivor histories are written once and read once ~100 us later by the same CTA: keep them in the
+		 * L2 set-aside so they are not written back to HBM in between (best effort, never fatal). */
+		if (!getenv("TB200_NO_L2_PERSIST") && prop.persistingL2CacheMaxSize > 0) {
+			const size_t set_aside = std::min<size_t>(scratch_bytes, (size_t)prop.persistingL2CacheMaxSize);
+			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
+				cudaStreamAttrValue av;
+				memset(&av, 0, sizeof(av));
+				av.accessPolicyWindow.base_ptr = ctx->d_lane_scratch;
+				av.accessPolicyWindow.num_bytes = std::min<size_t>(scratch_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+				av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)set_aside / (double)av.accessPolicyWindow.num_bytes);
+				av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+				av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+				cudaStreamSetAttribute(ctx->s_compute, cudaStreamAttributeAccessPolicyWindow, &av);
+			}
+			cudaGetLastError();
+		}
+#endif
 	}
 #ifndef TB_SIMT_EMULATION
 	if (cudaFuncSetAttribute(k_stage_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM) != cudaSuccess)

@@ -373,7 +373,7 @@ __device__ __forceinline__ void load_slot_bits(const uint32_t *__restrict__ slot
 	const uint4 *p = reinterpret_cast<const uint4 *>(slot_bits + k * 16);
 #pragma unroll
 	for (int i = 0; i < 4; ++i) {
-		const uint4 v = p[i];
+		const uint4 v = __ldcs(p + i);          /* read once: streaming, keeps L2 for the history scratch */
 		bw[4 * i] = v.x; bw[4 * i + 1] = v.y; bw[4 * i + 2] = v.z; bw[4 * i + 3] = v.w;
 	}
 }
@@ -560,12 +560,12 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 #pragma unroll
 				for (int c = 0; c < 18; ++c) {
 					const uint32_t hbits = (outw[c >> 1] >> (16 * (c & 1))) & 0xffff;
-					dst[c] = make_uint4(unpack4(hbits), unpack4(hbits >> 4), unpack4(hbits >> 8), unpack4(hbits >> 12));
+					__stcs(dst + c, make_uint4(unpack4(hbits), unpack4(hbits >> 4), unpack4(hbits >> 8), unpack4(hbits >> 12)));
 				}
 			}
 			if (a.type1_packed) {
 #pragma unroll
-				for (int i = 0; i < 9; ++i) a.type1_packed[ko * TYPE1_WORDS + i] = outw[i];
+				for (int i = 0; i < 9; ++i) __stcs(a.type1_packed + ko * TYPE1_WORDS + i, outw[i]);
 			}
 			SlotOut o;
 			o.slot_bit = (uint32_t)(a.a0 + (uint64_t)SLOT_BITS * k[h]);

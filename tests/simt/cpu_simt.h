@@ -163,6 +163,8 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t s)
 	return r;
 }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+template <typename T> static inline void __stcs(T *p, T v) { *p = v; }
 static inline unsigned umin(unsigned a, unsigned b) { return a < b ? a : b; }
 static inline unsigned umax(unsigned a, unsigned b) { return a > b ? a : b; }
 

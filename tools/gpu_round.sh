@@ -11,6 +11,6 @@ timeout 600 python bench.py --viterbi $VIT > gpurun_out/bench.json 2> gpurun_out
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2>> gpurun_out/bench.err; tail -c 600 gpurun_out/bench_ref.json
 if [ "${NCU:-1}" = "1" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --viterbi $VIT > gpurun_out/ncu_launch.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_decode|k_classify' -s 4 -c 2 -f -o gpurun_out/prof python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --viterbi $VIT > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_decode_lane|k_classify_tile' -s 2 -c 2 -f -o gpurun_out/prof python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --viterbi $VIT > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out/
 fi

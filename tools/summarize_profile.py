@@ -21,6 +21,21 @@ if os.path.exists(rep):
     idx = {h: i for i, h in enumerate(hdr)}
     lines.append("`ncu --set full --clock-control none --import-source on -k regex:'k_decode|k_classify' python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu`")
     lines.append("(10^6-burst config-2 stream per launch; cold-cache serialised replays: compare shares, not absolutes)")
+    consts = {"source": f"profiles/{tag}_summary.md (ncu --set full, 10^6-burst config-2 launch)"}
+    def _bytes(v, unit):
+        return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
+    for r in rows[2:]:
+        kname = r[idx['Kernel Name']].split("(")[0].split("::")[-1]
+        if float(r[idx["gpu__time_duration.sum"]]) > consts.get(kname, {}).get("_dur", 0):
+            consts[kname] = {"_dur": float(r[idx["gpu__time_duration.sum"]]),
+                             "dram_bytes_per_launch": _bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) +
+                                                      _bytes(r[idx["dram__bytes_write.sum"]], units[idx["dram__bytes_write.sum"]]),
+                             "thread_inst_per_launch": float(r[idx["smsp__inst_executed.sum"]]) * 32,
+                             "ncu_duration_us": float(r[idx["gpu__time_duration.sum"]])}
+    for v in consts.values():
+        if isinstance(v, dict):
+            v.pop("_dur", None)
+    json.dump(consts, open(os.path.join(out, "kernel_constants.json"), "w"), indent=1)
     for r in rows[2:]:
         lines += ["", f"## {r[idx['Kernel Name']]}", "", "| metric | value | unit |", "|---|---|---|"]
         for k in KEYS:
