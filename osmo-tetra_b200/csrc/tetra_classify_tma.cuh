@@ -88,8 +88,9 @@ struct WinGeom {
 
 __device__ __forceinline__ unsigned slot_window32(const WinGeom &g, uint32_t k)
 {
-	const uint32_t num = g.rel0 + 510u * k + 510u + g.chunk - 1;      /* < 2^30 for pieces up to 2^20 slots */
-	const uint32_t q = g.chunk == 64 ? num >> 6 : num / g.chunk;
+	/* 64-bit: a shard of the sharded path can hold more than 2^32 / 510 slots in one launch */
+	const uint64_t num = (uint64_t)g.rel0 + 510ull * k + 510u + g.chunk - 1;
+	const uint64_t q = g.chunk == 64 ? num >> 6 : (num <= 0xffffffffull ? (uint64_t)((uint32_t)num / g.chunk) : num / g.chunk);
 	uint64_t c = g.c00 + q;
 	const uint64_t lo = g.cmin + k;
 	if (c < lo) c = lo;

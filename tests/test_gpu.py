@@ -330,3 +330,77 @@ def test_config3_full_size(gpu, orc):
         keep = want["slot_bit"] < 510 * 198
         ok, msg = T.records_equal(want[keep], got[got["slot_bit"] < 510 * 198])
         assert ok, (k0, msg)
+
+
+def test_config4_full_size(gpu, orc):
+    """config 4 at full size: 10^8 bursts, every other one a SYNC burst announcing a random cell
+    (random MCC / MNC / colour code), so the scrambling code of every block is learned from the
+    stream itself; the AACH is an RM(30,14) code word scrambled with that code.  51 GB of input,
+    generated on the device.  Checks: both decoder forms agree bit for bit over the whole run, the
+    cell code each slot reports is the one announced by the latest CRC-good SB1 (recomputed on the
+    host from the delivered SB1 type-1 bits), and windows replayed on the CPU oracle give the same
+    records."""
+    import torch
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs ~65 GB of device memory")
+    n = 100_000_000
+    cfg = T.GenCfg(seed=0x7E7A0004, sb_period=2, lead_sb=2, ndb2_per_256=64, ber_per_65536=655,
+                   random_cell=1, lead_in_bits=333)
+    d, nbits = _gen_on_gpu(gpu, cfg, n)
+    ms = n + 16
+    out = {}
+    for variant in (T.VITERBI_LANE, T.VITERBI_WARP):
+        gpu.set_options(chunk_bits=64, viterbi=variant, pipeline_slots=0, output=T.OUT_PACKED)
+        ds = torch.zeros(ms * 16, dtype=torch.uint8, device="cuda")
+        dp = torch.zeros(ms * 9, dtype=torch.int32, device="cuda")
+        ns = gpu.lib.tb200_rx_stream_dev(gpu.h, C.c_void_p(d.data_ptr()), nbits, 3, C.c_void_p(ds.data_ptr()),
+                                         None, C.c_void_p(dp.data_ptr()), ms)
+        assert ns >= 0, gpu.err()
+        out[variant] = (ns, ds, dp, gpu.stats())
+    ns, ds, dp, st = out[T.VITERBI_LANE]
+    ns0, ds0, dp0, st0 = out[T.VITERBI_WARP]
+    assert ns == ns0 and torch.equal(ds[:ns * 16], ds0[:ns * 16]) and torch.equal(dp[:ns * 9], dp0[:ns * 9])
+    del ds0, dp0
+    assert st.lock_losses == st0.lock_losses
+    # a SYNC pattern at a wrong offset (expected ~0.1 times in 10^8 random bursts) costs lock and a few slots
+    assert n - 1 - 64 * (st.lock_losses + 1) <= ns <= n - 1
+    flags = ds.view(torch.int32).view(-1, 4)[:ns, 3].cpu().numpy().view(np.uint32) >> 24
+    kinds = np.bincount(flags & 3, minlength=4)
+    assert kinds[0] < 3e-4 * n and kinds[1] > 0.49 * n and kinds[3] > 0.1 * n
+    # the cell code of slot k is the one announced by the latest CRC-good SB1 at or before k: check a
+    # contiguous million slots on the host from the delivered SB1 type-1 bits (cc [4,10), mcc [31,41), mnc [41,55))
+    lo = 37_000_000
+    sl = ds[lo * 16:(lo + 1_000_000) * 16].cpu().numpy().view(T.SLOT_DTYPE)
+    pk = dp[lo * 9:(lo + 1_000_000) * 9].cpu().numpy().view(np.uint32).reshape(-1, 9)
+    bits2 = ((pk[:, :2, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(-1, 64).astype(np.uint32)
+
+    def field(a, b):
+        w = 1 << np.arange(b - a - 1, -1, -1, dtype=np.uint32)
+        return (bits2[:, a:b] * w).sum(axis=1)
+    code_here = (((field(4, 10) & 0x3f) | (field(41, 55) << 6) | (field(31, 41) << 20)) << 2) | 3
+    good = ((sl["flags"] & 3) == 1) & ((sl["flags"] & 4) != 0)
+    idx = np.where(good, np.arange(sl.size), -1)
+    last = np.maximum.accumulate(idx)
+    known = last >= 0
+    assert known.sum() > 0.99 * sl.size
+    assert np.array_equal(sl["scrambling_code"][known], code_here[last[known]].astype(np.uint32))
+    # CPU replay of windows that start at a SYNC burst (even k0): the oracle gives up the first burst for
+    # lock, decodes k0+1 without a cell code, and is in step with us from k0+2 (an SB) on
+    rng = np.random.default_rng(4)
+    if st.lock_losses == 0:
+        for k0 in [2 * int(x) for x in rng.integers(1, n // 2 - 200, 4)]:
+            a = 333 + 510 * k0
+            win = d[a:a + 510 * 200].cpu().numpy()
+            orc.reset(); orc.feed(win, 64)
+            want = orc.records()
+            want = want[want["slot_bit"] >= 510 * 2]
+            sel = np.arange(k0 + 2 - 1, k0 + 199 - 1)           # slot i of the run is burst i + 1
+            s = ds[int(sel[0]) * 16:(int(sel[-1]) + 1) * 16].cpu().numpy().view(T.SLOT_DTYPE).copy()
+            p = dp[int(sel[0]) * 9:(int(sel[-1]) + 1) * 9].cpu().numpy().view(np.uint32).reshape(-1, 9)
+            assert np.array_equal(s["slot_bit"], ((333 + 510 * (sel + 1)) & 0xffffffff).astype(np.uint32))
+            s["slot_bit"] = (510 * (sel + 1 - k0)).astype(np.uint32)
+            unp = ((p[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(s.size, 288).astype(np.uint8)
+            got = gpu.expand_records(s, unp)
+            keep = want["slot_bit"] < 510 * 198
+            ok, msg = T.records_equal(want[keep], got[got["slot_bit"] < 510 * 198])
+            assert ok, (k0, msg)

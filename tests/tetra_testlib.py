@@ -622,3 +622,74 @@ def check_stream_against(records, events, slots, got_records):
     assert np.array_equal(lev["buf_start_bit"], slots["slot_bit"])
     found = lev["rc"] >= 0
     assert np.array_equal(lev["offset"][found], slots["find_off"][found])
+
+
+# ------------------------------------------------------------------ one stream over several GPUs
+
+def shard_plan(n_slots_total, world):
+    """contiguous slot ranges per rank (the last ranks get the remainder)"""
+    per = (n_slots_total + world - 1) // world
+    return [(min(r * per, n_slots_total), min((r + 1) * per, n_slots_total)) for r in range(world)]
+
+
+SHARD_HALO = 4096 + 64        # look-ahead of the search window (tetra_burst_sync.c:117) + read-ahead
+
+
+def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=False, timers=None):
+    """BASELINE config 5: ONE stream, held by rank 0 (device tensor d_full, None elsewhere), decoded by
+    `world` ranks.  Rank 0 acquires lock on the head of the stream, scatters contiguous slot ranges
+    (+ look-ahead halo) with NCCL send/recv, every rank runs pass 1 (search, classification, SB1) on its
+    shard, the 32-byte summaries are all-gathered (the only exchange step of the path: the cell state),
+    every rank derives its carry-in and runs pass 2.  Results stay rank-local.
+    Returns (k0, k1, a0, d_slots, d_type1 or None, d_packed, summaries)."""
+    import torch
+    meta = torch.zeros(4, dtype=torch.int64, device=device)
+    if rank == 0:
+        ok, a0, cmin = g.find_lock(d_full.data_ptr(), n_bits)
+        meta[:] = torch.tensor([int(ok), a0, cmin, n_bits], dtype=torch.int64)
+    if world > 1:
+        dist.broadcast(meta, 0)
+    ok, a0, cmin, n_bits = (int(x) for x in meta.cpu())
+    if not ok:
+        raise RuntimeError("no lock on the head of the stream")
+    n_total = (n_bits - a0) // 510
+    plan = shard_plan(n_total, world)
+    k0, k1 = plan[rank]
+    n = k1 - k0
+
+    def span(r):
+        lo = a0 + 510 * plan[r][0]
+        hi = min(n_bits, a0 + 510 * plan[r][1] + SHARD_HALO)
+        return lo, max(hi, lo)
+    if timers is not None:
+        torch.cuda.synchronize(); timers["t_scatter0"] = __import__("time").perf_counter()
+    lo, hi = span(rank)
+    if rank == 0:
+        shard = d_full[lo:hi]
+        if world > 1:
+            reqs = [dist.isend(d_full[span(r)[0]:span(r)[1]], r) for r in range(1, world) if span(r)[1] > span(r)[0]]
+            for q in reqs:
+                q.wait()
+    else:
+        shard = torch.empty(hi - lo + 64, dtype=torch.uint8, device=device)[:hi - lo]
+        if hi > lo:
+            dist.recv(shard, 0)
+    if timers is not None:
+        torch.cuda.synchronize(); timers["t_scatter1"] = __import__("time").perf_counter()
+    s = g.shard_pass1(shard.data_ptr(), lo, hi - lo, lo, cmin + k0, n_bits, n)
+    mine = torch.frombuffer(bytearray(bytes(s)), dtype=torch.uint8).to(device)
+    gathered = [torch.zeros(32, dtype=torch.uint8, device=device) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(gathered, mine)
+    else:
+        gathered[0] = mine
+    summaries = [ShardSummary.from_buffer_copy(bytes(t.cpu().numpy().tobytes())) for t in gathered]
+    carry = g.shard_carry_in(summaries, rank)
+    d_slots = torch.zeros(max(n, 1) * 16, dtype=torch.uint8, device=device)
+    d_t1 = torch.zeros(max(n, 1) * 288, dtype=torch.uint8, device=device) if want_type1 else None
+    d_pk = torch.zeros(max(n, 1) * 9, dtype=torch.int32, device=device)
+    got = g.shard_pass2(carry, d_slots.data_ptr(), d_t1.data_ptr() if want_type1 else None, d_pk.data_ptr())
+    assert got == n, (got, n)
+    if timers is not None:
+        torch.cuda.synchronize(); timers["t_done"] = __import__("time").perf_counter()
+    return k0, k1, a0, d_slots, d_t1, d_pk, summaries
