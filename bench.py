@@ -344,6 +344,7 @@ def run_ours(args, rank, world, local_rank):
                 "constants_from": kc.get("source")}
     cores = os.cpu_count() or 1
     cpu = cpu_reference_rate(20000, cores) if (world == 1 and not args.no_cpu) else None
+    others = other_configs(g, T, torch, C) if (world == 1 and not args.no_e2e) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
@@ -360,7 +361,116 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline, "clocks": clocks}
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if others is not None:
+        line["other_configs"] = others
     print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def other_configs(g, T, torch, C):
+    """device-resident bursts/s on the shapes of BASELINE configs 3 and 4 (not the headline: context only)"""
+    out = {}
+    shapes = {"config3: mixed SB/NDB(1 and 2 channel) bursts, 333-bit lead-in, lock FSM, random cells, BER 1e-2":
+                  dict(sb_period=18, lead_sb=2, ndb2_per_256=64, ber_per_65536=655, random_cell=1, lead_in_bits=333),
+              "config4: every other burst a SYNC burst announcing a random cell (per-burst scrambling codes), AACH RM(30,14), BER 1e-2":
+                  dict(sb_period=2, lead_sb=2, ndb2_per_256=64, ber_per_65536=655, random_cell=1, lead_in_bits=333)}
+    n = 2_000_000
+    for name, kw in shapes.items():
+        cfg = T.GenCfg(seed=0x7E7A0003, **kw)
+        nbits = 510 * n + kw["lead_in_bits"]
+        d = torch.zeros(nbits + 64, dtype=torch.uint8, device="cuda")
+        assert g.lib.tb200_gen_stream_dev(g.h, C.byref(cfg), 0, n, C.c_void_p(d.data_ptr()), 1) == 0, g.err()
+        ms = n + 16
+        ds = torch.zeros(ms * 16, dtype=torch.uint8, device="cuda")
+        dt = torch.zeros(ms * 288, dtype=torch.uint8, device="cuda")
+        g.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, output=T.OUT_UNPACKED, pipeline_slots=0, profile=0)
+        def step():
+            ns = g.lib.tb200_rx_stream_dev(g.h, C.c_void_p(d.data_ptr()), nbits, 3, C.c_void_p(ds.data_ptr()),
+                                           C.c_void_p(dt.data_ptr()), None, ms)
+            assert ns > 0.99 * n, (ns, g.err())
+            return ns
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        k = 20
+        for _ in range(k):
+            ns = step()
+        torch.cuda.synchronize()
+        dt_s = time.perf_counter() - t0
+        st = g.stats()
+        flags = ds[:ns * 16].view(-1, 16)[:, 15]
+        kinds = torch.bincount((flags & 3).to(torch.int64), minlength=4).cpu().tolist()
+        out[name] = {"value": ns * k / dt_s, "unit": UNIT, "bursts_per_step": n, "slots_decoded": int(ns),
+                     "kinds": {"dropped": kinds[0], "sync": kinds[1], "ndb_schf": kinds[2], "ndb_two_blocks": kinds[3]},
+                     "lock_losses": int(st.lock_losses), "ms_per_step": dt_s / k * 1e3}
+        del d, ds, dt
+    return out
+
+
+def run_config5(args, rank, world, local_rank):
+    """BASELINE config 5: ONE stream of --total-bursts bursts (config-4 shape) held by rank 0, scattered over the
+    ranks with NCCL send/recv, pass 1 per shard, all-gather of the 32-byte cell-state summaries, pass 2.
+    Strong scaling: the total is fixed.  The timed region of `value` contains the scatter; `decode_only`
+    excludes it (shards already resident on their GPUs)."""
+    import torch
+    import tetra_testlib as T
+    import __graft_entry__ as G
+    if not os.path.exists(G.LIB):
+        G.build()
+    G.load_package().load_library()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    g = T.B200(device=local_rank)
+    n = args.total_bursts
+    cfg = T.GenCfg(seed=0x7E7A0005, sb_period=2, lead_sb=2, ndb2_per_256=64, ber_per_65536=655, random_cell=1, lead_in_bits=333)
+    nbits = 510 * n + 333
+    full = None
+    if rank == 0:
+        full = torch.zeros(nbits + 64, dtype=torch.uint8, device=dev)
+        assert g.lib.tb200_gen_stream_dev(g.h, C.byref(cfg), 0, n, C.c_void_p(full.data_ptr()), 1) == 0, g.err()
+        full = full[:nbits]
+    g.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, output=T.OUT_PACKED)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    tot_s = dec_s = 0.0
+    slots_total = 0
+    for it in range(args.warmup + args.steps):
+        if it == args.warmup and rank == 0:
+            sampler.start()
+        tm = {}
+        barrier()
+        t0 = time.perf_counter()
+        k0, k1, a0, d_slots, _, d_pk, summ = T.sharded_decode(g, dist, rank, world, full, nbits, dev, timers=tm)
+        barrier()
+        t1 = time.perf_counter()
+        if it >= args.warmup:
+            tot_s += t1 - t0
+            dec_s += (t1 - t0) - (tm["t_scatter1"] - tm["t_scatter0"])
+            slots_total = sum(s.n_slots for s in summ)
+        del d_slots, d_pk
+    clocks = sampler.stop() if rank == 0 else None
+    tot_s, dec_s = reduce_max(dist, [tot_s, dec_s], "cuda")
+    if rank == 0:
+        line = {"metric": METRIC, "value": slots_total * args.steps / tot_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": {"workload": f"config5: one stream of {n} bursts (config-4 shape) on rank 0, NCCL scatter of contiguous shards + "
+                                       "all-gather of 32-byte cell-state summaries", "total_bursts": n,
+                           "l2": "inputs larger than L2", "parallelism": f"one stream sharded x{world}", "output": "slot records + packed type-1 bits, rank-local"},
+                "decode_only": {"value": slots_total * args.steps / dec_s, "unit": UNIT, "ms_per_step": dec_s / args.steps * 1e3,
+                                "note": "scatter excluded (wall-clock between device synchronisations, max over ranks)"},
+                "scatter_bytes_per_step": int((nbits) * (world - 1) / world), "clocks": clocks}
+        print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
@@ -374,12 +484,19 @@ def main():
     ap.add_argument("--viterbi", type=int, default=1, help="0 warp-shuffle (one warp per burst), 1 lane (two trellises per thread)")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs: skip the host-buffer leg")
     ap.add_argument("--no-cpu", action="store_true", help="profiling runs: skip the CPU baseline leg")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
+                    help="config2: headline (independent streams per GPU); config5: one stream scattered over the GPUs with NCCL")
+    ap.add_argument("--total-bursts", type=int, default=100_000_000, help="config5: bursts in the one stream")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "config5":
+        if args.steps == 100:
+            args.steps = 5
+        run_config5(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
 

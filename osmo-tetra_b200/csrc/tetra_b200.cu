@@ -273,9 +273,11 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 		if (cudaMalloc((void **)&ctx->d_lane_scratch, scratch_bytes) != cudaSuccess)
 			return bail("cudaMalloc");
 #ifndef TB_SIMT_EMULATION
-		/* The survivor histories are written once and read once ~100 us later by the same CTA: keep them in the
-		 * L2 set-aside so they are not written back to HBM in between (best effort, never fatal). */
-		if (!getenv("TB200_NO_L2_PERSIST") && prop.persistingL2CacheMaxSize > 0) {
+		/* Optional (TB200_L2_PERSIST=1): pin the survivor histories (written once, read once ~100 us later by the
+		 * same CTA) in the L2 set-aside.  Measured: decode DRAM traffic 805 -> 551 MB per 10^6 bursts, but the
+		 * decode kernel is not DRAM bound (no gain) and the set-aside costs the HBM-bound kernels of the same
+		 * context 10-50 % (search 0.110 -> 0.120 ms, stand-alone stage 6.1 -> 2.7 TB/s), so it is off by default. */
+		if (getenv("TB200_L2_PERSIST") && prop.persistingL2CacheMaxSize > 0) {
 			const size_t set_aside = std::min<size_t>(scratch_bytes, (size_t)prop.persistingL2CacheMaxSize);
 			if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
 				cudaStreamAttrValue av;

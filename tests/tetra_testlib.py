@@ -685,9 +685,9 @@ def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=Fals
         gathered[0] = mine
     summaries = [ShardSummary.from_buffer_copy(bytes(t.cpu().numpy().tobytes())) for t in gathered]
     carry = g.shard_carry_in(summaries, rank)
-    d_slots = torch.zeros(max(n, 1) * 16, dtype=torch.uint8, device=device)
-    d_t1 = torch.zeros(max(n, 1) * 288, dtype=torch.uint8, device=device) if want_type1 else None
-    d_pk = torch.zeros(max(n, 1) * 9, dtype=torch.int32, device=device)
+    d_slots = torch.empty(max(n, 1) * 16, dtype=torch.uint8, device=device)
+    d_t1 = torch.empty(max(n, 1) * 288, dtype=torch.uint8, device=device) if want_type1 else None
+    d_pk = torch.empty(max(n, 1) * 9, dtype=torch.int32, device=device)
     got = g.shard_pass2(carry, d_slots.data_ptr(), d_t1.data_ptr() if want_type1 else None, d_pk.data_ptr())
     assert got == n, (got, n)
     if timers is not None:
