@@ -107,12 +107,21 @@ const char *tb200_version(void);
 #define TB200_VITERBI_WARP  0   /* one warp per burst, warp-shuffle ACS butterflies */
 #define TB200_VITERBI_LANE  1   /* one lane per coded block, registers-only ACS */
 
+/* how the bit stream handed to tb200_rx_stream_* is encoded */
+#define TB200_IN_BYTES   0   /* one bit per byte: the file format tetra-rx reads (tetra-rx.c:82-95), float_to_bits' output */
+#define TB200_IN_PACKED  1   /* eight bits per byte, stream bit i = byte i>>3, bit i&7 (4-byte aligned buffer) */
+#define TB200_IN_F32SYM  2   /* one float32 per symbol, the demodulator output float_to_bits reads (float_to_bits.c:128-164):
+                              * two hard bits per symbol, sliced on the device exactly like process_sym_fl + sym_int2bits
+                              * (float_to_bits.c:33-72) without the optional pseudo-AFC (-a); n_bits = 2 * symbols */
+
 struct tb200_options {
 	uint32_t chunk_bits;        /* read() size the caller models; tetra-rx.c:83 uses 64. 1..296 */
 	uint32_t output;            /* TB200_OUT_* bit mask */
 	uint32_t viterbi;           /* TB200_VITERBI_* */
 	uint32_t pipeline_slots;    /* slots per pipelined piece in the host-buffer path (0 = default) */
 	uint32_t profile;           /* 1: bracket every kernel with CUDA events on its stream (tb200_get_timing) */
+	uint32_t input;             /* TB200_IN_*; the packed / symbol formats need the whole stream in one call
+	                             * (TB200_FRESH | TB200_FINAL) and the lane kernels */
 };
 void tb200_default_options(struct tb200_options *opt);
 int  tb200_set_options(tb200_ctx *ctx, const struct tb200_options *opt);

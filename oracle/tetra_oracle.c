@@ -751,3 +751,28 @@ void orc_gen_stream(const struct orc_gen_cfg *c, uint64_t k0, uint64_t n, uint8_
 	for (uint64_t i = 0; i < n; i++)
 		orc_gen_burst(c, k0 + i, out + 510 * i);
 }
+
+/* ------------------------------------------------------------ symbol slicer --
+ * float_to_bits.c, the program between the demodulator and tetra-rx (receiver1:8):
+ * one float per pi/4-DQPSK symbol (phase step in units of pi/4) -> two unpacked bits.
+ * process_sym_fl (float_to_bits.c:33-50): strict comparisons, > 2 -> 3, > 0 -> 1, < -2 -> -3, else -1
+ * (so 2.0 -> 1, 0.0 -> -1, -2.0 -> -1, NaN -> -1); sym_int2bits (:52-76): 3 -> 0,1   1 -> 0,0
+ * -3 -> 1,1   -1 -> 1,0.  The optional pseudo-AFC (-a, :138-147) is a serial float IIR and is
+ * not restated: it is off by default in the reference and out of scope for the GPU path. */
+void orc_float_to_bits(const float *sym, size_t n, uint8_t *bits)
+{
+	for (size_t i = 0; i < n; i++) {
+		const float fl = sym[i];
+		int s;
+		if (fl > 2) s = 3;
+		else if (fl > 0) s = 1;
+		else if (fl < -2) s = -3;
+		else s = -1;
+		switch (s) {
+		case -3: bits[2 * i] = 1; bits[2 * i + 1] = 1; break;
+		case 1:  bits[2 * i] = 0; bits[2 * i + 1] = 0; break;
+		case 3:  bits[2 * i] = 0; bits[2 * i + 1] = 1; break;
+		default: bits[2 * i] = 1; bits[2 * i + 1] = 0; break;
+		}
+	}
+}

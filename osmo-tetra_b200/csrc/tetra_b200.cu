@@ -216,6 +216,7 @@ extern "C" void tb200_default_options(tb200_options *o)
 	o->viterbi = TB200_VITERBI_LANE;
 	o->pipeline_slots = 0;
 	o->profile = 0;
+	o->input = TB200_IN_BYTES;
 }
 
 extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
@@ -225,6 +226,10 @@ extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
 		return fail(ctx, TB200_E_ARG, "chunk_bits must be 1..296");
 	if (o->viterbi > TB200_VITERBI_LANE)
 		return fail(ctx, TB200_E_ARG, "unknown viterbi variant");
+	if (o->input > TB200_IN_F32SYM)
+		return fail(ctx, TB200_E_ARG, "unknown input format");
+	if (o->input != TB200_IN_BYTES && o->viterbi != TB200_VITERBI_LANE)
+		return fail(ctx, TB200_E_ARG, "packed / symbol input needs the lane kernels (TB200_VITERBI_LANE)");
 	ctx->opt = *o;
 	return 0;
 }
@@ -298,7 +303,9 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 		return bail("cudaFuncSetAttribute");
 	if (cudaFuncSetAttribute(k_classify_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_SMEM) != cudaSuccess)
 		return bail("cudaFuncSetAttribute");
-	if (cudaFuncSetAttribute(k_classify_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM) != cudaSuccess)
+	if (cudaFuncSetAttribute(k_classify_tile<IN_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem<IN_BYTES>()) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_classify_tile<IN_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem<IN_PACKED>()) != cudaSuccess ||
+	    cudaFuncSetAttribute(k_classify_tile<IN_F32SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem<IN_F32SYM>()) != cudaSuccess)
 		return bail("cudaFuncSetAttribute");
 #endif
 	if (const char *e = getenv("TB200_CLASSIFY")) ctx->classify_form = atoi(e);
@@ -414,12 +421,28 @@ struct Source {
 	const uint8_t *data;
 	uint64_t new_base;
 	uint64_t end;
+	int fmt;               /* IN_BYTES / IN_PACKED / IN_F32SYM; the packed formats start at stream bit 0 (no tail) */
 };
 
-/* copy stream bits [lo, hi) to device memory `dst` (host path) */
-static int stage_bits(tb200_ctx *ctx, const Source &src, uint64_t lo, uint64_t hi, uint8_t *dst, cudaStream_t st)
+/* bytes that hold `nbits` stream bits in format fmt */
+static inline size_t fmt_bytes(int fmt, uint64_t nbits)
 {
+	return fmt == IN_BYTES ? (size_t)nbits : fmt == IN_PACKED ? (size_t)((nbits + 7) / 8) : (size_t)(4 * ((nbits + 1) / 2));
+}
+
+/* copy stream bits [lo, hi) to device memory `dst` (host path); *dbase = stream bit that dst[0] bit 0 holds
+ * (lo for the byte format, lo rounded down to a 16-byte unit of the packed formats) */
+static int stage_bits(tb200_ctx *ctx, const Source &src, uint64_t lo, uint64_t hi, uint8_t *dst, cudaStream_t st, uint64_t *dbase)
+{
+	*dbase = lo;
 	if (hi <= lo) return 0;
+	if (src.fmt != IN_BYTES) {
+		const uint64_t lo_al = lo & ~(uint64_t)127;
+		*dbase = lo_al;
+		const size_t b0 = fmt_bytes(src.fmt, lo_al), b1 = fmt_bytes(src.fmt, hi);
+		CU(cudaMemcpyAsync(dst, src.data + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+		return 0;
+	}
 	if (lo < src.new_base) {
 		uint64_t h = std::min(hi, src.new_base);
 		CU(cudaMemcpyAsync(dst, ctx->tail.data() + (lo - ctx->tail_base), h - lo, cudaMemcpyHostToDevice, st));
@@ -436,7 +459,7 @@ static int stage_bits(tb200_ctx *ctx, const Source &src, uint64_t lo, uint64_t h
 /* every position p in [lo, hi) where the 38-bit SYNC training sequence starts; bits are
  * readable up to `avail` bytes from `bits`; position p <-> bits[p - base] */
 __global__ void __launch_bounds__(256)
-k_scan_sync(const uint8_t *bits, uint64_t base, uint64_t avail, uint64_t lo, uint64_t hi,
+k_scan_sync(const uint8_t *bits, int fmt, uint64_t base, uint64_t avail, uint64_t lo, uint64_t hi,
             const Tables *__restrict__ tab, uint32_t *hits, uint32_t cap)
 {
 	const unsigned lane = threadIdx.x & 31;
@@ -445,7 +468,8 @@ k_scan_sync(const uint8_t *bits, uint64_t base, uint64_t avail, uint64_t lo, uin
 	const uint8_t *end = bits + avail;
 	for (uint64_t p0 = lo + warp * 1024; p0 < hi; p0 += nwarps * 1024) {
 		uint32_t x0, x1, x2;
-		load_window(bits + (p0 - base), end, lane, x0, x1, x2);
+		if (fmt == IN_BYTES) load_window(bits + (p0 - base), end, lane, x0, x1, x2);
+		else                 load_window_fmt(bits, fmt, p0 - base, avail, lane, x0, x1, x2);
 		uint32_t My = 0xffffffffu;
 #pragma unroll
 		for (int b = 0; b < 32; ++b) {
@@ -467,7 +491,7 @@ k_scan_sync(const uint8_t *bits, uint64_t base, uint64_t avail, uint64_t lo, uin
 		uint32_t prev_word = __shfl_up_sync(FULL, x0, 1);
 		uint32_t first_prev = 0;
 		if (lane == 0) {
-			if (p0 > base) first_prev = bits[p0 - base - 1] & 1;
+			if (p0 > base) first_prev = fmt == IN_BYTES ? (bits[p0 - base - 1] & 1u) : (fetch32(bits, fmt, p0 - base - 1, avail) & 1u);
 		} else {
 			first_prev = prev_word >> 31;
 		}
@@ -509,19 +533,21 @@ static int scan_more_hits(tb200_ctx *ctx, const Source &src, uint64_t from, uint
 			const uint64_t rd_lo = (lo > first_bit) ? lo - 1 : lo;      /* one bit back for the blind-spot rule */
 			const uint64_t rd_hi = std::min<uint64_t>(hi + 64, src.end);
 			const size_t nb = (size_t)(rd_hi - rd_lo);
-			if (nb + 64 > ctx->region_cap) {
+			const size_t need = fmt_bytes(IN_F32SYM, (uint64_t)REGION_BITS + 512);
+			if (need > ctx->region_cap) {
 				CU(cudaDeviceSynchronize());
-				int rc = grow(ctx, &ctx->d_region, (size_t)REGION_BITS + 256);
+				int rc = grow(ctx, &ctx->d_region, need);
 				if (rc) return rc;
-				ctx->region_cap = (size_t)REGION_BITS + 256;
+				ctx->region_cap = need;
 			}
-			int rc = stage_bits(ctx, src, rd_lo, rd_hi, ctx->d_region, ctx->s_compute);
+			(void)nb;
+			int rc = stage_bits(ctx, src, rd_lo, rd_hi, ctx->d_region, ctx->s_compute, &dbase);
 			if (rc) return rc;
-			dbits = ctx->d_region; dbase = rd_lo; davail = nb;
+			dbits = ctx->d_region; davail = rd_hi - dbase;
 		}
 		CU(cudaMemsetAsync(ctx->d_hits, 0, sizeof(uint32_t) * 2, ctx->s_compute));
 		const unsigned blocks = (unsigned)std::min<uint64_t>((hi - lo + 8191) / 8192, (uint64_t)ctx->sm_count * 4);
-		TB_LAUNCH(k_scan_sync, blocks, 256, ctx->s_compute, dbits, dbase, davail, lo, hi, ctx->d_tab, ctx->d_hits, HIT_CAP);
+		TB_LAUNCH(k_scan_sync, blocks, 256, ctx->s_compute, dbits, src.fmt, dbase, davail, lo, hi, ctx->d_tab, ctx->d_hits, HIT_CAP);
 		ctx->stats.kernel_launches++;
 		CU(cudaGetLastError());
 		CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(uint32_t) * (2 + 2 * HIT_CAP), cudaMemcpyDeviceToHost, ctx->s_compute));
@@ -610,11 +636,19 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cuda
 		wg.cmin = g.cmin; wg.n_end = g.n_end; wg.a0 = g.a0;
 		uint32_t *sb_count = ctx->d_sb_list + ctx->ws_slots;
 		CU(cudaMemsetAsync(sb_count, 0, sizeof(uint32_t), st));
-		if (ctx->classify_form == 0) {
-			const unsigned tiles = (nb + CT_SLOTS - 1) / CT_SLOTS;
-			const unsigned cls_blocks = std::min<unsigned>(tiles, (unsigned)ctx->sm_count * 3);
-			TB_LAUNCH_SMEM(k_classify_tile, cls_blocks, CT_THREADS, CT_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits,
-			               ctx->d_sb_list, sb_count);
+		if (ctx->classify_form == 0 || g.fmt != IN_BYTES) {
+			const unsigned per_tile = g.fmt == IN_F32SYM ? TileFmt<IN_F32SYM>::SLOTS : CT_SLOTS;
+			const unsigned tiles = (nb + per_tile - 1) / per_tile;
+			const unsigned cls_blocks = std::min<unsigned>(tiles, (unsigned)ctx->sm_count * (g.fmt == IN_PACKED ? 8 : 3));
+			if (g.fmt == IN_BYTES)
+				TB_LAUNCH_SMEM(k_classify_tile<IN_BYTES>, cls_blocks, CT_THREADS, ct_smem<IN_BYTES>(), st, g, wg, ctx->d_tab, ctx->d_ws,
+				               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
+			else if (g.fmt == IN_PACKED)
+				TB_LAUNCH_SMEM(k_classify_tile<IN_PACKED>, cls_blocks, CT_THREADS, ct_smem<IN_PACKED>(), st, g, wg, ctx->d_tab, ctx->d_ws,
+				               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
+			else
+				TB_LAUNCH_SMEM(k_classify_tile<IN_F32SYM>, cls_blocks, CT_THREADS, ct_smem<IN_F32SYM>(), st, g, wg, ctx->d_tab, ctx->d_ws,
+				               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
 		} else {
 			const unsigned cls_groups = (nb + 31) / 32;
 			const unsigned cls_blocks = std::min<unsigned>((cls_groups + CLS_WARPS - 1) / CLS_WARPS, (unsigned)ctx->sm_count * 3);
@@ -670,11 +704,11 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 
 /* enqueue classify + scan + decode + carry for slots [k0, k0+nb) of the segment */
 static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32_t nb, const uint8_t *d_bits,
-                         uint64_t d_base, uint64_t d_avail, size_t piece_idx,
+                         uint64_t d_base, uint64_t d_avail, int fmt, size_t piece_idx,
                          SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base)
 {
 	RxGeom g;
-	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base;
+	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base; g.fmt = fmt;
 	g.a0 = seg.a0 + (uint64_t)SLOT_BITS * k0; g.cmin = seg.cmin + k0; g.n_end = seg.n_end;
 	g.chunk = seg.chunk; g.n_slots = nb;
 	cudaEvent_t *pe = nullptr;
@@ -725,7 +759,7 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 	if ((rc = ensure_workspace(ctx, P))) return rc;
 	if ((rc = ensure_pieces(ctx, npieces))) return rc;
 	/* bits a piece may touch: its slots plus the largest search window (<= 4096) */
-	const size_t piece_in = (size_t)P * SLOT_BITS + 4096 + 64;
+	const size_t piece_in = fmt_bytes(src.fmt, (uint64_t)P * SLOT_BITS + 4096 + 64 + 128) + 64;
 	if (!src.on_device && (rc = ensure_staging(ctx, piece_in, P))) return rc;
 	const bool host_out = !out.on_device;
 	if (src.on_device && host_out)
@@ -746,11 +780,11 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		if (src.on_device) {
 			dbits = src.data; dbase = src.new_base; davail = seg.n_end - src.new_base;
 		} else {
-			int r = stage_bits(ctx, src, lo, hi, ctx->d_in[b], ctx->s_h2d);
+			int r = stage_bits(ctx, src, lo, hi, ctx->d_in[b], ctx->s_h2d, &dbase);
 			if (r) return r;
 			CU(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
 			CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d[b], 0));
-			dbits = ctx->d_in[b]; dbase = lo; davail = hi - lo;
+			dbits = ctx->d_in[b]; davail = hi - dbase;
 		}
 		SlotOut *os; uint8_t *ot; uint32_t *op; uint64_t ob;
 		if (out.on_device) {
@@ -758,7 +792,7 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		} else {
 			os = ctx->d_oslots[b]; ot = ctx->d_otype1[b]; op = ctx->d_opacked[b]; ob = 0;
 		}
-		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, i, os, ot, op, ob);
+		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob);
 		if (r) return r;
 		CU(cudaEventRecord(ctx->ev_comp[b], ctx->s_compute));
 		cudaStream_t so = host_out ? ctx->s_d2h : ctx->s_compute;
@@ -942,12 +976,14 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 		return fail(ctx, TB200_E_ARG, "the device-resident call needs TB200_FRESH | TB200_FINAL");
 	if (!d_bits || !d_slots) return fail(ctx, TB200_E_ARG, "null buffer");
 	if (d_type1 && ((uintptr_t)d_type1 & 15)) return fail(ctx, TB200_E_ARG, "d_type1 must be 16-byte aligned");
+	if (ctx->opt.input != TB200_IN_BYTES && ((uintptr_t)d_bits & 3))
+		return fail(ctx, TB200_E_ARG, "packed / symbol input must be 4-byte aligned");
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	CU(cudaDeviceSynchronize());        /* the caller's buffers may still be in flight on its own streams */
 	reset_stream(ctx);
 	int rc = push_carry(ctx);
 	if (rc) return rc;
-	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits;
+	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
 	out.max_slots = max_slots; out.n = 0;
 	ctx->fed_end = n_bits;
@@ -963,6 +999,8 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 {
 	if (!ctx) return TB200_E_ARG;
 	if ((!bits && n_bits) || !slots) return fail(ctx, TB200_E_ARG, "null buffer");
+	if (ctx->opt.input != TB200_IN_BYTES && (flags & (TB200_FRESH | TB200_FINAL)) != (TB200_FRESH | TB200_FINAL))
+		return fail(ctx, TB200_E_ARG, "packed / symbol input must be given in one call (TB200_FRESH | TB200_FINAL)");
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	if (flags & TB200_FRESH) reset_stream(ctx);
 	int rc = push_carry(ctx);
@@ -970,6 +1008,7 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	const uint64_t kernels_before = ctx->stats.kernel_launches;
 	(void)kernels_before;
 	Source src; src.on_device = false; src.data = bits; src.new_base = ctx->fed_end; src.end = ctx->fed_end + n_bits;
+	src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = false; out.slots = slots; out.type1 = type1; out.packed = type1_packed;
 	out.max_slots = max_slots; out.n = 0;
 	ctx->fed_end += n_bits;
@@ -1384,7 +1423,7 @@ extern "C" int tb200_find_lock(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	CU(cudaDeviceSynchronize());
 	reset_stream(ctx);
-	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits;
+	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = IN_BYTES;
 	Outputs out; out.on_device = true; out.slots = nullptr; out.type1 = nullptr; out.packed = nullptr; out.max_slots = 0; out.n = 0;
 	ctx->fed_end = n_bits;
 	ctx->stop_at_lock = true;
@@ -1409,7 +1448,7 @@ extern "C" int tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t
 	if ((rc = ensure_workspace(ctx, n_slots ? n_slots : 1))) return rc;
 	if ((rc = ensure_pieces(ctx, 1))) return rc;
 	RxGeom g;
-	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.n_end = n_end;
+	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.n_end = n_end; g.fmt = IN_BYTES;
 	g.chunk = ctx->opt.chunk_bits; g.n_slots = n_slots;
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if (n_slots && (rc = enqueue_pass1(ctx, g, 0, nullptr))) return rc;

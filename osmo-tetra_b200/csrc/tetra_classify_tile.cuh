@@ -29,12 +29,25 @@
 
 namespace tb {
 
-constexpr int CT_SLOTS = 64;                                  /* slots per tile */
 constexpr int CT_THREADS = 256;
-constexpr int CT_RAW = ((15 + 510 * CT_SLOTS + 15) / 16) * 16;     /* bytes of one raw tile buffer (32 672) */
-constexpr int CT_BITW = CT_RAW / 32 + 4;                       /* words of the packed tile (+ read-ahead) */
-constexpr int CT_AROW = CT_SLOTS + 1;                          /* row pitch of the aligned slot words (odd: no bank conflicts on the transposed write) */
-constexpr size_t CT_SMEM = (size_t)2 * CT_RAW + (size_t)CT_BITW * 4 + (size_t)16 * CT_AROW * 4 + CT_SLOTS * 4 + 2 * 8;
+constexpr int CT_RAW = ((15 + 510 * 64 + 15) / 16) * 16;       /* bytes of one raw tile buffer (32 672) */
+constexpr int CT_BITW = ((CT_RAW / 32 + 8 + 3) / 4) * 4;       /* words of the packed tile (+ lead of a packed copy + read-ahead), 16-byte multiple */
+
+/* per input format: slots per tile and the size of one copy buffer.
+ *   BYTES   64 slots = 32 640 stream bytes, packed to bits by the CTA
+ *   PACKED  64 slots = 4 080 bytes that ARE the bit string: copied straight into it, no pack phase
+ *   F32SYM  32 slots = 8 160 symbols = 32 640 bytes, sliced to 2 bits per symbol by the CTA */
+template <int FMT> struct TileFmt;
+template <> struct TileFmt<IN_BYTES>  { static constexpr int SLOTS = 64, BUF = CT_RAW; };
+template <> struct TileFmt<IN_PACKED> { static constexpr int SLOTS = 64, BUF = CT_BITW * 4; };
+template <> struct TileFmt<IN_F32SYM> { static constexpr int SLOTS = 32, BUF = CT_RAW; };
+constexpr int CT_AROW = 64 + 1;                                /* row pitch of the aligned slot words (odd: no bank conflicts on the transposed write) */
+template <int FMT> constexpr size_t ct_smem()
+{
+	return (size_t)2 * TileFmt<FMT>::BUF + (FMT == IN_PACKED ? 0 : (size_t)CT_BITW * 4) + (size_t)16 * CT_AROW * 4 + 64 * 4 + 2 * 8;
+}
+constexpr int CT_SLOTS = 64;                                   /* slots per tile of the byte format (launch geometry helper) */
+constexpr size_t CT_SMEM = ct_smem<IN_BYTES>();
 
 /* two pattern bits (B, B+1) of the three downlink sequences against the 32 positions of word x0 */
 template <int B>
@@ -53,42 +66,55 @@ __device__ __forceinline__ void match_pair(uint32_t x0, uint32_t x1, uint32_t x2
 
 struct TileGeom {
 	const uint8_t *src;      /* 16-byte aligned start of the copy */
-	uint32_t lead;           /* bytes between src and the first slot of the tile (0..15) */
+	uint32_t lead;           /* stream BITS between the start of the copied bit string and the first slot of the tile */
 	uint32_t bytes;          /* copy size, multiple of 16 */
 	uint32_t k0, ns;         /* first slot, slots in the tile */
 	bool staged;             /* the aligned superset lies inside the caller's buffer: TMA copy */
 };
 
+template <int FMT>
 __device__ __forceinline__ TileGeom tile_geom(const RxGeom &g, uint32_t tile, uintptr_t buf_lo, uintptr_t buf_hi)
 {
+	constexpr uint32_t S = TileFmt<FMT>::SLOTS;
 	TileGeom t;
-	t.k0 = tile * CT_SLOTS;
-	t.ns = g.n_slots - t.k0 < (uint32_t)CT_SLOTS ? g.n_slots - t.k0 : (uint32_t)CT_SLOTS;
-	const uintptr_t p = reinterpret_cast<uintptr_t>(g.bits) + (size_t)((g.a0 - g.base_bit) + 510ull * t.k0);
+	t.k0 = tile * S;
+	t.ns = g.n_slots - t.k0 < S ? g.n_slots - t.k0 : S;
+	const uint64_t bit0 = (g.a0 - g.base_bit) + 510ull * t.k0;          /* first bit of the tile, relative to g.bits */
+	uintptr_t p;                                                         /* address of the unit that holds it */
+	uint32_t sub;                                                        /* bit inside that unit */
+	uint64_t span;                                                       /* bytes from p to the end of the tile's last bit */
+	if (FMT == IN_BYTES)       { p = reinterpret_cast<uintptr_t>(g.bits) + bit0;            sub = 0;                   span = 510ull * t.ns; }
+	else if (FMT == IN_PACKED) { p = reinterpret_cast<uintptr_t>(g.bits) + (bit0 >> 3);     sub = (uint32_t)(bit0 & 7); span = (sub + 510ull * t.ns + 7) >> 3; }
+	else                       { p = reinterpret_cast<uintptr_t>(g.bits) + 4 * (bit0 >> 1); sub = (uint32_t)(bit0 & 1); span = 4 * ((sub + 510ull * t.ns + 1) >> 1); }
 	const uintptr_t a = p & ~(uintptr_t)15;
 	t.src = reinterpret_cast<const uint8_t *>(a);
-	t.lead = (uint32_t)(p - a);
-	t.bytes = (t.lead + 510u * t.ns + 15u) & ~15u;
+	const uint32_t lead_bytes = (uint32_t)(p - a);
+	t.lead = FMT == IN_BYTES ? lead_bytes : FMT == IN_PACKED ? 8 * lead_bytes + sub : lead_bytes / 2 + sub;
+	t.bytes = (uint32_t)((lead_bytes + span + 15u) & ~15ull);
 	t.staged = a >= buf_lo && a + t.bytes <= buf_hi;
 	return t;
 }
 
+template <int FMT>
 __global__ void __launch_bounds__(CT_THREADS, 3)
 k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__restrict__ ws,
                 uint32_t *__restrict__ slot_bits, uint32_t *__restrict__ sb_list, uint32_t *__restrict__ sb_count)
 {
+	constexpr int S = TileFmt<FMT>::SLOTS, BUF = TileFmt<FMT>::BUF;
 	uint8_t *smem = TB_DYN_SMEM();
-	uint8_t *raw = smem;                                                 /* [2][CT_RAW] */
-	uint32_t *bitw = reinterpret_cast<uint32_t *>(smem + 2 * CT_RAW);     /* [CT_BITW] the tile as a dense bit string */
-	uint32_t *al = bitw + CT_BITW;                                       /* [16][CT_AROW] word j of slot s, slot-aligned */
-	uint32_t *first = al + 16 * CT_AROW;                                 /* [CT_SLOTS] (offset << 3 | type), ~0 = none */
-	uint64_t *bars = reinterpret_cast<uint64_t *>(first + CT_SLOTS);     /* [2] */
+	uint8_t *raw = smem;                                                 /* [2][BUF] copy buffers */
+	uint32_t *bitw_own = reinterpret_cast<uint32_t *>(smem + 2 * BUF);    /* [CT_BITW] the tile as a dense bit string (the copy buffer itself when PACKED) */
+	uint32_t *al = bitw_own + (FMT == IN_PACKED ? 0 : CT_BITW);          /* [16][CT_AROW] word j of slot s, slot-aligned */
+	uint32_t *first = al + 16 * CT_AROW;                                 /* [64] (offset << 3 | type), ~0 = none */
+	uint64_t *bars = reinterpret_cast<uint64_t *>(first + 64);           /* [2] */
 	const unsigned tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
 
+	/* bytes of the caller's buffer: g.n_bytes counts stream bits */
+	const uint64_t buf_bytes = FMT == IN_BYTES ? g.n_bytes : FMT == IN_PACKED ? (g.n_bytes + 7) >> 3 : 4 * ((g.n_bytes + 1) >> 1);
 	const uintptr_t buf_lo = (reinterpret_cast<uintptr_t>(g.bits) + 15) & ~(uintptr_t)15;
-	const uintptr_t buf_hi = (reinterpret_cast<uintptr_t>(g.bits) + g.n_bytes) & ~(uintptr_t)15;
-	const uint8_t *end = g.bits + g.n_bytes;
-	const uint32_t ntiles = (g.n_slots + CT_SLOTS - 1) / CT_SLOTS;
+	const uintptr_t buf_hi = (reinterpret_cast<uintptr_t>(g.bits) + buf_bytes) & ~(uintptr_t)15;
+	const uint8_t *end = g.bits + buf_bytes;
+	const uint32_t ntiles = (g.n_slots + S - 1) / S;
 
 	if (tid == 0) {
 		mbar_init(&bars[0], 1);
@@ -97,10 +123,10 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 	__syncthreads();
 	auto issue = [&](uint32_t tile, int b) {            /* thread 0 only */
 		if (tile >= ntiles) return;
-		const TileGeom t = tile_geom(g, tile, buf_lo, buf_hi);
+		const TileGeom t = tile_geom<FMT>(g, tile, buf_lo, buf_hi);
 		if (!t.staged) return;
 		mbar_expect_tx(&bars[b], t.bytes);
-		bulk_g2s(raw + (size_t)b * CT_RAW, t.src, t.bytes, &bars[b]);
+		bulk_g2s(raw + (size_t)b * BUF, t.src, t.bytes, &bars[b]);
 	};
 	if (tid == 0) issue(blockIdx.x, 0);
 	__syncthreads();
@@ -108,8 +134,9 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 	unsigned phase_bits = 0;                     /* bit b = parity the next wait on buffer b expects */
 	int b = 0;
 	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, b ^= 1) {
-		const TileGeom t = tile_geom(g, tile, buf_lo, buf_hi);
-		uint8_t *rb = raw + (size_t)b * CT_RAW;
+		const TileGeom t = tile_geom<FMT>(g, tile, buf_lo, buf_hi);
+		uint8_t *rb = raw + (size_t)b * BUF;
+		uint32_t *bitw = FMT == IN_PACKED ? reinterpret_cast<uint32_t *>(rb) : bitw_own;
 		if (tid == 0) issue(tile + gridDim.x, b ^ 1);         /* prefetch this CTA's next tile */
 		if (t.staged) {
 			mbar_wait(&bars[b], (phase_bits >> b) & 1u);
@@ -122,8 +149,8 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 			}
 			__syncthreads();
 		}
-		/* ---- pack: 16 bytes -> 16 bits, two quads per thread and round */
-		{
+		/* ---- pack: the copied tile -> dense bit string, two 16-byte quads per thread and round */
+		if (FMT == IN_BYTES) {                       /* 16 bytes -> 16 bits */
 			const uint32_t nq = t.bytes >> 4;
 			const uint4 *q4 = reinterpret_cast<const uint4 *>(rb);
 			uint16_t *bh = reinterpret_cast<uint16_t *>(bitw);
@@ -134,10 +161,22 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 				bh[q] = (uint16_t)pack16_dp4a(v0);
 				if (q1 < nq + 8) bh[q1] = (uint16_t)pack16_dp4a(v1);
 			}
-			if (tid < CT_SLOTS) first[tid] = 0xffffffffu;
+		} else if (FMT == IN_F32SYM) {               /* 4 symbols -> 8 bits (float_to_bits.c:33-72) */
+			const uint32_t nq = t.bytes >> 4;
+			const float4 *q4 = reinterpret_cast<const float4 *>(rb);
+			uint8_t *bb = reinterpret_cast<uint8_t *>(bitw);
+			for (uint32_t q = tid; q < nq + 16; q += CT_THREADS) {
+				uint32_t v = 0;
+				if (q < nq) {
+					const float4 f = q4[q];
+					v = slice_symbol(f.x) | (slice_symbol(f.y) << 2) | (slice_symbol(f.z) << 4) | (slice_symbol(f.w) << 6);
+				}
+				bb[q] = (uint8_t)v;
+			}
 		}
+		if (tid < 64) first[tid] = 0xffffffffu;
 		__syncthreads();
-		/* ---- align + emit: word j of slot s (bit i of the slot -> word i>>5 bit i&31); thread = (j, 4 slots).
+		/* ---- align + emit: word j of slot s (bit i of the slot -> word i>>5 bit i&31); thread = (j, S/16 slots).
 		 * 16 slots further on the stream is 255 words further on and equally aligned. */
 		{
 			const uint32_t j = tid & 15, s0 = tid >> 4;
@@ -145,7 +184,7 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 			const uint32_t *src = bitw + (dt >> 5) + j;
 			uint32_t *dst = slot_bits + (size_t)t.k0 * 16 + tid;
 #pragma unroll
-			for (int r = 0; r < 4; ++r) {
+			for (int r = 0; r < S / 16; ++r) {
 				const uint32_t s = s0 + 16 * r;
 				uint32_t v = __funnelshift_r(src[255 * r], src[255 * r + 1], sh);
 				if (j == 15) v &= 0x3fffffffu;
@@ -158,7 +197,7 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 		 * lane and lane + 32.  The expected offsets 214 (SYNC) and 244 (normal) sit in words 6 and 7, so
 		 * the other warps leave after 12 pattern bits almost always. */
 #pragma unroll 1
-		for (int r = 0; r < 2; ++r) {
+		for (int r = 0; r < S / 32; ++r) {
 			const uint32_t s = lane + 32 * r, j = wib;
 			const uint32_t x0 = al[j * CT_AROW + s], x1 = al[(j + 1) * CT_AROW + s];
 			uint32_t x2 = 0;
@@ -191,8 +230,8 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 			}
 		}
 		__syncthreads();
-		/* ---- decide: one thread per slot (warps 0 and 1) */
-		if (tid < CT_SLOTS) {
+		/* ---- decide: one thread per slot */
+		if (tid < S) {
 			const bool have = tid < t.ns;
 			const uint32_t k = t.k0 + tid;
 			const uint64_t ak = g.a0 + 510ull * k;
@@ -210,7 +249,7 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 				const unsigned Ws = __shfl_sync(FULL, W, src);
 				unsigned o2 = 0;
 				const uint32_t mask = (1u << TS_SYNC) | (1u << TS_NORM_1) | (1u << TS_NORM_2);
-				const int r2 = find_train_seq_warp(g.bits + off_b, end, Ws, mask, tab, &o2, nullptr);
+				const int r2 = find_train_seq_warp_fmt(g.bits, FMT, off_b, g.n_bytes, Ws, mask, tab, &o2, nullptr);
 				if ((int)lane == src) { rc = r2; off = o2; }
 			}
 			int kind = KIND_NONE;

@@ -261,6 +261,62 @@ __device__ __forceinline__ void load_window(const uint8_t *p, const uint8_t *end
 	x2 = (lane == 30) ? b0 : (lane == 31) ? b1 : n2;
 }
 
+/* ---- input formats of the bit stream (tb200_options.input) ------------------------------
+ * BYTES   one bit per byte, the reference's file format (tetra-rx.c:82-95)
+ * PACKED  eight bits per byte, stream bit i = byte i>>3 bit i&7
+ * F32SYM  one float per pi/4-DQPSK symbol as the demodulators write it; the two hard bits of a symbol
+ *         follow float_to_bits.c:33-72 (no AFC): >2 -> 01, (0,2] -> 00, < -2 -> 11, else 10 */
+enum { IN_BYTES = 0, IN_PACKED = 1, IN_F32SYM = 2 };
+
+/* float_to_bits.c:33-72: process_sym_fl + sym_int2bits; first bit of the symbol in bit 0 */
+__device__ __forceinline__ uint32_t slice_symbol(float fl)
+{
+	if (fl > 2.0f) return 2u;          /* sym  3 -> bits 0,1 */
+	if (fl > 0.0f) return 0u;          /* sym  1 -> bits 0,0 */
+	if (fl < -2.0f) return 3u;         /* sym -3 -> bits 1,1 */
+	return 1u;                         /* sym -1 -> bits 1,0 (also NaN, like the reference's comparisons) */
+}
+
+/* 32 stream bits [pos, pos+32) of a PACKED / F32SYM buffer that starts at stream bit 0 of `base`
+ * and holds `avail` bits; bits at or beyond avail read as zero.  Any pos; base 4-byte aligned. */
+__device__ __forceinline__ uint32_t fetch32(const uint8_t *base, int fmt, uint64_t pos, uint64_t avail)
+{
+	if (pos >= avail) return 0;
+	uint32_t v;
+	if (fmt == IN_PACKED) {
+		const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
+		const uint64_t i = pos >> 5, nw = (avail + 31) >> 5;
+		const uint32_t lo = w[i], hi = (i + 1 < nw) ? w[i + 1] : 0u;
+		v = __funnelshift_r(lo, hi, (uint32_t)(pos & 31));
+	} else {
+		const float *f = reinterpret_cast<const float *>(base);
+		const uint64_t s0 = pos >> 1, ns = (avail + 1) >> 1;
+		uint64_t acc = 0;
+#pragma unroll
+		for (int t = 0; t < 17; ++t)
+			if (s0 + t < ns) acc |= (uint64_t)slice_symbol(f[s0 + t]) << (2 * t);
+		v = (uint32_t)(acc >> (pos & 1));
+	}
+	const uint64_t left = avail - pos;
+	if (left < 32) v &= (1u << left) - 1;
+	return v;
+}
+
+/* load_window for the PACKED / F32SYM formats: same result layout */
+__device__ __forceinline__ void load_window_fmt(const uint8_t *base, int fmt, uint64_t pos, uint64_t avail, unsigned lane,
+                                                uint32_t &x0, uint32_t &x1, uint32_t &x2)
+{
+	const uint32_t XA = fetch32(base, fmt, pos + 32 * lane, avail);
+	const uint32_t XB = lane < 2 ? fetch32(base, fmt, pos + 1024 + 32 * lane, avail) : 0u;
+	uint32_t n1 = __shfl_sync(FULL, XA, (lane + 1) & 31);
+	uint32_t n2 = __shfl_sync(FULL, XA, (lane + 2) & 31);
+	uint32_t b0 = __shfl_sync(FULL, XB, 0);
+	uint32_t b1 = __shfl_sync(FULL, XB, 1);
+	x0 = XA;
+	x1 = (lane == 31) ? b0 : n1;
+	x2 = (lane == 30) ? b0 : (lane == 31) ? b1 : n2;
+}
+
 /* --------------------------------------------- training sequence search -- */
 
 __device__ __forceinline__ uint32_t low_mask(long long lim)   /* bits 0..lim set, none if lim < 0 */
@@ -274,9 +330,10 @@ __device__ __forceinline__ uint32_t low_mask(long long lim)   /* bits 0..lim set
  * enabled in `mask` (SYNC, NORM_1, NORM_2; the uplink ones are never enabled by the
  * receiver, tetra_burst_sync.c:76,118-120).  Returns the type or -1; *off = first offset.
  * On return from the first 1024-bit pass lane l < 16 also holds word l of the slot in *slotw. */
-__device__ inline int find_train_seq_warp(const uint8_t *p, const uint8_t *end, unsigned W,
-                                          uint32_t mask, const Tables *__restrict__ tab,
-                                          unsigned *off, uint32_t *slotw)
+template <typename LOAD>
+__device__ __forceinline__ int find_train_seq_core(LOAD load, unsigned W,
+                                                   uint32_t mask, const Tables *__restrict__ tab,
+                                                   unsigned *off, uint32_t *slotw)
 {
 	const unsigned lane = threadIdx.x & 31;
 	const bool en_y = mask & (1u << TS_SYNC), en_n = mask & (1u << TS_NORM_1), en_p = mask & (1u << TS_NORM_2);
@@ -284,8 +341,7 @@ __device__ inline int find_train_seq_warp(const uint8_t *p, const uint8_t *end, 
 	unsigned found_off = 0;
 	for (unsigned it = 0; it * 1024 < W; ++it) {
 		uint32_t x0, x1, x2;
-		const uint8_t *wend = p + W < end ? p + W : end;
-		load_window(p + 1024 * it, wend, lane, x0, x1, x2);
+		load(it, lane, x0, x1, x2);
 		if (it == 0 && slotw) *slotw = x0;
 		uint32_t My = 0xffffffffu, Mn = 0xffffffffu, Mp = 0xffffffffu;
 #pragma unroll
@@ -333,6 +389,30 @@ __device__ inline int find_train_seq_warp(const uint8_t *p, const uint8_t *end, 
 	}
 	*off = found_off;
 	return rc;
+}
+
+__device__ inline int find_train_seq_warp(const uint8_t *p, const uint8_t *end, unsigned W,
+                                          uint32_t mask, const Tables *__restrict__ tab,
+                                          unsigned *off, uint32_t *slotw)
+{
+	const uint8_t *wend = p + W < end ? p + W : end;
+	return find_train_seq_core([&](unsigned it, unsigned lane, uint32_t &x0, uint32_t &x1, uint32_t &x2) {
+		load_window(p + 1024 * it, wend, lane, x0, x1, x2);
+	}, W, mask, tab, off, slotw);
+}
+
+/* the same over a buffer in any input format: the window starts at stream bit `pos` of a buffer that
+ * holds `avail` bits from its stream bit 0 */
+__device__ inline int find_train_seq_warp_fmt(const uint8_t *base, int fmt, uint64_t pos, uint64_t avail, unsigned W,
+                                              uint32_t mask, const Tables *__restrict__ tab,
+                                              unsigned *off, uint32_t *slotw)
+{
+	if (fmt == IN_BYTES)
+		return find_train_seq_warp(base + pos, base + avail, W, mask, tab, off, slotw);
+	const uint64_t wend = pos + W < avail ? pos + W : avail;
+	return find_train_seq_core([&](unsigned it, unsigned lane, uint32_t &x0, uint32_t &x1, uint32_t &x2) {
+		load_window_fmt(base, fmt, pos + 1024ull * it, wend, lane, x0, x1, x2);
+	}, W, mask, tab, off, slotw);
 }
 
 /* ------------------------------------------------------------- scrambler -- */
@@ -595,13 +675,14 @@ __device__ __forceinline__ uint32_t field_msb_first(const uint32_t *w, unsigned 
 
 struct RxGeom {
 	const uint8_t *bits;       /* device buffer holding stream bits [base_bit, base_bit + n_bytes) */
-	uint64_t n_bytes;
+	uint64_t n_bytes;          /* stream BITS available from base_bit (= bytes in the 1-bit-per-byte format) */
 	uint64_t base_bit;
 	uint64_t a0;               /* absolute bit of slot 0 of this launch */
 	uint64_t cmin;             /* first tetra_burst_sync_in() call that may process slot 0 */
 	uint64_t n_end;            /* bits that the modelled calls deliver in total */
 	uint32_t chunk;            /* bits per modelled call (tetra-rx.c:83: 64) */
 	uint32_t n_slots;
+	int fmt;                   /* IN_BYTES / IN_PACKED / IN_F32SYM: how `bits` encodes the stream (base_bit % 128 == 0 unless bytes) */
 };
 
 /* bits the search sees for slot k: bits_in_buf when the slot is processed

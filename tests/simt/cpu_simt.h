@@ -33,6 +33,7 @@
 
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };
+struct float4 { float x, y, z, w; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
 static inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }

@@ -1,0 +1,89 @@
+"""Input front ends in front of the hot path: the symbol slicer of
+float_to_bits.c and bit-packed input.  CPU part: the oracle restatement against the reference's own
+float_to_bits program and its golden vector; the CUDA kernels under the SIMT emulator against the
+oracle.  The GPU part of the same checks lives in test_gpu_frontend.py."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import tetra_testlib as T
+from test_oracle import _stream
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "slicer.npz")
+
+
+def test_slicer_oracle_matches_golden(orc):
+    z = np.load(GOLD)
+    want = np.unpackbits(z["bits"])[:2 * z["sym"].size]
+    assert np.array_equal(orc.float_to_bits(z["sym"]), want)
+
+
+def test_slicer_oracle_matches_reference_program(orc):
+    if not os.path.exists(T.REF_FLOAT_TO_BITS):
+        pytest.skip("oracle/_ref/float_to_bits not built (no /root/reference here)")
+    rng = np.random.default_rng(5)
+    sym = (rng.standard_normal(100_000) * 3).astype(np.float32)
+    sym[::97] = 2.0; sym[1::97] = 0.0; sym[2::97] = -2.0; sym[3::97] = np.nan
+    with tempfile.TemporaryDirectory() as d:
+        want = T.ref_float_to_bits(sym, d)
+    assert np.array_equal(orc.float_to_bits(sym), want)
+
+
+def test_symbols_round_trip(orc):
+    rng = np.random.default_rng(6)
+    bits = rng.integers(0, 2, 20_000, dtype=np.uint8)
+    assert np.array_equal(orc.float_to_bits(T.bits_to_symbols(bits, rng, edge_share=0.2)), bits)
+
+
+def _ref_records(orc, bits):
+    orc.reset(); orc.feed(bits, 64)
+    return orc.records(), orc.events()
+
+
+@pytest.mark.parametrize("lead_in", [333, 334, 0, 77])
+def test_packed_input_emulated(emu, orc, lead_in):
+    """bit-packed stream in, same records as the reference chain on the unpacked stream (lock loss included)"""
+    bits, _ = _stream(orc, n=260, random_cell=1, lead_in_bits=lead_in)
+    want, ev = _ref_records(orc, bits)
+    emu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, input=T.IN_PACKED)
+    try:
+        slots, t1, _ = emu.rx_stream_host_raw(T.pack_bits(bits), bits.size)
+        T.check_stream_against(want, ev, slots, emu.expand_records(slots, t1))
+        emu.set_options(pipeline_slots=100)                    # several pieces: unaligned piece starts
+        slots, t1, _ = emu.rx_stream_host_raw(T.pack_bits(bits), bits.size)
+        T.check_stream_against(want, ev, slots, emu.expand_records(slots, t1))
+    finally:
+        emu.set_options(input=T.IN_BYTES, pipeline_slots=0)
+
+
+@pytest.mark.parametrize("lead_in", [333, 334])
+def test_symbol_input_emulated(emu, orc, lead_in):
+    """float32 symbols in: sliced on the 'device' like float_to_bits, then the usual chain"""
+    bits, _ = _stream(orc, n=200, random_cell=1, lead_in_bits=lead_in)
+    bits = bits[:bits.size & ~1]
+    rng = np.random.default_rng(7)
+    sym = T.bits_to_symbols(bits, rng)
+    assert np.array_equal(orc.float_to_bits(sym), bits)
+    want, ev = _ref_records(orc, bits)
+    emu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, input=T.IN_F32SYM)
+    try:
+        slots, t1, _ = emu.rx_stream_host_raw(sym, bits.size)
+        T.check_stream_against(want, ev, slots, emu.expand_records(slots, t1))
+        emu.set_options(pipeline_slots=70)
+        slots, t1, _ = emu.rx_stream_host_raw(sym, bits.size)
+        T.check_stream_against(want, ev, slots, emu.expand_records(slots, t1))
+    finally:
+        emu.set_options(input=T.IN_BYTES, pipeline_slots=0)
+
+
+def test_format_rules(emu):
+    emu.set_options(input=T.IN_PACKED, viterbi=T.VITERBI_LANE)
+    try:
+        with pytest.raises(RuntimeError):          # continuation is only defined for the byte format
+            emu.rx_stream_host_raw(np.zeros(64, np.uint8), 512, flags=T.TB200_FRESH)
+        with pytest.raises(ValueError):
+            emu.set_options(viterbi=T.VITERBI_WARP)
+    finally:
+        emu.set_options(input=T.IN_BYTES, viterbi=T.VITERBI_LANE)

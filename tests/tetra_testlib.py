@@ -245,10 +245,18 @@ class Oracle(_Recorder):
         lib.orc_gen_stream.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
         lib.orc_gen_burst.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
         lib.orc_gen_kind.argtypes = [C.c_void_p, C.c_uint64]
+        lib.orc_float_to_bits.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
 
     def feed(self, bits, chunk=64):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
         return self.lib.orc_feed(_ptr(bits), bits.size, chunk)
+
+    def float_to_bits(self, sym):
+        """float_to_bits.c without AFC: float32 symbols -> 2 unpacked bits each"""
+        sym = np.ascontiguousarray(sym, dtype=np.float32)
+        out = np.zeros(2 * sym.size, dtype=np.uint8)
+        self.lib.orc_float_to_bits(_ptr(sym), sym.size, _ptr(out))
+        return out
 
     def tp_sap(self, typ, blk_num, bits):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
@@ -359,12 +367,13 @@ assert SLOT_DTYPE.itemsize == 16
 
 TB200_FRESH, TB200_FINAL = 1, 2
 OUT_UNPACKED, OUT_PACKED = 1, 2
+IN_BYTES, IN_PACKED, IN_F32SYM = 0, 1, 2
 VITERBI_WARP, VITERBI_LANE = 0, 1
 
 
 class Options(C.Structure):
     _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
-                ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32)]
+                ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32), ("input", C.c_uint32)]
 
 
 class Timing(C.Structure):
@@ -492,6 +501,18 @@ class B200:
         type1 = np.zeros((max_slots, 288), dtype=np.uint8)
         packed = np.zeros((max_slots, 9), dtype=np.uint32)
         n = self.lib.tb200_rx_stream_host(self.h, _ptr(bits), bits.size, flags, _ptr(slots), _ptr(type1), _ptr(packed), max_slots)
+        if n < 0:
+            raise RuntimeError(f"tb200_rx_stream_host: {n}: {self.err()}")
+        return slots[:n], type1[:n], packed[:n]
+
+    def rx_stream_host_raw(self, buf, n_bits, flags=TB200_FRESH | TB200_FINAL):
+        """host call with the stream in the format options.input names (buf: any contiguous numpy array)"""
+        buf = np.ascontiguousarray(buf)
+        max_slots = int(self.lib.tb200_max_slots(n_bits)) + 16
+        slots = np.zeros(max_slots, dtype=SLOT_DTYPE)
+        type1 = np.zeros((max_slots, 288), dtype=np.uint8)
+        packed = np.zeros((max_slots, 9), dtype=np.uint32)
+        n = self.lib.tb200_rx_stream_host(self.h, _ptr(buf), n_bits, flags, _ptr(slots), _ptr(type1), _ptr(packed), max_slots)
         if n < 0:
             raise RuntimeError(f"tb200_rx_stream_host: {n}: {self.err()}")
         return slots[:n], type1[:n], packed[:n]
@@ -693,3 +714,43 @@ def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=Fals
     if timers is not None:
         torch.cuda.synchronize(); timers["t_done"] = __import__("time").perf_counter()
     return k0, k1, a0, d_slots, d_t1, d_pk, summaries
+
+
+def pack_bits(bits):
+    """1-bit-per-byte stream -> TB200_IN_PACKED buffer (stream bit i = byte i>>3 bit i&7), padded to 16 bytes"""
+    p = np.packbits(np.ascontiguousarray(bits, dtype=np.uint8) & 1, bitorder="little")
+    out = np.zeros((p.size + 15) // 16 * 16, dtype=np.uint8)
+    out[:p.size] = p
+    return out
+
+
+def bits_to_symbols(bits, rng, edge_share=0.02):
+    """float32 demodulator symbols that float_to_bits (no AFC) slices back to `bits` (even count):
+    00 -> (0, 2], 01 -> > 2, 11 -> < -2, 10 -> [-2, 0]; a share of the symbols sits exactly on the
+    decision edges 2.0 / 0.0 / -2.0 (float_to_bits.c:33-50: the comparisons are strict)"""
+    b = np.ascontiguousarray(bits, dtype=np.uint8).reshape(-1, 2)
+    code = b[:, 0] * 2 + b[:, 1]
+    u = rng.random(code.size).astype(np.float32)
+    lo = np.array([0.0, 2.0, -2.0, -7.0], dtype=np.float32)[code]      # 00, 01, 10, 11
+    hi = np.array([2.0, 7.0, 0.0, -2.0], dtype=np.float32)[code]
+    f = (lo + (hi - lo) * (0.02 + 0.96 * u)).astype(np.float32)
+    edge = rng.random(code.size) < edge_share
+    # per code, values on or next to the decision edges and the non-finite ones
+    table = np.array([[2.0, 1e-30, 1e-45, 1.9999999],                      # 00: (0, 2]
+                      [2.0000002, 7.0, np.inf, 3e38],                      # 01: > 2
+                      [-2.0, 0.0, np.nan, -0.0],                           # 10: [-2, 0] and NaN
+                      [-2.0000002, -7.0, -np.inf, -3e38]], dtype=np.float32)  # 11: < -2
+    pick = rng.integers(0, 4, code.size)
+    f[edge] = table[code[edge], pick[edge]]
+    return f.astype(np.float32)
+
+
+REF_FLOAT_TO_BITS = os.path.join(ROOT, "oracle", "_ref", "float_to_bits")
+
+
+def ref_float_to_bits(sym, tmpdir):
+    """run the reference's own float_to_bits program (compiled unmodified into oracle/_ref) on a file"""
+    fin, fout = os.path.join(tmpdir, "sym.f32"), os.path.join(tmpdir, "sym.bits")
+    np.ascontiguousarray(sym, dtype=np.float32).tofile(fin)
+    subprocess.check_call([REF_FLOAT_TO_BITS, fin, fout])
+    return np.fromfile(fout, dtype=np.uint8)
