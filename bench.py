@@ -268,6 +268,65 @@ def run_ours(args, rank, world, local_rank):
             step_host(packed=True)
         barrier()
         wall_e2e_packed = time.perf_counter() - t2
+    # ---- input front ends: the same stream bit-packed (64 B per burst) and as float32 symbols
+    front = None
+    if not args.no_e2e and world == 1:
+        front = {}
+        nb8 = (nbits + 7) // 8
+        pk_host = np.packbits(h_bits, bitorder="little")
+        h_pk_in_p = g.lib.tb200_host_alloc(nb8 + 64)
+        h_pk_in = np.ctypeslib.as_array(C.cast(h_pk_in_p, C.POINTER(C.c_uint8)), shape=(nb8,))
+        h_pk_in[:] = pk_host
+        d_pk_in = torch.from_numpy(pk_host).cuda()
+        d_pk_in = torch.cat([d_pk_in, torch.zeros(64, dtype=torch.uint8, device="cuda")])
+        code = d_bits[:nbits].view(-1, 2).to(torch.int64)
+        code = code[:, 0] * 2 + code[:, 1]
+        d_sym = (torch.tensor([1.0, 3.0, -1.0, -3.0], device="cuda")[code] +
+                 (torch.rand(code.numel(), device="cuda") - 0.5) * 1.9).to(torch.float32).contiguous()
+        del code
+
+        def timed(fn, k):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            for _ in range(k):
+                fn()
+            torch.cuda.synchronize()
+            return (time.perf_counter() - t) / k
+
+        def dev_step(buf):
+            ns = g.lib.tb200_rx_stream_dev(g.h, C.c_void_p(buf.data_ptr()), nbits, 3, C.c_void_p(d_slots.data_ptr()),
+                                           C.c_void_p(d_t1.data_ptr()), None, ms)
+            assert ns == n - 1, (ns, g.err())
+
+        def host_step_packed_in(packed_out):
+            ns = g.lib.tb200_rx_stream_host(g.h, h_pk_in_p, nbits, 3, h_slots_p, None if packed_out else h_t1_p,
+                                            h_pk_p if packed_out else None, ms)
+            assert ns == n - 1, (ns, g.err())
+        k = max(10, args.steps // 2)
+        g.set_options(profile=0, input=T.IN_PACKED, output=T.OUT_UNPACKED)
+        t_dev_pk = timed(lambda: dev_step(d_pk_in), k)
+        t_host_pk = timed(lambda: host_step_packed_in(False), k)
+        same_pk = bool(np.array_equal(np.ctypeslib.as_array(C.cast(h_slots_p, C.POINTER(C.c_uint8)), shape=((n - 1) * 16,)),
+                                      d_slots[:(n - 1) * 16].cpu().numpy()))
+        g.set_options(output=T.OUT_PACKED)
+        t_host_pk_pk = timed(lambda: host_step_packed_in(True), k)
+        g.set_options(input=T.IN_F32SYM, output=T.OUT_UNPACKED)
+        t_dev_sym = timed(lambda: dev_step(d_sym), k)
+        g.set_options(input=T.IN_BYTES, output=T.OUT_UNPACKED)
+        front = {"packed_input": {"device_resident": {"value": (n - 1) / t_dev_pk, "unit": UNIT, "ms_per_step": t_dev_pk * 1e3},
+                                  "e2e_host_buffers": {"value": (n - 1) / t_host_pk, "unit": UNIT, "ms_per_step": t_host_pk * 1e3,
+                                                       "h2d_bytes_per_step": nb8, "d2h_bytes_per_step": (n - 1) * (16 + 288),
+                                                       "matches_device_path": same_pk},
+                                  "e2e_host_buffers_packed_output": {"value": (n - 1) / t_host_pk_pk, "unit": UNIT,
+                                                                     "ms_per_step": t_host_pk_pk * 1e3, "h2d_bytes_per_step": nb8,
+                                                                     "d2h_bytes_per_step": (n - 1) * (16 + 36)},
+                                  "format": "8 stream bits per byte (TB200_IN_PACKED), 64 B per burst"},
+                 "symbol_input": {"device_resident": {"value": (n - 1) / t_dev_sym, "unit": UNIT, "ms_per_step": t_dev_sym * 1e3},
+                                  "format": "float32 per symbol (TB200_IN_F32SYM), sliced on the device like float_to_bits.c, 1020 B per burst"}}
+        g.lib.tb200_host_free(h_pk_in_p)
+        del d_pk_in, d_sym
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- the fused descramble + de-interleave stage on its own (north star: >= 70 % of the HBM roofline)
@@ -363,6 +422,8 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = cpu
     if others is not None:
         line["other_configs"] = others
+    if front is not None:
+        line["front_ends"] = front
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -64,6 +64,35 @@ __host__ __device__ constexpr unsigned rev4(unsigned v)
 	return ((v & 1) << 3) | ((v & 2) << 1) | ((v & 4) >> 1) | ((v & 8) >> 3);
 }
 
+/* a * 16 + b as one multiply-add on the FMA pipe (opaque, so that the optimiser does not turn the
+ * nibble packing into shifts + masks on the ALU pipe, which is the one the ACS loop saturates) */
+__device__ __forceinline__ uint32_t mad16_opaque(uint32_t a, uint32_t b)
+{
+#ifdef TB_SIMT_EMULATION
+	return a * 16 + b;
+#else
+	uint32_t r;
+	asm("mad.lo.u32 %0, %1, 16, %2;" : "=r"(r) : "r"(a), "r"(b));
+	return r;
+#endif
+}
+
+/* a * K + c as an integer multiply-add with a non-unit K.  The ACS loop saturates the ALU pipe (VIADDMNMX,
+ * LOP3, SHF live there) while the multiply-add pipe has room, so the branch metrics are built from the raw
+ * 0/1 received bits with the metric scale (16 per mismatch) folded into the multiplier: ptxas keeps such
+ * multiply-adds on the FMA pipe (it turns x*1+c and x*-1+c back into ALU adds). */
+template <int K>
+__device__ __forceinline__ uint32_t mad_k(uint32_t a, uint32_t c)
+{
+#ifdef TB_SIMT_EMULATION
+	return a * (uint32_t)K + c;
+#else
+	uint32_t r;
+	asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "n"(K), "r"(c));
+	return r;
+#endif
+}
+
 __device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b)
 {
 #ifdef TB_SIMT_EMULATION
@@ -91,12 +120,9 @@ __device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b)
  * earlier (bit-reversed), and also the four decoded bits of the previous group.
  * M0[c] = 16 * mismatches of output class c (per half); the complementary branch has class c ^ 3.
  * Cost: one add + one VIADDMNMX.U16x2 per state and step for two trellises. */
-template <int Q>
-__device__ __forceinline__ void acs2_step(uint32_t (&pm)[16], const uint32_t (&M0)[4])
+__device__ __forceinline__ void acs2_step(uint32_t (&pm)[16], const uint32_t (&M0)[4], const uint32_t (&M1)[4])
 {
-	uint32_t M1[4], nm[16];
-#pragma unroll
-	for (int c = 0; c < 4; ++c) M1[c] = M0[c] + (0x00010001u << Q);
+	uint32_t nm[16];
 #pragma unroll
 	for (int s = 0; s < 16; ++s) {
 		const unsigned c = branch_class(s >> 1) ^ ((s & 1) ? 3u : 0u);
@@ -121,7 +147,7 @@ __device__ __forceinline__ uint4 take_history(uint32_t (&pm)[16])
 			const unsigned s = rev4(4 * j + i);
 			const uint32_t h = pm[s] & 0x000f000fu;
 			pm[s] = sub_opaque(pm[s], h);
-			acc = acc * 16 + h;
+			acc = i == 3 ? h : mad16_opaque(acc, h);
 		}
 		W[j] = acc;
 	}
@@ -152,37 +178,45 @@ __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *
 		const unsigned bp = 12 * g, w = bp >> 5, sh = bp & 31;
 		const uint32_t vx = __funnelshift_r(cx[w * nt], cx[(w + 1) * nt], sh) & 0xfffu;
 		const uint32_t vy = __funnelshift_r(cy[w * nt], cy[(w + 1) * nt], sh) & 0xfffu;
-		const uint32_t z = (vx | (vy << 16)) << 4;          /* bits pre-scaled: value 16 where a 1 was received */
-		uint32_t live = 0xffffffffu;
-		if (MASKED) live = ((8 * g < nx) ? 0xffffu : 0u) | ((8 * g < ny) ? 0xffff0000u : 0u);
+		const uint32_t z = vx | (vy << 16);                 /* received bits of both trellises, 12 per half */
+		const uint32_t nz = ~z;
+		uint32_t live = 0x00010001u;
+		if (MASKED) live = ((8 * g < nx) ? 0x0001u : 0u) | ((8 * g < ny) ? 0x00010000u : 0u);
 #pragma unroll
 		for (int p = 0; p < 4; ++p) {
-			const uint32_t r1 = (z >> (3 * p)) & 0x00100010u;
-			const uint32_t r2 = (z >> (3 * p + 1)) & 0x00100010u;
-			const uint32_t r3 = (z >> (3 * p + 2)) & 0x00100010u;
-			uint32_t M0[4];
-			M0[0] = r1 + r2;                                  /* expected 00 */
-			M0[3] = 0x00200020u - M0[0];                      /* expected 11 */
-			M0[2] = 0x00100010u - r1 + r2;                    /* expected G1=1, G2=0 */
-			M0[1] = 0x00200020u - M0[2];                      /* expected G1=0, G2=1 */
-			if (MASKED) { M0[0] &= live; M0[1] &= live; M0[2] &= live; M0[3] &= live; }
-			if (p & 1) acs2_step<2>(pm, M0); else acs2_step<0>(pm, M0);
-			M0[0] = r3; M0[2] = 0x00100010u - r3;             /* odd step: only G1 was sent */
-			if (MASKED) { M0[0] &= live; M0[2] &= live; }
-			M0[1] = M0[0]; M0[3] = M0[2];
-			if (p & 1) {
-				acs2_step<3>(pm, M0);
-				dec[(2 * g + (p >> 1)) * nt] = take_history(pm);
-			} else {
-				acs2_step<1>(pm, M0);
-			}
+			/* raw 0/1 per half: r1, r2 = the two symbols of the even step, r3 = the one of the odd step;
+			 * q1 = 1 - r1.  Blocks that have ended in this lane (MASKED) see no symbols: all costs zero. */
+			const uint32_t r1 = (z >> (3 * p)) & live, q1 = (nz >> (3 * p)) & live;
+			const uint32_t r2 = (z >> (3 * p + 1)) & live;
+			const uint32_t r3 = (z >> (3 * p + 2)) & live;
+			const uint32_t t = r1 + r2;                       /* mismatches if 00 was sent: 0..2 */
+			const uint32_t u = q1 + r2;                       /* mismatches if G1=1, G2=0 was sent */
+			const uint32_t two = MASKED ? live * 32u : 0x00200020u, one = MASKED ? live * 16u : 0x00100010u;
+			uint32_t M0[4], M1[4];
+			const uint32_t te = (p & 1) ? 0x00040004u : 0x00010001u;     /* tag of step q = 0 / 2 */
+			const uint32_t to = (p & 1) ? 0x00080008u : 0x00020002u;     /* tag of step q = 1 / 3 */
+			M0[0] = mad_k<16>(t, 0u);           M1[0] = mad_k<16>(t, te);
+			M0[3] = mad_k<-16>(t, two);         M1[3] = mad_k<-16>(t, two + te);
+			M0[2] = mad_k<16>(u, 0u);           M1[2] = mad_k<16>(u, te);
+			M0[1] = mad_k<-16>(u, two);         M1[1] = mad_k<-16>(u, two + te);
+			acs2_step(pm, M0, M1);
+			M0[0] = mad_k<16>(r3, 0u);          M1[0] = mad_k<16>(r3, to);   /* odd step: only G1 was sent */
+			M0[2] = mad_k<-16>(r3, one);        M1[2] = mad_k<-16>(r3, one + to);
+			M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
+			acs2_step(pm, M0, M1);
+			if (p & 1) dec[(2 * g + (p >> 1)) * nt] = take_history(pm);
 		}
 	}
 	{
 		/* four flush steps: no received symbols, so no cost; both inputs stay allowed, the trace back
 		 * starts in state 0, which only the all-zero tail can reach */
 		const uint32_t Z0[4] = { 0, 0, 0, 0 };
-		acs2_step<0>(pm, Z0); acs2_step<1>(pm, Z0); acs2_step<2>(pm, Z0); acs2_step<3>(pm, Z0);
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const uint32_t tq = 0x00010001u << q;
+			const uint32_t Z1[4] = { tq, tq, tq, tq };
+			acs2_step(pm, Z0, Z1);
+		}
 		dec[(nmax >> 2) * nt] = take_history(pm);
 	}
 	/* Trace back, one group (= one decoded nibble) per step.  f = decoded nibble of group g = bit-reversed
