@@ -149,6 +149,7 @@ struct tb200_ctx {
 	uint32_t *d_slot_bits = nullptr;
 	int32_t *d_last_good = nullptr, *d_blk_last = nullptr, *d_blk_prev = nullptr;
 	uint32_t *d_sb_list = nullptr;   /* slots classified as SYNC bursts; [ws_slots] + counter at the end */
+	uint32_t *d_kind_list = nullptr; /* [4][ws_slots] slots grouped by kind + [4] counters at the end (k_scan_blocks) */
 	size_t ws_slots = 0;
 	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the lane kernels, one area per resident CTA */
 	unsigned lane_ctas = 0;               /* resident CTAs of the lane kernels (grid size) */
@@ -321,7 +322,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry); cudaFree(ctx->d_ws); cudaFree(ctx->d_slot_bits);
-	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev); cudaFree(ctx->d_sb_list);
+	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev); cudaFree(ctx->d_sb_list); cudaFree(ctx->d_kind_list);
 	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch);
 	for (int i = 0; i < NBUF; i++) {
 		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]);
@@ -364,6 +365,7 @@ static int ensure_workspace(tb200_ctx *ctx, size_t slots)
 	if ((rc = grow(ctx, &ctx->d_blk_last, slots / 1024 + 2))) return rc;
 	if ((rc = grow(ctx, &ctx->d_blk_prev, slots / 1024 + 2))) return rc;
 	if ((rc = grow(ctx, &ctx->d_sb_list, slots + 4))) return rc;
+	if ((rc = grow(ctx, &ctx->d_kind_list, 4 * slots + 4))) return rc;
 	ctx->ws_slots = slots;
 	return 0;
 }
@@ -665,7 +667,10 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cuda
 	}
 	if (pe) CU(cudaEventRecord(pe[1], st));
 	const unsigned nblk = (nb + 1023) / 1024;
-	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, ctx->d_ws, nb, ctx->d_last_good, ctx->d_blk_last, ctx->d_flags + piece_idx);
+	uint32_t *kind_count = ctx->d_kind_list + 4 * ctx->ws_slots;
+	CU(cudaMemsetAsync(kind_count, 0, 4 * sizeof(uint32_t), st));
+	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, ctx->d_ws, nb, ctx->d_last_good, ctx->d_blk_last, ctx->d_flags + piece_idx,
+	          kind_count, ctx->d_kind_list, (uint32_t)ctx->ws_slots);
 	TB_LAUNCH(k_scan_prefix, 1, 1024, st, ctx->d_blk_last, nblk, ctx->d_blk_prev);
 	if (pe) CU(cudaEventRecord(pe[2], st));
 	ctx->stats.kernel_launches += 3;
@@ -691,6 +696,7 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	a.type1 = (ctx->opt.output & TB200_OUT_UNPACKED) ? o_type1 : nullptr;
 	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
 	a.a0 = a0; a.out_base = out_base; a.n_slots = nb;
+	a.kind_count = ctx->d_kind_list + 4 * ctx->ws_slots; a.kind_list = ctx->d_kind_list; a.list_stride = (uint32_t)ctx->ws_slots;
 	if (lane) TB_LAUNCH_SMEM(k_decode_lane, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else      TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
 	if (pe) CU(cudaEventRecord(pe[3], st));

@@ -771,16 +771,33 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
  * before me" (or -1), the block's last one, and the first slot that loses lock. */
 __global__ void __launch_bounds__(1024)
 k_scan_blocks(const SlotWs *__restrict__ ws, uint32_t n_slots, int32_t *__restrict__ last_good,
-              int32_t *__restrict__ blk_last, uint32_t *__restrict__ first_unlock)
+              int32_t *__restrict__ blk_last, uint32_t *__restrict__ first_unlock,
+              uint32_t *__restrict__ kind_count, uint32_t *__restrict__ kind_list, uint32_t list_stride)
 {
 	__shared__ int32_t warp_last[32];
+	__shared__ uint32_t kcnt[4][32];     /* slots of kind c in warp w, then exclusive offsets */
+	__shared__ uint32_t kbase[4];
 	const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
 	const uint64_t k = (uint64_t)blockIdx.x * 1024 + tid;
 	int32_t v = -1;
+	int kind = -1;
 	if (k < n_slots) {
 		const SlotWs s = ws[k];
 		if (s.good_sb) v = (int32_t)k;
 		if (s.unlock) atomicMin(first_unlock, (uint32_t)k);
+		kind = s.kind;
+	}
+	/* slots grouped by kind (one list per TB200_KIND_*), so that the lane decode pass can give every warp
+	 * blocks of one length: ranks inside the warp by ballot, warp offsets by a scan, one atomic per kind
+	 * and thread block.  The order inside a list is arbitrary. */
+	uint32_t my_rank = 0;
+	if (kind_count) {
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			const unsigned m = __ballot_sync(FULL, kind == c);
+			if (kind == c) my_rank = __popc(m & ((1u << lane) - 1));
+			if (lane == 0) kcnt[c][w] = __popc(m);
+		}
 	}
 	/* inclusive max-scan inside the warp */
 #pragma unroll
@@ -798,11 +815,25 @@ k_scan_blocks(const SlotWs *__restrict__ ws, uint32_t n_slots, int32_t *__restri
 			if (lane >= (unsigned)d && o > x) x = o;
 		}
 		warp_last[lane] = x;
+	} else if (kind_count && w <= 4) {
+		/* warps 1..4: exclusive scan of the per-warp counts of kind w-1, block total -> one atomic */
+		const int c = (int)w - 1;
+		const uint32_t mine = kcnt[c][lane];
+		uint32_t x = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t o = __shfl_up_sync(FULL, x, d);
+			if (lane >= (unsigned)d) x += o;
+		}
+		kcnt[c][lane] = x - mine;
+		if (lane == 31) kbase[c] = x ? atomicAdd(&kind_count[c], x) : 0u;
 	}
 	__syncthreads();
 	if (w > 0) { const int32_t o = warp_last[w - 1]; if (o > v) v = o; }
 	if (k < n_slots) last_good[k] = v;
 	if (tid == 1023) blk_last[blockIdx.x] = v;
+	if (kind_count && kind >= 0)
+		kind_list[(size_t)kind * list_stride + kbase[kind] + kcnt[kind][w] + my_rank] = (uint32_t)k;
 }
 
 /* Scan, step b: exclusive running max over the block results (single thread block). */
@@ -899,6 +930,9 @@ struct DecodeArgs {
 	uint64_t a0;
 	uint64_t out_base;       /* index of this launch's slot 0 in the output arrays */
 	uint32_t n_slots;
+	const uint32_t *kind_count;   /* [4] slots per TB200_KIND_* (lane form only) */
+	const uint32_t *kind_list;    /* [4][list_stride] their indices */
+	uint32_t list_stride;
 };
 
 /* Pass 2 (warp-shuffle Viterbi form), one warp per slot: everything of tp_sap_udata_ind

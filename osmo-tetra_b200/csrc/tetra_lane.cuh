@@ -20,7 +20,6 @@ namespace tb {
 
 constexpr int LANE_DEC_ROWS = 296;     /* words per thread: 73 groups of 4 trellis steps x uint4, padded */
 constexpr int LANE_T3_ROWS = 14;
-constexpr int LANE_T3B_ROWS = 8;       /* second block of two-block bursts: 216 bits + one readable row */
 constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: one warp, 5 CTAs fit an SM's shared memory */
 
 /* dynamic shared memory of a lane kernel with NT threads, in 32-bit words.  The survivor
@@ -29,14 +28,13 @@ constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: on
  * (written once, read once a few microseconds later, 128-byte coalesced rows). */
 __host__ __device__ constexpr size_t lane_smem_words(int nt)
 {
-	return (size_t)2 * LANE_T3_ROWS * nt + (size_t)2 * LANE_T3B_ROWS * nt + 256 + 16 + (nt / 32) * 16;
+	return (size_t)2 * LANE_T3_ROWS * nt + 256 + 16 + (nt / 32) * 16;
 }
 __host__ __device__ constexpr size_t lane_scratch_words_per_cta(int nt) { return (size_t)LANE_DEC_ROWS * nt; }
 
 struct LaneSmem {
 	uint4 *dec;          /* [LANE_DEC_ROWS / 4][NT] in GLOBAL scratch: survivor histories, one uint4 per thread and group of 4 steps */
 	uint32_t *t3;        /* [2][LANE_T3_ROWS][NT] type-3 bits, later the decoded type-2 bits */
-	uint32_t *t3b;       /* [2][LANE_T3B_ROWS][NT] the same for BLK2 of two-block bursts */
 	uint32_t *crc_tab;   /* [256] reflected CRC-CCITT byte table, then [16] nibble table */
 	uint32_t *lfb;       /* [NT/32][16] per-warp scrambling sequence broadcast */
 	static constexpr int nt = LANE_NT;
@@ -45,12 +43,10 @@ struct LaneSmem {
 		uint32_t *p = reinterpret_cast<uint32_t *>(base);
 		dec = reinterpret_cast<uint4 *>(scratch + (size_t)blockIdx.x * lane_scratch_words_per_cta(nt));
 		t3 = p; p += 2 * LANE_T3_ROWS * nt;
-		t3b = p; p += 2 * LANE_T3B_ROWS * nt;
 		crc_tab = p; p += 256 + 16;
 		lfb = p;
 	}
 	__device__ __forceinline__ uint32_t *t3col(int tr, int tid) const { return t3 + (size_t)tr * LANE_T3_ROWS * nt + tid; }
-	__device__ __forceinline__ uint32_t *t3bcol(int tr, int tid) const { return t3b + (size_t)tr * LANE_T3B_ROWS * nt + tid; }
 };
 
 /* class of the (G1,G2) outputs of branch (state j, input 0): idx = 2*G1 + G2 */
@@ -474,7 +470,11 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
 }
 
 /* ============================================================= decode pass ==
- * Everything of tp_sap_udata_ind that needs the cell state, two slots per thread. */
+ * Everything of tp_sap_udata_ind that needs the cell state.  A thread decodes two coded blocks at once
+ * (the two packed trellises).  The slots were grouped by kind (k_scan_blocks), so a warp gets blocks of
+ * one length: 288 steps for two SCH/F slots, 144 for the two halves BLK1 / BLK2 of ONE two-block slot or
+ * for the SB2 blocks of two SYNC bursts; dropped slots only get their record.  Units are handed out
+ * longest first.  Warps that straddle two lists run the masked form of the trellis loop. */
 __global__ void __launch_bounds__(32)
 k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 {
@@ -485,21 +485,30 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 	constexpr int nt = LANE_NT;
 	uint32_t *bcast = sm.lfb + (tid >> 5) * 16;
 	const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-	const uint64_t npairs = ((uint64_t)a.n_slots + 1) / 2;
-	const uint64_t rounds = (npairs + nthreads - 1) / nthreads;
+	/* units per list: pairs of SCH/F slots, single two-block slots, pairs of SYNC bursts, pairs of dropped slots */
+	const uint32_t cF = a.kind_count[KIND_NDB_F], c2 = a.kind_count[KIND_NDB_2], cS = a.kind_count[KIND_SB], c0 = a.kind_count[KIND_NONE];
+	const uint64_t uF = (cF + 1) / 2, u2 = c2, uS = (cS + 1) / 2, u0 = (c0 + 1) / 2;
+	const uint64_t units = uF + u2 + uS + u0;
+	const uint64_t rounds = (units + nthreads - 1) / nthreads;
+	const uint32_t *lF = a.kind_list + (size_t)KIND_NDB_F * a.list_stride, *l2 = a.kind_list + (size_t)KIND_NDB_2 * a.list_stride;
+	const uint32_t *lS = a.kind_list + (size_t)KIND_SB * a.list_stride, *l0 = a.kind_list + (size_t)KIND_NONE * a.list_stride;
 
 	for (uint64_t r = 0; r < rounds; ++r) {
-		const uint64_t pair = r * nthreads + (uint64_t)blockIdx.x * blockDim.x + tid;
-		const uint64_t k[2] = { 2 * pair, 2 * pair + 1 };
+		const uint64_t u = r * nthreads + (uint64_t)blockIdx.x * blockDim.x + tid;
+		uint64_t k[2] = { ~0ull, ~0ull };
+		if (u < uF)                     { k[0] = lF[2 * u]; if (2 * u + 1 < cF) k[1] = lF[2 * u + 1]; }
+		else if (u < uF + u2)           { k[0] = l2[u - uF]; }
+		else if (u < uF + u2 + uS)      { const uint64_t i = u - uF - u2; k[0] = lS[2 * i]; if (2 * i + 1 < cS) k[1] = lS[2 * i + 1]; }
+		else if (u < units)             { const uint64_t i = u - uF - u2 - uS; k[0] = l0[2 * i]; if (2 * i + 1 < c0) k[1] = l0[2 * i + 1]; }
 		uint32_t code[2] = { 0, 0 }, flags[2] = { 0, 0 }, bbk[2] = { 0, 0 };
 		int kind[2] = { KIND_NONE, KIND_NONE };
 		int n[2] = { 0, 0 };
 		Tm tm[2];
-		/* load, descramble and de-interleave every block of the two slots; the packed slot words
+		/* load, descramble and de-interleave every block of the slots; the packed slot words
 		 * only live inside this loop body, so the ACS loop below runs with a small register set */
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
-			const bool have = k[h] < a.n_slots;
+			const bool have = k[h] != ~0ull;
 			tm[h].tn = tm[h].fn = tm[h].mn = 0;
 			bool good_sb = false, unlock = false;
 			if (have) {
@@ -525,17 +534,18 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 					xor_region<230, 0, 14>(bw, lf);
 					bbk[h] = extract_bits(bw, 230, 14);
 					gather_lane<5, PL_SCHF>(bw, col, nt); n[h] = 288;
-				} else {
+				} else if (h == 0) {
+					/* two-block slot: BLK1 on trellis X, BLK2 on trellis Y of this thread (k[1] is unused) */
 					xor_region<14, 0, 216>(bw, lf);
 					xor_region<282, 0, 216>(bw, lf);
 					xor_region<230, 0, 14>(bw, lf);
 					bbk[h] = extract_bits(bw, 230, 14);
-					gather_lane<1, PL_BLK1>(bw, col, nt); n[h] = 144;
-					gather_lane<1, PL_BLK2>(bw, sm.t3bcol(h, tid), nt);
+					gather_lane<1, PL_BLK1>(bw, sm.t3col(0, tid), nt);
+					gather_lane<1, PL_BLK2>(bw, sm.t3col(1, tid), nt);
+					n[0] = n[1] = 144;
 				}
 			}
 		}
-		/* round 1: SB2 / SCH-F / BLK1 */
 		int nmax = n[0] > n[1] ? n[0] : n[1];
 #pragma unroll
 		for (int d = 16; d > 0; d >>= 1) {
@@ -543,6 +553,10 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			nmax = o > nmax ? o : nmax;
 		}
 		if (nmax) viterbi_pair(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], nmax);
+		if (kind[0] == KIND_NDB_2) {
+			if (crc_ok_col(sm, sm.t3col(0, tid), 140)) flags[0] |= F_CRC_A;
+			if (crc_ok_col(sm, sm.t3col(1, tid), 140)) flags[0] |= F_CRC_B;
+		}
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
 			const uint32_t *col = sm.t3col(h, tid);
@@ -551,28 +565,16 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 				if (tm_is_bnch(tm[h])) flags[h] |= F_BNCH;
 			} else if (kind[h] == KIND_NDB_F) {
 				if (crc_ok_col(sm, col, 284)) flags[h] |= F_CRC_A;
-			} else if (kind[h] == KIND_NDB_2) {
-				if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_A;
 			}
-		}
-		/* round 2: BLK2 of two-block bursts */
-		const bool any2 = __ballot_sync(FULL, kind[0] == KIND_NDB_2 || kind[1] == KIND_NDB_2) != 0;
-		if (any2) {
-			__syncwarp();
-			const int m0 = kind[0] == KIND_NDB_2 ? 144 : 0, m1 = kind[1] == KIND_NDB_2 ? 144 : 0;
-			viterbi_pair(sm.dec + tid, sm.t3bcol(0, tid), sm.t3bcol(1, tid), m0, m1, 144);
-#pragma unroll
-			for (int h = 0; h < 2; ++h)
-				if (kind[h] == KIND_NDB_2 && crc_ok_col(sm, sm.t3bcol(h, tid), 140)) flags[h] |= F_CRC_B;
 		}
 		/* assemble the slot's type-1 string in the reference's delivery order and store */
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
-			if (k[h] >= a.n_slots) continue;
+			if (k[h] == ~0ull) continue;
 			uint32_t outw[9];
 #pragma unroll
 			for (int i = 0; i < 9; ++i) outw[i] = 0;
-			const uint32_t *col = sm.t3col(h, tid), *colb = sm.t3bcol(h, tid);
+			const uint32_t *col = sm.t3col(h, tid);
 			const uint32_t bb = bbk[h];
 			const SlotWs w = a.ws[k[h]];
 			if (kind[h] == KIND_SB) {
@@ -584,6 +586,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 				put_lane(outw, 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
 				put_lane(outw, 14, 268, [&](int i) { return col[i * nt]; });
 			} else if (kind[h] == KIND_NDB_2) {
+				const uint32_t *colb = sm.t3col(1, tid);
 				put_lane(outw, 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
 				put_lane(outw, 14, 124, [&](int i) { return col[i * nt]; });
 				put_lane(outw, 138, 124, [&](int i) { return colb[i * nt]; });
