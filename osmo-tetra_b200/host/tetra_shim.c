@@ -14,6 +14,14 @@
  * tetra-rx has no end-of-stream call, so the tail is flushed from an atexit() handler, or
  * explicitly with tetra_b200_shim_flush().  Compiled against the reference's own headers.
  *
+ * Drop-in depths:
+ *   default                    PHY + lower MAC on the GPU, primitives to upper_mac_prim_recv()  (depth B)
+ *   -DTETRA_B200_SHIM_L0_ONLY  only the PHY (lock, training-sequence search, slot classification) on the
+ *                              GPU; every delivered slot goes to the REFERENCE's own tetra_burst_rx_cb()
+ *                              (phy/tetra_burst.c:341-379, keep phy/tetra_burst.o) and from there into the
+ *                              reference's tp_sap_udata_ind() / lower MAC: isolates sync + slicing parity (depth A)
+ *   depth C (GPU lower MAC behind the reference's PHY) is the batched leaf tb200_decode_blocks().
+ *
  * Not reproduced: the stdout text of the PHY / lower MAC (SURVEY 8b "text side-channel") and the
  * is_traffic dump path (tetra_lower_mac.c:194-241).  read() sizes must be constant (64 in
  * tetra-rx.c:83) except for the last one; other call patterns are rejected loudly.
@@ -37,13 +45,23 @@
 
 struct tetra_phy_state t_phy_state;
 
+#ifdef TETRA_B200_SHIM_L0_ONLY
+#define SHIM_HIST 8192u      /* bits of earlier batches kept in front of the batch: a slot may start in them */
+#else
+#define SHIM_HIST 0u
+#endif
+
 static struct {
 	tb200_ctx *ctx;
 	uint8_t *bits;
 	size_t n_bits, cap_bits, batch_bits;
+	uint8_t *hist;         /* L0-only depth: [SHIM_HIST bits of history][the batch = bits] */
+	size_t n_hist;
+	uint64_t fed_before;   /* stream bits handed to the library before this batch */
 	unsigned int chunk;
 	int short_read_seen;
 	int started;
+	int finished;          /* the stream was flushed: a second flush (atexit after an explicit one) does nothing */
 	struct tetra_rx_state *trs;
 	struct tb200_slot *slots;
 	uint8_t *type1;
@@ -57,6 +75,7 @@ static void shim_die(const char *msg)
 	exit(1);
 }
 
+#ifndef TETRA_B200_SHIM_L0_ONLY
 /* what tp_sap_udata_ind does after the arithmetic: allocate the primitive, fill it, hand it up,
  * re-invoke while the upper MAC consumed only part of the block (tetra_lower_mac.c:326-352) */
 static void deliver(const struct tb200_record *r, void *priv)
@@ -93,11 +112,14 @@ static void deliver(const struct tb200_record *r, void *priv)
 	talloc_free(msg);
 	talloc_free(ttp);
 }
+#endif
 
 static void shim_run(int final)
 {
-	if (!S.ctx || (!S.n_bits && !final))
+	if (!S.ctx || S.finished || (!S.n_bits && !final))
 		return;
+	if (final)
+		S.finished = 1;
 	uint32_t flags = (S.started ? 0 : TB200_FRESH) | (final ? TB200_FINAL : 0);
 	long n = tb200_rx_stream_host(S.ctx, S.bits, S.n_bits, flags, S.slots, S.type1, NULL, S.max_slots);
 	if (n < 0) {
@@ -105,11 +127,34 @@ static void shim_run(int final)
 		exit(1);
 	}
 	S.started = 1;
+	void *priv = S.trs ? S.trs->burst_cb_priv : NULL;
+#ifdef TETRA_B200_SHIM_L0_ONLY
+	/* what the LOCKED arm of tetra_burst_sync_in does per slot (phy/tetra_burst_sync.c:113-143): advance the
+	 * slot counter, then hand a slot whose training sequence sits where it should to the reference's slicer */
+	const uint64_t buf0 = S.fed_before - S.n_hist;             /* stream bit of hist[SHIM_HIST - n_hist] */
+	for (long i = 0; i < n; i++) {
+		const struct tb200_slot *sl = &S.slots[i];
+		tetra_tdma_time_add_tn(&t_phy_state.time, 1);
+		if ((sl->flags & TB200_F_KIND_MASK) == TB200_KIND_NONE)
+			continue;
+		const uint64_t abs = buf0 + (uint32_t)(sl->slot_bit - (uint32_t)buf0);
+		if (abs < buf0 || abs + TB200_BITS_PER_SLOT > S.fed_before + S.n_bits)
+			shim_die("slot outside the retained bits");
+		tetra_burst_rx_cb(S.hist + (SHIM_HIST - S.n_hist) + (abs - buf0), TB200_BITS_PER_SLOT, sl->find_rc, priv);
+	}
+	{       /* keep the last SHIM_HIST bits for slots that start in this batch and complete in the next */
+		const size_t have = S.n_hist + S.n_bits, keep = have < SHIM_HIST ? have : SHIM_HIST;
+		memmove(S.hist + (SHIM_HIST - keep), S.hist + (SHIM_HIST - S.n_hist) + (have - keep), keep);
+		S.n_hist = keep;
+	}
+	S.fed_before += S.n_bits;
+	S.n_bits = 0;
+#else
 	S.n_bits = 0;
 	size_t nrec = tb200_expand_records(S.slots, S.type1, (size_t)n, S.rec, 3 * S.max_slots);
-	void *priv = S.trs ? S.trs->burst_cb_priv : NULL;
 	for (size_t i = 0; i < nrec; i++)
 		deliver(&S.rec[i], priv);
+#endif
 	struct tb200_rx_carry c;
 	tb200_get_carry(S.ctx, &c);
 	if (S.trs) {                      /* mirror what callers could look at */
@@ -118,7 +163,9 @@ static void shim_run(int final)
 		S.trs->bitbuf_start_bitnum = (unsigned int)c.buf_start_bit;
 		S.trs->next_frame_start_bitnum = (unsigned int)c.next_frame_start;
 	}
+#ifndef TETRA_B200_SHIM_L0_ONLY      /* at the L0-only depth the reference's lower MAC owns the time (tetra_lower_mac.c:302) */
 	t_phy_state.time.tn = c.tn; t_phy_state.time.fn = c.fn; t_phy_state.time.mn = c.mn;
+#endif
 }
 
 void tetra_b200_shim_flush(void)
@@ -142,7 +189,8 @@ static void shim_init(unsigned int first_len)
 		shim_die(tb200_last_error(S.ctx));
 	S.chunk = first_len;
 	S.cap_bits = S.batch_bits + 4096;
-	S.bits = tb200_host_alloc(S.cap_bits);
+	S.hist = tb200_host_alloc(S.cap_bits + SHIM_HIST);
+	S.bits = S.hist ? S.hist + SHIM_HIST : NULL;
 	S.max_slots = tb200_max_slots(S.cap_bits) + 16;
 	S.slots = tb200_host_alloc(S.max_slots * sizeof(*S.slots));
 	S.type1 = tb200_host_alloc(S.max_slots * TB200_TYPE1_STRIDE);

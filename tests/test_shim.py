@@ -74,3 +74,44 @@ def test_shim_delivers_reference_primitives(orc):
     ok, msg = T.records_equal(want, got)
     assert ok, msg
     assert trs.state == orc.rx_state()
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF_SRC) and T.have_ref()), reason="reference build not present")
+def test_shim_l0_only_feeds_reference_lower_mac(orc):
+    """Drop-in depth A: only the PHY on the 'GPU' (SIMT-emulation build).  The shim hands every
+    delivered slot to the REFERENCE's own tetra_burst_rx_cb (phy/tetra_burst.o) and from there into the
+    reference's tp_sap_udata_ind / lower MAC (compiled in place, oracle/_ref/obj); the records at
+    upper_mac_prim_recv must be those of the all-reference receiver, lock loss and dropped bursts included."""
+    import glob
+    simt = T.build_simt()
+    os.makedirs(BUILD, exist_ok=True)
+    objdir = os.path.join(T.ROOT, "oracle", "_ref", "obj")
+    objs = [o for o in glob.glob(os.path.join(objdir, "**", "*.o"), recursive=True) if not o.endswith("tetra_burst_sync.o")]
+    so = os.path.join(BUILD, "libshim_l0.so")
+    subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-shared", "-DTETRA_B200_SHIM_L0_ONLY", "-I" + REF_SRC,
+                           "-I" + os.path.join(T.ROOT, "oracle", "stubs"), "-I" + os.path.join(T.ROOT, "include"),
+                           os.path.join(T.ROOT, "osmo-tetra_b200", "host", "tetra_shim.c")] + objs +
+                          [simt, "-Wl,--wrap=tetra_find_train_seq", "-Wl,-rpath," + os.path.dirname(simt), "-o", so])
+    bits, _ = _stream(orc, n=120, random_cell=1, sb_period=7)
+    bits[333 + 510 * 40 + 244:333 + 510 * 40 + 266] = 0           # a wiped training sequence: lock loss + re-acquisition
+    full = T.Ref()
+    full.reset(); full.feed(bits, 64)
+    want = full.records().copy()
+    os.environ["TETRA_B200_BATCH_BITS"] = "12288"          # several GPU batches, slots straddling them
+    lib = C.CDLL(so)
+    lib.ref_feed.restype = C.c_long
+    lib.ref_feed.argtypes = [C.c_void_p, C.c_size_t, C.c_uint, C.c_int]
+    lib.ref_rm3014_init()
+    lib.ref_reset()
+    b = np.ascontiguousarray(bits)
+    lib.ref_feed(b.ctypes.data_as(C.c_void_p), b.size, 64, 1)
+    lib.tetra_b200_shim_flush()
+    lib.ref_num_records.restype = C.c_size_t
+    lib.ref_records.restype = C.c_void_p
+    n = lib.ref_num_records()
+    got = np.frombuffer(C.string_at(lib.ref_records(), n * 288), dtype=T.RECORD_DTYPE).copy()
+    assert n == want.size
+    got["slot_bit"] = want["slot_bit"]                     # bitbuf_start_bitnum is not visible at this depth
+    ok, msg = T.records_equal(want, got)
+    assert ok, msg
+    assert int(want["crc_ok"].sum()) > 100
