@@ -688,14 +688,18 @@ def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=Fals
     if rank == 0:
         shard = d_full[lo:hi]
         if world > 1:
-            reqs = [dist.isend(d_full[span(r)[0]:span(r)[1]], r) for r in range(1, world) if span(r)[1] > span(r)[0]]
-            for q in reqs:
+            # one NCCL group: the sends to all peers run concurrently and share rank 0's NVLink egress
+            ops = [dist.P2POp(dist.isend, d_full[span(r)[0]:span(r)[1]], r) for r in range(1, world) if span(r)[1] > span(r)[0]]
+            for q in (dist.batch_isend_irecv(ops) if ops else []):
                 q.wait()
     else:
         shard = torch.empty(hi - lo + 64, dtype=torch.uint8, device=device)[:hi - lo]
         if hi > lo:
-            dist.recv(shard, 0)
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, shard, 0)]):
+                q.wait()
     if timers is not None:
+        if world > 1:
+            dist.barrier()          # the scatter ends when the last rank has its shard
         torch.cuda.synchronize(); timers["t_scatter1"] = __import__("time").perf_counter()
     s = g.shard_pass1(shard.data_ptr(), lo, hi - lo, lo, cmin + k0, n_bits, n)
     mine = torch.frombuffer(bytearray(bytes(s)), dtype=torch.uint8).to(device)
