@@ -25,7 +25,7 @@ if os.path.exists(rep):
     def _bytes(v, unit):
         return float(v) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[unit]
     for r in rows[2:]:
-        kname = r[idx['Kernel Name']].split("(")[0].split("::")[-1]
+        kname = r[idx['Kernel Name']].split("(")[0].split("::")[-1].replace("void ", "").split("<")[0].strip()
         if float(r[idx["gpu__time_duration.sum"]]) > consts.get(kname, {}).get("_dur", 0):
             consts[kname] = {"_dur": float(r[idx["gpu__time_duration.sum"]]),
                              "dram_bytes_per_launch": _bytes(r[idx["dram__bytes_read.sum"]], units[idx["dram__bytes_read.sum"]]) +
