@@ -179,6 +179,7 @@ struct tb200_ctx {
 	uint64_t tail_base = 0;
 	uint64_t fed_end = 0;            /* absolute bits handed to the ctx so far */
 	DevCarry h_carry;
+	DevCarry *h_carry_pin = nullptr;   /* pinned: [0] upload staging, [1] download staging (ordered on s_compute) */
 	bool stop_at_lock = false;       /* tb200_find_lock: return from rx_run as soon as LOCKED is reached */
 	/* sharded decode: what pass 1 left for pass 2 */
 	uint64_t shard_a0 = 0;
@@ -312,6 +313,7 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 	if (const char *e = getenv("TB200_CLASSIFY")) ctx->classify_form = atoi(e);
 	if (cudaMalloc((void **)&ctx->d_hits, sizeof(uint32_t) * (2 * 8192 + 2)) != cudaSuccess) return bail("cudaMalloc");
 	if (cudaHostAlloc((void **)&ctx->h_hits, sizeof(uint32_t) * (2 * 8192 + 2), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
+	if (cudaHostAlloc((void **)&ctx->h_carry_pin, 2 * sizeof(DevCarry), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
 	*out = ctx;
 	return 0;
 }
@@ -328,7 +330,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]);
 		cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]);
 	}
-	cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_hits); cudaFree(ctx->d_region);
+	cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_hits); cudaFreeHost(ctx->h_carry_pin); cudaFree(ctx->d_region);
 	cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
 	delete ctx;
 }
@@ -825,32 +827,41 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 			if (ctx->h_flags[i - 1] != 0xffffffffu) { bad_piece = i - 1; break; }
 		}
 	}
+	/* the state after the last valid slot becomes the start of the chain again: optimistically from the last
+	 * piece, enqueued behind its kernels so that it costs no extra round trip */
+	auto carry_over = [&](size_t last) -> int {
+		CU(cudaMemcpyAsync(&ctx->h_carry_pin[1], ctx->d_carry + last + 1, sizeof(DevCarry), cudaMemcpyDeviceToHost, ctx->s_compute));
+		CU(cudaMemcpyAsync(ctx->d_carry, ctx->d_carry + last + 1, sizeof(DevCarry), cudaMemcpyDeviceToDevice, ctx->s_compute));
+		return 0;
+	};
+	if (bad_piece == npieces && (rc = carry_over(npieces - 1))) return rc;
 	CU(cudaStreamSynchronize(ctx->s_h2d));
 	CU(cudaStreamSynchronize(ctx->s_compute));
 	CU(cudaStreamSynchronize(ctx->s_d2h));
 	if (bad_piece == npieces && ctx->h_flags[npieces - 1] != 0xffffffffu) bad_piece = npieces - 1;
 
-	size_t last_piece;
 	if (bad_piece < npieces) {
 		/* redo the piece that lost lock, cut right after the losing slot, so that outputs and
 		 * the carried cell state stop exactly where the reference's LOCKED state stops */
 		const uint32_t u = ctx->h_flags[bad_piece];
 		uint64_t k0; uint32_t nb;
 		piece_range(bad_piece, &k0, &nb);
+		if (bad_piece == 0) {
+			/* the chain start was overwritten by the optimistic carry-over: put it back */
+			ctx->h_carry_pin[0] = ctx->h_carry;
+			CU(cudaMemcpyAsync(ctx->d_carry, &ctx->h_carry_pin[0], sizeof(DevCarry), cudaMemcpyHostToDevice, ctx->s_compute));
+		}
 		if ((rc = issue(bad_piece, u + 1))) return rc;
+		if ((rc = carry_over(bad_piece))) return rc;
 		CU(cudaStreamSynchronize(ctx->s_h2d));
 		CU(cudaStreamSynchronize(ctx->s_compute));
 		CU(cudaStreamSynchronize(ctx->s_d2h));
 		*valid = k0 + u + 1;
 		*lost = true;
-		last_piece = bad_piece;
 	} else {
 		*valid = n_slots;
-		last_piece = npieces - 1;
 	}
-	/* the state after the last valid slot becomes the start of the chain again */
-	CU(cudaMemcpy(&ctx->h_carry, ctx->d_carry + last_piece + 1, sizeof(DevCarry), cudaMemcpyDeviceToHost));
-	CU(cudaMemcpy(ctx->d_carry, &ctx->h_carry, sizeof(DevCarry), cudaMemcpyHostToDevice));
+	ctx->h_carry = ctx->h_carry_pin[1];
 	out.n += *valid;
 	return 0;
 }
@@ -970,7 +981,11 @@ static int push_carry(tb200_ctx *ctx)
 {
 	int rc = ensure_pieces(ctx, 1);
 	if (rc) return rc;
-	CU(cudaMemcpy(ctx->d_carry, &ctx->h_carry, sizeof(DevCarry), cudaMemcpyHostToDevice));
+	/* ordered with the kernels: async copy on the compute stream from pinned staging (a plain cudaMemcpy from
+	 * pageable memory runs on the legacy stream, which our non-blocking streams do not wait for) */
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	ctx->h_carry_pin[0] = ctx->h_carry;
+	CU(cudaMemcpyAsync(ctx->d_carry, &ctx->h_carry_pin[0], sizeof(DevCarry), cudaMemcpyHostToDevice, ctx->s_compute));
 	return 0;
 }
 
