@@ -549,16 +549,23 @@ static int scan_more_hits(tb200_ctx *ctx, const Source &src, uint64_t from, uint
 			if (rc) return rc;
 			dbits = ctx->d_region; davail = rd_hi - dbase;
 		}
-		CU(cudaMemsetAsync(ctx->d_hits, 0, sizeof(uint32_t) * 2, ctx->s_compute));
+		CU(cudaMemsetAsync(ctx->d_hits, 0, sizeof(uint32_t) * (2 + 2 * 64), ctx->s_compute));
 		const unsigned blocks = (unsigned)std::min<uint64_t>((hi - lo + 8191) / 8192, (uint64_t)ctx->sm_count * 4);
 		TB_LAUNCH(k_scan_sync, blocks, 256, ctx->s_compute, dbits, src.fmt, dbase, davail, lo, hi, ctx->d_tab, ctx->d_hits, HIT_CAP);
 		ctx->stats.kernel_launches++;
 		CU(cudaGetLastError());
-		CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(uint32_t) * (2 + 2 * HIT_CAP), cudaMemcpyDeviceToHost, ctx->s_compute));
+		/* the list is short (a SYNC sequence per 18-odd bursts): fetch the count and the first entries, the rest only if needed */
+		const uint32_t first = 64;
+		CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(uint32_t) * (2 + 2 * first), cudaMemcpyDeviceToHost, ctx->s_compute));
 		CU(cudaStreamSynchronize(ctx->s_compute));
 		const uint32_t n = ctx->h_hits[0];
 		if (n > HIT_CAP)
 			return fail(ctx, TB200_E_STATE, "SYNC hit list overflow (%u hits in %u bits)", n, REGION_BITS);
+		if (n > first) {
+			CU(cudaMemcpyAsync(ctx->h_hits + 2 + 2 * first, ctx->d_hits + 2 + 2 * first, sizeof(uint32_t) * 2 * (n - first),
+			                   cudaMemcpyDeviceToHost, ctx->s_compute));
+			CU(cudaStreamSynchronize(ctx->s_compute));
+		}
 		const size_t old = ctx->hits.size();
 		for (uint32_t i = 0; i < n; i++) {
 			SyncHit h;
