@@ -162,6 +162,26 @@ long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits, 
 /* Upper bound on the slots a stream of n_bits can yield. */
 uint64_t tb200_max_slots(uint64_t n_bits);
 
+/* Optional side outputs, for callers that reproduce the reference's text output (tetra-rx prints them).
+ *
+ * CRC registers: after tb200_set_crc_buffer(ctx, buf) every rx call also writes, per slot and at the same index as
+ * the slot record, the CRC-16 register values the reference prints as "CRC COMP: 0x%04x" (tetra_lower_mac.c:258-267):
+ * bits 0-15 = SB1 / SCH-F / BLK1, bits 16-31 = SB2 / BLK2 (0x1d0f = good, 0 = no such block).  `buf` lives where the
+ * slot records live (device memory for tb200_rx_stream_dev, host memory for tb200_rx_stream_host) and holds
+ * max_slots words; NULL switches the output off.
+ *
+ * Lock acquisitions of the last rx call, i.e. every "found SYNC training sequence in bit #%u"
+ * (tetra_burst_sync.c:79): `offset` is that number (relative to bitbuf[0]), `call` the tetra_burst_sync_in()
+ * call that found it, `next_slot` the index of the first slot record delivered after it. */
+struct tb200_lock_event {
+	uint64_t next_slot;
+	uint64_t call;
+	uint32_t offset;
+	uint32_t pad;
+};
+int    tb200_set_crc_buffer(tb200_ctx *ctx, uint32_t *crc);
+size_t tb200_get_lock_events(const tb200_ctx *ctx, struct tb200_lock_event *ev, size_t max_events);
+
 int tb200_get_carry(const tb200_ctx *ctx, struct tb200_rx_carry *out);
 int tb200_get_stats(const tb200_ctx *ctx, struct tb200_stats *out);
 

@@ -163,6 +163,9 @@ struct tb200_ctx {
 	SlotOut *d_oslots[NBUF] = {nullptr, nullptr, nullptr};
 	uint8_t *d_otype1[NBUF] = {nullptr, nullptr, nullptr};
 	uint32_t *d_opacked[NBUF] = {nullptr, nullptr, nullptr};
+	uint32_t *d_ocrc[NBUF] = {nullptr, nullptr, nullptr};
+	uint32_t *user_crc = nullptr;    /* optional CRC-register output (tb200_set_crc_buffer), same residency as the slots */
+	std::vector<tb200_lock_event> lock_events;   /* lock acquisitions of the last rx call */
 	size_t out_cap = 0;
 	/* UNLOCKED search */
 	uint32_t *d_hits = nullptr;      /* [0] = count, then (pos_lo, pos_hi|prev<<31) pairs */
@@ -237,6 +240,21 @@ extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
 }
 
 extern "C" const char *tb200_last_error(const tb200_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" int tb200_set_crc_buffer(tb200_ctx *ctx, uint32_t *crc)
+{
+	if (!ctx) return TB200_E_ARG;
+	ctx->user_crc = crc;
+	return 0;
+}
+
+extern "C" size_t tb200_get_lock_events(const tb200_ctx *ctx, tb200_lock_event *ev, size_t max_events)
+{
+	if (!ctx) return 0;
+	const size_t n = ctx->lock_events.size();
+	for (size_t i = 0; ev && i < n && i < max_events; i++) ev[i] = ctx->lock_events[i];
+	return n;
+}
 
 extern "C" int tb200_create(tb200_ctx **out, int device)
 {
@@ -327,7 +345,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev); cudaFree(ctx->d_sb_list); cudaFree(ctx->d_kind_list);
 	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch);
 	for (int i = 0; i < NBUF; i++) {
-		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]);
+		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]); cudaFree(ctx->d_ocrc[i]);
 		cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]);
 	}
 	cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_hits); cudaFreeHost(ctx->h_carry_pin); cudaFree(ctx->d_region);
@@ -409,6 +427,7 @@ static int ensure_staging(tb200_ctx *ctx, size_t in_bytes, size_t slots)
 			if ((rc = grow(ctx, &ctx->d_oslots[i], slots))) return rc;
 			if ((rc = grow(ctx, &ctx->d_otype1[i], slots * TYPE1_STRIDE))) return rc;
 			if ((rc = grow(ctx, &ctx->d_opacked[i], slots * TYPE1_WORDS))) return rc;
+			if ((rc = grow(ctx, &ctx->d_ocrc[i], slots))) return rc;
 		}
 		ctx->out_cap = slots;
 	}
@@ -610,6 +629,7 @@ struct Outputs {
 	tb200_slot *slots;
 	uint8_t *type1;
 	uint32_t *packed;
+	uint32_t *crc;               /* optional (tb200_set_crc_buffer) */
 	uint64_t max_slots;
 	uint64_t n;                  /* slots written so far */
 };
@@ -689,7 +709,7 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cuda
 
 /* pass 2 of a piece: everything that needs the cell state carried in d_carry[piece_idx] */
 static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_idx, cudaEvent_t *pe,
-                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base)
+                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc = nullptr)
 {
 	cudaStream_t st = ctx->s_compute;
 	const bool lane = ctx->opt.viterbi == TB200_VITERBI_LANE;
@@ -706,6 +726,7 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
 	a.a0 = a0; a.out_base = out_base; a.n_slots = nb;
 	a.kind_count = ctx->d_kind_list + 4 * ctx->ws_slots; a.kind_list = ctx->d_kind_list; a.list_stride = (uint32_t)ctx->ws_slots;
+	a.crc = o_crc;
 	if (lane) TB_LAUNCH_SMEM(k_decode_lane, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else      TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
 	if (pe) CU(cudaEventRecord(pe[3], st));
@@ -720,7 +741,7 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 /* enqueue classify + scan + decode + carry for slots [k0, k0+nb) of the segment */
 static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32_t nb, const uint8_t *d_bits,
                          uint64_t d_base, uint64_t d_avail, int fmt, size_t piece_idx,
-                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base)
+                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc)
 {
 	RxGeom g;
 	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base; g.fmt = fmt;
@@ -740,7 +761,7 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	}
 	int rc = enqueue_pass1(ctx, g, piece_idx, pe);
 	if (rc) return rc;
-	return enqueue_pass2(ctx, g.a0, nb, piece_idx, pe, o_slots, o_type1, o_packed, out_base);
+	return enqueue_pass2(ctx, g.a0, nb, piece_idx, pe, o_slots, o_type1, o_packed, out_base, o_crc);
 }
 
 /* Process slots [0, n_slots) of a LOCKED segment, optimistically assuming lock is kept;
@@ -801,13 +822,13 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 			CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d[b], 0));
 			dbits = ctx->d_in[b]; davail = hi - dbase;
 		}
-		SlotOut *os; uint8_t *ot; uint32_t *op; uint64_t ob;
+		SlotOut *os; uint8_t *ot; uint32_t *op; uint64_t ob; uint32_t *oc;
 		if (out.on_device) {
-			os = (SlotOut *)out.slots; ot = out.type1; op = out.packed; ob = out.n + k0;
+			os = (SlotOut *)out.slots; ot = out.type1; op = out.packed; ob = out.n + k0; oc = out.crc;
 		} else {
-			os = ctx->d_oslots[b]; ot = ctx->d_otype1[b]; op = ctx->d_opacked[b]; ob = 0;
+			os = ctx->d_oslots[b]; ot = ctx->d_otype1[b]; op = ctx->d_opacked[b]; ob = 0; oc = out.crc ? ctx->d_ocrc[b] : nullptr;
 		}
-		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob);
+		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob, oc);
 		if (r) return r;
 		CU(cudaEventRecord(ctx->ev_comp[b], ctx->s_compute));
 		cudaStream_t so = host_out ? ctx->s_d2h : ctx->s_compute;
@@ -819,6 +840,8 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 				CU(cudaMemcpyAsync(out.type1 + o0 * TYPE1_STRIDE, ot, (size_t)nb * TYPE1_STRIDE, cudaMemcpyDeviceToHost, so));
 			if (out.packed && (ctx->opt.output & TB200_OUT_PACKED))
 				CU(cudaMemcpyAsync(out.packed + o0 * TYPE1_WORDS, op, (size_t)nb * TYPE1_WORDS * 4, cudaMemcpyDeviceToHost, so));
+			if (out.crc)
+				CU(cudaMemcpyAsync(out.crc + o0, oc, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		}
 		CU(cudaMemcpyAsync(ctx->h_flags + i, ctx->d_flags + i, sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		CU(cudaEventRecord(ctx->ev_d2h[b], so));
@@ -930,6 +953,11 @@ static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
 			rx.state = TB200_RX_KNOW_FSTART;
 			rx.next_frame_start = pos + 296;
 			ctx->stats.lock_acquisitions++;
+			{
+				tb200_lock_event le;
+				le.next_slot = out.n; le.call = c; le.offset = (uint32_t)(pos - rx.buf_start); le.pad = 0;
+				ctx->lock_events.push_back(le);
+			}
 			continue;
 		}
 		/* KNOW_FSTART */
@@ -1013,7 +1041,8 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 	if (rc) return rc;
 	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
-	out.max_slots = max_slots; out.n = 0;
+	out.crc = ctx->user_crc; out.max_slots = max_slots; out.n = 0;
+	ctx->lock_events.clear();
 	ctx->fed_end = n_bits;
 	profile_begin(ctx);
 	rc = rx_run(ctx, src, true, out);
@@ -1038,7 +1067,8 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	Source src; src.on_device = false; src.data = bits; src.new_base = ctx->fed_end; src.end = ctx->fed_end + n_bits;
 	src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = false; out.slots = slots; out.type1 = type1; out.packed = type1_packed;
-	out.max_slots = max_slots; out.n = 0;
+	out.crc = ctx->user_crc; out.max_slots = max_slots; out.n = 0;
+	ctx->lock_events.clear();
 	ctx->fed_end += n_bits;
 	profile_begin(ctx);
 	rc = rx_run(ctx, src, (flags & TB200_FINAL) != 0, out);
@@ -1452,7 +1482,7 @@ extern "C" int tb200_find_lock(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n
 	CU(cudaDeviceSynchronize());
 	reset_stream(ctx);
 	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = IN_BYTES;
-	Outputs out; out.on_device = true; out.slots = nullptr; out.type1 = nullptr; out.packed = nullptr; out.max_slots = 0; out.n = 0;
+	Outputs out; out.on_device = true; out.slots = nullptr; out.type1 = nullptr; out.packed = nullptr; out.crc = nullptr; out.max_slots = 0; out.n = 0;
 	ctx->fed_end = n_bits;
 	ctx->stop_at_lock = true;
 	int rc = rx_run(ctx, src, true, out);

@@ -257,7 +257,7 @@ k_classify_tma(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__r
 			w.sb1_t1[0] = 0; w.sb1_t1[1] = 0; w.sb_code = 0;
 			w.find_off = (uint16_t)off; w.window = (uint16_t)W;
 			w.find_rc = (int8_t)rc; w.good_sb = 0; w.kind = (uint8_t)kind; w.unlock = unlock;
-			w.tn = w.fn = w.mn = w.cc = 0; w.mcc = w.mnc = 0; w.pad = 0;
+			w.tn = w.fn = w.mn = w.cc = 0; w.mcc = w.mnc = 0; w.sb1_crc = 0;
 			ws[k] = w;
 		}
 		__syncwarp();

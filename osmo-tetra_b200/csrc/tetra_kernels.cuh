@@ -152,7 +152,7 @@ struct SlotWs {
 	uint8_t  unlock;         /* receiver leaves LOCKED after this slot */
 	uint8_t  tn, fn, mn, cc; /* SYNC PDU fields (raw) */
 	uint16_t mcc, mnc;
-	uint32_t pad;
+	uint32_t sb1_crc;        /* CRC-16 register after SB1's 76 bits (0x1d0f = good), for the optional CRC output */
 };
 static_assert(sizeof(SlotWs) == 32, "SlotWs layout");
 
@@ -733,7 +733,7 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
 			S.bw[lane] = xw;
 		}
 		uint32_t good = 0, t1lo = 0, t1hi = 0, code = 0;
-		uint32_t tn = 0, fn = 0, mn = 0, cc = 0, mcc = 0, mnc = 0;
+		uint32_t tn = 0, fn = 0, mn = 0, cc = 0, mcc = 0, mnc = 0, sb1_crc = 0;
 		if (DO_SB1 && kind == KIND_SB) {
 			if (lane < 16) S.lf[lane] = tab->lfsr_sb1[lane];
 			if (lane < 4) S.bw[16 + lane] = 0;
@@ -742,6 +742,7 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
 			viterbi_warp<80>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
 			const uint32_t crc = crc16_half(S.t2[0], 76, 0, tab);
 			good = (crc == 0x1d0f);
+			sb1_crc = crc;
 			t1lo = S.t2[0][0];
 			t1hi = S.t2[0][1] & 0x0fffffffu;
 			/* SYNC PDU fields, tetra_lower_mac.c:291-297 */
@@ -760,7 +761,7 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
 			w.find_off = (uint16_t)off; w.window = (uint16_t)W;
 			w.find_rc = (int8_t)rc; w.good_sb = (uint8_t)good; w.kind = (uint8_t)kind; w.unlock = unlock;
 			w.tn = (uint8_t)tn; w.fn = (uint8_t)fn; w.mn = (uint8_t)mn; w.cc = (uint8_t)cc;
-			w.mcc = (uint16_t)mcc; w.mnc = (uint16_t)mnc; w.pad = 0;
+			w.mcc = (uint16_t)mcc; w.mnc = (uint16_t)mnc; w.sb1_crc = sb1_crc;
 			ws[k] = w;
 		}
 		__syncwarp();
@@ -933,6 +934,7 @@ struct DecodeArgs {
 	const uint32_t *kind_count;   /* [4] slots per TB200_KIND_* (lane form only) */
 	const uint32_t *kind_list;    /* [4][list_stride] their indices */
 	uint32_t list_stride;
+	uint32_t *crc;                /* optional: CRC-16 registers per slot, block A (SB1 / SCH-F / BLK1) | block B (SB2 / BLK2) << 16 */
 };
 
 /* Pass 2 (warp-shuffle Viterbi form), one warp per slot: everything of tp_sap_udata_ind
@@ -952,6 +954,7 @@ k_decode_warp(DecodeArgs a)
 		cell_state(k, a.ws, a.last_good, a.blk_prev, a.carry, &tm, &code);
 		const int kind = w.kind;
 		uint32_t flags = (uint32_t)kind | (w.unlock ? F_UNLOCK : 0);
+		uint32_t crcs = 0;
 
 		if (lane < 16) S.bw[lane] = a.slot_bits[k * 16 + lane];
 		if (lane < 4) S.bw[16 + lane] = 0;
@@ -973,6 +976,7 @@ k_decode_warp(DecodeArgs a)
 			viterbi_warp<144>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
 			const uint32_t crc = crc16_half(S.t2[0], 140, 1, tab);
 			if (crc == 0x1d0f) flags |= F_CRC_B;
+			crcs = (w.sb1_crc & 0xffffu) | (crc << 16);
 			if (tm_is_bnch(tm)) flags |= F_BNCH;
 			put_bits(S.outw, 0, S.sb1, 60, lane);
 			put_bits(S.outw, 60, S.bbk, 14, lane);
@@ -986,6 +990,7 @@ k_decode_warp(DecodeArgs a)
 			viterbi_warp<288>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
 			const uint32_t crc = crc16_half(S.t2[0], 284, 2, tab);
 			if (crc == 0x1d0f) flags |= F_CRC_A;
+			crcs = crc & 0xffffu;
 			put_bits(S.outw, 0, S.bbk, 14, lane);
 			put_bits(S.outw, 14, S.t2[0], 268, lane);
 		} else if (kind == KIND_NDB_2) {
@@ -1000,6 +1005,7 @@ k_decode_warp(DecodeArgs a)
 			const uint32_t okA = __shfl_sync(FULL, crc == 0x1d0f, 0), okB = __shfl_sync(FULL, crc == 0x1d0f, 16);
 			if (okA) flags |= F_CRC_A;
 			if (okB) flags |= F_CRC_B;
+			crcs = (__shfl_sync(FULL, crc, 0) & 0xffffu) | (__shfl_sync(FULL, crc, 16) << 16);
 			put_bits(S.outw, 0, S.bbk, 14, lane);
 			put_bits(S.outw, 14, S.t2[0], 124, lane);
 			put_bits(S.outw, 138, S.t2[1], 124, lane);
@@ -1015,6 +1021,7 @@ k_decode_warp(DecodeArgs a)
 			o.time = (uint16_t)(tm.tn | (tm.fn << 3) | (tm.mn << 8));
 			o.find_rc = w.find_rc; o.flags = (uint8_t)flags;
 			a.slots[ko] = o;
+			if (a.crc) a.crc[ko] = crcs;
 		}
 		__syncwarp();
 	}

@@ -259,7 +259,13 @@ __device__ __forceinline__ void viterbi_pair(uint4 *dec, uint32_t *cx, uint32_t 
 /* CRC-16-CCITT of the first L type-2 bits of a column, reflected byte-table form of
  * crc_simple.c:65-82 (register bit-reversed, so packed LSB-first bytes feed it directly);
  * returns true when the residue is TETRA_CRC_OK (0x1d0f, tetra_common.h:69). L % 8 == 4. */
+__device__ __forceinline__ uint32_t crc_col(const LaneSmem &sm, const uint32_t *col, int L);
 __device__ __forceinline__ bool crc_ok_col(const LaneSmem &sm, const uint32_t *col, int L)
+{
+	return crc_col(sm, col, L) == 0x1d0f;
+}
+/* the CRC register itself, in the reference's bit order (what tetra-rx prints as "CRC COMP: 0x%04x") */
+__device__ __forceinline__ uint32_t crc_col(const LaneSmem &sm, const uint32_t *col, int L)
 {
 	uint32_t r = 0xffff;
 	constexpr int nt = LANE_NT;
@@ -271,7 +277,7 @@ __device__ __forceinline__ bool crc_ok_col(const LaneSmem &sm, const uint32_t *c
 	const int bp = L & ~7;
 	const uint32_t nib = (col[(bp >> 5) * nt] >> (bp & 31)) & 0xf;
 	r = (r >> 4) ^ sm.crc_tab[256 + ((r ^ nib) & 0xf)];
-	return r == 0xf0b8;               /* bit-reversed 0x1d0f */
+	return __brev(r) >> 16;           /* the table form keeps the register bit-reversed (0xf0b8 = good) */
 }
 
 /* ---- descrambling in the burst domain ------------------------------------------- */
@@ -449,7 +455,8 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
 			if (n[h]) {
 				const uint32_t *col = sm.t3col(h, tid);
 				constexpr int nt = LANE_NT;
-				const bool good = crc_ok_col(sm, col, 76);
+				const uint32_t crc1 = crc_col(sm, col, 76);
+				const bool good = crc1 == 0x1d0f;
 				const uint32_t w0 = col[0], w1 = col[nt], w2 = col[2 * nt];
 				const uint32_t t2[4] = { w0, w1, w2, 0 };
 				SlotWs w = ws[k[h]];
@@ -462,6 +469,7 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
 				w.mcc = (uint16_t)field_msb_first(t2, 31, 10);
 				w.mnc = (uint16_t)field_msb_first(t2, 41, 14);
 				w.sb_code = scramb_init_from(w.mcc, w.mnc, w.cc);
+				w.sb1_crc = crc1;
 				ws[k[h]] = w;
 			}
 		}
@@ -553,18 +561,25 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			nmax = o > nmax ? o : nmax;
 		}
 		if (nmax) viterbi_pair(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], nmax);
+		uint32_t crcs[2] = { 0, 0 };            /* block A | block B << 16 of each slot */
 		if (kind[0] == KIND_NDB_2) {
-			if (crc_ok_col(sm, sm.t3col(0, tid), 140)) flags[0] |= F_CRC_A;
-			if (crc_ok_col(sm, sm.t3col(1, tid), 140)) flags[0] |= F_CRC_B;
+			const uint32_t ca = crc_col(sm, sm.t3col(0, tid), 140), cb = crc_col(sm, sm.t3col(1, tid), 140);
+			if (ca == 0x1d0f) flags[0] |= F_CRC_A;
+			if (cb == 0x1d0f) flags[0] |= F_CRC_B;
+			crcs[0] = ca | (cb << 16);
 		}
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
 			const uint32_t *col = sm.t3col(h, tid);
 			if (kind[h] == KIND_SB) {
-				if (crc_ok_col(sm, col, 140)) flags[h] |= F_CRC_B;
+				const uint32_t cb = crc_col(sm, col, 140);
+				if (cb == 0x1d0f) flags[h] |= F_CRC_B;
+				crcs[h] = cb << 16;             /* SB1's half is added from the slot state below */
 				if (tm_is_bnch(tm[h])) flags[h] |= F_BNCH;
 			} else if (kind[h] == KIND_NDB_F) {
-				if (crc_ok_col(sm, col, 284)) flags[h] |= F_CRC_A;
+				const uint32_t ca = crc_col(sm, col, 284);
+				if (ca == 0x1d0f) flags[h] |= F_CRC_A;
+				crcs[h] = ca;
 			}
 		}
 		/* assemble the slot's type-1 string in the reference's delivery order and store */
@@ -611,6 +626,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			o.time = (uint16_t)(tm[h].tn | (tm[h].fn << 3) | (tm[h].mn << 8));
 			o.find_rc = w.find_rc; o.flags = (uint8_t)flags[h];
 			a.slots[ko] = o;
+			if (a.crc) a.crc[ko] = crcs[h] | (kind[h] == KIND_SB ? (w.sb1_crc & 0xffffu) : 0u);
 		}
 		__syncwarp();
 	}

@@ -1,0 +1,159 @@
+/*
+ * tetra_rx_b200.c - file-in / text-out receiver on top of libtetra_b200.so: the counterpart of
+ * `tetra-rx <bits-file>` (src/tetra-rx.c:40-103) for the part of its output that the PHY and the lower MAC
+ * produce.  It reads a stream file, decodes it on the GPU in one batch call and prints, in stream order,
+ * exactly the lines the reference prints from phy/tetra_burst_sync.c and lower_mac/tetra_lower_mac.c:
+ *
+ *   found SYNC training sequence in bit #N            tetra_burst_sync.c:79
+ *   (empty line) BURST                                tetra_burst_sync.c:114-116
+ *   BNCH FOLLOWS                                      tetra_lower_mac.c:170-173
+ *   CRC COMP: 0x1d0f OK / CRC COMP: 0x.... WRONG      tetra_lower_mac.c:258-267
+ *   <SB1|SB2|NDB|SCH/F> mn/fn/tn/sn type1: <bits>     tetra_lower_mac.c:264-265
+ *   TMB-SAP SYNC CC ... TN ... FN ... MN ... MCC ... MNC ...   tetra_lower_mac.c:283-289
+ *
+ * and on stderr the "#### ..." complaints of tetra_burst_sync.c:126,136,139.  That is the text the
+ * reference's regression harness counts (tetra-rx-tests.sh:56 greps "^CRC COMP: 0x.+ OK").  The upper MAC
+ * (everything tetra-rx prints from upper_mac_prim_recv() on) is not part of this tool: link the real one
+ * through tetra_shim.c for that.
+ *
+ * usage: tetra-rx-b200 [-f bytes|packed|f32] [-c read_size_bits] [-g cuda_device] <stream-file>
+ *   bytes   one bit per byte, what tetra-rx reads (default)      packed  eight bits per byte
+ *   f32     float32 symbols, what float_to_bits reads
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "tetra_b200.h"
+
+static const char *ubit_dump(const uint8_t *bits, unsigned int len)      /* osmo_ubit_dump: '0' / '1' per bit */
+{
+	static char buf[512];
+	unsigned int i;
+	for (i = 0; i < len && i < sizeof(buf) - 1; i++)
+		buf[i] = bits[i] ? '1' : '0';
+	buf[i] = 0;
+	return buf;
+}
+
+static unsigned int bits_to_uint(const uint8_t *bits, unsigned int len)   /* tetra_common.c:31-39, MSB first */
+{
+	unsigned int v = 0;
+	while (len--)
+		v = (v << 1) | (*bits++ & 1);
+	return v;
+}
+
+struct tm3 { uint32_t tn, fn, mn; };
+
+static const char *time_dump(const struct tm3 *t)                          /* tetra_tdma.c:85-92, sn is never set */
+{
+	static char buf[64];
+	snprintf(buf, sizeof(buf), "%02u/%02u/%u/%03u", t->mn, t->fn, t->tn, 0u);
+	return buf;
+}
+
+static void crc_lines(const char *name, const struct tm3 *t, uint32_t crc, int ok, const uint8_t *type1, unsigned int len)
+{
+	printf("CRC COMP: 0x%04x ", crc & 0xffff);
+	if (ok) {
+		printf("OK\n");
+		printf("%s %s type1: %s\n", name, time_dump(t), ubit_dump(type1, len));
+	} else
+		printf("WRONG\n");
+}
+
+int main(int argc, char **argv)
+{
+	const char *fmt = "bytes", *path = NULL;
+	unsigned int chunk = 64;
+	int device = 0;
+	for (int i = 1; i < argc; i++) {
+		if (!strcmp(argv[i], "-f") && i + 1 < argc) fmt = argv[++i];
+		else if (!strcmp(argv[i], "-c") && i + 1 < argc) chunk = (unsigned int)atoi(argv[++i]);
+		else if (!strcmp(argv[i], "-g") && i + 1 < argc) device = atoi(argv[++i]);
+		else path = argv[i];
+	}
+	if (!path) {
+		fprintf(stderr, "usage: %s [-f bytes|packed|f32] [-c read_size_bits] [-g cuda_device] <stream-file>\n", argv[0]);
+		return 2;
+	}
+	uint32_t input = !strcmp(fmt, "packed") ? TB200_IN_PACKED : !strcmp(fmt, "f32") ? TB200_IN_F32SYM : TB200_IN_BYTES;
+
+	FILE *f = fopen(path, "rb");
+	if (!f) { perror("open"); return 1; }
+	fseek(f, 0, SEEK_END);
+	const long fsize = ftell(f);
+	fseek(f, 0, SEEK_SET);
+	uint8_t *data = tb200_host_alloc((size_t)fsize + 64);
+	if (!data || fread(data, 1, (size_t)fsize, f) != (size_t)fsize) { fprintf(stderr, "read failed\n"); return 1; }
+	fclose(f);
+	const uint64_t n_bits = input == TB200_IN_BYTES ? (uint64_t)fsize : input == TB200_IN_PACKED ? 8ull * fsize : (uint64_t)fsize / 4 * 2;
+
+	tb200_ctx *rx;
+	if (tb200_create(&rx, device) != 0) { fprintf(stderr, "no usable CUDA device (there is no CPU lower MAC in this build)\n"); return 1; }
+	struct tb200_options opt;
+	tb200_default_options(&opt);
+	opt.chunk_bits = chunk; opt.output = TB200_OUT_UNPACKED; opt.input = input;
+	if (tb200_set_options(rx, &opt) != 0) { fprintf(stderr, "%s\n", tb200_last_error(rx)); return 1; }
+	const uint64_t cap = tb200_max_slots(n_bits) + 16;
+	struct tb200_slot *slots = tb200_host_alloc(cap * sizeof(*slots));
+	uint8_t *type1 = tb200_host_alloc(cap * TB200_TYPE1_STRIDE);
+	uint32_t *crc = tb200_host_alloc(cap * sizeof(*crc));
+	if (!slots || !type1 || !crc) { fprintf(stderr, "out of memory\n"); return 1; }
+	tb200_set_crc_buffer(rx, crc);
+	const long n = tb200_rx_stream_host(rx, data, n_bits, TB200_FRESH | TB200_FINAL, slots, type1, NULL, cap);
+	if (n < 0) { fprintf(stderr, "%s\n", tb200_last_error(rx)); return 1; }
+	const size_t n_ev = tb200_get_lock_events(rx, NULL, 0);
+	struct tb200_lock_event *ev = calloc(n_ev ? n_ev : 1, sizeof(*ev));
+	tb200_get_lock_events(rx, ev, n_ev);
+
+	struct tm3 cur = { 0, 0, 0 };                    /* t_phy_state.time: zero at start (tetra_burst_sync.c:34) */
+	size_t e = 0;
+	for (long i = 0; i <= n; i++) {
+		while (e < n_ev && ev[e].next_slot == (uint64_t)i)
+			printf("found SYNC training sequence in bit #%u\n", ev[e++].offset);
+		if (i == n)
+			break;
+		const struct tb200_slot *s = &slots[i];
+		const uint8_t *t1 = type1 + (size_t)i * TB200_TYPE1_STRIDE;
+		const int kind = s->flags & TB200_F_KIND_MASK;
+		tb200_debug_time_advance(&cur.tn, &cur.fn, &cur.mn, 1);         /* tetra_burst_sync.c:113 */
+		printf("\nBURST\n");
+		if (kind == TB200_KIND_NONE) {
+			if (s->find_rc < 0)
+				fprintf(stderr, "#### could not find successive burst training sequence\n");
+			else
+				fprintf(stderr, "#### SYNC burst at offset %u?!?\n", (unsigned int)s->find_off);
+			continue;
+		}
+		struct tm3 post = { s->time & 7u, (s->time >> 3) & 31u, (s->time >> 8) & 63u };
+		if (kind == TB200_KIND_SB) {
+			/* SB1 is printed with the time before the SYNC PDU is applied (time_str is taken on entry) */
+			crc_lines("SB1", &cur, crc[i], (s->flags & TB200_F_CRC_A) != 0, t1, 60);
+			printf("TMB-SAP SYNC CC %s(0x%02x) ", ubit_dump(t1 + 4, 6), bits_to_uint(t1 + 4, 6));
+			printf("TN %s(%u) ", ubit_dump(t1 + 10, 2), bits_to_uint(t1 + 10, 2) + 1);
+			printf("FN %s(%2u) ", ubit_dump(t1 + 12, 5), bits_to_uint(t1 + 12, 5));
+			printf("MN %s(%2u) ", ubit_dump(t1 + 17, 6), bits_to_uint(t1 + 17, 6));
+			printf("MCC %s(%u) ", ubit_dump(t1 + 31, 10), bits_to_uint(t1 + 31, 10));
+			printf("MNC %s(%u)\n", ubit_dump(t1 + 41, 14), bits_to_uint(t1 + 41, 14));
+			cur = post;                                                  /* tetra_lower_mac.c:302 */
+			if (s->flags & TB200_F_BNCH)
+				printf("BNCH FOLLOWS\n");
+			crc_lines("SB2", &cur, crc[i] >> 16, (s->flags & TB200_F_CRC_B) != 0, t1 + 74, 124);
+		} else if (kind == TB200_KIND_NDB_F) {
+			crc_lines("SCH/F", &cur, crc[i], (s->flags & TB200_F_CRC_A) != 0, t1 + 14, 268);
+		} else {
+			crc_lines("NDB", &cur, crc[i], (s->flags & TB200_F_CRC_A) != 0, t1 + 14, 124);
+			crc_lines("NDB", &cur, crc[i] >> 16, (s->flags & TB200_F_CRC_B) != 0, t1 + 138, 124);
+		}
+		if (cur.tn != post.tn || cur.fn != post.fn || cur.mn != post.mn) {
+			fprintf(stderr, "internal error: slot %ld time %s differs from the device's\n", i, time_dump(&cur));
+			return 3;
+		}
+	}
+	fflush(stdout);
+	tb200_destroy(rx);
+	return 0;
+}
