@@ -492,10 +492,18 @@ def run_config5(args, rank, world, local_rank):
     cfg = T.GenCfg(seed=0x7E7A0005, sb_period=2, lead_sb=2, ndb2_per_256=64, ber_per_65536=655, random_cell=1, lead_in_bits=333)
     nbits = 510 * n + 333
     full = None
+    handle = None
     if rank == 0:
-        full = torch.zeros(nbits + 64, dtype=torch.uint8, device=dev)
+        buf = T.DevBuffer(g, nbits + 64)            # exportable memory: the peer mode maps it into the other ranks
+        full = buf.tensor(dev)
         assert g.lib.tb200_gen_stream_dev(g.h, C.byref(cfg), 0, n, C.c_void_p(full.data_ptr()), 1) == 0, g.err()
         full = full[:nbits]
+    if args.peer and world > 1:
+        hb = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            hb.copy_(torch.frombuffer(bytearray(buf.export()), dtype=torch.uint8))
+        dist.broadcast(hb, 0)
+        handle = bytes(hb.cpu().numpy().tobytes())
     g.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, output=T.OUT_PACKED)
 
     def barrier():
@@ -511,7 +519,7 @@ def run_config5(args, rank, world, local_rank):
         tm = {}
         barrier()
         t0 = time.perf_counter()
-        k0, k1, a0, d_slots, _, d_pk, summ = T.sharded_decode(g, dist, rank, world, full, nbits, dev, timers=tm)
+        k0, k1, a0, d_slots, _, d_pk, summ = T.sharded_decode(g, dist, rank, world, full, nbits, dev, timers=tm, peer_handle=handle)
         barrier()
         t1 = time.perf_counter()
         if it >= args.warmup:
@@ -525,8 +533,9 @@ def run_config5(args, rank, world, local_rank):
         line = {"metric": METRIC, "value": slots_total * args.steps / tot_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": tot_s / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-                "config": {"workload": f"config5: one stream of {n} bursts (config-4 shape) on rank 0, NCCL scatter of contiguous shards + "
-                                       "all-gather of 32-byte cell-state summaries", "total_bursts": n,
+                "config": {"workload": f"config5: one stream of {n} bursts (config-4 shape) on rank 0, " +
+                                       ("shards read in place over NVLink by the search kernels (peer-mapped memory)" if handle else
+                                        "NCCL scatter of contiguous shards") + " + all-gather of 32-byte cell-state summaries", "total_bursts": n,
                            "l2": "inputs larger than L2", "parallelism": f"one stream sharded x{world}", "output": "slot records + packed type-1 bits, rank-local"},
                 "decode_only": {"value": slots_total * args.steps / dec_s, "unit": UNIT, "ms_per_step": dec_s / args.steps * 1e3,
                                 "note": "scatter excluded (wall-clock between device synchronisations, max over ranks)"},
@@ -548,6 +557,7 @@ def main():
     ap.add_argument("--workload", default="config2", choices=["config2", "config5"],
                     help="config2: headline (independent streams per GPU); config5: one stream scattered over the GPUs with NCCL")
     ap.add_argument("--total-bursts", type=int, default=100_000_000, help="config5: bursts in the one stream")
+    ap.add_argument("--peer", action="store_true", help="config5: no scatter, every rank's search kernel reads its shard from rank 0's memory over NVLink")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -291,6 +291,18 @@ void tb200_shard_carry_in(const struct tb200_shard_summary *all, int rank, const
 long tb200_shard_pass2(tb200_ctx *ctx, const struct tb200_rx_carry *carry_in, struct tb200_slot *d_slots,
                        uint8_t *d_type1, uint32_t *d_type1_packed);
 
+/* One stream read by several GPUs without a copy: the rank that holds the stream allocates it with
+ * tb200_dev_alloc (plain device memory, exportable), exports a 64-byte handle, the other ranks (one process
+ * per GPU) import it and hand the mapped pointer (+ byte offset of their shard) to tb200_shard_pass1: the
+ * search kernel then pulls its shard straight out of the owner's HBM over NVLink (TMA bulk copies from peer
+ * memory), instead of waiting for a scatter to finish first.  The pointer passed to export must be the
+ * start of a tb200_dev_alloc allocation. */
+void *tb200_dev_alloc(tb200_ctx *ctx, size_t bytes);
+void  tb200_dev_free(tb200_ctx *ctx, void *p);
+int   tb200_ipc_export(tb200_ctx *ctx, const void *d_ptr, uint8_t handle[64]);
+int   tb200_ipc_import(tb200_ctx *ctx, const uint8_t handle[64], void **d_ptr);
+int   tb200_ipc_close(tb200_ctx *ctx, void *d_ptr);
+
 /* ---- introspection used by the tests ------------------------------------------------ */
 
 /* n x tetra_tdma_time_add_tn(tm, 1) (tetra_tdma.c:75-79) in closed form, as the kernels do it */

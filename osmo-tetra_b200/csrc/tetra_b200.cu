@@ -241,6 +241,64 @@ extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
 
 extern "C" const char *tb200_last_error(const tb200_ctx *ctx) { return ctx ? ctx->err : "null ctx"; }
 
+/* ---- device memory another process can map (one stream read by several GPUs over NVLink) ---- */
+
+extern "C" void *tb200_dev_alloc(tb200_ctx *ctx, size_t bytes)
+{
+	if (!ctx || cudaSetDevice(ctx->device) != cudaSuccess) return nullptr;
+	void *p = nullptr;
+	if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+extern "C" void tb200_dev_free(tb200_ctx *ctx, void *p)
+{
+	if (ctx) cudaSetDevice(ctx->device);
+	cudaFree(p);
+}
+
+extern "C" int tb200_ipc_export(tb200_ctx *ctx, const void *d_ptr, uint8_t handle[64])
+{
+	if (!ctx || !d_ptr || !handle) return TB200_E_ARG;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+#ifdef TB_SIMT_EMULATION
+	return fail(ctx, TB200_E_STATE, "no IPC in the emulation build");
+#else
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	cudaIpcMemHandle_t h;
+	CU(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
+	memcpy(handle, &h, 64);
+	return 0;
+#endif
+}
+
+extern "C" int tb200_ipc_import(tb200_ctx *ctx, const uint8_t handle[64], void **d_ptr)
+{
+	if (!ctx || !d_ptr || !handle) return TB200_E_ARG;
+#ifdef TB_SIMT_EMULATION
+	return fail(ctx, TB200_E_STATE, "no IPC in the emulation build");
+#else
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle, 64);
+	CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return 0;
+#endif
+}
+
+extern "C" int tb200_ipc_close(tb200_ctx *ctx, void *d_ptr)
+{
+	if (!ctx) return TB200_E_ARG;
+#ifdef TB_SIMT_EMULATION
+	(void)d_ptr;
+	return 0;
+#else
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	CU(cudaIpcCloseMemHandle(d_ptr));
+	return 0;
+#endif
+}
+
 extern "C" int tb200_set_crc_buffer(tb200_ctx *ctx, uint32_t *crc)
 {
 	if (!ctx) return TB200_E_ARG;

@@ -23,7 +23,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n_bursts, q):
+def _worker(rank, world, port, n_bursts, q, peer=False):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -47,8 +47,20 @@ def _worker(rank, world, port, n_bursts, q):
                                    C.c_void_p(dt.data_ptr()), C.c_void_p(dp.data_ptr()), ms)
     assert ns == n_bursts - 1, (ns, g.err())
     # the sharded run: only rank 0 hands its copy in
+    handle = None
+    src = full[:nbits] if rank == 0 else None
+    if peer:
+        # no scatter: rank 0 puts the stream into exportable memory, the others map it and read it over NVLink
+        hb = torch.zeros(64, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            buf = T.DevBuffer(g, nbits + 64)
+            src = buf.tensor(dev)[:nbits]
+            src.copy_(full[:nbits])
+            hb.copy_(torch.frombuffer(bytearray(buf.export()), dtype=torch.uint8))
+        dist.broadcast(hb, 0)
+        handle = bytes(hb.cpu().numpy().tobytes())
     k0, k1, a0, s_slots, s_t1, s_pk, summaries = T.sharded_decode(
-        g, dist, rank, world, full[:nbits] if rank == 0 else None, nbits, dev, want_type1=True)
+        g, dist, rank, world, src, nbits, dev, want_type1=True, peer_handle=handle)
     n = k1 - k0
     ok = (torch.equal(s_slots[:n * 16], ds[k0 * 16:k1 * 16]) and torch.equal(s_t1[:n * 288], dt[k0 * 288:k1 * 288])
           and torch.equal(s_pk[:n * 9], dp[k0 * 9:k1 * 9]))
@@ -60,8 +72,8 @@ def _worker(rank, world, port, n_bursts, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
-def test_one_stream_scattered_over_gpus(world):
+@pytest.mark.parametrize("world,peer", [(2, False), (2, True), (4, False), (8, False), (8, True)])
+def test_one_stream_scattered_over_gpus(world, peer):
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < world:
@@ -70,7 +82,7 @@ def test_one_stream_scattered_over_gpus(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_bursts, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_bursts, q, peer)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=600) for _ in range(world))

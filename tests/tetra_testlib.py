@@ -458,6 +458,12 @@ class B200:
                                           C.c_uint32, C.POINTER(ShardSummary)]
         lib.tb200_shard_carry_in.argtypes = [C.c_void_p, C.c_int, C.POINTER(Carry), C.POINTER(Carry)]
         lib.tb200_shard_carry_in.restype = None
+        lib.tb200_dev_alloc.restype = C.c_void_p
+        lib.tb200_dev_alloc.argtypes = [C.c_void_p, C.c_size_t]
+        lib.tb200_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+        lib.tb200_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.tb200_ipc_import.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        lib.tb200_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         lib.tb200_shard_pass2.restype = C.c_long
         lib.tb200_shard_pass2.argtypes = [C.c_void_p, C.POINTER(Carry), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.tb200_host_alloc.restype = C.c_void_p
@@ -656,12 +662,56 @@ def shard_plan(n_slots_total, world):
 SHARD_HALO = 4096 + 64        # look-ahead of the search window (tetra_burst_sync.c:117) + read-ahead
 
 
-def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=False, timers=None):
+class DevBuffer:
+    """device memory from tb200_dev_alloc (exportable to other processes), viewable as a torch uint8 tensor"""
+
+    def __init__(self, g, nbytes):
+        self.g, self.nbytes = g, nbytes
+        self.ptr = g.lib.tb200_dev_alloc(g.h, nbytes)
+        if not self.ptr:
+            raise MemoryError("tb200_dev_alloc")
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
+
+    def tensor(self, device):
+        import torch
+        return torch.as_tensor(self, device=device)
+
+    def export(self):
+        h = (C.c_uint8 * 64)()
+        if self.g.lib.tb200_ipc_export(self.g.h, C.c_void_p(self.ptr), h):
+            raise RuntimeError(self.g.err())
+        return bytes(h)
+
+    def free(self):
+        if self.ptr:
+            self.g.lib.tb200_dev_free(self.g.h, C.c_void_p(self.ptr))
+            self.ptr = None
+
+
+_peer_maps = {}
+
+
+def peer_pointer(g, handle):
+    """map another rank's exported buffer (cached per handle: opening is a millisecond-scale call)"""
+    key = (id(g), handle)
+    if key not in _peer_maps:
+        p = C.c_void_p()
+        hb = (C.c_uint8 * 64).from_buffer_copy(handle)
+        if g.lib.tb200_ipc_import(g.h, hb, C.byref(p)):
+            raise RuntimeError(g.err())
+        _peer_maps[key] = p.value
+    return _peer_maps[key]
+
+
+def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=False, timers=None, peer_handle=None):
     """BASELINE config 5: ONE stream, held by rank 0 (device tensor d_full, None elsewhere), decoded by
-    `world` ranks.  Rank 0 acquires lock on the head of the stream, scatters contiguous slot ranges
-    (+ look-ahead halo) with NCCL send/recv, every rank runs pass 1 (search, classification, SB1) on its
-    shard, the 32-byte summaries are all-gathered (the only exchange step of the path: the cell state),
-    every rank derives its carry-in and runs pass 2.  Results stay rank-local.
+    `world` ranks.  Rank 0 acquires lock on the head of the stream; every rank takes a contiguous slot range
+    (+ look-ahead halo) and runs pass 1 (search, classification, SB1) on it, the 32-byte summaries are
+    all-gathered (the only exchange step of the path: the cell state), every rank derives its carry-in and
+    runs pass 2.  Results stay rank-local.  How a rank gets at its shard:
+      peer_handle is None   rank 0 scatters the shards with NCCL send/recv, then the kernels run
+      peer_handle = bytes   (rank 0's exported buffer, see DevBuffer) no copy at all: the search kernel of
+                            every rank reads its shard straight out of rank 0's HBM over NVLink
     Returns (k0, k1, a0, d_slots, d_type1 or None, d_packed, summaries)."""
     import torch
     meta = torch.zeros(4, dtype=torch.int64, device=device)
@@ -685,8 +735,11 @@ def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=Fals
     if timers is not None:
         torch.cuda.synchronize(); timers["t_scatter0"] = __import__("time").perf_counter()
     lo, hi = span(rank)
-    if rank == 0:
+    if peer_handle is not None:
+        shard_ptr = (d_full.data_ptr() if rank == 0 else peer_pointer(g, peer_handle)) + lo
+    elif rank == 0:
         shard = d_full[lo:hi]
+        shard_ptr = shard.data_ptr()
         if world > 1:
             # one NCCL group: the sends to all peers run concurrently and share rank 0's NVLink egress
             ops = [dist.P2POp(dist.isend, d_full[span(r)[0]:span(r)[1]], r) for r in range(1, world) if span(r)[1] > span(r)[0]]
@@ -694,6 +747,7 @@ def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=Fals
                 q.wait()
     else:
         shard = torch.empty(hi - lo + 64, dtype=torch.uint8, device=device)[:hi - lo]
+        shard_ptr = shard.data_ptr()
         if hi > lo:
             for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, shard, 0)]):
                 q.wait()
@@ -701,7 +755,7 @@ def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=Fals
         if world > 1:
             dist.barrier()          # the scatter ends when the last rank has its shard
         torch.cuda.synchronize(); timers["t_scatter1"] = __import__("time").perf_counter()
-    s = g.shard_pass1(shard.data_ptr(), lo, hi - lo, lo, cmin + k0, n_bits, n)
+    s = g.shard_pass1(shard_ptr, lo, hi - lo, lo, cmin + k0, n_bits, n)
     mine = torch.frombuffer(bytearray(bytes(s)), dtype=torch.uint8).to(device)
     gathered = [torch.zeros(32, dtype=torch.uint8, device=device) for _ in range(world)]
     if world > 1:
