@@ -458,12 +458,13 @@ class B200:
                                           C.c_uint32, C.POINTER(ShardSummary)]
         lib.tb200_shard_carry_in.argtypes = [C.c_void_p, C.c_int, C.POINTER(Carry), C.POINTER(Carry)]
         lib.tb200_shard_carry_in.restype = None
-        lib.tb200_dev_alloc.restype = C.c_void_p
-        lib.tb200_dev_alloc.argtypes = [C.c_void_p, C.c_size_t]
-        lib.tb200_dev_free.argtypes = [C.c_void_p, C.c_void_p]
-        lib.tb200_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-        lib.tb200_ipc_import.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-        lib.tb200_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+        if hasattr(lib, "tb200_dev_alloc"):          # (A/B runs load older builds of the library)
+            lib.tb200_dev_alloc.restype = C.c_void_p
+            lib.tb200_dev_alloc.argtypes = [C.c_void_p, C.c_size_t]
+            lib.tb200_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+            lib.tb200_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+            lib.tb200_ipc_import.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+            lib.tb200_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         lib.tb200_shard_pass2.restype = C.c_long
         lib.tb200_shard_pass2.argtypes = [C.c_void_p, C.POINTER(Carry), C.c_void_p, C.c_void_p, C.c_void_p]
         lib.tb200_host_alloc.restype = C.c_void_p
