@@ -351,6 +351,7 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 		                                                   lane_smem_words(LANE_NT) * sizeof(uint32_t)) != cudaSuccess || per_sm < 1)
 			return bail("cudaOccupancyMaxActiveBlocksPerMultiprocessor");
 #endif
+		if (const char *e = getenv("TB200_LANE_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
 		ctx->lane_ctas = (unsigned)(ctx->sm_count * per_sm);
 		const size_t scratch_bytes = (size_t)ctx->lane_ctas * lane_scratch_words_per_cta(LANE_NT) * sizeof(uint32_t);
 		if (cudaMalloc((void **)&ctx->d_lane_scratch, scratch_bytes) != cudaSuccess)
