@@ -260,10 +260,10 @@ extern "C" void tb200_dev_free(tb200_ctx *ctx, void *p)
 extern "C" int tb200_ipc_export(tb200_ctx *ctx, const void *d_ptr, uint8_t handle[64])
 {
 	if (!ctx || !d_ptr || !handle) return TB200_E_ARG;
-	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
 #ifdef TB_SIMT_EMULATION
 	return fail(ctx, TB200_E_STATE, "no IPC in the emulation build");
 #else
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	cudaIpcMemHandle_t h;
 	CU(cudaIpcGetMemHandle(&h, const_cast<void *>(d_ptr)));
