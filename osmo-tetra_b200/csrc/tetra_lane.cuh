@@ -248,11 +248,144 @@ __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *
 	}
 }
 
+/* ---- the same decoder for warps whose lanes all carry two blocks of the same length (the normal case
+ * once the slots are grouped by kind): groups of EIGHT steps.  Metrics in units of 256, tags 2^q for
+ * q = 0..7, so the low BYTE of a state's metric is the decision history of its survivor through eight
+ * steps = the eight decoded bits that end four steps before the group does, and its low nibble is (bit
+ * reversed) the state the survivor had when the group began.  History extraction, packing and the trace
+ * back cost half as much per step as in the four-step form.  65 535 / 256 = 255 mismatches fit a metric,
+ * a 288-step block can collect 432, so every eighth group the common minimum is subtracted (metrics only
+ * ever get compared, so this changes nothing).  The four flush steps stay a four-step group. ---- */
+
+template <int K>
+__device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b)
+{
+#ifdef TB_SIMT_EMULATION
+	return a * (uint32_t)K + b;
+#else
+	uint32_t r;
+	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "n"(K), "r"(b));
+	return r;
+#endif
+}
+
+/* strip the history bytes; word i of the result holds positions 4i..4i+3 (position = rev4(state)) */
+__device__ __forceinline__ void take_history8(uint32_t (&pm)[16], uint4 &hx, uint4 &hy)
+{
+	uint32_t W[8];          /* W[j]: positions 2j, 2j+1; low half = trellis X, high half = trellis Y */
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		const unsigned s1 = rev4(2 * j + 1), s0 = rev4(2 * j);
+		const uint32_t h1 = pm[s1] & 0x00ff00ffu, h0 = pm[s0] & 0x00ff00ffu;
+		pm[s1] = sub_opaque(pm[s1], h1);
+		pm[s0] = sub_opaque(pm[s0], h0);
+		W[j] = mad_opaque<256>(h1, h0);
+	}
+	hx = make_uint4(__byte_perm(W[0], W[1], 0x5410), __byte_perm(W[2], W[3], 0x5410),
+	                __byte_perm(W[4], W[5], 0x5410), __byte_perm(W[6], W[7], 0x5410));
+	hy = make_uint4(__byte_perm(W[0], W[1], 0x7632), __byte_perm(W[2], W[3], 0x7632),
+	                __byte_perm(W[4], W[5], 0x7632), __byte_perm(W[6], W[7], 0x7632));
+}
+
+/* byte f (0..15) of the 128-bit value h */
+__device__ __forceinline__ uint32_t byte128(const uint4 &h, uint32_t f)
+{
+	const uint32_t lo = (f & 4) ? h.y : h.x, hi = (f & 4) ? h.w : h.z;
+	const uint32_t w = (f & 8) ? hi : lo;
+	return (w >> ((f & 3) * 8)) & 0xffu;
+}
+
+__device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t *cy, int n)
+{
+	uint32_t pm[16];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x40004000u : 0u;     /* start in state 0 (osmo_conv_decode) */
+	constexpr int nt = LANE_NT;
+	const int groups = n / 8;                          /* 4 step pairs = 12 type-3 bits per group */
+	for (int g = 0; g < groups; ++g) {
+		const unsigned bp = 12 * g, w = bp >> 5, sh = bp & 31;
+		const uint32_t vx = __funnelshift_r(cx[w * nt], cx[(w + 1) * nt], sh) & 0xfffu;
+		const uint32_t vy = __funnelshift_r(cy[w * nt], cy[(w + 1) * nt], sh) & 0xfffu;
+		const uint32_t z = vx | (vy << 16);                 /* received bits of both trellises, 12 per half */
+		const uint32_t nz = ~z;
+#pragma unroll
+		for (int p = 0; p < 4; ++p) {
+			const uint32_t r1 = (z >> (3 * p)) & 0x00010001u, q1 = (nz >> (3 * p)) & 0x00010001u;
+			const uint32_t r2 = (z >> (3 * p + 1)) & 0x00010001u;
+			const uint32_t r3 = (z >> (3 * p + 2)) & 0x00010001u;
+			const uint32_t t = r1 + r2;                       /* mismatches if 00 was sent: 0..2 */
+			const uint32_t u = q1 + r2;                       /* mismatches if G1=1, G2=0 was sent */
+			const uint32_t te = 0x00010001u << (2 * p), to = 0x00020002u << (2 * p);
+			uint32_t M0[4], M1[4];
+			M0[0] = mad_k<256>(t, 0u);              M1[0] = mad_k<256>(t, te);
+			M0[3] = mad_k<-256>(t, 0x02000200u);    M1[3] = mad_k<-256>(t, 0x02000200u + te);
+			M0[2] = mad_k<256>(u, 0u);              M1[2] = mad_k<256>(u, te);
+			M0[1] = mad_k<-256>(u, 0x02000200u);    M1[1] = mad_k<-256>(u, 0x02000200u + te);
+			acs2_step(pm, M0, M1);
+			M0[0] = mad_k<256>(r3, 0u);             M1[0] = mad_k<256>(r3, to);      /* odd step: only G1 was sent */
+			M0[2] = mad_k<-256>(r3, 0x01000100u);   M1[2] = mad_k<-256>(r3, 0x01000100u + to);
+			M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
+			acs2_step(pm, M0, M1);
+		}
+		uint4 hx, hy;
+		take_history8(pm, hx, hy);
+		dec[(2 * g) * nt] = hx;
+		dec[(2 * g + 1) * nt] = hy;
+		if ((g & 7) == 7) {            /* keep the metrics small: subtract the per-trellis minimum */
+			uint32_t m = pm[0];
+#pragma unroll
+			for (int i = 1; i < 16; ++i) m = __viaddmin_u16x2(pm[i], 0u, m);
+#pragma unroll
+			for (int i = 0; i < 16; ++i) pm[i] = sub_opaque(pm[i], m);
+		}
+	}
+	uint4 hf;
+	{
+		/* four flush steps: no received symbols, so no cost; both inputs stay allowed, the trace back
+		 * starts in state 0, which only the all-zero tail can reach.  The metrics are multiples of 256
+		 * here, so the four-step form (tags 1, 2, 4, 8; low nibble) applies unchanged. */
+		const uint32_t Z0[4] = { 0, 0, 0, 0 };
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			const uint32_t tq = 0x00010001u << q;
+			const uint32_t Z1[4] = { tq, tq, tq, tq };
+			acs2_step(pm, Z0, Z1);
+		}
+		hf = take_history(pm);
+	}
+	/* Trace back.  The flush group gives the last four decoded bits (= index into the last eight-step
+	 * group); the byte at position f of group g holds decoded bits [8g-4, 8g+4), its low nibble is the index
+	 * into group g-1.  A 64-bit shift register collects them; after group g its bit 0 is decoded bit 8g-4,
+	 * so output word wi leaves as bits [4, 36) right after group 4*wi. */
+	uint32_t fx = nibble64(hf.x, hf.y, 0), fy = nibble64(hf.z, hf.w, 0);
+	uint32_t xlo = fx, xhi = 0, ylo = fy, yhi = 0;
+	for (int wi = (n - 1) >> 5; wi >= 0; --wi) {
+		const int ghi = 4 * wi + 3 < groups - 1 ? 4 * wi + 3 : groups - 1;
+		const int cnt = ghi - 4 * wi + 1;                  /* 2 or 4 groups */
+		const uint4 *dp = dec + (size_t)(2 * ghi) * nt;
+		for (int i = 0; i < cnt; i += 2) {
+			uint4 bx[2], by[2];
+#pragma unroll
+			for (int u = 0; u < 2; ++u) { bx[u] = dp[-2 * u * nt]; by[u] = dp[(1 - 2 * u) * nt]; }     /* loads first: latency overlaps */
+			dp -= 4 * nt;
+#pragma unroll
+			for (int u = 0; u < 2; ++u) {
+				const uint32_t b0 = byte128(bx[u], fx), b1 = byte128(by[u], fy);
+				fx = b0 & 15u; fy = b1 & 15u;
+				xhi = __funnelshift_l(xlo, xhi, 8); xlo = (xlo << 8) | b0;
+				yhi = __funnelshift_l(ylo, yhi, 8); ylo = (ylo << 8) | b1;
+			}
+		}
+		cx[wi * nt] = __funnelshift_r(xlo, xhi, 4);
+		cy[wi * nt] = __funnelshift_r(ylo, yhi, 4);
+	}
+}
+
 __device__ __forceinline__ void viterbi_pair(uint4 *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	/* warp-uniform choice: no masking work when every lane carries two full-length blocks */
 	const bool uniform = __all_sync(FULL, nx == nmax && ny == nmax);
-	if (uniform) viterbi_pair_t<false>(dec, cx, cy, nx, ny, nmax);
+	if (uniform) viterbi_pair_u8(dec, cx, cy, nmax);
 	else         viterbi_pair_t<true>(dec, cx, cy, nx, ny, nmax);
 }
 
@@ -483,7 +616,7 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
  * one length: 288 steps for two SCH/F slots, 144 for the two halves BLK1 / BLK2 of ONE two-block slot or
  * for the SB2 blocks of two SYNC bursts; dropped slots only get their record.  Units are handed out
  * longest first.  Warps that straddle two lists run the masked form of the trellis loop. */
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 16)
 k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 {
 	LaneSmem sm(TB_DYN_SMEM(), scratch);
