@@ -3,17 +3,22 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA path through the C ABI)
   python bench.py --impl reference ...                          the reference's own CPU code (oracle/_ref)
+  python bench.py --workload config5 [--peer] ...               BASELINE config 5: one stream on rank 0 decoded by all ranks
   N > 1 is launched by the driver under torch.distributed.run, one rank per GPU.
 
 A "step" is one pass of the hot path over one batch: BASELINE.json configs[1], 10^6 synthetic SCH/F
 bursts (RCPC 2/3, K=5 Viterbi) as one continuous downlink stream (two leading SYNC bursts give lock
 and the cell code, an SB every 64th burst after that), BER 1e-2 on the payload bits.
 
-  value       bursts/s with the stream already resident in HBM (tb200_rx_stream_dev)
-  e2e         the same through tb200_rx_stream_host: pinned HOST buffers in and out, H2D and D2H
-              copies inside the timed region
-  roofline    the dominant kernel against the measured HBM copy peak (+ integer-ALU view)
+  value         bursts/s with the stream already resident in HBM (tb200_rx_stream_dev); N > 1: every rank
+                decodes its own stream (weak scaling, no data-path collective)
+  e2e           the same through tb200_rx_stream_host: pinned HOST buffers in and out, H2D and D2H
+                copies inside the timed region
+  roofline      the dominant kernel against the measured HBM copy peak (+ integer-issue view), the
+                training-sequence search kernel and the stand-alone descramble + de-interleave stage
   cpu_baseline  the reference's lower MAC compiled in place (oracle/_ref), all host cores, bounded sample
+  other_configs device-resident bursts/s on the shapes of BASELINE configs 3 and 4 (N = 1 only)
+  front_ends    the same stream bit-packed and as float32 symbols (N = 1 only)
 """
 import argparse
 import ctypes as C
