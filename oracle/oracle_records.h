@@ -30,3 +30,16 @@ struct tb_fsm_event {
 	int32_t  rc;                /* enum tetra_train_seq or -1 */
 	uint32_t offset;
 };                                  /* 24 bytes */
+
+/* What the reference's upper MAC feeds back into the lower MAC when it parses an AACH block
+ * (rx_aach, tetra_upper_mac.c:423-455 with macpdu_decode_access_assign, tetra_mac_pdu.c:257-330):
+ * on frames other than 18, headers 1..3 carry the downlink usage marker in field 1 (bits [2,8));
+ * a marker above 3 means the slot carries traffic.  The stealing flags are reset.  Used by the
+ * recorders of the tests to exercise tetra_lower_mac.c:190-241 and the shim's mirror of it. */
+#define TB_EMULATE_RX_AACH(cur_burst, bits, fn) do { \
+		unsigned hdr_ = ((bits)[0] << 1) | (bits)[1], f1_ = 0, dl_ = 0; \
+		for (int i_ = 0; i_ < 6; i_++) f1_ = (f1_ << 1) | ((bits)[2 + i_] & 1); \
+		if ((fn) != 18 && hdr_ != 0) dl_ = f1_; \
+		(cur_burst).is_traffic = dl_ > 3 ? (int)dl_ : 0; \
+		(cur_burst).blk1_stolen = 0; (cur_burst).blk2_stolen = 0; \
+	} while (0)

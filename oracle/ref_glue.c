@@ -41,14 +41,18 @@ static struct tetra_mac_state *g_tms;
 static struct tetra_crypto_state *g_tcs;
 static uint32_t g_call_index;
 static int g_record_enabled = 1;
+static int g_feedback;              /* emulate the upper MAC's AACH feedback (is_traffic), see oracle_records.h */
+static char g_dumpdir[512];
 
 int upper_mac_prim_recv(struct osmo_prim_hdr *op, void *priv)
 {
 	struct tetra_tmvsap_prim *tmvp = (struct tetra_tmvsap_prim *)op;
 	struct tmv_unitdata_param *tup = &tmvp->u.unitdata;
 	struct msgb *msg = op->msg;
-	(void)priv;
-
+	if (g_feedback && priv && tup->lchan == TETRA_LC_AACH) {
+		struct tetra_mac_state *tms = priv;
+		TB_EMULATE_RX_AACH(tms->cur_burst, msg->l1h, tup->tdma_time.fn);
+	}
 	if (!g_record_enabled)
 		return -1;
 	if (g_nrec == g_caprec) {
@@ -143,6 +147,16 @@ void ref_reset(void)
 }
 
 void ref_set_recording(int on) { g_record_enabled = on; }
+
+/* switch the emulated AACH feedback on; traffic blocks are then dumped into `dumpdir` by the reference
+ * (tetra_lower_mac.c:198-241) instead of being decoded.  Call after ref_reset(). */
+void ref_set_feedback(int on, const char *dumpdir)
+{
+	g_feedback = on;
+	snprintf(g_dumpdir, sizeof(g_dumpdir), "%s", dumpdir ? dumpdir : "");
+	if (g_tms)
+		g_tms->dumpdir = g_dumpdir[0] ? g_dumpdir : NULL;
+}
 
 /* feed like tetra-rx.c:82-95: read() chunks of `chunk` bytes (64 there) */
 long ref_feed(const uint8_t *bits, size_t n, unsigned int chunk, int quiet)

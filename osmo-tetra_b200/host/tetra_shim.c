@@ -22,8 +22,10 @@
  *                              reference's tp_sap_udata_ind() / lower MAC: isolates sync + slicing parity (depth A)
  *   depth C (GPU lower MAC behind the reference's PHY) is the batched leaf tb200_decode_blocks().
  *
- * Not reproduced: the stdout text of the PHY / lower MAC (SURVEY 8b "text side-channel") and the
- * is_traffic dump path (tetra_lower_mac.c:194-241).  read() sizes must be constant (64 in
+ * Upper-MAC feedback: when the upper MAC marks the current slot as traffic (tms->cur_burst.is_traffic, set in
+ * rx_aach, tetra_upper_mac.c:444-452) the shim withholds the same primitives the reference lower MAC withholds
+ * (tetra_lower_mac.c:190-241).  Not reproduced: the traffic dump files written on that path, and the stdout
+ * text of the PHY / lower MAC (tetra_rx_b200.c prints that text, byte for byte).  read() sizes must be constant (64 in
  * tetra-rx.c:83) except for the last one; other call patterns are rejected loudly.
  */
 #include <stdint.h>
@@ -152,8 +154,26 @@ static void shim_run(int final)
 #else
 	S.n_bits = 0;
 	size_t nrec = tb200_expand_records(S.slots, S.type1, (size_t)n, S.rec, 3 * S.max_slots);
-	for (size_t i = 0; i < nrec; i++)
-		deliver(&S.rec[i], priv);
+	struct tetra_mac_state *tms = priv;
+	for (size_t i = 0; i < nrec; i++) {
+		const struct tb200_record *r = &S.rec[i];
+		if (tms && tms->cur_burst.is_traffic) {
+			/* the upper MAC has just seen an AACH that marks this slot as traffic (tetra_upper_mac.c:444-452):
+			 * what tetra_lower_mac.c:190-241 does with the blocks that follow.  BLK1 of a normal burst counts as
+			 * stolen and is still decoded; SCH/F and an un-stolen block 2 are NOT handed to the upper MAC (the
+			 * reference writes their soft bits to <dumpdir>/traffic_*.out for an external codec; that dump is
+			 * not reproduced here, see DESIGN.md "out of scope"). */
+			if (r->type1_len == 124 && r->blk_num == 1)
+				tms->cur_burst.blk1_stolen = true;
+			if (r->type1_len == 268 || (r->blk_num == 2 && !tms->cur_burst.blk2_stolen)) {
+				static int warned;
+				if (!warned++)
+					fprintf(stderr, "tetra_b200 shim: traffic slots are skipped, the traffic dump files are not written\n");
+				continue;
+			}
+		}
+		deliver(r, priv);
+	}
 #endif
 	struct tb200_rx_carry c;
 	tb200_get_carry(S.ctx, &c);

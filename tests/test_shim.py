@@ -115,3 +115,87 @@ def test_shim_l0_only_feeds_reference_lower_mac(orc):
     ok, msg = T.records_equal(want, got)
     assert ok, msg
     assert int(want["crc_ok"].sum()) > 100
+
+
+TRAFFIC_RECORDER = RECORDER.replace('''	return -1;
+}''', '''	if (priv && u->lchan == TETRA_LC_AACH) {
+		struct tetra_mac_state *tms = priv;
+		TB_EMULATE_RX_AACH(tms->cur_burst, op->msg->l1h, u->tdma_time.fn);
+	}
+	return -1;
+}
+static struct tetra_mac_state g_tms;
+void *shimtest_tms(void) { return &g_tms; }''', 1)
+
+
+def _plant_aach(ref, bits, lead, k, two_block, info14, code):
+    """overwrite the broadcast block of normal burst k with the RM(30,14) code word of info14, scrambled with the cell code"""
+    word = ref.rm3014(info14)
+    cw = np.array([(word >> (29 - i)) & 1 for i in range(30)], dtype=np.uint8)
+    cw = ref.scramb_bits(code, cw)
+    a = lead + 510 * k
+    bits[a + 230:a + 244] = cw[:14]
+    bits[a + 266:a + 282] = cw[14:]
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF_SRC) and T.have_ref()), reason="reference build not present")
+def test_shim_follows_the_traffic_feedback(orc, tmp_path):
+    """tms->cur_burst.is_traffic, set by the upper MAC when an AACH marks a slot as traffic
+    (tetra_upper_mac.c:444-452), makes the reference lower MAC divert SCH/F and un-stolen second blocks to
+    its dump files instead of delivering them (tetra_lower_mac.c:190-241).  The shim must withhold exactly
+    the same primitives.  Both sides run with a recorder that emulates that feedback (oracle_records.h)."""
+    ref = T.Ref()
+    cfg = T.GenCfg(seed=0x7E7A0077, sb_period=9, lead_sb=2, ndb2_per_256=96, ber_per_65536=300, random_cell=0, lead_in_bits=123)
+    n = 120
+    bits = orc.gen_stream(cfg, 0, n).copy()
+    code = ref.scramb_get_init(262, 42, 1)
+    rng = np.random.default_rng(9)
+    marked = 0
+    for k in range(3, n - 1):
+        if orc.lib.orc_gen_kind(C.byref(cfg), k) == T.TS_SYNC or rng.random() > 0.4:
+            continue
+        hdr = int(rng.integers(0, 4))
+        usage = int(rng.choice([0, 2, 3, 4, 9, 40]))
+        info = (hdr << 12) | (usage << 6) | int(rng.integers(0, 64))
+        _plant_aach(ref, bits, 123, k, None, info, code)
+        marked += hdr != 0 and usage > 3
+    assert marked > 5
+    # the all-reference receiver with the emulated feedback and a dump directory
+    ref.reset()
+    ref.lib.ref_set_feedback(1, str(tmp_path).encode())
+    ref.feed(bits, 64)
+    want = ref.records().copy()
+    ref.lib.ref_set_feedback(0, None)
+    plain = T.Ref(); plain.reset(); plain.feed(bits, 64)
+    assert 0 < want.size < plain.records().size               # the feedback really withheld primitives
+    assert any(f.startswith("traffic_") for f in os.listdir(tmp_path))
+    # the shim (PHY + lower MAC on the emulated GPU) with the same feedback in its recorder
+    simt = T.build_simt()
+    os.makedirs(BUILD, exist_ok=True)
+    rec_c = os.path.join(BUILD, "shim_recorder_traffic.c")
+    open(rec_c, "w").write(TRAFFIC_RECORDER)
+    so = os.path.join(BUILD, "libshimtest_traffic.so")
+    subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-shared", "-I" + REF_SRC, "-I" + os.path.join(T.ROOT, "oracle", "stubs"),
+                           "-I" + os.path.join(T.ROOT, "oracle"), "-I" + os.path.join(T.ROOT, "include"),
+                           os.path.join(T.ROOT, "osmo-tetra_b200", "host", "tetra_shim.c"), rec_c, simt,
+                           "-Wl,-rpath," + os.path.dirname(simt), "-o", so])
+    os.environ["TETRA_B200_BATCH_BITS"] = "16384"
+    lib = C.CDLL(so)
+    lib.shimtest_tms.restype = C.c_void_p
+    class Trs(C.Structure):
+        _fields_ = [("state", C.c_int), ("bits_in_buf", C.c_uint), ("bitbuf", C.c_uint8 * 4096),
+                    ("start", C.c_uint), ("next", C.c_uint), ("priv", C.c_void_p)]
+    trs = Trs()
+    trs.priv = lib.shimtest_tms()
+    for pos in range(0, bits.size, 64):
+        chunk = np.ascontiguousarray(bits[pos:pos + 64])
+        lib.tetra_burst_sync_in(C.byref(trs), chunk.ctypes.data_as(C.c_void_p), chunk.size)
+    lib.tetra_b200_shim_flush()
+    lib.shimtest_n.restype = C.c_size_t
+    lib.shimtest_rec.restype = C.c_void_p
+    m = lib.shimtest_n()
+    got = np.frombuffer(C.string_at(lib.shimtest_rec(), m * 288), dtype=T.RECORD_DTYPE).copy()
+    assert m == want.size
+    got["slot_bit"] = want["slot_bit"]
+    ok, msg = T.records_equal(want, got)
+    assert ok, msg
