@@ -24,8 +24,9 @@
  *
  * Upper-MAC feedback: when the upper MAC marks the current slot as traffic (tms->cur_burst.is_traffic, set in
  * rx_aach, tetra_upper_mac.c:444-452) the shim withholds the same primitives the reference lower MAC withholds
- * (tetra_lower_mac.c:190-241).  Not reproduced: the traffic dump files written on that path, and the stdout
- * text of the PHY / lower MAC (tetra_rx_b200.c prints that text, byte for byte).  read() sizes must be constant (64 in
+ * (tetra_lower_mac.c:190-241) and writes the same <dumpdir>/traffic_*.out / .txt files for SCH/F-shaped
+ * traffic slots.  Not reproduced: the dump of a 216-bit second block (the reference fills half of it from
+ * uninitialised memory) and the stdout text of the PHY / lower MAC (tetra_rx_b200.c prints that text).  read() sizes must be constant (64 in
  * tetra-rx.c:83) except for the last one; other call patterns are rejected loudly.
  */
 #include <stdint.h>
@@ -47,17 +48,13 @@
 
 struct tetra_phy_state t_phy_state;
 
-#ifdef TETRA_B200_SHIM_L0_ONLY
 #define SHIM_HIST 8192u      /* bits of earlier batches kept in front of the batch: a slot may start in them */
-#else
-#define SHIM_HIST 0u
-#endif
 
 static struct {
 	tb200_ctx *ctx;
 	uint8_t *bits;
 	size_t n_bits, cap_bits, batch_bits;
-	uint8_t *hist;         /* L0-only depth: [SHIM_HIST bits of history][the batch = bits] */
+	uint8_t *hist;         /* [SHIM_HIST bits of history][the batch = bits] */
 	size_t n_hist;
 	uint64_t fed_before;   /* stream bits handed to the library before this batch */
 	unsigned int chunk;
@@ -116,6 +113,59 @@ static void deliver(const struct tb200_record *r, void *priv)
 }
 #endif
 
+/* raw bits of the slot that starts at (wrapping) stream bit slot_bit, from the retained history + batch */
+static const uint8_t *slot_raw_bits(uint32_t slot_bit)
+{
+	const uint64_t buf0 = S.fed_before - S.n_hist;             /* stream bit of hist[SHIM_HIST - n_hist] */
+	const uint64_t abs = buf0 + (uint32_t)(slot_bit - (uint32_t)buf0);
+	if (abs < buf0 || abs + TB200_BITS_PER_SLOT > S.fed_before + S.n_bits)
+		shim_die("slot outside the retained bits");
+	return S.hist + (SHIM_HIST - S.n_hist) + (abs - buf0);
+}
+
+#ifndef TETRA_B200_SHIM_L0_ONLY
+/* The traffic dump of an SCH/F-shaped slot (tetra_lower_mac.c:198-241): the 432 descrambled type-4 bits as
+ * +-127 soft values in the 690-word frame the ETSI codec tools read, appended to
+ * <dumpdir>/traffic_<usage>_<tsn>.out, and the SSI appended to the matching .txt.  Host-side mirror: the
+ * scrambling sequence is the LFSR of tetra_scramb.c:34-50 (fb = parity(state & 0xDB710641), shifted in at bit 31). */
+static void dump_traffic_schf(const struct tetra_mac_state *tms, const uint8_t *burst, uint32_t code)
+{
+	char fname[4096];
+	int16_t block[690];
+	uint8_t type4[432];
+	uint32_t st = code;
+	for (int m = 0; m < 432; m++) {
+		uint32_t fb = 0;
+		if (code) {
+			fb = (uint32_t)__builtin_parity(st & 0xDB710641u);
+			st = (st >> 1) | (fb << 31);
+		}
+		type4[m] = burst[m < 216 ? 14 + m : 66 + m] ^ (uint8_t)fb;       /* tetra_burst.c:363-373 */
+	}
+	snprintf(fname, sizeof(fname), "%s/traffic_%d_%d.out", tms->dumpdir, tms->cur_burst.is_traffic, tms->tsn);
+	FILE *f = fopen(fname, "ab");
+	if (!f) {
+		fprintf(stderr, "Could not open dump file %s for writing\n", fname);
+		exit(1);
+	}
+	memset(block, 0x00, sizeof(block));
+	for (int i = 0; i < 6; i++)
+		block[115 * i] = 0x6b21 + i;
+	for (int i = 0; i < 114; i++) block[1 + i] = type4[i] ? -127 : 127;
+	for (int i = 0; i < 114; i++) block[116 + i] = type4[114 + i] ? -127 : 127;
+	for (int i = 0; i < 114; i++) block[231 + i] = type4[228 + i] ? -127 : 127;
+	for (int i = 0; i < 90; i++) block[346 + i] = type4[342 + i] ? -127 : 127;
+	fwrite(block, sizeof(int16_t), 690, f);
+	fclose(f);
+	snprintf(fname, sizeof(fname), "%s/traffic_%d_%d.txt", tms->dumpdir, tms->cur_burst.is_traffic, tms->tsn);
+	f = fopen(fname, "a");
+	if (f) {
+		fprintf(f, "%d\n", tms->ssi);
+		fclose(f);
+	}
+}
+#endif
+
 static void shim_run(int final)
 {
 	if (!S.ctx || S.finished || (!S.n_bits && !final))
@@ -133,26 +183,14 @@ static void shim_run(int final)
 #ifdef TETRA_B200_SHIM_L0_ONLY
 	/* what the LOCKED arm of tetra_burst_sync_in does per slot (phy/tetra_burst_sync.c:113-143): advance the
 	 * slot counter, then hand a slot whose training sequence sits where it should to the reference's slicer */
-	const uint64_t buf0 = S.fed_before - S.n_hist;             /* stream bit of hist[SHIM_HIST - n_hist] */
 	for (long i = 0; i < n; i++) {
 		const struct tb200_slot *sl = &S.slots[i];
 		tetra_tdma_time_add_tn(&t_phy_state.time, 1);
 		if ((sl->flags & TB200_F_KIND_MASK) == TB200_KIND_NONE)
 			continue;
-		const uint64_t abs = buf0 + (uint32_t)(sl->slot_bit - (uint32_t)buf0);
-		if (abs < buf0 || abs + TB200_BITS_PER_SLOT > S.fed_before + S.n_bits)
-			shim_die("slot outside the retained bits");
-		tetra_burst_rx_cb(S.hist + (SHIM_HIST - S.n_hist) + (abs - buf0), TB200_BITS_PER_SLOT, sl->find_rc, priv);
+		tetra_burst_rx_cb((uint8_t *)slot_raw_bits(sl->slot_bit), TB200_BITS_PER_SLOT, sl->find_rc, priv);
 	}
-	{       /* keep the last SHIM_HIST bits for slots that start in this batch and complete in the next */
-		const size_t have = S.n_hist + S.n_bits, keep = have < SHIM_HIST ? have : SHIM_HIST;
-		memmove(S.hist + (SHIM_HIST - keep), S.hist + (SHIM_HIST - S.n_hist) + (have - keep), keep);
-		S.n_hist = keep;
-	}
-	S.fed_before += S.n_bits;
-	S.n_bits = 0;
 #else
-	S.n_bits = 0;
 	size_t nrec = tb200_expand_records(S.slots, S.type1, (size_t)n, S.rec, 3 * S.max_slots);
 	struct tetra_mac_state *tms = priv;
 	for (size_t i = 0; i < nrec; i++) {
@@ -160,21 +198,33 @@ static void shim_run(int final)
 		if (tms && tms->cur_burst.is_traffic) {
 			/* the upper MAC has just seen an AACH that marks this slot as traffic (tetra_upper_mac.c:444-452):
 			 * what tetra_lower_mac.c:190-241 does with the blocks that follow.  BLK1 of a normal burst counts as
-			 * stolen and is still decoded; SCH/F and an un-stolen block 2 are NOT handed to the upper MAC (the
-			 * reference writes their soft bits to <dumpdir>/traffic_*.out for an external codec; that dump is
-			 * not reproduced here, see DESIGN.md "out of scope"). */
+			 * stolen and is still decoded; SCH/F and an un-stolen block 2 are NOT handed to the upper MAC: the
+			 * reference writes their descrambled bits to <dumpdir>/traffic_*.out for an external codec.  The
+			 * SCH/F dump is reproduced; the dump of a 216-bit block 2 is not (the reference reads 216
+			 * uninitialised stack bytes into it, tetra_lower_mac.c:221-228: there is nothing to be exact against). */
 			if (r->type1_len == 124 && r->blk_num == 1)
 				tms->cur_burst.blk1_stolen = true;
-			if (r->type1_len == 268 || (r->blk_num == 2 && !tms->cur_burst.blk2_stolen)) {
+			if (r->type1_len == 268) {
+				dump_traffic_schf(tms, slot_raw_bits(r->slot_bit), r->scrambling_code);
+				continue;
+			}
+			if (r->blk_num == 2 && !tms->cur_burst.blk2_stolen) {
 				static int warned;
 				if (!warned++)
-					fprintf(stderr, "tetra_b200 shim: traffic slots are skipped, the traffic dump files are not written\n");
+					fprintf(stderr, "tetra_b200 shim: traffic in a second half slot: block withheld, its dump is not written\n");
 				continue;
 			}
 		}
 		deliver(r, priv);
 	}
 #endif
+	{       /* keep the last SHIM_HIST bits for slots that start in this batch and complete in the next */
+		const size_t have = S.n_hist + S.n_bits, keep = have < SHIM_HIST ? have : SHIM_HIST;
+		memmove(S.hist + (SHIM_HIST - keep), S.hist + (SHIM_HIST - S.n_hist) + (have - keep), keep);
+		S.n_hist = keep;
+	}
+	S.fed_before += S.n_bits;
+	S.n_bits = 0;
 	struct tb200_rx_carry c;
 	tb200_get_carry(S.ctx, &c);
 	if (S.trs) {                      /* mirror what callers could look at */

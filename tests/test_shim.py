@@ -125,7 +125,8 @@ TRAFFIC_RECORDER = RECORDER.replace('''	return -1;
 	return -1;
 }
 static struct tetra_mac_state g_tms;
-void *shimtest_tms(void) { return &g_tms; }''', 1)
+void *shimtest_tms(void) { return &g_tms; }
+void shimtest_set_dumpdir(const char *d) { g_tms.dumpdir = strdup(d); }''', 1)
 
 
 def _plant_aach(ref, bits, lead, k, two_block, info14, code):
@@ -138,14 +139,15 @@ def _plant_aach(ref, bits, lead, k, two_block, info14, code):
     bits[a + 266:a + 282] = cw[14:]
 
 
+@pytest.mark.parametrize("ndb2", [0, 96])
 @pytest.mark.skipif(not (os.path.isdir(REF_SRC) and T.have_ref()), reason="reference build not present")
-def test_shim_follows_the_traffic_feedback(orc, tmp_path):
+def test_shim_follows_the_traffic_feedback(orc, tmp_path, ndb2):
     """tms->cur_burst.is_traffic, set by the upper MAC when an AACH marks a slot as traffic
     (tetra_upper_mac.c:444-452), makes the reference lower MAC divert SCH/F and un-stolen second blocks to
     its dump files instead of delivering them (tetra_lower_mac.c:190-241).  The shim must withhold exactly
     the same primitives.  Both sides run with a recorder that emulates that feedback (oracle_records.h)."""
     ref = T.Ref()
-    cfg = T.GenCfg(seed=0x7E7A0077, sb_period=9, lead_sb=2, ndb2_per_256=96, ber_per_65536=300, random_cell=0, lead_in_bits=123)
+    cfg = T.GenCfg(seed=0x7E7A0077, sb_period=9, lead_sb=2, ndb2_per_256=ndb2, ber_per_65536=300, random_cell=0, lead_in_bits=123)
     n = 120
     bits = orc.gen_stream(cfg, 0, n).copy()
     code = ref.scramb_get_init(262, 42, 1)
@@ -161,20 +163,22 @@ def test_shim_follows_the_traffic_feedback(orc, tmp_path):
         marked += hdr != 0 and usage > 3
     assert marked > 5
     # the all-reference receiver with the emulated feedback and a dump directory
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
     ref.reset()
-    ref.lib.ref_set_feedback(1, str(tmp_path).encode())
+    ref.lib.ref_set_feedback(1, str(ref_dir).encode())
     ref.feed(bits, 64)
     want = ref.records().copy()
     ref.lib.ref_set_feedback(0, None)
     plain = T.Ref(); plain.reset(); plain.feed(bits, 64)
     assert 0 < want.size < plain.records().size               # the feedback really withheld primitives
-    assert any(f.startswith("traffic_") for f in os.listdir(tmp_path))
+    assert any(f.startswith("traffic_") for f in os.listdir(ref_dir))
     # the shim (PHY + lower MAC on the emulated GPU) with the same feedback in its recorder
     simt = T.build_simt()
     os.makedirs(BUILD, exist_ok=True)
     rec_c = os.path.join(BUILD, "shim_recorder_traffic.c")
     open(rec_c, "w").write(TRAFFIC_RECORDER)
-    so = os.path.join(BUILD, "libshimtest_traffic.so")
+    so = os.path.join(BUILD, f"libshimtest_traffic{ndb2}.so")        # a fresh library per case: the shim keeps one receiver per process
     subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-shared", "-I" + REF_SRC, "-I" + os.path.join(T.ROOT, "oracle", "stubs"),
                            "-I" + os.path.join(T.ROOT, "oracle"), "-I" + os.path.join(T.ROOT, "include"),
                            os.path.join(T.ROOT, "osmo-tetra_b200", "host", "tetra_shim.c"), rec_c, simt,
@@ -187,6 +191,9 @@ def test_shim_follows_the_traffic_feedback(orc, tmp_path):
                     ("start", C.c_uint), ("next", C.c_uint), ("priv", C.c_void_p)]
     trs = Trs()
     trs.priv = lib.shimtest_tms()
+    shim_dir = tmp_path / "shim"
+    shim_dir.mkdir()
+    lib.shimtest_set_dumpdir(str(shim_dir).encode())
     for pos in range(0, bits.size, 64):
         chunk = np.ascontiguousarray(bits[pos:pos + 64])
         lib.tetra_burst_sync_in(C.byref(trs), chunk.ctypes.data_as(C.c_void_p), chunk.size)
@@ -199,3 +206,11 @@ def test_shim_follows_the_traffic_feedback(orc, tmp_path):
     got["slot_bit"] = want["slot_bit"]
     ok, msg = T.records_equal(want, got)
     assert ok, msg
+    # the traffic dump of the SCH/F-shaped slots: same files, same bytes (this stream has no two-block slots,
+    # whose dump the reference fills from uninitialised memory)
+    if ndb2:
+        return
+    ref_files = sorted(f for f in os.listdir(ref_dir) if f.startswith("traffic_"))
+    assert ref_files and ref_files == sorted(os.listdir(shim_dir))
+    for f in ref_files:
+        assert open(os.path.join(ref_dir, f), "rb").read() == open(os.path.join(shim_dir, f), "rb").read(), f
