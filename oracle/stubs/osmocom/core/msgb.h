@@ -6,6 +6,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <osmocom/core/linuxlist.h>
+#include <osmocom/core/utils.h>       /* the real msgb.h pulls these in; upper-MAC files rely on it */
+#include <osmocom/core/bits.h>
+#include <osmocom/core/talloc.h>
 
 struct msgb {
 	struct llist_head list;
@@ -19,9 +22,15 @@ struct msgb {
 	unsigned char _data[0];
 };
 
+#ifndef MSGB_STANDIN_SLACK
+#define MSGB_STANDIN_SLACK 16384
+#endif
 static inline struct msgb *msgb_alloc(uint16_t size, const char *name)
 {
-	struct msgb *m = (struct msgb *)calloc(1, sizeof(*m) + size);
+	/* MSGB_STANDIN_SLACK zeroed bytes behind the buffer: the reference's upper MAC reads (and prints) well past the
+	 * end of short or damaged PDUs (negative length fields); with the slack both builds print the same zeros
+	 * there instead of whatever the heap holds, which makes whole-program output comparable */
+	struct msgb *m = (struct msgb *)calloc(1, sizeof(*m) + size + MSGB_STANDIN_SLACK);
 	(void)name;
 	if (!m)
 		return NULL;

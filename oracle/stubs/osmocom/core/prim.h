@@ -1,6 +1,8 @@
 /* TEST INFRASTRUCTURE ONLY - stand-in for libosmocore <osmocom/core/prim.h>
  * (see bits.h in this directory for why). */
 #pragma once
+#include <osmocom/core/msgb.h>      /* the real header pulls these in, crypto/tetra_crypto.c relies on it */
+#include <osmocom/core/talloc.h>
 #include <stdint.h>
 
 struct msgb;

@@ -6,3 +6,5 @@
 
 #define talloc_zero(ctx, type)  ((type *)calloc(1, sizeof(type)))
 #define talloc_free(ptr)        free(ptr)
+#define talloc_zero_array(ctx, type, n)        ((type *)calloc((n), sizeof(type)))
+#define talloc_realloc(ctx, ptr, type, n)      ((type *)realloc((ptr), (size_t)(n) * sizeof(type)))

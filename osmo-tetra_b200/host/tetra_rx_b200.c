@@ -26,43 +26,7 @@
 #include <string.h>
 
 #include "tetra_b200.h"
-
-static const char *ubit_dump(const uint8_t *bits, unsigned int len)      /* osmo_ubit_dump: '0' / '1' per bit */
-{
-	static char buf[512];
-	unsigned int i;
-	for (i = 0; i < len && i < sizeof(buf) - 1; i++)
-		buf[i] = bits[i] ? '1' : '0';
-	buf[i] = 0;
-	return buf;
-}
-
-static unsigned int bits_to_uint(const uint8_t *bits, unsigned int len)   /* tetra_common.c:31-39, MSB first */
-{
-	unsigned int v = 0;
-	while (len--)
-		v = (v << 1) | (*bits++ & 1);
-	return v;
-}
-
-struct tm3 { uint32_t tn, fn, mn; };
-
-static const char *time_dump(const struct tm3 *t)                          /* tetra_tdma.c:85-92, sn is never set */
-{
-	static char buf[64];
-	snprintf(buf, sizeof(buf), "%02u/%02u/%u/%03u", t->mn, t->fn, t->tn, 0u);
-	return buf;
-}
-
-static void crc_lines(const char *name, const struct tm3 *t, uint32_t crc, int ok, const uint8_t *type1, unsigned int len)
-{
-	printf("CRC COMP: 0x%04x ", crc & 0xffff);
-	if (ok) {
-		printf("OK\n");
-		printf("%s %s type1: %s\n", name, time_dump(t), ubit_dump(type1, len));
-	} else
-		printf("WRONG\n");
-}
+#include "tetra_text.h"
 
 int main(int argc, char **argv)
 {
@@ -109,47 +73,21 @@ int main(int argc, char **argv)
 	struct tb200_lock_event *ev = calloc(n_ev ? n_ev : 1, sizeof(*ev));
 	tb200_get_lock_events(rx, ev, n_ev);
 
-	struct tm3 cur = { 0, 0, 0 };                    /* t_phy_state.time: zero at start (tetra_burst_sync.c:34) */
+	struct tb200_text txt = { 0, 0, 0 };             /* t_phy_state.time: zero at start (tetra_burst_sync.c:34) */
 	size_t e = 0;
 	for (long i = 0; i <= n; i++) {
 		while (e < n_ev && ev[e].next_slot == (uint64_t)i)
-			printf("found SYNC training sequence in bit #%u\n", ev[e++].offset);
+			tb200_text_lock(ev[e++].offset);
 		if (i == n)
 			break;
 		const struct tb200_slot *s = &slots[i];
 		const uint8_t *t1 = type1 + (size_t)i * TB200_TYPE1_STRIDE;
 		const int kind = s->flags & TB200_F_KIND_MASK;
-		tb200_debug_time_advance(&cur.tn, &cur.fn, &cur.mn, 1);         /* tetra_burst_sync.c:113 */
-		printf("\nBURST\n");
-		if (kind == TB200_KIND_NONE) {
-			if (s->find_rc < 0)
-				fprintf(stderr, "#### could not find successive burst training sequence\n");
-			else
-				fprintf(stderr, "#### SYNC burst at offset %u?!?\n", (unsigned int)s->find_off);
-			continue;
-		}
-		struct tm3 post = { s->time & 7u, (s->time >> 3) & 31u, (s->time >> 8) & 63u };
-		if (kind == TB200_KIND_SB) {
-			/* SB1 is printed with the time before the SYNC PDU is applied (time_str is taken on entry) */
-			crc_lines("SB1", &cur, crc[i], (s->flags & TB200_F_CRC_A) != 0, t1, 60);
-			printf("TMB-SAP SYNC CC %s(0x%02x) ", ubit_dump(t1 + 4, 6), bits_to_uint(t1 + 4, 6));
-			printf("TN %s(%u) ", ubit_dump(t1 + 10, 2), bits_to_uint(t1 + 10, 2) + 1);
-			printf("FN %s(%2u) ", ubit_dump(t1 + 12, 5), bits_to_uint(t1 + 12, 5));
-			printf("MN %s(%2u) ", ubit_dump(t1 + 17, 6), bits_to_uint(t1 + 17, 6));
-			printf("MCC %s(%u) ", ubit_dump(t1 + 31, 10), bits_to_uint(t1 + 31, 10));
-			printf("MNC %s(%u)\n", ubit_dump(t1 + 41, 14), bits_to_uint(t1 + 41, 14));
-			cur = post;                                                  /* tetra_lower_mac.c:302 */
-			if (s->flags & TB200_F_BNCH)
-				printf("BNCH FOLLOWS\n");
-			crc_lines("SB2", &cur, crc[i] >> 16, (s->flags & TB200_F_CRC_B) != 0, t1 + 74, 124);
-		} else if (kind == TB200_KIND_NDB_F) {
-			crc_lines("SCH/F", &cur, crc[i], (s->flags & TB200_F_CRC_A) != 0, t1 + 14, 268);
-		} else {
-			crc_lines("NDB", &cur, crc[i], (s->flags & TB200_F_CRC_A) != 0, t1 + 14, 124);
-			crc_lines("NDB", &cur, crc[i] >> 16, (s->flags & TB200_F_CRC_B) != 0, t1 + 138, 124);
-		}
-		if (cur.tn != post.tn || cur.fn != post.fn || cur.mn != post.mn) {
-			fprintf(stderr, "internal error: slot %ld time %s differs from the device's\n", i, time_dump(&cur));
+		const int nblk = tb200_text_slot(&txt, s);
+		for (int b = 0; b < nblk; b++)
+			tb200_text_block(&txt, s, b, crc[i], t1 + tb200_text_block_offset(kind, b));
+		if (nblk && (txt.tn != (s->time & 7u) || txt.fn != ((s->time >> 3) & 31u) || txt.mn != ((s->time >> 8) & 63u))) {
+			fprintf(stderr, "internal error: slot %ld time %s differs from the device's\n", i, tb200_text_time(&txt));
 			return 3;
 		}
 	}

@@ -10,9 +10,15 @@
  * TMV-SAP primitive the reference builds (tetra_lower_mac.c:129-140,162-167,276-352) to
  *     int upper_mac_prim_recv(struct osmo_prim_hdr *op, void *priv)              tetra_upper_mac.h:22
  *
- * Bits are queued and decoded on the GPU in batches (TETRA_B200_BATCH_BITS, default 8 Mi bits);
- * tetra-rx has no end-of-stream call, so the tail is flushed from an atexit() handler, or
- * explicitly with tetra_b200_shim_flush().  Compiled against the reference's own headers.
+ * Bits are queued and decoded on the GPU in batches (TETRA_B200_BATCH_BITS, default 8 Mi bits).
+ * tetra-rx has no end-of-stream call: it reads until read() returns 0, prints "EOF", frees its state and
+ * exits (tetra-rx.c:82-102).  Built with -DTETRA_B200_SHIM_WRAP_READ and linked with -Wl,--wrap=read the
+ * shim sees that read() itself: when the descriptor that feeds tetra_burst_sync_in() reports end of file
+ * the queued tail is decoded and delivered before read() returns, i.e. before "EOF" is printed and before
+ * the receiver state is freed - the program's output is then identical to the all-reference build
+ * (tests/test_program.py).  Other callers end the stream with tetra_b200_shim_flush() while the receiver
+ * state is still alive; an atexit() handler is only the last resort.  Compiled against the reference's
+ * own headers.
  *
  * Drop-in depths:
  *   default                    PHY + lower MAC on the GPU, primitives to upper_mac_prim_recv()  (depth B)
@@ -43,10 +49,15 @@
 #include <tetra_upper_mac.h>
 #include <phy/tetra_burst.h>
 #include <phy/tetra_burst_sync.h>
+#include <crypto/tetra_crypto.h>
 
 #include "tetra_b200.h"
+#include "tetra_text.h"
 
 struct tetra_phy_state t_phy_state;
+
+/* crypto/tetra_crypto.c:416; weak so that callers without the crypto archive (test recorders) still link */
+void update_current_network(struct tetra_crypto_state *tcs, int mcc, int mnc) __attribute__((weak));
 
 #define SHIM_HIST 8192u      /* bits of earlier batches kept in front of the batch: a slot may start in them */
 
@@ -65,6 +76,9 @@ static struct {
 	struct tb200_slot *slots;
 	uint8_t *type1;
 	struct tb200_record *rec;
+	uint32_t *crc;         /* CRC registers per slot, for the text */
+	int text;              /* print what the reference's PHY + lower MAC print (TETRA_B200_TEXT=0 switches it off) */
+	struct tb200_text txt;
 	size_t max_slots;
 } S;
 
@@ -193,30 +207,59 @@ static void shim_run(int final)
 #else
 	size_t nrec = tb200_expand_records(S.slots, S.type1, (size_t)n, S.rec, 3 * S.max_slots);
 	struct tetra_mac_state *tms = priv;
-	for (size_t i = 0; i < nrec; i++) {
-		const struct tb200_record *r = &S.rec[i];
-		if (tms && tms->cur_burst.is_traffic) {
-			/* the upper MAC has just seen an AACH that marks this slot as traffic (tetra_upper_mac.c:444-452):
-			 * what tetra_lower_mac.c:190-241 does with the blocks that follow.  BLK1 of a normal burst counts as
-			 * stolen and is still decoded; SCH/F and an un-stolen block 2 are NOT handed to the upper MAC: the
-			 * reference writes their descrambled bits to <dumpdir>/traffic_*.out for an external codec.  The
-			 * SCH/F dump is reproduced; the dump of a 216-bit block 2 is not (the reference reads 216
-			 * uninitialised stack bytes into it, tetra_lower_mac.c:221-228: there is nothing to be exact against). */
-			if (r->type1_len == 124 && r->blk_num == 1)
-				tms->cur_burst.blk1_stolen = true;
-			if (r->type1_len == 268) {
-				dump_traffic_schf(tms, slot_raw_bits(r->slot_bit), r->scrambling_code);
-				continue;
+	/* lock acquisitions of this batch, for the "found SYNC training sequence" lines */
+	struct tb200_lock_event ev[64];
+	size_t n_ev = S.text ? tb200_get_lock_events(S.ctx, ev, 64) : 0, e = 0, ri = 0;
+	if (n_ev > 64) n_ev = 64;
+	for (long i = 0; i <= n; i++) {
+		while (e < n_ev && ev[e].next_slot == (uint64_t)i)
+			tb200_text_lock(ev[e++].offset);
+		if (i == n)
+			break;
+		const struct tb200_slot *sl = &S.slots[i];
+		const int kind = sl->flags & TB200_F_KIND_MASK;
+		const int nblk = S.text ? tb200_text_slot(&S.txt, sl) : (kind == TB200_KIND_NONE ? 0 : kind == TB200_KIND_NDB_F ? 2 : 3);
+		for (int b = 0; b < nblk && ri < nrec; b++) {
+			const struct tb200_record *r = &S.rec[ri++];
+			/* the reference takes the traffic branch before it prints anything about the block (:190-241 precede :258) */
+			if (tms && tms->cur_burst.is_traffic) {
+				/* the upper MAC has just seen an AACH that marks this slot as traffic (tetra_upper_mac.c:444-452):
+				 * what tetra_lower_mac.c:190-241 does with the blocks that follow.  BLK1 of a normal burst counts as
+				 * stolen and is still decoded; SCH/F and an un-stolen block 2 are NOT handed to the upper MAC: the
+				 * reference writes their descrambled bits to <dumpdir>/traffic_*.out for an external codec.  The
+				 * SCH/F dump is reproduced; the dump of a 216-bit block 2 is not (the reference reads 216
+				 * uninitialised stack bytes into it, tetra_lower_mac.c:221-228: there is nothing to be exact against). */
+				if (r->type1_len == 124 && r->blk_num == 1)
+					tms->cur_burst.blk1_stolen = true;
+				if (r->type1_len == 268) {
+					dump_traffic_schf(tms, slot_raw_bits(r->slot_bit), r->scrambling_code);
+					continue;
+				}
+				if (r->blk_num == 2 && !tms->cur_burst.blk2_stolen) {
+					static int warned;
+					if (!warned++)
+						fprintf(stderr, "tetra_b200 shim: traffic in a second half slot: block withheld, its dump is not written\n");
+					continue;
+				}
 			}
-			if (r->blk_num == 2 && !tms->cur_burst.blk2_stolen) {
-				static int warned;
-				if (!warned++)
-					fprintf(stderr, "tetra_b200 shim: traffic in a second half slot: block withheld, its dump is not written\n");
-				continue;
+			if (S.text)
+				tb200_text_block(&S.txt, sl, b, S.crc[i], r->type1);
+			if (kind == TB200_KIND_SB && b == 0 && tms && tms->tcs) {
+				/* after every SB1 the reference hands the cell in force to the crypto state
+				 * (tetra_lower_mac.c:304-308); the cell is the one behind the slot's scrambling code
+				 * (tetra_scramb.c:87-99: ((cc | mnc << 6 | mcc << 20) << 2) | 3, all zero before the first good SB1) */
+				struct tetra_crypto_state *tcs = tms->tcs;
+				const uint32_t code = sl->scrambling_code;
+				const int cc = (code >> 2) & 0x3f, mnc = (code >> 8) & 0x3fff, mcc = (code >> 22) & 0x3ff;
+				tcs->cc = cc;
+				if ((tcs->mcc != mcc || tcs->mnc != mnc) && update_current_network)
+					update_current_network(tcs, mcc, mnc);
 			}
+			deliver(r, priv);
 		}
-		deliver(r, priv);
 	}
+	if (S.text)
+		fflush(stdout);
 #endif
 	{       /* keep the last SHIM_HIST bits for slots that start in this batch and complete in the next */
 		const size_t have = S.n_hist + S.n_bits, keep = have < SHIM_HIST ? have : SHIM_HIST;
@@ -243,6 +286,26 @@ void tetra_b200_shim_flush(void)
 	shim_run(1);
 }
 
+#ifdef TETRA_B200_SHIM_WRAP_READ
+/* link with -Wl,--wrap=read: end of file on the descriptor that feeds the receiver ends the stream */
+#include <unistd.h>
+ssize_t __real_read(int fd, void *buf, size_t count);
+static const void *g_last_read_buf;
+static int g_last_read_fd = -1, g_stream_fd = -1;
+
+ssize_t __wrap_read(int fd, void *buf, size_t count)
+{
+	const ssize_t n = __real_read(fd, buf, count);
+	if (n > 0) {
+		g_last_read_buf = buf;
+		g_last_read_fd = fd;
+	} else if (n == 0 && fd == g_stream_fd) {
+		shim_run(1);
+	}
+	return n;
+}
+#endif
+
 static void shim_init(unsigned int first_len)
 {
 	const char *e = getenv("TETRA_B200_BATCH_BITS");
@@ -265,8 +328,12 @@ static void shim_init(unsigned int first_len)
 	S.slots = tb200_host_alloc(S.max_slots * sizeof(*S.slots));
 	S.type1 = tb200_host_alloc(S.max_slots * TB200_TYPE1_STRIDE);
 	S.rec = malloc(3 * S.max_slots * sizeof(*S.rec));
-	if (!S.bits || !S.slots || !S.type1 || !S.rec)
+	S.crc = tb200_host_alloc(S.max_slots * sizeof(*S.crc));
+	if (!S.bits || !S.slots || !S.type1 || !S.rec || !S.crc)
 		shim_die("out of memory");
+	const char *t = getenv("TETRA_B200_TEXT");
+	S.text = !(t && t[0] == '0');
+	tb200_set_crc_buffer(S.ctx, S.crc);
 	atexit(tetra_b200_shim_flush);
 }
 
@@ -275,6 +342,10 @@ int tetra_burst_sync_in(struct tetra_rx_state *trs, uint8_t *bits, unsigned int 
 	if (!S.ctx)
 		shim_init(len);
 	S.trs = trs;
+#ifdef TETRA_B200_SHIM_WRAP_READ
+	if (bits == g_last_read_buf)
+		g_stream_fd = g_last_read_fd;         /* the descriptor whose data reaches the receiver */
+#endif
 	if (S.short_read_seen && len)
 		shim_die("a short read() was followed by more data: only constant read sizes are modelled");
 	if (len != S.chunk)
