@@ -1,9 +1,10 @@
 """osmo-tetra_b200 - B200-native TETRA lower-MAC receive chain (type-5 bits -> type-1 bits).
 
 The product is the CUDA library `libtetra_b200.so` built from csrc/ (C ABI in
-include/tetra_b200.h).  This module is only the loader the tests, bench.py and
-__graft_entry__ use: it finds the in-tree library and refuses to continue without it -
-there is no CPU implementation behind this package.
+include/tetra_b200.h); `host/` holds the C side that plugs it into the reference
+(tetra_shim.c, tetra_rx_b200.c).  `binding.py` is the ctypes face of the C ABI (class B200,
+the record layouts, the multi-GPU sharding driver); this module finds the in-tree library and
+refuses to continue without it - there is no CPU implementation behind this package.
 """
 import ctypes
 import os

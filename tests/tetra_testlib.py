@@ -34,25 +34,11 @@ BLK = {  # type345, type2, type1, a   (tetra_lower_mac.c:55-102)
     T_SCH_F: (432, 288, 268, 103),
 }
 
-RECORD_DTYPE = np.dtype([
-    ("slot_bit", "<u4"), ("lchan", "u1"), ("crc_ok", "u1"), ("blk_num", "u1"),
-    ("tn", "u1"), ("fn", "u1"), ("mn", "u1"), ("type1_len", "<u2"),
-    ("scrambling_code", "<u4"), ("type1", "u1", (272,)),
-])
-assert RECORD_DTYPE.itemsize == 288
-
 EVENT_DTYPE = np.dtype([
     ("call_index", "<u4"), ("buf_start_bit", "<u4"), ("window", "<u4"),
     ("mask", "<u4"), ("rc", "<i4"), ("offset", "<u4"),
 ])
 assert EVENT_DTYPE.itemsize == 24
-
-
-class GenCfg(C.Structure):
-    """struct orc_gen_cfg (oracle/tetra_oracle.c) == struct tb200_gen_cfg (include/tetra_b200.h)"""
-    _fields_ = [("seed", C.c_uint64), ("sb_period", C.c_uint32), ("lead_sb", C.c_uint32),
-                ("ndb2_per_256", C.c_uint32), ("ber_per_65536", C.c_uint32),
-                ("random_cell", C.c_uint32), ("lead_in_bits", C.c_uint32)]
 
 
 def _ptr(a):
@@ -361,46 +347,33 @@ def records_equal(a, b):
 PRODUCT_SO = os.path.join(ROOT, "osmo-tetra_b200", "libtetra_b200.so")
 SIMT_SO = os.path.join(ROOT, "tests", "simt", "_build", "libtetra_b200_simt.so")
 
-SLOT_DTYPE = np.dtype([("slot_bit", "<u4"), ("scrambling_code", "<u4"), ("find_off", "<u2"),
-                       ("window", "<u2"), ("time", "<u2"), ("find_rc", "i1"), ("flags", "u1")])
-assert SLOT_DTYPE.itemsize == 16
+# ---- the product's own ctypes binding (osmo-tetra_b200/binding.py), re-exported for the tests
 
-TB200_FRESH, TB200_FINAL = 1, 2
-OUT_UNPACKED, OUT_PACKED = 1, 2
-IN_BYTES, IN_PACKED, IN_F32SYM = 0, 1, 2
-VITERBI_WARP, VITERBI_LANE = 0, 1
-
-
-class Options(C.Structure):
-    _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
-                ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32), ("input", C.c_uint32)]
-
-
-class Timing(C.Structure):
-    _fields_ = [("total_ms", C.c_float), ("classify_ms", C.c_float), ("scan_ms", C.c_float), ("decode_ms", C.c_float),
-                ("launches_classify", C.c_uint32), ("launches_scan", C.c_uint32), ("launches_decode", C.c_uint32),
-                ("pieces", C.c_uint32), ("slots", C.c_uint64), ("leaf_ms", C.c_float), ("search_ms", C.c_float)]
+def _load_binding():
+    import importlib.util
+    import sys
+    name = "osmo_tetra_b200_binding"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "osmo-tetra_b200", "binding.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
 
 
-class Carry(C.Structure):
-    _fields_ = [("stream_bits", C.c_uint64), ("buf_start_bit", C.c_uint64), ("next_frame_start", C.c_uint64),
-                ("calls", C.c_uint64), ("state", C.c_uint32), ("bits_in_buf", C.c_uint32),
-                ("scramb_init", C.c_uint32), ("mcc", C.c_uint16), ("mnc", C.c_uint16),
-                ("colour_code", C.c_uint8), ("tn", C.c_uint8), ("fn", C.c_uint8), ("mn", C.c_uint8)]
+_B = _load_binding()
+RECORD_DTYPE, SLOT_DTYPE, GenCfg, Options, Timing, Carry, ShardSummary, Stats = (
+    _B.RECORD_DTYPE, _B.SLOT_DTYPE, _B.GenCfg, _B.Options, _B.Timing, _B.Carry, _B.ShardSummary, _B.Stats)
+TB200_FRESH, TB200_FINAL, OUT_UNPACKED, OUT_PACKED = _B.TB200_FRESH, _B.TB200_FINAL, _B.OUT_UNPACKED, _B.OUT_PACKED
+IN_BYTES, IN_PACKED, IN_F32SYM, VITERBI_WARP, VITERBI_LANE = _B.IN_BYTES, _B.IN_PACKED, _B.IN_F32SYM, _B.VITERBI_WARP, _B.VITERBI_LANE
+shard_plan, SHARD_HALO, DevBuffer, peer_pointer, sharded_decode, pack_bits = (
+    _B.shard_plan, _B.SHARD_HALO, _B.DevBuffer, _B.peer_pointer, _B.sharded_decode, _B.pack_bits)
 
 
-class ShardSummary(C.Structure):
-    _fields_ = [("n_slots", C.c_uint32), ("first_unlock", C.c_uint32), ("has_good_sb", C.c_uint32),
-                ("scramb_init", C.c_uint32), ("slots_after", C.c_uint32), ("mcc", C.c_uint16), ("mnc", C.c_uint16),
-                ("tn", C.c_uint8), ("fn", C.c_uint8), ("mn", C.c_uint8), ("cc", C.c_uint8), ("pad", C.c_uint32)]
-
-
-assert C.sizeof(ShardSummary) == 32
-
-
-class Stats(C.Structure):
-    _fields_ = [(n, C.c_uint64) for n in ("slots", "bursts_decoded", "blocks", "crc_ok_blocks",
-                                           "lock_losses", "lock_acquisitions", "kernel_launches")]
+def B200(emulate=False, device=0):
+    """the product binding; emulate=True: on the SIMT-emulation build of the CUDA sources (CPU tests)"""
+    return _B.B200(device=device, lib_path=build_simt() if emulate else None)
 
 
 def build_simt():
@@ -420,196 +393,6 @@ def build_simt():
         os.path.join(ROOT, "tests", "simt", "cpu_simt.cpp"), "-o", SIMT_SO])
     return SIMT_SO
 
-
-class B200:
-    """ctypes view of include/tetra_b200.h.  emulate=True loads the SIMT-emulation build (CPU tests)."""
-
-    def __init__(self, emulate=False, device=0):
-        path = build_simt() if emulate else PRODUCT_SO
-        if not os.path.exists(path):
-            raise RuntimeError(f"{path} is missing - run __graft_entry__.build() first")
-        lib = self.lib = C.CDLL(path)
-        lib.tb200_version.restype = C.c_char_p
-        lib.tb200_last_error.restype = C.c_char_p
-        lib.tb200_last_error.argtypes = [C.c_void_p]
-        lib.tb200_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
-        lib.tb200_destroy.argtypes = [C.c_void_p]
-        lib.tb200_set_options.argtypes = [C.c_void_p, C.POINTER(Options)]
-        for f in (lib.tb200_rx_stream_host, lib.tb200_rx_stream_dev):
-            f.restype = C.c_long
-            f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
-        lib.tb200_max_slots.restype = C.c_uint64
-        lib.tb200_max_slots.argtypes = [C.c_uint64]
-        lib.tb200_expand_records.restype = C.c_size_t
-        lib.tb200_expand_records.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
-        lib.tb200_get_carry.argtypes = [C.c_void_p, C.POINTER(Carry)]
-        lib.tb200_get_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
-        lib.tb200_get_timing.argtypes = [C.c_void_p, C.POINTER(Timing)]
-        lib.tb200_measure_int_peak.restype = C.c_double
-        lib.tb200_measure_int_peak.argtypes = [C.c_void_p]
-        lib.tb200_find_train_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64,
-                                             C.c_uint32, C.c_void_p, C.c_void_p]
-        lib.tb200_decode_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
-        lib.tb200_descramble_deinterleave.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
-                                                      C.c_uint32, C.c_uint32, C.c_int]
-        lib.tb200_gen_stream_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
-        lib.tb200_find_lock.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
-        lib.tb200_shard_pass1.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
-                                          C.c_uint32, C.POINTER(ShardSummary)]
-        lib.tb200_shard_carry_in.argtypes = [C.c_void_p, C.c_int, C.POINTER(Carry), C.POINTER(Carry)]
-        lib.tb200_shard_carry_in.restype = None
-        if hasattr(lib, "tb200_dev_alloc"):          # (A/B runs load older builds of the library)
-            lib.tb200_dev_alloc.restype = C.c_void_p
-            lib.tb200_dev_alloc.argtypes = [C.c_void_p, C.c_size_t]
-            lib.tb200_dev_free.argtypes = [C.c_void_p, C.c_void_p]
-            lib.tb200_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-            lib.tb200_ipc_import.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
-            lib.tb200_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
-        lib.tb200_shard_pass2.restype = C.c_long
-        lib.tb200_shard_pass2.argtypes = [C.c_void_p, C.POINTER(Carry), C.c_void_p, C.c_void_p, C.c_void_p]
-        lib.tb200_host_alloc.restype = C.c_void_p
-        lib.tb200_host_alloc.argtypes = [C.c_size_t]
-        lib.tb200_host_free.argtypes = [C.c_void_p]
-        self.emulate = emulate
-        h = C.c_void_p()
-        rc = lib.tb200_create(C.byref(h), device)
-        if rc != 0:
-            raise RuntimeError(f"tb200_create failed ({rc}): no CUDA device and no CPU path")
-        self.h = h
-        self.opt = Options()
-        lib.tb200_default_options(C.byref(self.opt))
-
-    def close(self):
-        if self.h:
-            self.lib.tb200_destroy(self.h)
-            self.h = None
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
-    def err(self):
-        return self.lib.tb200_last_error(self.h).decode()
-
-    def set_options(self, **kw):
-        for k, v in kw.items():
-            setattr(self.opt, k, v)
-        rc = self.lib.tb200_set_options(self.h, C.byref(self.opt))
-        if rc:
-            raise ValueError(self.err())
-
-    def rx_stream_host(self, bits, flags=TB200_FRESH | TB200_FINAL, max_slots=None):
-        bits = np.ascontiguousarray(bits, dtype=np.uint8)
-        if max_slots is None:
-            max_slots = int(self.lib.tb200_max_slots(bits.size)) + 16
-        slots = np.zeros(max_slots, dtype=SLOT_DTYPE)
-        type1 = np.zeros((max_slots, 288), dtype=np.uint8)
-        packed = np.zeros((max_slots, 9), dtype=np.uint32)
-        n = self.lib.tb200_rx_stream_host(self.h, _ptr(bits), bits.size, flags, _ptr(slots), _ptr(type1), _ptr(packed), max_slots)
-        if n < 0:
-            raise RuntimeError(f"tb200_rx_stream_host: {n}: {self.err()}")
-        return slots[:n], type1[:n], packed[:n]
-
-    def rx_stream_host_raw(self, buf, n_bits, flags=TB200_FRESH | TB200_FINAL):
-        """host call with the stream in the format options.input names (buf: any contiguous numpy array)"""
-        buf = np.ascontiguousarray(buf)
-        max_slots = int(self.lib.tb200_max_slots(n_bits)) + 16
-        slots = np.zeros(max_slots, dtype=SLOT_DTYPE)
-        type1 = np.zeros((max_slots, 288), dtype=np.uint8)
-        packed = np.zeros((max_slots, 9), dtype=np.uint32)
-        n = self.lib.tb200_rx_stream_host(self.h, _ptr(buf), n_bits, flags, _ptr(slots), _ptr(type1), _ptr(packed), max_slots)
-        if n < 0:
-            raise RuntimeError(f"tb200_rx_stream_host: {n}: {self.err()}")
-        return slots[:n], type1[:n], packed[:n]
-
-    def expand_records(self, slots, type1):
-        slots = np.ascontiguousarray(slots); type1 = np.ascontiguousarray(type1)
-        n = self.lib.tb200_expand_records(_ptr(slots), _ptr(type1), slots.size, None, 0)
-        rec = np.zeros(n, dtype=RECORD_DTYPE)
-        self.lib.tb200_expand_records(_ptr(slots), _ptr(type1), slots.size, _ptr(rec), n)
-        return rec
-
-    def records_host(self, bits, flags=TB200_FRESH | TB200_FINAL):
-        slots, type1, _ = self.rx_stream_host(bits, flags)
-        return self.expand_records(slots, type1)
-
-    def carry(self):
-        c = Carry()
-        self.lib.tb200_get_carry(self.h, C.byref(c))
-        return c
-
-    def stats(self):
-        s = Stats()
-        self.lib.tb200_get_stats(self.h, C.byref(s))
-        return s
-
-    def timing(self):
-        t = Timing()
-        self.lib.tb200_get_timing(self.h, C.byref(t))
-        return t
-
-    # ---- sharded decode (pointers are raw device addresses; host addresses under emulation)
-    def find_lock(self, d_bits_ptr, n_bits):
-        a0, cmin = C.c_uint64(0), C.c_uint64(0)
-        rc = self.lib.tb200_find_lock(self.h, C.c_void_p(d_bits_ptr), n_bits, C.byref(a0), C.byref(cmin))
-        if rc < 0:
-            raise RuntimeError(self.err())
-        return rc == 1, a0.value, cmin.value
-
-    def shard_pass1(self, d_bits_ptr, base_bit, n_bytes, a0, cmin, n_end, n_slots):
-        s = ShardSummary()
-        rc = self.lib.tb200_shard_pass1(self.h, C.c_void_p(d_bits_ptr), base_bit, n_bytes, a0, cmin, n_end, n_slots, C.byref(s))
-        if rc:
-            raise RuntimeError(self.err())
-        return s
-
-    def shard_carry_in(self, summaries, rank, initial=None):
-        arr = (ShardSummary * len(summaries))(*summaries)
-        init = initial or Carry()
-        out = Carry()
-        self.lib.tb200_shard_carry_in(arr, rank, C.byref(init), C.byref(out))
-        return out
-
-    def shard_pass2(self, carry, d_slots_ptr, d_type1_ptr, d_packed_ptr=None):
-        n = self.lib.tb200_shard_pass2(self.h, C.byref(carry), C.c_void_p(d_slots_ptr), C.c_void_p(d_type1_ptr),
-                                       C.c_void_p(d_packed_ptr) if d_packed_ptr else None)
-        if n < 0:
-            raise RuntimeError(self.err())
-        return n
-
-    def find_train_seq(self, bits, starts, lens, mask):
-        bits = np.ascontiguousarray(bits, dtype=np.uint8)
-        starts = np.ascontiguousarray(starts, dtype=np.uint64); lens = np.ascontiguousarray(lens, dtype=np.uint32)
-        rc = np.zeros(starts.size, dtype=np.int32); off = np.zeros(starts.size, dtype=np.uint32)
-        r = self.lib.tb200_find_train_seq(self.h, _ptr(bits), bits.size, _ptr(starts), _ptr(lens), starts.size, mask, _ptr(rc), _ptr(off))
-        if r:
-            raise RuntimeError(self.err())
-        return rc, off
-
-    def decode_blocks(self, blk_type, type5, codes):
-        k, _, t1, _ = BLK[blk_type]
-        type5 = np.ascontiguousarray(type5, dtype=np.uint8).reshape(-1, k)
-        codes = np.ascontiguousarray(codes, dtype=np.uint32)
-        n = type5.shape[0]
-        out = np.zeros((n, t1), dtype=np.uint8); ok = np.zeros(n, dtype=np.uint8)
-        r = self.lib.tb200_decode_blocks(self.h, blk_type, _ptr(type5), _ptr(codes), n, _ptr(out), _ptr(ok))
-        if r:
-            raise RuntimeError(self.err())
-        return out, ok
-
-    def descramble_deinterleave(self, type5, codes, K, a):
-        type5 = np.ascontiguousarray(type5, dtype=np.uint8).reshape(-1, K)
-        codes = np.ascontiguousarray(codes, dtype=np.uint32)
-        out = np.zeros_like(type5)
-        r = self.lib.tb200_descramble_deinterleave(self.h, _ptr(type5), _ptr(out), _ptr(codes), type5.shape[0], K, a, 0)
-        if r:
-            raise RuntimeError(self.err())
-        return out
-
-
-# --------------------------------------------------------------------------- golden fixtures
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 
@@ -653,135 +436,6 @@ def check_stream_against(records, events, slots, got_records):
 
 
 # ------------------------------------------------------------------ one stream over several GPUs
-
-def shard_plan(n_slots_total, world):
-    """contiguous slot ranges per rank (the last ranks get the remainder)"""
-    per = (n_slots_total + world - 1) // world
-    return [(min(r * per, n_slots_total), min((r + 1) * per, n_slots_total)) for r in range(world)]
-
-
-SHARD_HALO = 4096 + 64        # look-ahead of the search window (tetra_burst_sync.c:117) + read-ahead
-
-
-class DevBuffer:
-    """device memory from tb200_dev_alloc (exportable to other processes), viewable as a torch uint8 tensor"""
-
-    def __init__(self, g, nbytes):
-        self.g, self.nbytes = g, nbytes
-        self.ptr = g.lib.tb200_dev_alloc(g.h, nbytes)
-        if not self.ptr:
-            raise MemoryError("tb200_dev_alloc")
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2}
-
-    def tensor(self, device):
-        import torch
-        return torch.as_tensor(self, device=device)
-
-    def export(self):
-        h = (C.c_uint8 * 64)()
-        if self.g.lib.tb200_ipc_export(self.g.h, C.c_void_p(self.ptr), h):
-            raise RuntimeError(self.g.err())
-        return bytes(h)
-
-    def free(self):
-        if self.ptr:
-            self.g.lib.tb200_dev_free(self.g.h, C.c_void_p(self.ptr))
-            self.ptr = None
-
-
-_peer_maps = {}
-
-
-def peer_pointer(g, handle):
-    """map another rank's exported buffer (cached per handle: opening is a millisecond-scale call)"""
-    key = (id(g), handle)
-    if key not in _peer_maps:
-        p = C.c_void_p()
-        hb = (C.c_uint8 * 64).from_buffer_copy(handle)
-        if g.lib.tb200_ipc_import(g.h, hb, C.byref(p)):
-            raise RuntimeError(g.err())
-        _peer_maps[key] = p.value
-    return _peer_maps[key]
-
-
-def sharded_decode(g, dist, rank, world, d_full, n_bits, device, want_type1=False, timers=None, peer_handle=None):
-    """BASELINE config 5: ONE stream, held by rank 0 (device tensor d_full, None elsewhere), decoded by
-    `world` ranks.  Rank 0 acquires lock on the head of the stream; every rank takes a contiguous slot range
-    (+ look-ahead halo) and runs pass 1 (search, classification, SB1) on it, the 32-byte summaries are
-    all-gathered (the only exchange step of the path: the cell state), every rank derives its carry-in and
-    runs pass 2.  Results stay rank-local.  How a rank gets at its shard:
-      peer_handle is None   rank 0 scatters the shards with NCCL send/recv, then the kernels run
-      peer_handle = bytes   (rank 0's exported buffer, see DevBuffer) no copy at all: the search kernel of
-                            every rank reads its shard straight out of rank 0's HBM over NVLink
-    Returns (k0, k1, a0, d_slots, d_type1 or None, d_packed, summaries)."""
-    import torch
-    meta = torch.zeros(4, dtype=torch.int64, device=device)
-    if rank == 0:
-        ok, a0, cmin = g.find_lock(d_full.data_ptr(), n_bits)
-        meta[:] = torch.tensor([int(ok), a0, cmin, n_bits], dtype=torch.int64)
-    if world > 1:
-        dist.broadcast(meta, 0)
-    ok, a0, cmin, n_bits = (int(x) for x in meta.cpu())
-    if not ok:
-        raise RuntimeError("no lock on the head of the stream")
-    n_total = (n_bits - a0) // 510
-    plan = shard_plan(n_total, world)
-    k0, k1 = plan[rank]
-    n = k1 - k0
-
-    def span(r):
-        lo = a0 + 510 * plan[r][0]
-        hi = min(n_bits, a0 + 510 * plan[r][1] + SHARD_HALO)
-        return lo, max(hi, lo)
-    if timers is not None:
-        torch.cuda.synchronize(); timers["t_scatter0"] = __import__("time").perf_counter()
-    lo, hi = span(rank)
-    if peer_handle is not None:
-        shard_ptr = (d_full.data_ptr() if rank == 0 else peer_pointer(g, peer_handle)) + lo
-    elif rank == 0:
-        shard = d_full[lo:hi]
-        shard_ptr = shard.data_ptr()
-        if world > 1:
-            # one NCCL group: the sends to all peers run concurrently and share rank 0's NVLink egress
-            ops = [dist.P2POp(dist.isend, d_full[span(r)[0]:span(r)[1]], r) for r in range(1, world) if span(r)[1] > span(r)[0]]
-            for q in (dist.batch_isend_irecv(ops) if ops else []):
-                q.wait()
-    else:
-        shard = torch.empty(hi - lo + 64, dtype=torch.uint8, device=device)[:hi - lo]
-        shard_ptr = shard.data_ptr()
-        if hi > lo:
-            for q in dist.batch_isend_irecv([dist.P2POp(dist.irecv, shard, 0)]):
-                q.wait()
-    if timers is not None:
-        if world > 1:
-            dist.barrier()          # the scatter ends when the last rank has its shard
-        torch.cuda.synchronize(); timers["t_scatter1"] = __import__("time").perf_counter()
-    s = g.shard_pass1(shard_ptr, lo, hi - lo, lo, cmin + k0, n_bits, n)
-    mine = torch.frombuffer(bytearray(bytes(s)), dtype=torch.uint8).to(device)
-    gathered = [torch.zeros(32, dtype=torch.uint8, device=device) for _ in range(world)]
-    if world > 1:
-        dist.all_gather(gathered, mine)
-    else:
-        gathered[0] = mine
-    summaries = [ShardSummary.from_buffer_copy(bytes(t.cpu().numpy().tobytes())) for t in gathered]
-    carry = g.shard_carry_in(summaries, rank)
-    d_slots = torch.empty(max(n, 1) * 16, dtype=torch.uint8, device=device)
-    d_t1 = torch.empty(max(n, 1) * 288, dtype=torch.uint8, device=device) if want_type1 else None
-    d_pk = torch.empty(max(n, 1) * 9, dtype=torch.int32, device=device)
-    got = g.shard_pass2(carry, d_slots.data_ptr(), d_t1.data_ptr() if want_type1 else None, d_pk.data_ptr())
-    assert got == n, (got, n)
-    if timers is not None:
-        torch.cuda.synchronize(); timers["t_done"] = __import__("time").perf_counter()
-    return k0, k1, a0, d_slots, d_t1, d_pk, summaries
-
-
-def pack_bits(bits):
-    """1-bit-per-byte stream -> TB200_IN_PACKED buffer (stream bit i = byte i>>3 bit i&7), padded to 16 bytes"""
-    p = np.packbits(np.ascontiguousarray(bits, dtype=np.uint8) & 1, bitorder="little")
-    out = np.zeros((p.size + 15) // 16 * 16, dtype=np.uint8)
-    out[:p.size] = p
-    return out
-
 
 def bits_to_symbols(bits, rng, edge_share=0.02):
     """float32 demodulator symbols that float_to_bits (no AFC) slices back to `bits` (even count):
