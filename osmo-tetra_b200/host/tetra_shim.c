@@ -59,6 +59,11 @@ struct tetra_phy_state t_phy_state;
 /* crypto/tetra_crypto.c:416; weak so that callers without the crypto archive (test recorders) still link */
 void update_current_network(struct tetra_crypto_state *tcs, int mcc, int mnc) __attribute__((weak));
 
+#ifdef TETRA_B200_SHIM_L0_ONLY
+/* the reference's slicer, phy/tetra_burst.c:341-379 (tetra_burst_sync.c:36 forward-declares it the same way) */
+void tetra_burst_rx_cb(const uint8_t *burst, unsigned int len, enum tetra_train_seq type, void *priv);
+#endif
+
 #define SHIM_HIST 8192u      /* bits of earlier batches kept in front of the batch: a slot may start in them */
 
 static struct {
@@ -202,7 +207,7 @@ static void shim_run(int final)
 		tetra_tdma_time_add_tn(&t_phy_state.time, 1);
 		if ((sl->flags & TB200_F_KIND_MASK) == TB200_KIND_NONE)
 			continue;
-		tetra_burst_rx_cb((uint8_t *)slot_raw_bits(sl->slot_bit), TB200_BITS_PER_SLOT, sl->find_rc, priv);
+		tetra_burst_rx_cb(slot_raw_bits(sl->slot_bit), TB200_BITS_PER_SLOT, (enum tetra_train_seq)sl->find_rc, priv);
 	}
 #else
 	size_t nrec = tb200_expand_records(S.slots, S.type1, (size_t)n, S.rec, 3 * S.max_slots);
