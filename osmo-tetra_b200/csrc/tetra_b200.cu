@@ -834,14 +834,18 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 	if (out.n + n_slots > out.max_slots)
 		return fail(ctx, TB200_E_ARG, "output arrays too small: need %llu slots, have %llu",
 		            (unsigned long long)(out.n + n_slots), (unsigned long long)out.max_slots);
-	uint32_t P = ctx->opt.pipeline_slots ? ctx->opt.pipeline_slots : (src.on_device ? (1u << 20) : (1u << 17));
+	/* slots per piece: device-resident input 2^20; host input 2^17 with a ramp (below), bit-packed host input 2^18
+	 * without one: its copies are 8x smaller, so the per-piece launch and synchronisation cost weighs more (measured:
+	 * 10^6 bursts packed in and out 2.36 -> 2.00 ms) */
+	const bool packed_host = !src.on_device && src.fmt == IN_PACKED;
+	uint32_t P = ctx->opt.pipeline_slots ? ctx->opt.pipeline_slots : (src.on_device ? (1u << 20) : packed_host ? (1u << 18) : (1u << 17));
 	if (P > n_slots) P = (uint32_t)n_slots;
 	/* piece boundaries; the host path ramps the first pieces up (P/16, P/8, ...) so that the first
 	 * copy is short and compute / copy-back start early */
 	std::vector<uint64_t> pstart;
 	{
 		uint64_t k = 0;
-		uint32_t cur = (!src.on_device && !ctx->opt.pipeline_slots && P >= 16384) ? P / 16 : P;
+		uint32_t cur = (!src.on_device && !packed_host && !ctx->opt.pipeline_slots && P >= 16384) ? P / 16 : P;
 		while (k < n_slots) {
 			pstart.push_back(k);
 			k += cur;

@@ -35,5 +35,35 @@ def main():
                 if it: best = min(best, dt)
             print(f"out={name:8s} piece={P:7d}: {best*1e3:7.2f} ms -> {ns/best/1e6:7.1f} M bursts/s  (H2D {nbits/best/1e9:.1f} GB/s)")
 
+def packed():
+    """bit-packed input (64 B per burst): piece size sweep"""
+    n = 1_000_000
+    g = T.B200()
+    cfg = T.GenCfg(seed=0x7E7A0002, sb_period=64, lead_sb=2, ndb2_per_256=0, ber_per_65536=655, random_cell=0, lead_in_bits=0)
+    nbits = 510 * n
+    d_bits = torch.empty(nbits + 64, dtype=torch.uint8, device="cuda")
+    assert g.lib.tb200_gen_stream_dev(g.h, C.byref(cfg), 0, n, C.c_void_p(d_bits.data_ptr()), 0) == 0
+    pk = np.packbits(d_bits[:nbits].cpu().numpy(), bitorder="little")
+    ms = n + 16
+    hb = g.lib.tb200_host_alloc(pk.size + 64); hs = g.lib.tb200_host_alloc(ms * 16); ht = g.lib.tb200_host_alloc(ms * 288); hp = g.lib.tb200_host_alloc(ms * 36)
+    np.ctypeslib.as_array(C.cast(hb, C.POINTER(C.c_uint8)), shape=(pk.size,))[:] = pk
+    for out_mode, name in ((T.OUT_UNPACKED, "unpacked"), (T.OUT_PACKED, "packed")):
+        for P in (0, 65536, 131072, 262144, 524288, 1048576):
+            g.set_options(output=out_mode, pipeline_slots=P, profile=0, viterbi=1, input=T.IN_PACKED)
+            tp = ht if out_mode & T.OUT_UNPACKED else None
+            pp = hp if out_mode & T.OUT_PACKED else None
+            best = 1e9
+            for it in range(6):
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                ns = g.lib.tb200_rx_stream_host(g.h, hb, nbits, 3, hs, tp, pp, ms)
+                dt = time.perf_counter() - t0
+                assert ns == n - 1, g.err()
+                if it: best = min(best, dt)
+            print(f"packed in, out={name:8s} piece={P:7d}: {best*1e3:7.2f} ms -> {ns/best/1e6:7.1f} M bursts/s")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "packed":
+        packed()
+        sys.exit(0)
     main()
