@@ -237,8 +237,10 @@ int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type5, uint8_t 
                                   const uint32_t *codes, uint64_t n, uint32_t K, uint32_t a,
                                   int is_device);
 
-/* whole tp_sap_udata_ind arithmetic for n blocks of one type (tetra_lower_mac.c:143-280):
- * type-5 bytes in; type-1 bytes (type1_bits each) and crc_ok flags out. Host pointers. */
+/* whole tp_sap_udata_ind arithmetic for n blocks of one type (tetra_lower_mac.c:143-280), every row of
+ * tetra_blk_param[] (tetra_lower_mac.c:55-102): SB1, SB2, NDB, SCH/F, the uplink SCH/HU (168 -> 92 bits, a = 13)
+ * and BBK (first 14 descrambled bits, crc_ok = 1).  type-5 bytes in; type-1 bytes (type1_bits each) and crc_ok
+ * flags out.  Host pointers. */
 int tb200_decode_blocks(tb200_ctx *ctx, int blk_type, const uint8_t *type5, const uint32_t *codes,
                         uint64_t n, uint8_t *type1, uint8_t *crc_ok);
 

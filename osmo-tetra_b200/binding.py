@@ -16,7 +16,7 @@ TS_NORM_1, TS_NORM_2, TS_NORM_3, TS_SYNC, TS_EXT = 0, 1, 2, 3, 4          # enum
 T_SB1, T_SB2, T_NDB, T_BBK, T_SCH_HU, T_SCH_F = 0, 1, 2, 3, 4, 5          # enum tp_sap_data_type
 BLK = {  # type345, type2, type1, a   (tetra_lower_mac.c:55-102)
     T_SB1: (120, 80, 60, 11), T_SB2: (216, 144, 124, 101), T_NDB: (216, 144, 124, 101),
-    T_SCH_F: (432, 288, 268, 103), T_BBK: (30, 30, 14, 0),
+    T_SCH_F: (432, 288, 268, 103), T_BBK: (30, 30, 14, 0), T_SCH_HU: (168, 112, 92, 13),
 }
 
 RECORD_DTYPE = np.dtype([

@@ -72,8 +72,8 @@ static void build_tables(Tables *t)
 		t->crc_pow[d] = crc16_host(msg.data(), d + 1, 0);
 	}
 	std::fill(msg.begin(), msg.end(), 0);
-	const int Ls[3] = {76, 140, 284};
-	for (int i = 0; i < 3; i++)
+	const int Ls[4] = {76, 140, 284, 108};
+	for (int i = 0; i < 4; i++)
 		t->crc_init[i] = crc16_host(msg.data(), Ls[i], 0xffff);
 
 	/* reflected CRC tables: register bit-reversed, polynomial 0x1021 -> 0x8408 */
@@ -1328,7 +1328,14 @@ k_leaf_decode(int blk_type, const uint8_t *type5, const uint32_t *codes, uint64_
 			leaf_decode_one<0>(sm[wib], type5 + i * 120, codes[i], tab, type1 + i * 60, crc_ok + i, lane, variant);
 		else if (blk_type == TB200_T_SCH_F)
 			leaf_decode_one<5>(sm[wib], type5 + i * 432, codes[i], tab, type1 + i * 268, crc_ok + i, lane, variant);
-		else
+		else if (blk_type == TB200_T_SCH_HU)
+			leaf_decode_one<4>(sm[wib], type5 + i * 168, codes[i], tab, type1 + i * 92, crc_ok + i, lane, variant);
+		else if (blk_type == TB200_T_BBK) {
+			/* no channel decoding in the reference (tetra_lower_mac.c:268-274): the first 14 descrambled bits, CRC flag 1 */
+			const uint32_t lw = lfsr_word(codes[i], 0, tab);
+			if (lane < 14) type1[i * 14 + lane] = (type5[i * 30 + lane] ^ (lw >> lane)) & 1;
+			if (lane == 0) crc_ok[i] = 1;
+		} else
 			leaf_decode_one<1>(sm[wib], type5 + i * 216, codes[i], tab, type1 + i * 124, crc_ok + i, lane, variant);
 	}
 }
@@ -1419,6 +1426,8 @@ extern "C" int tb200_decode_blocks(tb200_ctx *ctx, int blk_type, const uint8_t *
 	case TB200_T_SB1: K = 120; T1 = 60; break;
 	case TB200_T_SB2: case TB200_T_NDB: K = 216; T1 = 124; break;
 	case TB200_T_SCH_F: K = 432; T1 = 268; break;
+	case TB200_T_SCH_HU: K = 168; T1 = 92; break;
+	case TB200_T_BBK: K = 30; T1 = 14; break;
 	default: return fail(ctx, TB200_E_ARG, "block type %d is not decoded by the receive path", blk_type);
 	}
 	if (n == 0) return 0;

@@ -43,7 +43,7 @@ struct Tables {
 	/* CRC-16-CCITT: contribution of a set message bit at distance d from the end,
 	 * x^(16+d) mod 0x11021 (crc_simple.c:65-82 is linear in the message) */
 	uint16_t crc_pow[288];
-	uint16_t crc_init[4];           /* 0xffff pushed through L zero bits, L = 76, 140, 284 */
+	uint16_t crc_init[4];           /* 0xffff pushed through L zero bits, L = 76, 140, 284, 108 */
 	/* tetra_find_train_seq's pre-filter never sees in[20] (tetra_burst.c:288-294): a true
 	 * match at offset k <= 20 is reported only if the distorted filter value still equals
 	 * one of the five 22-bit prefixes.  blind_ok[seq][prev] bit k: seq 0=y 1=n 2=p,
@@ -68,6 +68,7 @@ template <int BT> struct Blk;
 template <> struct Blk<0> { static constexpr int K = 120, N = 80,  T1 = 60,  A = 11,  CRCI = 0; };  /* SB1 */
 template <> struct Blk<1> { static constexpr int K = 216, N = 144, T1 = 124, A = 101, CRCI = 1; };  /* SB2 / NDB half */
 template <> struct Blk<5> { static constexpr int K = 432, N = 288, T1 = 268, A = 103, CRCI = 2; };  /* SCH/F */
+template <> struct Blk<4> { static constexpr int K = 168, N = 112, T1 = 92,  A = 13,  CRCI = 3; };  /* SCH/HU (uplink; leaf operator only) */
 
 /* where type-5 bit m of a block sits inside the 510-bit burst, tetra_burst.c:31-47,347-372 */
 enum Placement { PL_RAW = 0, PL_SB1 = 1, PL_BLK2 = 2, PL_BLK1 = 3, PL_SCHF = 4 };

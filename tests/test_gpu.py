@@ -404,3 +404,24 @@ def test_config4_full_size(gpu, orc):
             keep = want["slot_bit"] < 510 * 198
             ok, msg = T.records_equal(want[keep], got[got["slot_bit"] < 510 * 198])
             assert ok, (k0, msg)
+
+
+@pytest.mark.parametrize("variant", [T.VITERBI_WARP, T.VITERBI_LANE])
+def test_leaf_decode_uplink_and_bbk(gpu, orc, variant):
+    """SCH/HU (168 -> 92 bits) and BBK through the batched leaf operator, against the oracle block by block"""
+    from test_simt import _uplink_blocks
+    rng = np.random.default_rng(23)
+    gpu.set_options(viterbi=variant)
+    t5, codes = _uplink_blocks(orc, 300, rng, 0.02)
+    t5[280:] = rng.integers(0, 2, (20, 168))
+    out, ok = gpu.decode_blocks(T.T_SCH_HU, t5, codes)
+    for i in range(t5.shape[0]):
+        orc.reset(); orc.set_cell(int(codes[i])); orc.tp_sap(T.T_SCH_HU, 0, t5[i])
+        r = orc.records()[0]
+        assert np.array_equal(r["type1"][:92], out[i]) and int(r["crc_ok"]) == int(ok[i]), i
+    bb = rng.integers(0, 2, (64, 30)).astype(np.uint8)
+    out, ok = gpu.decode_blocks(T.T_BBK, bb, codes[:64])
+    for i in range(64):
+        orc.reset(); orc.set_cell(int(codes[i])); orc.tp_sap(T.T_BBK, 0, bb[i])
+        assert np.array_equal(orc.records()[0]["type1"][:14], out[i]) and ok[i] == 1
+    gpu.set_options(viterbi=T.VITERBI_LANE)

@@ -164,3 +164,39 @@ def test_stream_continuation(emu, orc):
         pos = c
     ok, msg = T.records_equal(want, np.concatenate(got))
     assert ok, msg
+
+
+def _uplink_blocks(orc, n, rng, ber):
+    """SCH/HU blocks built with the oracle's TX-side functions: 92 type-1 bits + CRC-16 + 4 tail bits -> rate-2/3
+    RCPC -> (168, 13) interleaver -> scrambler, then bit errors"""
+    t5 = np.zeros((n, 168), np.uint8); codes = rng.integers(1, 2**32, n, dtype=np.uint64).astype(np.uint32)
+    for i in range(n):
+        t1 = rng.integers(0, 2, 92).astype(np.uint8)
+        crc = orc.crc16(t1) ^ 0xffff
+        t2 = np.concatenate([t1, [(crc >> (15 - b)) & 1 for b in range(16)], [0, 0, 0, 0]]).astype(np.uint8)
+        t3 = orc.punct_2_3(orc.conv_encode(t2), 168)
+        t5[i] = orc.scramb_bits(int(codes[i]), orc.interleave(168, 13, t3))
+    flips = rng.random(t5.shape) < ber
+    return t5 ^ flips.astype(np.uint8), codes
+
+
+@pytest.mark.parametrize("variant", [T.VITERBI_WARP, T.VITERBI_LANE])
+def test_leaf_decode_uplink_and_bbk(emu, orc, variant):
+    """the two rows of tetra_blk_param[] the downlink receiver never produces: SCH/HU (168 -> 92) and BBK"""
+    rng = np.random.default_rng(21)
+    emu.set_options(viterbi=variant)
+    t5, codes = _uplink_blocks(orc, 24, rng, 0.02)
+    t5[20:] = rng.integers(0, 2, (4, 168))                     # pure noise: ties everywhere
+    out, ok = emu.decode_blocks(T.T_SCH_HU, t5, codes)
+    for i in range(t5.shape[0]):
+        orc.reset(); orc.set_cell(int(codes[i])); orc.tp_sap(T.T_SCH_HU, 0, t5[i])
+        r = orc.records()[0]
+        assert np.array_equal(r["type1"][:92], out[i]) and int(r["crc_ok"]) == int(ok[i]), i
+    assert ok[:20].sum() >= 12
+    bb = rng.integers(0, 2, (16, 30)).astype(np.uint8)
+    out, ok = emu.decode_blocks(T.T_BBK, bb, codes[:16])
+    for i in range(16):
+        orc.reset(); orc.set_cell(int(codes[i])); orc.tp_sap(T.T_BBK, 0, bb[i])
+        r = orc.records()[0]
+        assert np.array_equal(r["type1"][:14], out[i]) and ok[i] == 1
+    emu.set_options(viterbi=T.VITERBI_LANE)
