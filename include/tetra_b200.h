@@ -88,7 +88,10 @@ typedef struct tb200_ctx tb200_ctx;
 /* ---- life cycle ---------------------------------------------------------- */
 
 /* One context per GPU/process; `device` is the CUDA ordinal.  Returns 0 or a negative
- * TB200_E_* code.  Fails (never falls back to the CPU) when no CUDA device is usable. */
+ * TB200_E_* code.  Fails (never falls back to the CPU) when no CUDA device is usable.
+ * A context is a single receiver (like the reference's globals t_phy_state / _tcd): calls on one context
+ * must not overlap; several contexts may be used from several threads, also on the same GPU
+ * (tools/overlap_probe.py: two receivers on one GPU give +10 % aggregate throughput). */
 int  tb200_create(tb200_ctx **out, int device);
 void tb200_destroy(tb200_ctx *ctx);
 const char *tb200_last_error(const tb200_ctx *ctx);
