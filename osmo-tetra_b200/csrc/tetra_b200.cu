@@ -493,6 +493,21 @@ static int ensure_staging(tb200_ctx *ctx, size_t in_bytes, size_t slots)
 	return 0;
 }
 
+/* TB200_TRACE=1: host-side time stamps of one call (stderr), for hunting host round trips */
+#include <chrono>
+struct HostTrace {
+	bool on = getenv("TB200_TRACE") != nullptr;
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	void mark(const char *what)
+	{
+		if (!on) return;
+		const auto t = std::chrono::steady_clock::now();
+		fprintf(stderr, "[tb200 trace] %-28s +%7.1f us\n", what, std::chrono::duration<double, std::micro>(t - t0).count());
+	}
+};
+static HostTrace *g_trace = nullptr;
+#define TB_TRACE(what) do { if (g_trace) g_trace->mark(what); } while (0)
+
 /* ------------------------------------------------------------ the source -- */
 
 /* Where the stream bits of this call live.  Absolute bit i of the stream is
@@ -636,6 +651,7 @@ static int scan_more_hits(tb200_ctx *ctx, const Source &src, uint64_t from, uint
 		const uint32_t first = 64;
 		CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(uint32_t) * (2 + 2 * first), cudaMemcpyDeviceToHost, ctx->s_compute));
 		CU(cudaStreamSynchronize(ctx->s_compute));
+		TB_TRACE("sync-hit list on host");
 		const uint32_t n = ctx->h_hits[0];
 		if (n > HIT_CAP)
 			return fail(ctx, TB200_E_STATE, "SYNC hit list overflow (%u hits in %u bits)", n, REGION_BITS);
@@ -928,9 +944,11 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		return 0;
 	};
 	if (bad_piece == npieces && (rc = carry_over(npieces - 1))) return rc;
+	TB_TRACE("pieces enqueued");
 	CU(cudaStreamSynchronize(ctx->s_h2d));
 	CU(cudaStreamSynchronize(ctx->s_compute));
 	CU(cudaStreamSynchronize(ctx->s_d2h));
+	TB_TRACE("pieces done");
 	if (bad_piece == npieces && ctx->h_flags[npieces - 1] != 0xffffffffu) bad_piece = npieces - 1;
 
 	if (bad_piece < npieces) {
@@ -1097,11 +1115,15 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 	if (d_type1 && ((uintptr_t)d_type1 & 15)) return fail(ctx, TB200_E_ARG, "d_type1 must be 16-byte aligned");
 	if (ctx->opt.input != TB200_IN_BYTES && ((uintptr_t)d_bits & 3))
 		return fail(ctx, TB200_E_ARG, "packed / symbol input must be 4-byte aligned");
+	HostTrace trace;
+	g_trace = trace.on ? &trace : nullptr;
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	CU(cudaDeviceSynchronize());        /* the caller's buffers may still be in flight on its own streams */
+	TB_TRACE("entry sync");
 	reset_stream(ctx);
 	int rc = push_carry(ctx);
 	if (rc) return rc;
+	TB_TRACE("carry pushed");
 	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
 	out.crc = ctx->user_crc; out.max_slots = max_slots; out.n = 0;
@@ -1109,6 +1131,8 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 	ctx->fed_end = n_bits;
 	profile_begin(ctx);
 	rc = rx_run(ctx, src, true, out);
+	TB_TRACE("rx_run done");
+	g_trace = nullptr;
 	if (rc) return rc;
 	if ((rc = profile_end(ctx))) return rc;
 	return (long)out.n;
