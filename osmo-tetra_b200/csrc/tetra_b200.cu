@@ -10,7 +10,6 @@
  */
 #include "tetra_kernels.cuh"
 #include "tetra_lane.cuh"
-#include "tetra_classify_tma.cuh"
 #include "tetra_classify_tile.cuh"
 #include "tetra_stage_tma.cuh"
 #include "tetra_gen.cuh"
@@ -153,7 +152,6 @@ struct tb200_ctx {
 	size_t ws_slots = 0;
 	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the lane kernels, one area per resident CTA */
 	unsigned lane_ctas = 0;               /* resident CTAs of the lane kernels (grid size) */
-	int classify_form = 0;                /* 0: CTA per tile of 64 slots (default), 1: thread per slot (env TB200_CLASSIFY=1) */
 	uint32_t *d_flags = nullptr;     /* first unlocking slot per piece */
 	uint32_t *h_flags = nullptr;     /* pinned mirror */
 	size_t flags_cap = 0;
@@ -380,14 +378,11 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 #ifndef TB_SIMT_EMULATION
 	if (cudaFuncSetAttribute(k_stage_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM) != cudaSuccess)
 		return bail("cudaFuncSetAttribute");
-	if (cudaFuncSetAttribute(k_classify_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_SMEM) != cudaSuccess)
-		return bail("cudaFuncSetAttribute");
 	if (cudaFuncSetAttribute(k_classify_tile<IN_BYTES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem<IN_BYTES>()) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_classify_tile<IN_PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem<IN_PACKED>()) != cudaSuccess ||
 	    cudaFuncSetAttribute(k_classify_tile<IN_F32SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct_smem<IN_F32SYM>()) != cudaSuccess)
 		return bail("cudaFuncSetAttribute");
 #endif
-	if (const char *e = getenv("TB200_CLASSIFY")) ctx->classify_form = atoi(e);
 	if (cudaMalloc((void **)&ctx->d_hits, sizeof(uint32_t) * (2 * 8192 + 2)) != cudaSuccess) return bail("cudaMalloc");
 	if (cudaHostAlloc((void **)&ctx->h_hits, sizeof(uint32_t) * (2 * 8192 + 2), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
 	if (cudaHostAlloc((void **)&ctx->h_carry_pin, 2 * sizeof(DevCarry), cudaHostAllocDefault) != cudaSuccess) return bail("cudaHostAlloc");
@@ -742,25 +737,18 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cuda
 		wg.cmin = g.cmin; wg.n_end = g.n_end; wg.a0 = g.a0;
 		uint32_t *sb_count = ctx->d_sb_list + ctx->ws_slots;
 		CU(cudaMemsetAsync(sb_count, 0, sizeof(uint32_t), st));
-		if (ctx->classify_form == 0 || g.fmt != IN_BYTES) {
-			const unsigned per_tile = g.fmt == IN_F32SYM ? TileFmt<IN_F32SYM>::SLOTS : CT_SLOTS;
-			const unsigned tiles = (nb + per_tile - 1) / per_tile;
-			const unsigned cls_blocks = std::min<unsigned>(tiles, (unsigned)ctx->sm_count * (g.fmt == IN_PACKED ? 8 : 3));
-			if (g.fmt == IN_BYTES)
-				TB_LAUNCH_SMEM(k_classify_tile<IN_BYTES>, cls_blocks, CT_THREADS, ct_smem<IN_BYTES>(), st, g, wg, ctx->d_tab, ctx->d_ws,
-				               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
-			else if (g.fmt == IN_PACKED)
-				TB_LAUNCH_SMEM(k_classify_tile<IN_PACKED>, cls_blocks, CT_THREADS, ct_smem<IN_PACKED>(), st, g, wg, ctx->d_tab, ctx->d_ws,
-				               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
-			else
-				TB_LAUNCH_SMEM(k_classify_tile<IN_F32SYM>, cls_blocks, CT_THREADS, ct_smem<IN_F32SYM>(), st, g, wg, ctx->d_tab, ctx->d_ws,
-				               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
-		} else {
-			const unsigned cls_groups = (nb + 31) / 32;
-			const unsigned cls_blocks = std::min<unsigned>((cls_groups + CLS_WARPS - 1) / CLS_WARPS, (unsigned)ctx->sm_count * 3);
-			TB_LAUNCH_SMEM(k_classify_tma, cls_blocks, CLS_WARPS * 32, CLS_SMEM, st, g, wg, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits,
-			               ctx->d_sb_list, sb_count);
-		}
+		const unsigned per_tile = g.fmt == IN_F32SYM ? TileFmt<IN_F32SYM>::SLOTS : CT_SLOTS;
+		const unsigned tiles = (nb + per_tile - 1) / per_tile;
+		const unsigned cls_blocks = std::min<unsigned>(tiles, (unsigned)ctx->sm_count * (g.fmt == IN_PACKED ? 8 : 3));
+		if (g.fmt == IN_BYTES)
+			TB_LAUNCH_SMEM(k_classify_tile<IN_BYTES>, cls_blocks, CT_THREADS, ct_smem<IN_BYTES>(), st, g, wg, ctx->d_tab, ctx->d_ws,
+			               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
+		else if (g.fmt == IN_PACKED)
+			TB_LAUNCH_SMEM(k_classify_tile<IN_PACKED>, cls_blocks, CT_THREADS, ct_smem<IN_PACKED>(), st, g, wg, ctx->d_tab, ctx->d_ws,
+			               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
+		else
+			TB_LAUNCH_SMEM(k_classify_tile<IN_F32SYM>, cls_blocks, CT_THREADS, ct_smem<IN_F32SYM>(), st, g, wg, ctx->d_tab, ctx->d_ws,
+			               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
 		if (pe) CU(cudaEventRecord(pe[5], st));
 		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
 		               ctx->d_tab, ctx->d_lane_scratch);

@@ -1,9 +1,9 @@
 /*
  * tetra_classify_tile.cuh - pass 1 (training-sequence search + slot packing), one CTA per TILE of slots.
  *
- * The thread-per-slot form (tetra_classify_tma.cuh) stages 528 bytes per slot and can keep only six
- * warps on an SM; it is latency bound at 65 % of the HBM roofline.  Slots of a LOCKED stream are back to
- * back, so here a CTA takes 64 consecutive slots = one contiguous 32 640-byte piece of the stream:
+ * (An earlier thread-per-slot form staged 528 bytes per slot, could keep only six warps on an SM and was
+ * latency bound at 65 % of the HBM roofline; profiles/r01c.)  Slots of a LOCKED stream are back to back, so
+ * a CTA takes 64 consecutive slots = one contiguous 32 640-byte piece of the stream:
  *
  *   copy   one cp.async.bulk (TMA bulk copy) brings the 16-byte aligned superset of the tile into shared
  *          memory; two tile buffers per CTA, the copy of the CTA's next tile is in flight while the
@@ -25,9 +25,30 @@
  */
 #pragma once
 #include "tetra_kernels.cuh"
-#include "tetra_classify_tma.cuh"
+#include "tetra_async.cuh"
 
 namespace tb {
+
+/* bits_in_buf when slot k is processed, in 32-bit arithmetic relative to the launch
+ * (same value as slot_window(); rel = first slot's offset inside its read() chunk) */
+struct WinGeom {
+	uint32_t chunk, rel0;        /* rel0 = a0 mod chunk */
+	uint64_t c00;                /* a0 div chunk */
+	uint64_t cmin, n_end, a0;
+};
+
+__device__ __forceinline__ unsigned slot_window32(const WinGeom &g, uint32_t k)
+{
+	/* 64-bit: a shard of the sharded path can hold more than 2^32 / 510 slots in one launch */
+	const uint64_t num = (uint64_t)g.rel0 + 510ull * k + 510u + g.chunk - 1;
+	const uint64_t q = g.chunk == 64 ? num >> 6 : (num <= 0xffffffffull ? (uint64_t)((uint32_t)num / g.chunk) : num / g.chunk);
+	uint64_t c = g.c00 + q;
+	const uint64_t lo = g.cmin + k;
+	if (c < lo) c = lo;
+	uint64_t t = c * g.chunk;
+	if (t > g.n_end) t = g.n_end;
+	return (unsigned)(t - (g.a0 + 510ull * k));
+}
 
 constexpr int CT_THREADS = 256;
 constexpr int CT_RAW = ((15 + 510 * 64 + 15) / 16) * 16;       /* bytes of one raw tile buffer (32 672) */

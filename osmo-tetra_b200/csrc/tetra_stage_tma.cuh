@@ -11,7 +11,7 @@
  * the SM as ONE 13 824-byte bulk store per warp.  Two row sets per warp are in flight.
  */
 #pragma once
-#include "tetra_classify_tma.cuh"
+#include "tetra_async.cuh"
 
 namespace tb {
 
