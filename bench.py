@@ -117,7 +117,7 @@ def _cpu_worker(args):
     return n_bursts, dt
 
 
-def cpu_reference_rate(n_bursts_per_core, cores):
+def cpu_reference_rate(n_bursts_per_core, cores, one_core=False):
     """bursts/s of the reference's CPU path on `cores` processes, each over its own self-contained stream"""
     import tetra_testlib as T
     T.ensure_oracle_built()
@@ -129,7 +129,13 @@ def cpu_reference_rate(n_bursts_per_core, cores):
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     slowest = max(r[1] for r in res)
-    return {"value": total / slowest, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+    one = None
+    if one_core:
+        with ctx.Pool(1) as pool:                          # the same sample on ONE core, nothing else running
+            nb, dt1 = pool.map(_cpu_worker, [(SEED + 999, n_bursts_per_core, use_ref)])[0]
+        one = nb / dt1
+    return {"value": total / slowest, "unit": UNIT, "cores": cores, "one_core": one,
+            "kind": "reference" if use_ref else "port",
             "sample": f"{cores} processes x {n_bursts_per_core} bursts of the bench workload (own seed each), "
                       f"64-byte reads, stdout silenced, {'oracle/_ref = reference lower MAC compiled in place + restated osmo_conv_decode (libosmocore absent)' if use_ref else 'oracle port'}; "
                       f"slowest process {slowest:.2f} s, pool wall {wall:.2f} s"}
@@ -407,7 +413,7 @@ def run_ours(args, rank, world, local_rank):
                 "step_share": {"classify": t_cls / t_total, "scan": t_scan / t_total, "decode": t_dec / t_total},
                 "constants_from": kc.get("source")}
     cores = os.cpu_count() or 1
-    cpu = cpu_reference_rate(20000, cores) if (world == 1 and not args.no_cpu) else None
+    cpu = cpu_reference_rate(20000, cores, one_core=True) if (world == 1 and not args.no_cpu) else None
     others = other_configs(g, T, torch, C) if (world == 1 and not args.no_e2e) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
