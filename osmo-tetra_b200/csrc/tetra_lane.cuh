@@ -1,14 +1,16 @@
 /*
- * tetra_lane.cuh - the throughput form of the decode pass: one THREAD owns two slots.
+ * tetra_lane.cuh - the throughput form of the decode pass: one THREAD owns two coded blocks.
  *
  * The warp-per-slot kernels of tetra_kernels.cuh spend ~20k warp instructions per SCH/F burst,
  * almost all of it shuffles and lane-redundant work around a 16-state trellis that cannot use
  * 32 lanes.  Here the trellis lives entirely in one thread's registers and two independent
  * trellises are packed into the 16-bit halves of each register, so every add-compare-select
- * is one VIADD + one VIADDMNMX.U16x2 for two blocks at once; survivor decisions are taken from
- * the sign of a packed difference and stored bit-packed (16 bits per trellis per step) in
- * shared memory for the trace back.  Descrambling is a handful of word XORs in the burst
- * domain and de-interleaving + de-puncturing is a fully unrolled constant-index bit gather.
+ * is one add + one VIADDMNMX.U16x2 for two blocks at once.  The survivor decisions are not
+ * extracted per step: a tag below the metric's unit makes the packed minimum carry them along
+ * (acs2_step), so that after 4 (or 8) steps the low nibble (byte) of every metric is the history
+ * of its survivor; histories go to a per-CTA scratch area in global memory and the trace back
+ * walks them one group at a time.  Descrambling is a handful of word XORs in the burst domain
+ * and de-interleaving + de-puncturing is a fully unrolled constant-index bit gather.
  *
  * Semantics are those of the reference chain (tetra_lower_mac.c:143-357, viterbi.c:6-25,
  * libosmocore osmo_conv_decode): see viterbi_warp() in tetra_kernels.cuh for the rules.
