@@ -253,6 +253,22 @@ int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits,
                          const uint64_t *starts, const uint32_t *lens, uint64_t n, uint32_t mask,
                          int32_t *rc, uint32_t *offset);
 
+/* GSMTAP framing of the decoded blocks: what tetra_gsmtap_makemsg (tetra_gsmtap.c:31-63) builds
+ * when rx_tmv_unitdata_ind hands it a CRC-good block (tetra_upper_mac.c:480-488), for every block of n_slots slots:
+ * a 16-byte GSMTAP v2 header (type TETRA_I1, timeslot tn-1, frame_number (mn*18+fn) in network order, sub_type
+ * BSCH / AACH / BNCH / SCH_F or 0 for an unknown channel) + the type-1 bits eight per byte, first bit in the MSB
+ * (osmo_ubit2pbit).  Frames are written back to back in the reference's delivery order (SB1, AACH, SB2 / AACH, SCH/F /
+ * AACH, BLK1, BLK2); blocks with a wrong CRC produce none.  Frame lengths: AACH 18, SB1 24, SB2 / NDB half 32, SCH/F 50
+ * bytes.  `slots` / `type1_packed` are the outputs of tb200_rx_stream_* (TB200_OUT_PACKED).  slot_off (may be NULL)
+ * receives n_slots + 1 byte offsets: the frames of slot i are frames[slot_off[i] .. slot_off[i+1]).  frames == NULL
+ * only counts.  Returns the number of bytes (written or needed), *n_frames (host pointer, may be NULL) the number of
+ * frames; TB200_E_ARG if cap_bytes is too small.  is_device: slots, type1_packed, frames and slot_off are device
+ * pointers (else host pointers, copied inside the call).  Not reproduced: the extra frames the reference sends when its
+ * upper MAC re-enters a block that holds several PDUs (tetra_lower_mac.c:330-352) - those depend on the parse. */
+#define TB200_GSMTAP_SLOT_MAX 82
+long long tb200_gsmtap_pack(tb200_ctx *ctx, const struct tb200_slot *slots, const uint32_t *type1_packed, uint64_t n_slots,
+                            uint8_t *frames, uint64_t cap_bytes, uint64_t *slot_off, uint64_t *n_frames, int is_device);
+
 /* ---- synthetic downlink generator (bench / test input, TX side) ----------------- */
 struct tb200_gen_cfg {
 	uint64_t seed;

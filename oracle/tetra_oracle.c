@@ -776,3 +776,46 @@ void orc_float_to_bits(const float *sym, size_t n, uint8_t *bits)
 		}
 	}
 }
+
+/* ----------------------------------------------------------- GSMTAP framing --
+ * What tetra_gsmtap_makemsg (tetra_gsmtap.c:31-63) builds for every CRC-good primitive the upper MAC sees
+ * (rx_tmv_unitdata_ind, tetra_upper_mac.c:480-488: timeslot = tn - 1, sub-slot / level / snr 0):
+ * struct gsmtap_hdr of libosmocore's gsmtap.h (absent here; restated from the published GSMTAP v2 format:
+ * version 2, hdr_len 4 words, type 5 = TETRA_I1, timeslot, arfcn 0, signal 0, snr 0, frame number in network
+ * order, sub_type, antenna 0, sub_slot, reserved 0; msgb_alloc zeroes what is not set) + osmo_ubit2pbit of the
+ * type-1 bits (eight per byte, first bit in the MSB, zero padding).  frame number = (hn*60 + mn)*18 + fn
+ * (tetra_tdma.c:96-99) with hn = 0: the lower MAC never sets it.  sub_type = lchan2gsmtap[lchan]
+ * (tetra_gsmtap.c:18-27): SCH_F 5, AACH 2, BSCH 1, BNCH 6, 0 for TETRA_LC_UNKNOWN. */
+size_t orc_gsmtap_frames(const struct tb_record *rec, size_t n, uint8_t *out, size_t cap, size_t *n_frames)
+{
+	size_t len = 0, frames = 0;
+	for (size_t i = 0; i < n; i++) {
+		const struct tb_record *r = &rec[i];
+		if (!r->crc_ok)
+			continue;
+		const unsigned nb = (r->type1_len + 7u) / 8u;
+		if (out && len + 16 + nb <= cap) {
+			uint8_t *h = out + len;
+			const uint32_t fnum = (uint32_t)r->mn * 18u + r->fn;
+			unsigned sub = 0;
+			switch (r->lchan) {          /* enum tetra_log_chan, tetra_common.h:22-39 */
+			case 1: sub = 5; break;      /* SCH/F */
+			case 8: sub = 2; break;      /* AACH */
+			case 10: sub = 1; break;     /* BSCH */
+			case 11: sub = 6; break;     /* BNCH */
+			default: break;
+			}
+			memset(h, 0, 16 + nb);
+			h[0] = 2; h[1] = 4; h[2] = 5; h[3] = (uint8_t)(r->tn - 1);
+			h[8] = fnum >> 24; h[9] = fnum >> 16; h[10] = fnum >> 8; h[11] = fnum;
+			h[12] = (uint8_t)sub;
+			for (unsigned b = 0; b < r->type1_len; b++)
+				h[16 + b / 8] |= (uint8_t)((r->type1[b] & 1) << (7 - b % 8));
+		}
+		len += 16 + nb;
+		frames++;
+	}
+	if (n_frames)
+		*n_frames = frames;
+	return len;
+}

@@ -113,6 +113,10 @@ class B200:
         lib.tb200_decode_blocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]
         lib.tb200_descramble_deinterleave.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
                                                       C.c_uint32, C.c_uint32, C.c_int]
+        if hasattr(lib, "tb200_gsmtap_pack"):
+            lib.tb200_gsmtap_pack.restype = C.c_longlong
+            lib.tb200_gsmtap_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64,
+                                              C.c_void_p, C.POINTER(C.c_uint64), C.c_int]
         lib.tb200_gen_stream_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_int]
         lib.tb200_find_lock.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         lib.tb200_shard_pass1.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
@@ -268,6 +272,20 @@ class B200:
         if r:
             raise RuntimeError(self.err())
         return out
+
+    def gsmtap_pack(self, slots, packed):
+        """GSMTAP frames of every CRC-good block of the slots (host arrays): (frame bytes, slot offsets, n_frames)"""
+        slots = np.ascontiguousarray(slots); packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        nf = C.c_uint64(0)
+        need = self.lib.tb200_gsmtap_pack(self.h, _ptr(slots), _ptr(packed), slots.size, None, 0, None, C.byref(nf), 0)
+        if need < 0:
+            raise RuntimeError(self.err())
+        frames = np.zeros(max(need, 2), dtype=np.uint8)
+        off = np.zeros(slots.size + 1, dtype=np.uint64)
+        got = self.lib.tb200_gsmtap_pack(self.h, _ptr(slots), _ptr(packed), slots.size, _ptr(frames), need, _ptr(off), C.byref(nf), 0)
+        if got != need:
+            raise RuntimeError(f"tb200_gsmtap_pack: {got} != {need}: {self.err()}")
+        return frames[:need], off, nf.value
 
 
 # --------------------------------------------------------------------------- golden fixtures

@@ -13,6 +13,7 @@
 #include "tetra_classify_tile.cuh"
 #include "tetra_stage_tma.cuh"
 #include "tetra_gen.cuh"
+#include "tetra_gsmtap.cuh"
 #include "../../include/tetra_b200.h"
 
 #include <algorithm>
@@ -1498,6 +1499,78 @@ extern "C" int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type
 		cudaFree(a5); cudaFree(a3); cudaFree(ac);
 	}
 	return 0;
+}
+
+/* ----------------------------------------------------------- GSMTAP framing -- */
+
+extern "C" long long tb200_gsmtap_pack(tb200_ctx *ctx, const tb200_slot *slots, const uint32_t *type1_packed, uint64_t n_slots,
+                                       uint8_t *frames, uint64_t cap_bytes, uint64_t *slot_off, uint64_t *n_frames,
+                                       int is_device)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (n_slots && (!slots || (frames && !type1_packed))) return fail(ctx, TB200_E_ARG, "null argument");
+	if ((uintptr_t)frames & 1) return fail(ctx, TB200_E_ARG, "frames must be 2-byte aligned");
+	if (n_frames) *n_frames = 0;
+	if (n_slots == 0) return 0;
+	const uint64_t tiles = (n_slots + GT_THREADS - 1) / GT_THREADS;
+	if (tiles > 0x7fffffffull) return fail(ctx, TB200_E_ARG, "too many slots for one call");
+	const SlotOut *d_slots = reinterpret_cast<const SlotOut *>(slots);
+	const uint32_t *d_packed = type1_packed;
+	SlotOut *a_slots = nullptr; uint32_t *a_packed = nullptr; uint8_t *a_frames = nullptr; uint64_t *a_off = nullptr, *d_tot = nullptr;
+	auto release = [&]() { cudaFree(a_slots); cudaFree(a_packed); cudaFree(a_frames); cudaFree(a_off); cudaFree(d_tot); };
+#define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); \
+	return fail(ctx, TB200_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
+	if (!is_device) {
+		CUR(cudaMalloc((void **)&a_slots, n_slots * sizeof(SlotOut)));
+		CUR(cudaMemcpy(a_slots, slots, n_slots * sizeof(SlotOut), cudaMemcpyHostToDevice));
+		d_slots = a_slots;
+		if (frames) {
+			CUR(cudaMalloc((void **)&a_packed, n_slots * TYPE1_WORDS * 4));
+			CUR(cudaMemcpy(a_packed, type1_packed, n_slots * TYPE1_WORDS * 4, cudaMemcpyHostToDevice));
+			d_packed = a_packed;
+		}
+	}
+	CUR(cudaMalloc((void **)&d_tot, (tiles + 1) * 8));
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	if (ctx->opt.profile) {
+		CUR(cudaEventCreateWithFlags(&e0, 0)); CUR(cudaEventCreateWithFlags(&e1, 0));
+		CUR(cudaEventRecord(e0, ctx->s_compute));
+	}
+	TB_LAUNCH(k_gsmtap_sizes, (unsigned)tiles, GT_THREADS, ctx->s_compute, d_slots, n_slots, d_tot);
+	TB_LAUNCH(k_gsmtap_scan, 1, 1024, ctx->s_compute, d_tot, tiles);
+	uint64_t total = 0;
+	CUR(cudaMemcpyAsync(&total, d_tot + tiles, 8, cudaMemcpyDeviceToHost, ctx->s_compute));
+	CUR(cudaStreamSynchronize(ctx->s_compute));
+	const uint64_t bytes = total & ((1ull << 40) - 1);
+	if (n_frames) *n_frames = total >> 40;
+	if (frames) {
+		if (bytes > cap_bytes) {
+			release();
+			return fail(ctx, TB200_E_ARG, "GSMTAP frames need %llu bytes, the buffer holds %llu", (unsigned long long)bytes, (unsigned long long)cap_bytes);
+		}
+		uint8_t *d_frames = frames; uint64_t *d_off = slot_off;
+		if (!is_device) {
+			CUR(cudaMalloc((void **)&a_frames, bytes + 16));
+			d_frames = a_frames;
+			if (slot_off) { CUR(cudaMalloc((void **)&a_off, (n_slots + 1) * 8)); d_off = a_off; }
+		}
+		TB_LAUNCH(k_gsmtap_emit, (unsigned)tiles, GT_THREADS, ctx->s_compute, d_slots, d_packed, n_slots, d_tot,
+		          reinterpret_cast<uint16_t *>(d_frames), d_off);
+		if (d_off) CUR(cudaMemcpyAsync(d_off + n_slots, &bytes, 8, cudaMemcpyHostToDevice, ctx->s_compute));
+		if (ctx->opt.profile) CUR(cudaEventRecord(e1, ctx->s_compute));
+		CUR(cudaGetLastError());
+		CUR(cudaStreamSynchronize(ctx->s_compute));
+		if (ctx->opt.profile) CUR(cudaEventElapsedTime(&ctx->timing.leaf_ms, e0, e1));
+		if (!is_device) {
+			CUR(cudaMemcpy(frames, a_frames, bytes, cudaMemcpyDeviceToHost));
+			if (slot_off) CUR(cudaMemcpy(slot_off, a_off, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));
+		}
+	}
+	if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+	release();
+#undef CUR
+	return (long long)bytes;
 }
 
 /* -------------------------------------------------------------- generator -- */

@@ -32,8 +32,9 @@
  * rx_aach, tetra_upper_mac.c:444-452) the shim withholds the same primitives the reference lower MAC withholds
  * (tetra_lower_mac.c:190-241) and writes the same <dumpdir>/traffic_*.out / .txt files for SCH/F-shaped
  * traffic slots.  Not reproduced: the dump of a 216-bit second block (the reference fills half of it from
- * uninitialised memory) and the stdout text of the PHY / lower MAC (tetra_rx_b200.c prints that text).  read() sizes must be constant (64 in
- * tetra-rx.c:83) except for the last one; other call patterns are rejected loudly.
+ * uninitialised memory).  The stdout / stderr text of the reference's PHY and lower MAC is printed from
+ * tetra_text.h in the reference's order (TETRA_B200_TEXT=0 switches it off).  read() sizes must be constant
+ * (64 in tetra-rx.c:83) except for the last one; other call patterns are rejected loudly.
  */
 #include <stdint.h>
 #include <stdio.h>

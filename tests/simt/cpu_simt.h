@@ -30,6 +30,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __shared__ static
 #define __constant__ static
+#define __align__(n) __attribute__((aligned(n)))
 
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };

@@ -100,6 +100,18 @@ class _Recorder:
     def set_recording(self, on):
         self._f("set_recording")(int(on))
 
+    def gsmtap_frames(self, records):
+        """GSMTAP frames of the CRC-good records, back to back (bytes), and their number"""
+        f = self._f("gsmtap_frames")
+        f.restype = C.c_size_t
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        records = np.ascontiguousarray(records)
+        nf = C.c_size_t(0)
+        need = f(_ptr(records), records.size, None, 0, C.byref(nf))
+        out = np.zeros(max(need, 1), dtype=np.uint8)
+        f(_ptr(records), records.size, _ptr(out), need, C.byref(nf))
+        return out[:need], nf.value
+
     def set_time(self, tn, fn, mn):
         self._f("set_time")(C.c_uint32(tn), C.c_uint32(fn), C.c_uint32(mn))
 
