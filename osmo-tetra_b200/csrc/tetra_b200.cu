@@ -1539,29 +1539,33 @@ extern "C" long long tb200_gsmtap_pack(tb200_ctx *ctx, const tb200_slot *slots, 
 	}
 	TB_LAUNCH(k_gsmtap_sizes, (unsigned)tiles, GT_THREADS, ctx->s_compute, d_slots, n_slots, d_tot);
 	TB_LAUNCH(k_gsmtap_scan, 1, 1024, ctx->s_compute, d_tot, tiles);
-	uint64_t total = 0;
-	CUR(cudaMemcpyAsync(&total, d_tot + tiles, 8, cudaMemcpyDeviceToHost, ctx->s_compute));
-	CUR(cudaStreamSynchronize(ctx->s_compute));
-	const uint64_t bytes = total & ((1ull << 40) - 1);
-	if (n_frames) *n_frames = total >> 40;
+	uint8_t *d_frames = frames; uint64_t *d_off = slot_off;
 	if (frames) {
-		if (bytes > cap_bytes) {
-			release();
-			return fail(ctx, TB200_E_ARG, "GSMTAP frames need %llu bytes, the buffer holds %llu", (unsigned long long)bytes, (unsigned long long)cap_bytes);
-		}
-		uint8_t *d_frames = frames; uint64_t *d_off = slot_off;
+		/* the emit pass is queued before the total is known (no host round trip between the passes); it checks
+		 * the capacity itself */
 		if (!is_device) {
-			CUR(cudaMalloc((void **)&a_frames, bytes + 16));
+			CUR(cudaMalloc((void **)&a_frames, std::min<uint64_t>(cap_bytes, n_slots * GT_SLOT_MAX) + 16));
 			d_frames = a_frames;
 			if (slot_off) { CUR(cudaMalloc((void **)&a_off, (n_slots + 1) * 8)); d_off = a_off; }
 		}
 		TB_LAUNCH(k_gsmtap_emit, (unsigned)tiles, GT_THREADS, ctx->s_compute, d_slots, d_packed, n_slots, d_tot,
-		          reinterpret_cast<uint16_t *>(d_frames), d_off);
-		if (d_off) CUR(cudaMemcpyAsync(d_off + n_slots, &bytes, 8, cudaMemcpyHostToDevice, ctx->s_compute));
+		          reinterpret_cast<uint16_t *>(d_frames), cap_bytes, d_off);
 		if (ctx->opt.profile) CUR(cudaEventRecord(e1, ctx->s_compute));
-		CUR(cudaGetLastError());
-		CUR(cudaStreamSynchronize(ctx->s_compute));
+	}
+	uint64_t total = 0;
+	CUR(cudaMemcpyAsync(&total, d_tot + tiles, 8, cudaMemcpyDeviceToHost, ctx->s_compute));
+	CUR(cudaGetLastError());
+	CUR(cudaStreamSynchronize(ctx->s_compute));
+	const uint64_t bytes = total & ((1ull << 40) - 1);
+	if (n_frames) *n_frames = total >> 40;
+	if (frames) {
 		if (ctx->opt.profile) CUR(cudaEventElapsedTime(&ctx->timing.leaf_ms, e0, e1));
+		if (bytes > cap_bytes) {
+			if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+			release();
+			return fail(ctx, TB200_E_ARG, "GSMTAP frames need %llu bytes, the buffer holds %llu", (unsigned long long)bytes, (unsigned long long)cap_bytes);
+		}
+		if (d_off) CUR(cudaMemcpy(d_off + n_slots, &bytes, 8, cudaMemcpyHostToDevice));
 		if (!is_device) {
 			CUR(cudaMemcpy(frames, a_frames, bytes, cudaMemcpyDeviceToHost));
 			if (slot_off) CUR(cudaMemcpy(slot_off, a_off, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));

@@ -119,13 +119,19 @@ __device__ __forceinline__ unsigned gt_put_frame(uint16_t *dst, const uint32_t *
 
 __global__ void __launch_bounds__(GT_THREADS)
 k_gsmtap_emit(const SlotOut *__restrict__ slots, const uint32_t *__restrict__ packed, uint64_t n,
-              const uint64_t *__restrict__ tile_base, uint16_t *__restrict__ frames, uint64_t *__restrict__ slot_off)
+              const uint64_t *__restrict__ tile_base, uint16_t *__restrict__ frames, uint64_t cap_bytes,
+              uint64_t *__restrict__ slot_off)
 {
 	__shared__ uint64_t warp_tot[GT_THREADS / 32];
 	__shared__ uint32_t pw[GT_THREADS * TYPE1_WORDS + 1];
 	__shared__ __align__(16) uint16_t stage[GT_THREADS * GT_SLOT_MAX / 2 + 8];
 	const uint64_t tile0 = (uint64_t)blockIdx.x * GT_THREADS;
 	const unsigned cnt = (unsigned)umin64((uint64_t)GT_THREADS, n - tile0);
+	const uint64_t n_tiles = gridDim.x;
+	/* the host launches this pass before it knows the total: nothing is written when the buffer is too small
+	 * (the host then reports the size needed) */
+	if ((tile_base[n_tiles] & ((1ull << 40) - 1)) > cap_bytes)
+		return;
 	/* the tile's packed type-1 words, coalesced */
 	for (unsigned k = threadIdx.x; k < cnt * TYPE1_WORDS; k += GT_THREADS)
 		pw[k] = packed[tile0 * TYPE1_WORDS + k];
