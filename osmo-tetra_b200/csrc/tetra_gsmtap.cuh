@@ -94,27 +94,35 @@ k_gsmtap_scan(uint64_t *__restrict__ tile_tot, uint64_t n_tiles)
 	if (threadIdx.x == 0) tile_tot[n_tiles] = total;
 }
 
-/* one frame into the tile's staging area (16-bit units; every frame length and offset is even) */
-__device__ __forceinline__ unsigned gt_put_frame(uint16_t *dst, const uint32_t *w, unsigned off, unsigned len, uint32_t sub,
-                                                 uint32_t ts, uint32_t fnum)
+/* one frame into the tile's staging area (16-bit units; every frame length and offset is even).  OFF / LEN: the
+ * block's place in the slot's type-1 string, compile-time so that every word index and shift is an immediate.
+ * h1 = type | timeslot << 8, f_hi / f_lo = htonl(frame_number) as two 16-bit units. */
+template <int OFF, int LEN>
+__device__ __forceinline__ uint16_t *gt_put_frame(uint16_t *dst, const uint32_t *w, uint32_t h1, uint32_t f_hi, uint32_t f_lo,
+                                                  uint32_t sub)
 {
 	dst[0] = (uint16_t)(GT_VERSION | (GT_HDR / 4) << 8);
-	dst[1] = (uint16_t)(GT_TYPE_TETRA_I1 | (ts & 0xff) << 8);
+	dst[1] = (uint16_t)h1;
 	dst[2] = 0;                                                  /* arfcn */
 	dst[3] = 0;                                                  /* signal_dbm, snr_db */
-	dst[4] = (uint16_t)(((fnum >> 24) & 0xff) | ((fnum >> 16) & 0xff) << 8);   /* htonl(frame_number) */
-	dst[5] = (uint16_t)(((fnum >> 8) & 0xff) | (fnum & 0xff) << 8);
+	dst[4] = (uint16_t)f_hi;
+	dst[5] = (uint16_t)f_lo;
 	dst[6] = (uint16_t)sub;                                      /* sub_type, antenna_nr */
 	dst[7] = 0;                                                  /* sub_slot, res */
-	const unsigned halves = (len + 15) / 16;
-	for (unsigned h = 0; h < halves; h++) {
-		const unsigned p = off + 16 * h, rem = len - 16 * h;
-		uint32_t x = __funnelshift_r(w[p >> 5], w[(p >> 5) + 1], p & 31) & 0xffffu;
-		if (rem < 16) x &= (1u << rem) - 1;
-		const uint32_t r = __brev(x);                            /* bit i -> bit 31-i: MSB-first inside each byte */
-		dst[8 + h] = (uint16_t)((r >> 24) | ((r >> 16) & 0xff) << 8);
+	constexpr int WORDS = LEN / 32, REM = LEN % 32;
+	/* 32 type-1 bits (LSB first) -> 4 frame bytes (first bit in the MSB of the first byte): reverse the bits,
+	 * then the bytes */
+#pragma unroll
+	for (int k = 0; k <= WORDS; k++) {
+		const int p = OFF + 32 * k;
+		if (k == WORDS && REM == 0) break;
+		uint32_t x = (p & 31) ? __funnelshift_r(w[p >> 5], w[(p >> 5) + 1], p & 31) : w[p >> 5];
+		if (k == WORDS) x &= (1u << REM) - 1;
+		const uint32_t sw = __byte_perm(__brev(x), 0, 0x0123);
+		dst[8 + 2 * k] = (uint16_t)sw;
+		if (k < WORDS || REM > 16) dst[9 + 2 * k] = (uint16_t)(sw >> 16);
 	}
-	return 8 + halves;
+	return dst + 8 + (LEN + 15) / 16;
 }
 
 __global__ void __launch_bounds__(GT_THREADS)
@@ -123,7 +131,7 @@ k_gsmtap_emit(const SlotOut *__restrict__ slots, const uint32_t *__restrict__ pa
               uint64_t *__restrict__ slot_off)
 {
 	__shared__ uint64_t warp_tot[GT_THREADS / 32];
-	__shared__ uint32_t pw[GT_THREADS * TYPE1_WORDS + 1];
+	__shared__ __align__(16) uint32_t pw[GT_THREADS * TYPE1_WORDS + 4];
 	__shared__ __align__(16) uint16_t stage[GT_THREADS * GT_SLOT_MAX / 2 + 8];
 	const uint64_t tile0 = (uint64_t)blockIdx.x * GT_THREADS;
 	const unsigned cnt = (unsigned)umin64((uint64_t)GT_THREADS, n - tile0);
@@ -133,8 +141,14 @@ k_gsmtap_emit(const SlotOut *__restrict__ slots, const uint32_t *__restrict__ pa
 	if ((tile_base[n_tiles] & ((1ull << 40) - 1)) > cap_bytes)
 		return;
 	/* the tile's packed type-1 words, coalesced */
-	for (unsigned k = threadIdx.x; k < cnt * TYPE1_WORDS; k += GT_THREADS)
-		pw[k] = packed[tile0 * TYPE1_WORDS + k];
+	if (cnt == GT_THREADS && ((uintptr_t)packed & 15) == 0) {        /* a full tile is 9216 bytes: whole uint4s */
+		const uint4 *src = reinterpret_cast<const uint4 *>(packed + tile0 * TYPE1_WORDS);
+		for (unsigned k = threadIdx.x; k < GT_THREADS * TYPE1_WORDS / 4; k += GT_THREADS)
+			reinterpret_cast<uint4 *>(pw)[k] = src[k];
+	} else {
+		for (unsigned k = threadIdx.x; k < cnt * TYPE1_WORDS; k += GT_THREADS)
+			pw[k] = packed[tile0 * TYPE1_WORDS + k];
+	}
 	if (threadIdx.x == 0) pw[cnt * TYPE1_WORDS] = 0;
 	uint32_t flags = 0, time = 0;
 	if (threadIdx.x < cnt) {
@@ -155,20 +169,22 @@ k_gsmtap_emit(const SlotOut *__restrict__ slots, const uint32_t *__restrict__ pa
 		const int kind = flags & 3;
 		const bool a = flags & F_CRC_A, b = flags & F_CRC_B;
 		const uint32_t tn = time & 7u, fn = (time >> 3) & 31u, mn = (time >> 8) & 63u;
-		const uint32_t ts = tn - 1, fnum = mn * 18 + fn;         /* tetra_upper_mac.c:484, tetra_tdma.c:96-99 */
+		const uint32_t fnum = mn * 18 + fn;                      /* tetra_tdma.c:96-99 with hn = 0 */
+		const uint32_t h1 = GT_TYPE_TETRA_I1 | ((tn - 1) & 0xff) << 8;          /* timeslot tn - 1, tetra_upper_mac.c:484 */
+		const uint32_t f_hi = ((fnum >> 24) & 0xff) | ((fnum >> 16) & 0xff) << 8, f_lo = ((fnum >> 8) & 0xff) | (fnum & 0xff) << 8;
 		const uint32_t *w = pw + threadIdx.x * TYPE1_WORDS;
 		uint16_t *d = stage + phase + my_off / 2;
 		if (kind == KIND_SB) {
-			if (a) d += gt_put_frame(d, w, 0, 60, GT_BSCH, ts, fnum);
-			d += gt_put_frame(d, w, 60, 14, GT_AACH, ts, fnum);
-			if (b) d += gt_put_frame(d, w, 74, 124, (flags & F_BNCH) ? GT_BNCH : 0, ts, fnum);
+			if (a) d = gt_put_frame<0, 60>(d, w, h1, f_hi, f_lo, GT_BSCH);
+			d = gt_put_frame<60, 14>(d, w, h1, f_hi, f_lo, GT_AACH);
+			if (b) d = gt_put_frame<74, 124>(d, w, h1, f_hi, f_lo, (flags & F_BNCH) ? GT_BNCH : 0);
 		} else if (kind == KIND_NDB_F) {
-			d += gt_put_frame(d, w, 0, 14, GT_AACH, ts, fnum);
-			if (a) d += gt_put_frame(d, w, 14, 268, GT_SCH_F, ts, fnum);
+			d = gt_put_frame<0, 14>(d, w, h1, f_hi, f_lo, GT_AACH);
+			if (a) d = gt_put_frame<14, 268>(d, w, h1, f_hi, f_lo, GT_SCH_F);
 		} else if (kind == KIND_NDB_2) {
-			d += gt_put_frame(d, w, 0, 14, GT_AACH, ts, fnum);
-			if (a) d += gt_put_frame(d, w, 14, 124, 0, ts, fnum);
-			if (b) d += gt_put_frame(d, w, 138, 124, 0, ts, fnum);
+			d = gt_put_frame<0, 14>(d, w, h1, f_hi, f_lo, GT_AACH);
+			if (a) d = gt_put_frame<14, 124>(d, w, h1, f_hi, f_lo, 0);
+			if (b) d = gt_put_frame<138, 124>(d, w, h1, f_hi, f_lo, 0);
 		}
 	}
 	__syncthreads();
