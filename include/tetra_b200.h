@@ -266,6 +266,8 @@ int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits,
  * pointers (else host pointers, copied inside the call).  Not reproduced: the extra frames the reference sends when its
  * upper MAC re-enters a block that holds several PDUs (tetra_lower_mac.c:330-352) - those depend on the parse. */
 #define TB200_GSMTAP_SLOT_MAX 82
+/* length of a frame from byte 12 of its header (sub_type): AACH 18, BSCH 24, SCH/F 50, BNCH / unknown channel 32 */
+#define TB200_GSMTAP_FRAME_LEN(sub_type) ((sub_type) == 2 ? 18u : (sub_type) == 1 ? 24u : (sub_type) == 5 ? 50u : 32u)
 long long tb200_gsmtap_pack(tb200_ctx *ctx, const struct tb200_slot *slots, const uint32_t *type1_packed, uint64_t n_slots,
                             uint8_t *frames, uint64_t cap_bytes, uint64_t *slot_off, uint64_t *n_frames, int is_device);
 

@@ -16,9 +16,12 @@
  * (everything tetra-rx prints from upper_mac_prim_recv() on) is not part of this tool: link the real one
  * through tetra_shim.c for that.
  *
- * usage: tetra-rx-b200 [-f bytes|packed|f32] [-c read_size_bits] [-g cuda_device] <stream-file>
+ * usage: tetra-rx-b200 [-f bytes|packed|f32] [-c read_size_bits] [-g cuda_device] [-p out.pcap] <stream-file>
  *   bytes   one bit per byte, what tetra-rx reads (default)      packed  eight bits per byte
  *   f32     float32 symbols, what float_to_bits reads
+ *   -p      also write the GSMTAP frames of the CRC-good blocks (tb200_gsmtap_pack: what the reference sends
+ *           to UDP port 4729 through tetra_gsmtap_sendmsg, tetra_upper_mac.c:480-488) as a pcap file of
+ *           IPv4/UDP packets, one per frame, 127.0.0.1 -> 127.0.0.1:4729, for wireshark
  */
 #include <stdint.h>
 #include <stdio.h>
@@ -28,19 +31,43 @@
 #include "tetra_b200.h"
 #include "tetra_text.h"
 
+static void put16be(uint8_t *p, unsigned v) { p[0] = (uint8_t)(v >> 8); p[1] = (uint8_t)v; }
+
+/* one GSMTAP frame as a raw-IPv4 pcap record (LINKTYPE_RAW): pcap record header, IPv4, UDP, payload */
+static void pcap_packet(FILE *f, const uint8_t *frame, unsigned len, uint64_t usec)
+{
+	const uint32_t rec[4] = { (uint32_t)(usec / 1000000u), (uint32_t)(usec % 1000000u), 28 + len, 28 + len };
+	uint8_t h[28] = { 0x45, 0 };
+	put16be(h + 2, 28 + len);                    /* total length */
+	h[8] = 64; h[9] = 17;                        /* TTL, UDP */
+	h[12] = h[16] = 127; h[15] = h[19] = 1;      /* 127.0.0.1 -> 127.0.0.1 */
+	uint32_t sum = 0;
+	for (int i = 0; i < 20; i += 2)
+		sum += (uint32_t)h[i] << 8 | h[i + 1];
+	while (sum >> 16)
+		sum = (sum & 0xffff) + (sum >> 16);
+	put16be(h + 10, ~sum & 0xffff);
+	put16be(h + 20, 4729); put16be(h + 22, 4729);    /* GSMTAP_UDP_PORT */
+	put16be(h + 24, 8 + len);                    /* UDP length; checksum 0 = none */
+	fwrite(rec, sizeof(rec), 1, f);
+	fwrite(h, sizeof(h), 1, f);
+	fwrite(frame, len, 1, f);
+}
+
 int main(int argc, char **argv)
 {
-	const char *fmt = "bytes", *path = NULL;
+	const char *fmt = "bytes", *path = NULL, *pcap = NULL;
 	unsigned int chunk = 64;
 	int device = 0;
 	for (int i = 1; i < argc; i++) {
 		if (!strcmp(argv[i], "-f") && i + 1 < argc) fmt = argv[++i];
 		else if (!strcmp(argv[i], "-c") && i + 1 < argc) chunk = (unsigned int)atoi(argv[++i]);
 		else if (!strcmp(argv[i], "-g") && i + 1 < argc) device = atoi(argv[++i]);
+		else if (!strcmp(argv[i], "-p") && i + 1 < argc) pcap = argv[++i];
 		else path = argv[i];
 	}
 	if (!path) {
-		fprintf(stderr, "usage: %s [-f bytes|packed|f32] [-c read_size_bits] [-g cuda_device] <stream-file>\n", argv[0]);
+		fprintf(stderr, "usage: %s [-f bytes|packed|f32] [-c read_size_bits] [-g cuda_device] [-p out.pcap] <stream-file>\n", argv[0]);
 		return 2;
 	}
 	uint32_t input = !strcmp(fmt, "packed") ? TB200_IN_PACKED : !strcmp(fmt, "f32") ? TB200_IN_F32SYM : TB200_IN_BYTES;
@@ -59,16 +86,44 @@ int main(int argc, char **argv)
 	if (tb200_create(&rx, device) != 0) { fprintf(stderr, "no usable CUDA device (there is no CPU lower MAC in this build)\n"); return 1; }
 	struct tb200_options opt;
 	tb200_default_options(&opt);
-	opt.chunk_bits = chunk; opt.output = TB200_OUT_UNPACKED; opt.input = input;
+	opt.chunk_bits = chunk; opt.output = TB200_OUT_UNPACKED | (pcap ? TB200_OUT_PACKED : 0); opt.input = input;
 	if (tb200_set_options(rx, &opt) != 0) { fprintf(stderr, "%s\n", tb200_last_error(rx)); return 1; }
 	const uint64_t cap = tb200_max_slots(n_bits) + 16;
 	struct tb200_slot *slots = tb200_host_alloc(cap * sizeof(*slots));
 	uint8_t *type1 = tb200_host_alloc(cap * TB200_TYPE1_STRIDE);
 	uint32_t *crc = tb200_host_alloc(cap * sizeof(*crc));
-	if (!slots || !type1 || !crc) { fprintf(stderr, "out of memory\n"); return 1; }
+	uint32_t *packed = pcap ? tb200_host_alloc(cap * TB200_TYPE1_WORDS * sizeof(uint32_t)) : NULL;
+	if (!slots || !type1 || !crc || (pcap && !packed)) { fprintf(stderr, "out of memory\n"); return 1; }
 	tb200_set_crc_buffer(rx, crc);
-	const long n = tb200_rx_stream_host(rx, data, n_bits, TB200_FRESH | TB200_FINAL, slots, type1, NULL, cap);
+	const long n = tb200_rx_stream_host(rx, data, n_bits, TB200_FRESH | TB200_FINAL, slots, type1, packed, cap);
 	if (n < 0) { fprintf(stderr, "%s\n", tb200_last_error(rx)); return 1; }
+	if (pcap) {
+		/* frames of the whole file in one device pass, then one pcap record per frame; the capture time of a
+		 * frame is its slot's place in the stream (85/6 ms per slot) */
+		uint64_t n_frames = 0;
+		const long long need = tb200_gsmtap_pack(rx, slots, packed, (uint64_t)n, NULL, 0, NULL, &n_frames, 0);
+		uint8_t *frames = need >= 0 ? malloc((size_t)need + 2) : NULL;
+		uint64_t *off = malloc(((size_t)n + 1) * sizeof(*off));
+		if (need < 0 || !frames || !off ||
+		    tb200_gsmtap_pack(rx, slots, packed, (uint64_t)n, frames, (uint64_t)need, off, &n_frames, 0) != need) {
+			fprintf(stderr, "GSMTAP framing failed: %s\n", tb200_last_error(rx));
+			return 1;
+		}
+		FILE *pf = fopen(pcap, "wb");
+		if (!pf) { perror("open pcap"); return 1; }
+		const uint32_t gh[6] = { 0xa1b2c3d4u, 2u | 4u << 16, 0, 0, 65535, 101 /* LINKTYPE_RAW */ };
+		fwrite(gh, sizeof(gh), 1, pf);
+		for (long i = 0; i < n; i++) {
+			uint64_t p = off[i];
+			while (p < off[i + 1]) {
+				const unsigned len = TB200_GSMTAP_FRAME_LEN(frames[p + 12]);
+				pcap_packet(pf, frames + p, len, (uint64_t)i * 85000u / 6u);
+				p += len;
+			}
+		}
+		fclose(pf);
+		free(frames); free(off);
+	}
 	const size_t n_ev = tb200_get_lock_events(rx, NULL, 0);
 	struct tb200_lock_event *ev = calloc(n_ev ? n_ev : 1, sizeof(*ev));
 	tb200_get_lock_events(rx, ev, n_ev);

@@ -86,3 +86,55 @@ def test_cli_text_matches_reference_gpu(gpu, orc):
             got = subprocess.run([cli, "-c", str(chunk), path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True).stdout
             assert want.count(b"CRC COMP") > 1000
             assert got == want, (seed, chunk)
+
+
+def _pcap_payloads(path):
+    """(timestamps in us, UDP payloads) of a LINKTYPE_RAW pcap written by tetra-rx-b200 -p; checks the headers"""
+    raw = open(path, "rb").read()
+    magic, ver, _, _, snap, link = np.frombuffer(raw[:24], dtype="<u4")
+    assert magic == 0xa1b2c3d4 and ver == (2 | 4 << 16) and link == 101
+    p, ts, out = 24, [], []
+    while p < len(raw):
+        sec, usec, incl, orig = np.frombuffer(raw[p:p + 16], dtype="<u4")
+        pkt = raw[p + 16:p + 16 + incl]
+        assert incl == orig and pkt[0] == 0x45 and pkt[9] == 17 and int.from_bytes(pkt[2:4], "big") == incl
+        words = np.frombuffer(pkt[:20], dtype=">u2").astype(np.uint32).sum()
+        while words >> 16:
+            words = (words & 0xffff) + (words >> 16)
+        assert words == 0xffff                                        # IPv4 header checksum
+        assert int.from_bytes(pkt[22:24], "big") == 4729 and int.from_bytes(pkt[24:26], "big") == incl - 20
+        ts.append(int(sec) * 1_000_000 + int(usec)); out.append(pkt[28:])
+        p += 16 + incl
+    return ts, out
+
+
+def _check_pcap(cli, orc, d, seed, n_bursts):
+    bits, chunk = make_case(orc, seed, n_bursts)
+    path = os.path.join(d, f"g{seed}.bits")
+    bits.tofile(path)
+    pc = os.path.join(d, f"g{seed}.pcap")
+    subprocess.run([cli, "-c", str(chunk), "-p", pc, path], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, check=True)
+    orc.reset(); orc.feed(bits, chunk)
+    rec = orc.records()
+    good = rec[rec["crc_ok"] != 0]
+    ts, frames = _pcap_payloads(pc)
+    assert len(frames) == good.size > 20
+    want, _ = orc.gsmtap_frames(rec)
+    assert b"".join(frames) == want.tobytes()
+    assert ts == sorted(ts) and ts[-1] > 0
+
+
+def test_cli_pcap_emulated(orc):
+    """-p: one IPv4/UDP packet to port 4729 per CRC-good block, payload = the reference's GSMTAP frame"""
+    simt = T.build_simt()
+    with tempfile.TemporaryDirectory() as d:
+        cli = build_cli(simt, os.path.join(d, "tetra-rx-b200"))
+        for seed in (2001, 2004):
+            _check_pcap(cli, orc, d, seed, 90)
+
+
+@pytest.mark.gpu
+def test_cli_pcap_gpu(gpu, orc):
+    with tempfile.TemporaryDirectory() as d:
+        cli = build_cli(T.PRODUCT_SO, os.path.join(d, "tetra-rx-b200"))
+        _check_pcap(cli, orc, d, 2101, 1500)
