@@ -441,7 +441,7 @@ def run_ours(args, rank, world, local_rank):
                 "step_share": {"classify": t_cls / t_total, "scan": t_scan / t_total, "decode": t_dec / t_total},
                 "constants_from": kc.get("source")}
     cores = os.cpu_count() or 1
-    cpu = cpu_reference_rate(20000, cores, one_core=True) if (world == 1 and not args.no_cpu) else None
+    cpu = cpu_reference_rate(40000, cores, one_core=True) if (world == 1 and not args.no_cpu) else None
     others = other_configs(g, T, torch, C) if (world == 1 and not args.no_e2e) else None
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
