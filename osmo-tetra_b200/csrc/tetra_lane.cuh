@@ -255,33 +255,23 @@ __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *
  * q = 0..7, so the low BYTE of a state's metric is the decision history of its survivor through eight
  * steps = the eight decoded bits that end four steps before the group does, and its low nibble is (bit
  * reversed) the state the survivor had when the group began.  History extraction, packing and the trace
- * back cost half as much per step as in the four-step form.  65 535 / 256 = 255 mismatches fit a metric,
+ * back cost half as much per step as in the four-step form; the mismatch counts of two step pairs are
+ * formed field-wise in one word (step_pair_u8<256> / <32>).  65 535 / 256 = 255 mismatches fit a metric,
  * a 288-step block can collect 432, so every eighth group the common minimum is subtracted (metrics only
  * ever get compared, so this changes nothing).  The four flush steps stay a four-step group. ---- */
 
-template <int K>
-__device__ __forceinline__ uint32_t mad_opaque(uint32_t a, uint32_t b)
-{
-#ifdef TB_SIMT_EMULATION
-	return a * (uint32_t)K + b;
-#else
-	uint32_t r;
-	asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "n"(K), "r"(b));
-	return r;
-#endif
-}
-
-/* strip the history bytes; word i of the result holds positions 4i..4i+3 (position = rev4(state)) */
+/* strip the history bytes; word i of the result holds positions 4i..4i+3 (position = rev4(state)).
+ * One PRMT pulls the two history bytes (trellis X, trellis Y) of two states into one word, one AND per
+ * state clears them. */
 __device__ __forceinline__ void take_history8(uint32_t (&pm)[16], uint4 &hx, uint4 &hy)
 {
 	uint32_t W[8];          /* W[j]: positions 2j, 2j+1; low half = trellis X, high half = trellis Y */
 #pragma unroll
 	for (int j = 0; j < 8; ++j) {
 		const unsigned s1 = rev4(2 * j + 1), s0 = rev4(2 * j);
-		const uint32_t h1 = pm[s1] & 0x00ff00ffu, h0 = pm[s0] & 0x00ff00ffu;
-		pm[s1] = sub_opaque(pm[s1], h1);
-		pm[s0] = sub_opaque(pm[s0], h0);
-		W[j] = mad_opaque<256>(h1, h0);
+		W[j] = __byte_perm(pm[s0], pm[s1], 0x6240);     /* s0.b0, s1.b0, s0.b2, s1.b2 */
+		pm[s1] &= 0xff00ff00u;
+		pm[s0] &= 0xff00ff00u;
 	}
 	hx = make_uint4(__byte_perm(W[0], W[1], 0x5410), __byte_perm(W[2], W[3], 0x5410),
 	                __byte_perm(W[4], W[5], 0x5410), __byte_perm(W[6], W[7], 0x5410));
@@ -297,6 +287,24 @@ __device__ __forceinline__ uint32_t byte128(const uint4 &h, uint32_t f)
 	return (w >> ((f & 3) * 8)) & 0xffu;
 }
 
+/* two trellis steps (an even one with two received symbols, an odd one with one) of the eight-step form.
+ * t, u, r3: mismatch counts per half, scaled so that count * K = 256 per mismatch; p = pair index in the group. */
+template <int K>
+__device__ __forceinline__ void step_pair_u8(uint32_t (&pm)[16], uint32_t t, uint32_t u, uint32_t r3, int p)
+{
+	const uint32_t te = 0x00010001u << (2 * p), to = 0x00020002u << (2 * p);
+	uint32_t M0[4], M1[4];
+	M0[0] = mad_k<K>(t, 0u);                M1[0] = mad_k<K>(t, te);
+	M0[3] = mad_k<-K>(t, 0x02000200u);      M1[3] = mad_k<-K>(t, 0x02000200u + te);
+	M0[2] = mad_k<K>(u, 0u);                M1[2] = mad_k<K>(u, te);
+	M0[1] = mad_k<-K>(u, 0x02000200u);      M1[1] = mad_k<-K>(u, 0x02000200u + te);
+	acs2_step(pm, M0, M1);
+	M0[0] = mad_k<K>(r3, 0u);               M1[0] = mad_k<K>(r3, to);        /* odd step: only G1 was sent */
+	M0[2] = mad_k<-K>(r3, 0x01000100u);     M1[2] = mad_k<-K>(r3, 0x01000100u + to);
+	M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
+	acs2_step(pm, M0, M1);
+}
+
 __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t *cy, int n)
 {
 	uint32_t pm[16];
@@ -309,25 +317,17 @@ __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t 
 		const uint32_t vx = __funnelshift_r(cx[w * nt], cx[(w + 1) * nt], sh) & 0xfffu;
 		const uint32_t vy = __funnelshift_r(cy[w * nt], cy[(w + 1) * nt], sh) & 0xfffu;
 		const uint32_t z = vx | (vy << 16);                 /* received bits of both trellises, 12 per half */
-		const uint32_t nz = ~z;
+		/* the mismatch counts of two step pairs at a time: the symbols of pairs 2h, 2h+1 sit at bits 0-2 and 3-5;
+		 * field-wise sums leave t, u of pair 2h in bits 0-1 and of pair 2h+1 in bits 3-4 (weight 8, made up for by
+		 * the multiplier 32 instead of 256) */
 #pragma unroll
-		for (int p = 0; p < 4; ++p) {
-			const uint32_t r1 = (z >> (3 * p)) & 0x00010001u, q1 = (nz >> (3 * p)) & 0x00010001u;
-			const uint32_t r2 = (z >> (3 * p + 1)) & 0x00010001u;
-			const uint32_t r3 = (z >> (3 * p + 2)) & 0x00010001u;
-			const uint32_t t = r1 + r2;                       /* mismatches if 00 was sent: 0..2 */
-			const uint32_t u = q1 + r2;                       /* mismatches if G1=1, G2=0 was sent */
-			const uint32_t te = 0x00010001u << (2 * p), to = 0x00020002u << (2 * p);
-			uint32_t M0[4], M1[4];
-			M0[0] = mad_k<256>(t, 0u);              M1[0] = mad_k<256>(t, te);
-			M0[3] = mad_k<-256>(t, 0x02000200u);    M1[3] = mad_k<-256>(t, 0x02000200u + te);
-			M0[2] = mad_k<256>(u, 0u);              M1[2] = mad_k<256>(u, te);
-			M0[1] = mad_k<-256>(u, 0x02000200u);    M1[1] = mad_k<-256>(u, 0x02000200u + te);
-			acs2_step(pm, M0, M1);
-			M0[0] = mad_k<256>(r3, 0u);             M1[0] = mad_k<256>(r3, to);      /* odd step: only G1 was sent */
-			M0[2] = mad_k<-256>(r3, 0x01000100u);   M1[2] = mad_k<-256>(r3, 0x01000100u + to);
-			M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
-			acs2_step(pm, M0, M1);
+		for (int h = 0; h < 2; ++h) {
+			const uint32_t zz = h ? (z >> 6) : z;
+			const uint32_t A = zz & 0x00090009u, B = (zz >> 1) & 0x00090009u, C3 = (zz >> 2) & 0x00090009u;
+			const uint32_t T = A + B;                         /* mismatches if 00 was sent: 0..2 per field */
+			const uint32_t U = (A ^ 0x00090009u) + B;         /* mismatches if G1=1, G2=0 was sent */
+			step_pair_u8<256>(pm, T & 0x00030003u, U & 0x00030003u, C3 & 0x00010001u, 2 * h);
+			step_pair_u8<32>(pm, T & 0x00180018u, U & 0x00180018u, C3 & 0x00080008u, 2 * h + 1);
 		}
 		uint4 hx, hy;
 		take_history8(pm, hx, hy);
