@@ -179,3 +179,41 @@ def test_gsmtap_pack_gpu_million(gpu, orc):
         assert np.array_equal(out[off[i]:off[i + 1]], want), i
     algo = ns * (16 + 36) + need
     print(f"gsmtap_pack: {ns} slots, {need} bytes in {ms_leaf:.3f} ms = {algo / ms_leaf / 1e6:.0f} GB/s algorithmic")
+
+
+def _random_slots(rng, n):
+    """slot records of every kind / CRC / BNCH / time combination with random type-1 bits (no decode involved)"""
+    slots = np.zeros(n, dtype=T.SLOT_DTYPE)
+    kind = rng.integers(0, 4, n)
+    slots["flags"] = kind | (rng.integers(0, 2, n) << 2) | (rng.integers(0, 2, n) << 3) | (rng.integers(0, 2, n) << 4)
+    # NDB with SCH/F has no second CRC flag, and BNCH only exists on SYNC bursts
+    slots["flags"] &= np.where(kind == 2, 0xff ^ 0x18, np.where(kind == 1, 0xff, 0xff ^ 0x10)).astype(np.uint8)
+    slots["time"] = rng.integers(0, 5, n) | (rng.integers(0, 32, n) << 3) | (rng.integers(0, 64, n) << 8)   # tn = 0 included
+    t1 = np.zeros((n, 288), dtype=np.uint8)
+    nbits = np.array([0, 198, 282, 262])[kind]
+    for i in range(n):
+        t1[i, :nbits[i]] = rng.integers(0, 2, nbits[i])
+    packed = np.packbits(t1, axis=1, bitorder="little").view("<u4").reshape(n, 9)
+    return slots, t1, np.ascontiguousarray(packed)
+
+
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 1000])
+def test_gsmtap_pack_random_slots_emulated(emu, orc, ref, n):
+    """every kind, flag and time value (tn = 0 gives timeslot 255 like the reference's uint8 tn - 1): kernels = oracle =
+    the reference's tetra_gsmtap.c"""
+    slots, t1, packed = _random_slots(np.random.default_rng(100 + n), n)
+    rec = emu.expand_records(slots, t1)
+    want, nf = orc.gsmtap_frames(rec)
+    want_ref, nf_ref = ref.gsmtap_frames(rec)
+    assert nf == nf_ref and np.array_equal(want, want_ref)
+    got, off, ng = emu.gsmtap_pack(slots, packed)
+    assert ng == nf and np.array_equal(got, want)
+    assert off[-1] == want.size and np.all(np.diff(off.astype(np.int64)) <= 82)
+
+
+@pytest.mark.gpu
+def test_gsmtap_pack_random_slots_gpu(gpu, orc):
+    slots, t1, packed = _random_slots(np.random.default_rng(7), 70_001)
+    want, nf = orc.gsmtap_frames(gpu.expand_records(slots, t1))
+    got, off, ng = gpu.gsmtap_pack(slots, packed)
+    assert ng == nf and np.array_equal(got, want) and off[-1] == want.size
