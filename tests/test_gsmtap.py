@@ -197,7 +197,7 @@ def _random_slots(rng, n):
     return slots, t1, np.ascontiguousarray(packed)
 
 
-@pytest.mark.parametrize("n", [1, 255, 256, 257, 1000])
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 1000, 270_000])      # 270 000 slots: more tiles than scan threads
 def test_gsmtap_pack_random_slots_emulated(emu, orc, ref, n):
     """every kind, flag and time value (tn = 0 gives timeslot 255 like the reference's uint8 tn - 1): kernels = oracle =
     the reference's tetra_gsmtap.c"""
