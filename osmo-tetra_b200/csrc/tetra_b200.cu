@@ -1518,7 +1518,12 @@ extern "C" long long tb200_gsmtap_pack(tb200_ctx *ctx, const tb200_slot *slots, 
 	const SlotOut *d_slots = reinterpret_cast<const SlotOut *>(slots);
 	const uint32_t *d_packed = type1_packed;
 	SlotOut *a_slots = nullptr; uint32_t *a_packed = nullptr; uint8_t *a_frames = nullptr; uint64_t *a_off = nullptr, *d_tot = nullptr;
-	auto release = [&]() { cudaFree(a_slots); cudaFree(a_packed); cudaFree(a_frames); cudaFree(a_off); cudaFree(d_tot); };
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	auto release = [&]() {
+		cudaFree(a_slots); cudaFree(a_packed); cudaFree(a_frames); cudaFree(a_off); cudaFree(d_tot);
+		if (e0) cudaEventDestroy(e0);
+		if (e1) cudaEventDestroy(e1);
+	};
 #define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); \
 	return fail(ctx, TB200_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } } while (0)
 	if (!is_device) {
@@ -1532,7 +1537,6 @@ extern "C" long long tb200_gsmtap_pack(tb200_ctx *ctx, const tb200_slot *slots, 
 		}
 	}
 	CUR(cudaMalloc((void **)&d_tot, (tiles + 1) * 8));
-	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	if (ctx->opt.profile) {
 		CUR(cudaEventCreateWithFlags(&e0, 0)); CUR(cudaEventCreateWithFlags(&e1, 0));
 		CUR(cudaEventRecord(e0, ctx->s_compute));
@@ -1561,7 +1565,6 @@ extern "C" long long tb200_gsmtap_pack(tb200_ctx *ctx, const tb200_slot *slots, 
 	if (frames) {
 		if (ctx->opt.profile) CUR(cudaEventElapsedTime(&ctx->timing.leaf_ms, e0, e1));
 		if (bytes > cap_bytes) {
-			if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
 			release();
 			return fail(ctx, TB200_E_ARG, "GSMTAP frames need %llu bytes, the buffer holds %llu", (unsigned long long)bytes, (unsigned long long)cap_bytes);
 		}
@@ -1571,7 +1574,6 @@ extern "C" long long tb200_gsmtap_pack(tb200_ctx *ctx, const tb200_slot *slots, 
 			if (slot_off) CUR(cudaMemcpy(slot_off, a_off, (n_slots + 1) * 8, cudaMemcpyDeviceToHost));
 		}
 	}
-	if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
 	release();
 #undef CUR
 	return (long long)bytes;
