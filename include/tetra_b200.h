@@ -253,6 +253,15 @@ int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits,
                          const uint64_t *starts, const uint32_t *lens, uint64_t n, uint32_t mask,
                          int32_t *rc, uint32_t *offset);
 
+/* tetra_rcpc_depunct (tetra_conv_enc.c:226-248) for n blocks laid out back to back, any of the reference's seven
+ * puncturers (enum tetra_rcpc_puncturer, tetra_conv_enc.h:16-24: 0 = 2/3, 1 = 1/3, 2 = 292/432, 3 = 148/432,
+ * 4 = 112/168, 5 = 72/162, 6 = 38/80): `len` type-3 bytes per block in, `mother_len` mother-code bytes per block out,
+ * filled with 0xff (erased) first like the caller of the reference does (tetra_lower_mac.c:249).  The receive chain
+ * itself only ever uses 2/3 and folds it into the trellis loop; this is the function on its own, as a parity
+ * checkpoint.  TB200_E_ARG for an unknown puncturer (-EINVAL in the reference). */
+int tb200_rcpc_depunct(tb200_ctx *ctx, int puncturer, const uint8_t *type3, uint32_t len, uint64_t n,
+                       uint8_t *mother, uint32_t mother_len, int is_device);
+
 /* GSMTAP framing of the decoded blocks: what tetra_gsmtap_makemsg (tetra_gsmtap.c:31-63) builds
  * when rx_tmv_unitdata_ind hands it a CRC-good block (tetra_upper_mac.c:480-488), for every block of n_slots slots:
  * a 16-byte GSMTAP v2 header (type TETRA_I1, timeslot tn-1, frame_number (mn*18+fn) in network order, sub_type

@@ -273,6 +273,17 @@ class B200:
             raise RuntimeError(self.err())
         return out
 
+    def rcpc_depunct(self, puncturer, type3, mother_len):
+        """tetra_rcpc_depunct over the rows of type3 (n x len bytes) -> n x mother_len bytes, 0xff where nothing was sent"""
+        type3 = np.ascontiguousarray(type3, dtype=np.uint8)
+        n, ln = type3.shape
+        out = np.zeros((n, mother_len), dtype=np.uint8)
+        self.lib.tb200_rcpc_depunct.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_int]
+        r = self.lib.tb200_rcpc_depunct(self.h, puncturer, _ptr(type3), ln, n, _ptr(out), mother_len, 0)
+        if r:
+            raise RuntimeError(self.err())
+        return out
+
     def gsmtap_pack(self, slots, packed):
         """GSMTAP frames of every CRC-good block of the slots (host arrays): (frame bytes, slot offsets, n_frames)"""
         slots = np.ascontiguousarray(slots); packed = np.ascontiguousarray(packed, dtype=np.uint32)

@@ -1501,6 +1501,69 @@ extern "C" int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type
 	return 0;
 }
 
+/* ------------------------------------------------------------ de-puncturing -- */
+
+/* one of the reference's seven puncturers (struct puncturer, tetra_conv_enc.c:103-110,128-198): type-3 bit j
+ * (1-based) is mother-code bit k = period * ((i-1)/t) + P[i - t*((i-1)/t)] with i = i_func(j) */
+struct PunctDef {
+	uint8_t P[24];
+	uint8_t t, period, ifunc;      /* ifunc: 0 i = j, 1 i = j + (j-1)/65 (292/432), 2 i = j + (j-1)/35 (148/432) */
+};
+
+static const PunctDef k_punct_defs[7] = {
+	{ { 0, 1, 2, 5 }, 3, 8, 0 },                                                          /* TETRA_RCPC_PUNCT_2_3 */
+	{ { 0, 1, 2, 3, 5, 6, 7 }, 6, 8, 0 },                                                 /* 1_3 */
+	{ { 0, 1, 2, 5 }, 3, 8, 1 },                                                          /* 292_432 */
+	{ { 0, 1, 2, 3, 5, 6, 7 }, 6, 8, 2 },                                                 /* 148_432 */
+	{ { 0, 1, 2, 4 }, 3, 6, 0 },                                                          /* 112_168 (speech) */
+	{ { 0, 1, 2, 3, 4, 5, 7, 8, 10, 11 }, 9, 12, 0 },                                     /* 72_162 */
+	{ { 0, 1, 2, 3, 4, 5, 7, 8, 10, 11, 13, 14, 16, 17, 19, 20, 22, 23 }, 17, 24, 0 },    /* 38_80 */
+};
+
+__global__ void __launch_bounds__(256)
+k_rcpc_depunct(const uint8_t *__restrict__ type3, uint32_t len, uint64_t n, uint8_t *__restrict__ mother, uint32_t mother_len,
+               PunctDef pd)
+{
+	const uint64_t total = n * len, stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+		const uint64_t b = idx / len;
+		const uint32_t j = (uint32_t)(idx - b * len) + 1;
+		const uint32_t i = pd.ifunc == 1 ? j + (j - 1) / 65 : pd.ifunc == 2 ? j + (j - 1) / 35 : j;
+		const uint32_t q = (i - 1) / pd.t;
+		const uint32_t k = pd.period * q + pd.P[i - pd.t * q];
+		if (k - 1 < mother_len)
+			mother[b * mother_len + (k - 1)] = type3[idx];
+	}
+}
+
+extern "C" int tb200_rcpc_depunct(tb200_ctx *ctx, int puncturer, const uint8_t *type3, uint32_t len, uint64_t n,
+                                  uint8_t *mother, uint32_t mother_len, int is_device)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (puncturer < 0 || puncturer >= 7) return fail(ctx, TB200_E_ARG, "unknown puncturer %d", puncturer);   /* -EINVAL in the reference */
+	if (len == 0 || mother_len == 0 || !type3 || !mother) return fail(ctx, TB200_E_ARG, "bad argument");
+	if (n == 0) return 0;
+	const uint8_t *d3 = type3; uint8_t *dm = mother;
+	uint8_t *a3 = nullptr, *am = nullptr;
+	if (!is_device) {
+		CU(cudaMalloc((void **)&a3, n * len)); CU(cudaMalloc((void **)&am, n * mother_len));
+		CU(cudaMemcpy(a3, type3, n * len, cudaMemcpyHostToDevice));
+		d3 = a3; dm = am;
+	}
+	/* the caller of the reference function fills the mother buffer with 0xff first (tetra_lower_mac.c:249) */
+	CU(cudaMemsetAsync(dm, 0xff, n * mother_len, ctx->s_compute));
+	const unsigned blocks = (unsigned)std::min<uint64_t>((n * len + 255) / 256, (uint64_t)ctx->sm_count * 16);
+	TB_LAUNCH(k_rcpc_depunct, blocks, 256, ctx->s_compute, d3, len, n, dm, mother_len, k_punct_defs[puncturer]);
+	CU(cudaGetLastError());
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	if (!is_device) {
+		CU(cudaMemcpy(mother, am, n * mother_len, cudaMemcpyDeviceToHost));
+		cudaFree(a3); cudaFree(am);
+	}
+	return 0;
+}
+
 /* ----------------------------------------------------------- GSMTAP framing -- */
 
 extern "C" long long tb200_gsmtap_pack(tb200_ctx *ctx, const tb200_slot *slots, const uint32_t *type1_packed, uint64_t n_slots,
