@@ -13,6 +13,7 @@
 
 #include <stdint.h>
 #include <stddef.h>
+#include "tetra_tie_rule.h"
 
 #ifdef __cplusplus
 extern "C" {
@@ -123,8 +124,10 @@ struct tb200_options {
 	uint32_t viterbi;           /* TB200_VITERBI_* */
 	uint32_t pipeline_slots;    /* slots per pipelined piece in the host-buffer path (0 = default) */
 	uint32_t profile;           /* 1: bracket every kernel with CUDA events on its stream (tb200_get_timing) */
-	uint32_t input;             /* TB200_IN_*; the packed / symbol formats need the whole stream in one call
-	                             * (TB200_FRESH | TB200_FINAL) and the lane kernels */
+	uint32_t input;             /* TB200_IN_*; the packed / symbol formats need the lane kernels */
+	uint32_t viterbi_tie;       /* survivor on equal path metrics (tetra_tie_rule.h): 0 = predecessor s>>1 (libosmocore's
+	                             * osmo_conv_decode as restated, viterbi_cch.c:58-66), 1 = predecessor (s>>1)|8.  The default is
+	                             * TETRA_VITERBI_TIE_DEFAULT, the compile-time switch the CPU oracle shares */
 };
 void tb200_default_options(struct tb200_options *opt);
 int  tb200_set_options(tb200_ctx *ctx, const struct tb200_options *opt);

@@ -38,6 +38,12 @@
 #include <osmocom/core/utils.h>
 #include <osmocom/core/bitvec.h>
 
+#include "../include/tetra_tie_rule.h"
+
+/* the tie rule both restatements apply (include/tetra_tie_rule.h); run-time override for the tests */
+static int g_tie = TETRA_VITERBI_TIE_DEFAULT;
+void oracle_conv_set_tie(int tie) { g_tie = tie ? TETRA_TIE_KEEPS_HIGH_PRED : TETRA_TIE_KEEPS_LOW_PRED; }
+
 /* ---------------------------------------------------------------- Viterbi -- */
 
 #define MAX_STEPS 1024
@@ -84,10 +90,12 @@ int oracle_conv_decode_acc(const struct osmo_conv_code *code, const sbit_t *in, 
 				m += seq[j] * (((o >> (N - 1 - j)) & 1) ? -1 : 1);
 			int s0 = sat16(sums[2 * i] + m), s1 = sat16(sums[2 * i + 1] - m);
 			int s2 = sat16(sums[2 * i] - m), s3 = sat16(sums[2 * i + 1] + m);
-			if (s0 >= s1) { nsums[i] = s0; paths[t][i] = 0; }
-			else          { nsums[i] = s1; paths[t][i] = 1; }
-			if (s2 >= s3) { nsums[i + ns / 2] = s2; paths[t][i + ns / 2] = 0; }
-			else          { nsums[i + ns / 2] = s3; paths[t][i + ns / 2] = 1; }
+			/* libosmocore: "sum0 >= sum1" keeps acc state 2i (oldest bit 0); the other rule makes it strict */
+			const int hi = g_tie == TETRA_TIE_KEEPS_HIGH_PRED;
+			if (hi ? s0 > s1 : s0 >= s1) { nsums[i] = s0; paths[t][i] = 0; }
+			else                         { nsums[i] = s1; paths[t][i] = 1; }
+			if (hi ? s2 > s3 : s2 >= s3) { nsums[i + ns / 2] = s2; paths[t][i + ns / 2] = 0; }
+			else                         { nsums[i + ns / 2] = s3; paths[t][i + ns / 2] = 1; }
 		}
 		if (t % intrvl == 0) {
 			int16_t mn = nsums[0];
@@ -140,7 +148,8 @@ int oracle_conv_decode_gen(const struct osmo_conv_code *code, const sbit_t *in, 
 					if (sym[m])
 						nae += (ov ? sym[m] : -sym[m]) + 127;
 				}
-				if (ae_next[st] > nae) {
+				/* libosmocore: strict, so the predecessor scanned first (the lower state) keeps a tie */
+				if (g_tie == TETRA_TIE_KEEPS_HIGH_PRED ? ae_next[st] >= nae : ae_next[st] > nae) {
 					ae_next[st] = nae;
 					hist[t][st] = s;
 				}
@@ -159,6 +168,7 @@ int oracle_conv_decode_gen(const struct osmo_conv_code *code, const sbit_t *in, 
 	return 0;
 }
 
+#ifndef ORACLE_STANDIN_CONV_ONLY      /* pin_conv.c links the real libosmocore next to the two restatements */
 int osmo_conv_decode(const struct osmo_conv_code *code, const sbit_t *input, ubit_t *output)
 {
 	static int variant = -1;
@@ -247,6 +257,8 @@ int bitvec_set_uint(struct bitvec *bv, unsigned int in, unsigned int count)
 			return -1;
 	return 0;
 }
+
+#endif /* ORACLE_STANDIN_CONV_ONLY */
 
 /* test hook: decode with an explicit variant (0 = acc, 1 = generic) and the TETRA mother
  * code tables rebuilt from the generator polynomials (viterbi_cch.c:28-48) */

@@ -19,6 +19,12 @@
 #include <string.h>
 
 #include "oracle_records.h"
+#include "../include/tetra_tie_rule.h"
+
+/* Viterbi tie rule (include/tetra_tie_rule.h): compile-time default, run-time override for the tests */
+static int g_tie = TETRA_VITERBI_TIE_DEFAULT;
+void orc_set_tie(int tie) { g_tie = tie ? TETRA_TIE_KEEPS_HIGH_PRED : TETRA_TIE_KEEPS_LOW_PRED; }
+int orc_get_tie(void) { return g_tie; }
 
 /* ------------------------------------------------------------ constants -- */
 
@@ -146,7 +152,8 @@ void orc_conv_encode(const uint8_t *in, int len, uint8_t *mother)
  * disagree with the branch output; start in state 0; n data steps then 4 flush
  * steps whose symbols are all erased; trace back from state 0; on equal cost the
  * survivor is the predecessor whose oldest register bit is 0 (state t>>1 rather
- * than (t>>1)|8 in the table numbering of viterbi_cch.c:42-48). */
+ * than (t>>1)|8 in the table numbering of viterbi_cch.c:42-48) - or the other one
+ * when the tie switch of include/tetra_tie_rule.h says so. */
 int orc_viterbi(const uint8_t *mother, uint8_t *out, int n)
 {
 	enum { NS = 16 };
@@ -178,7 +185,7 @@ int orc_viterbi(const uint8_t *mother, uint8_t *out, int n)
 			unsigned b = s & 1, p0 = s >> 1, p1 = p0 | 8;
 			uint32_t c0 = pm[p0] + __builtin_popcount((mother_out(p0, b) ^ val) & known);
 			uint32_t c1 = pm[p1] + __builtin_popcount((mother_out(p1, b) ^ val) & known);
-			if (c1 < c0) { nm[s] = c1; d |= 1u << s; }
+			if (g_tie == TETRA_TIE_KEEPS_HIGH_PRED ? c1 <= c0 : c1 < c0) { nm[s] = c1; d |= 1u << s; }
 			else         { nm[s] = c0; }
 		}
 		dec[t] = d;

@@ -46,11 +46,13 @@ TB200_FRESH, TB200_FINAL = 1, 2
 OUT_UNPACKED, OUT_PACKED = 1, 2
 IN_BYTES, IN_PACKED, IN_F32SYM = 0, 1, 2
 VITERBI_WARP, VITERBI_LANE = 0, 1
+TIE_LOW_PRED, TIE_HIGH_PRED = 0, 1        # include/tetra_tie_rule.h
 
 
 class Options(C.Structure):
     _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
-                ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32), ("input", C.c_uint32)]
+                ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32), ("input", C.c_uint32),
+                ("viterbi_tie", C.c_uint32)]
 
 
 class Timing(C.Structure):

@@ -221,6 +221,7 @@ extern "C" void tb200_default_options(tb200_options *o)
 	o->pipeline_slots = 0;
 	o->profile = 0;
 	o->input = TB200_IN_BYTES;
+	o->viterbi_tie = TETRA_VITERBI_TIE_DEFAULT;
 }
 
 extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
@@ -232,6 +233,8 @@ extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
 		return fail(ctx, TB200_E_ARG, "unknown viterbi variant");
 	if (o->input > TB200_IN_F32SYM)
 		return fail(ctx, TB200_E_ARG, "unknown input format");
+	if (o->viterbi_tie > 1)
+		return fail(ctx, TB200_E_ARG, "viterbi_tie must be 0 or 1");
 	if (o->input != TB200_IN_BYTES && o->viterbi != TB200_VITERBI_LANE)
 		return fail(ctx, TB200_E_ARG, "packed / symbol input needs the lane kernels (TB200_VITERBI_LANE)");
 	ctx->opt = *o;
@@ -346,7 +349,7 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 	{
 		int per_sm = 8;
 #ifndef TB_SIMT_EMULATION
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_lane, LANE_NT,
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_lane<false>, LANE_NT,
 		                                                   lane_smem_words(LANE_NT) * sizeof(uint32_t)) != cudaSuccess || per_sm < 1)
 			return bail("cudaOccupancyMaxActiveBlocksPerMultiprocessor");
 #endif
@@ -751,8 +754,12 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cuda
 			TB_LAUNCH_SMEM(k_classify_tile<IN_F32SYM>, cls_blocks, CT_THREADS, ct_smem<IN_F32SYM>(), st, g, wg, ctx->d_tab, ctx->d_ws,
 			               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
 		if (pe) CU(cudaEventRecord(pe[5], st));
-		TB_LAUNCH_SMEM(k_sb1_lane, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
-		               ctx->d_tab, ctx->d_lane_scratch);
+		if (ctx->opt.viterbi_tie)
+			TB_LAUNCH_SMEM(k_sb1_lane<true>, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
+			               ctx->d_tab, ctx->d_lane_scratch);
+		else
+			TB_LAUNCH_SMEM(k_sb1_lane<false>, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
+			               ctx->d_tab, ctx->d_lane_scratch);
 		ctx->stats.kernel_launches++;
 	} else {
 		TB_LAUNCH(k_classify<true>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
@@ -791,8 +798,10 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	a.a0 = a0; a.out_base = out_base; a.n_slots = nb;
 	a.kind_count = ctx->d_kind_list + 4 * ctx->ws_slots; a.kind_list = ctx->d_kind_list; a.list_stride = (uint32_t)ctx->ws_slots;
 	a.crc = o_crc;
-	if (lane) TB_LAUNCH_SMEM(k_decode_lane, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
-	else      TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
+	a.tie_hi = (int)ctx->opt.viterbi_tie;
+	if (lane && ctx->opt.viterbi_tie) TB_LAUNCH_SMEM(k_decode_lane<true>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
+	else if (lane)                    TB_LAUNCH_SMEM(k_decode_lane<false>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
+	else                              TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
 	if (pe) CU(cudaEventRecord(pe[3], st));
 	CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
 	TB_LAUNCH(k_finalize_carry, 1, 32, st, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, nb, ctx->d_carry + piece_idx + 1);
@@ -810,7 +819,7 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	RxGeom g;
 	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base; g.fmt = fmt;
 	g.a0 = seg.a0 + (uint64_t)SLOT_BITS * k0; g.cmin = seg.cmin + k0; g.n_end = seg.n_end;
-	g.chunk = seg.chunk; g.n_slots = nb;
+	g.chunk = seg.chunk; g.n_slots = nb; g.tie_hi = (int)ctx->opt.viterbi_tie;
 	cudaEvent_t *pe = nullptr;
 	if (ctx->opt.profile) {
 		while (ctx->prof_ev.size() < ctx->prof_used + 6) {
@@ -1300,7 +1309,7 @@ k_leaf_find(const uint8_t *bits, uint64_t n_bytes, const uint64_t *starts, const
 
 template <int BT>
 __device__ __forceinline__ void leaf_decode_one(WarpSmem &S, const uint8_t *type5, uint32_t code, const Tables *tab,
-                                                uint8_t *type1, uint8_t *crc_ok, unsigned lane, int variant)
+                                                uint8_t *type1, uint8_t *crc_ok, unsigned lane, int variant, bool tie_hi)
 {
 	constexpr int K = Blk<BT>::K, N = Blk<BT>::N, T1 = Blk<BT>::T1;
 	uint32_t x0, x1, x2;
@@ -1314,11 +1323,11 @@ __device__ __forceinline__ void leaf_decode_one(WarpSmem &S, const uint8_t *type
 	gather_type3<BT, PL_RAW>(S.bw, S.lf, S.t3[0], lane);
 	uint32_t crc;
 	if (variant == TB200_VITERBI_LANE) {
-		if (lane == 0) viterbi_lane<N>(S.t3[0], S.dec, S.t2[0]);
+		if (lane == 0) viterbi_lane<N>(S.t3[0], S.dec, S.t2[0], tie_hi);
 		__syncwarp();
 		crc = crc16_serial(S.t2[0], T1 + 16);
 	} else {
-		viterbi_warp<N>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
+		viterbi_warp<N>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0], tie_hi);
 		crc = crc16_half(S.t2[0], T1 + 16, Blk<BT>::CRCI, tab);
 	}
 	put_bits(S.outw, 0, S.t2[0], T1, lane);
@@ -1331,25 +1340,26 @@ __device__ __forceinline__ void leaf_decode_one(WarpSmem &S, const uint8_t *type
 
 __global__ void __launch_bounds__(256)
 k_leaf_decode(int blk_type, const uint8_t *type5, const uint32_t *codes, uint64_t n, const Tables *__restrict__ tab,
-              uint8_t *type1, uint8_t *crc_ok, int variant)
+              uint8_t *type1, uint8_t *crc_ok, int variant, int tie)
 {
+	const bool tie_hi = tie != 0;
 	__shared__ WarpSmem sm[8];
 	const unsigned lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const uint64_t nwarps = (uint64_t)gridDim.x * (blockDim.x >> 5);
 	for (uint64_t i = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib; i < n; i += nwarps) {
 		if (blk_type == TB200_T_SB1)
-			leaf_decode_one<0>(sm[wib], type5 + i * 120, codes[i], tab, type1 + i * 60, crc_ok + i, lane, variant);
+			leaf_decode_one<0>(sm[wib], type5 + i * 120, codes[i], tab, type1 + i * 60, crc_ok + i, lane, variant, tie_hi);
 		else if (blk_type == TB200_T_SCH_F)
-			leaf_decode_one<5>(sm[wib], type5 + i * 432, codes[i], tab, type1 + i * 268, crc_ok + i, lane, variant);
+			leaf_decode_one<5>(sm[wib], type5 + i * 432, codes[i], tab, type1 + i * 268, crc_ok + i, lane, variant, tie_hi);
 		else if (blk_type == TB200_T_SCH_HU)
-			leaf_decode_one<4>(sm[wib], type5 + i * 168, codes[i], tab, type1 + i * 92, crc_ok + i, lane, variant);
+			leaf_decode_one<4>(sm[wib], type5 + i * 168, codes[i], tab, type1 + i * 92, crc_ok + i, lane, variant, tie_hi);
 		else if (blk_type == TB200_T_BBK) {
 			/* no channel decoding in the reference (tetra_lower_mac.c:268-274): the first 14 descrambled bits, CRC flag 1 */
 			const uint32_t lw = lfsr_word(codes[i], 0, tab);
 			if (lane < 14) type1[i * 14 + lane] = (type5[i * 30 + lane] ^ (lw >> lane)) & 1;
 			if (lane == 0) crc_ok[i] = 1;
 		} else
-			leaf_decode_one<1>(sm[wib], type5 + i * 216, codes[i], tab, type1 + i * 124, crc_ok + i, lane, variant);
+			leaf_decode_one<1>(sm[wib], type5 + i * 216, codes[i], tab, type1 + i * 124, crc_ok + i, lane, variant, tie_hi);
 	}
 }
 
@@ -1450,7 +1460,7 @@ extern "C" int tb200_decode_blocks(tb200_ctx *ctx, int blk_type, const uint8_t *
 	CU(cudaMemcpy(d5, type5, n * K, cudaMemcpyHostToDevice));
 	CU(cudaMemcpy(dcode, codes, n * 4, cudaMemcpyHostToDevice));
 	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, 4096);
-	TB_LAUNCH(k_leaf_decode, blocks, 256, ctx->s_compute, blk_type, d5, dcode, n, ctx->d_tab, d1, dc, (int)ctx->opt.viterbi);
+	TB_LAUNCH(k_leaf_decode, blocks, 256, ctx->s_compute, blk_type, d5, dcode, n, ctx->d_tab, d1, dc, (int)ctx->opt.viterbi, (int)ctx->opt.viterbi_tie);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(ctx->s_compute));
 	CU(cudaMemcpy(type1, d1, n * T1, cudaMemcpyDeviceToHost));
@@ -1733,7 +1743,7 @@ extern "C" int tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t
 	if ((rc = ensure_pieces(ctx, 1))) return rc;
 	RxGeom g;
 	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.n_end = n_end; g.fmt = IN_BYTES;
-	g.chunk = ctx->opt.chunk_bits; g.n_slots = n_slots;
+	g.chunk = ctx->opt.chunk_bits; g.n_slots = n_slots; g.tie_hi = (int)ctx->opt.viterbi_tie;
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if (n_slots && (rc = enqueue_pass1(ctx, g, 0, nullptr))) return rc;
 	tb200_shard_summary *d_sum = reinterpret_cast<tb200_shard_summary *>(ctx->d_hits);    /* small scratch */

@@ -464,7 +464,7 @@ __device__ __forceinline__ void gather_type3(const uint32_t *bw, const uint32_t 
  * decisions into a word of `dec` for the bit-packed trace back. */
 template <int N>
 __device__ inline void viterbi_warp(const uint32_t *t3a, const uint32_t *t3b, bool two,
-                                    uint32_t *dec, uint32_t *t2a, uint32_t *t2b)
+                                    uint32_t *dec, uint32_t *t2a, uint32_t *t2b, bool tie_hi)
 {
 	const unsigned lane = threadIdx.x & 31, s = lane & 15, half = lane >> 4, base = two ? (lane & 16) : 0;
 	const uint32_t *t3 = (two && half) ? t3b : t3a;
@@ -486,7 +486,7 @@ __device__ inline void viterbi_warp(const uint32_t *t3a, const uint32_t *t3b, bo
 			const uint32_t m0 = data ? (((v & 3) + 1) >> 1) : 0, m1 = data ? 2 - m0 : 0;
 			const uint32_t c0 = __shfl_sync(FULL, pm, src0) + m0;
 			const uint32_t c1 = __shfl_sync(FULL, pm, src1) + m1;
-			const bool d = c1 < c0;
+			const bool d = tie_hi ? c1 <= c0 : c1 < c0;      /* include/tetra_tie_rule.h */
 			pm = d ? c1 : c0;
 			const uint32_t bal = __ballot_sync(FULL, d);
 			if (lane == 0) dec[2 * q] = bal;
@@ -495,7 +495,7 @@ __device__ inline void viterbi_warp(const uint32_t *t3a, const uint32_t *t3b, bo
 			const uint32_t m0 = data ? (v >> 2) : 0, m1 = data ? 1 - m0 : 0;
 			const uint32_t c0 = __shfl_sync(FULL, pm, src0) + m0;
 			const uint32_t c1 = __shfl_sync(FULL, pm, src1) + m1;
-			const bool d = c1 < c0;
+			const bool d = tie_hi ? c1 <= c0 : c1 < c0;      /* include/tetra_tie_rule.h */
 			pm = d ? c1 : c0;
 			const uint32_t bal = __ballot_sync(FULL, d);
 			if (lane == 0) dec[2 * q + 1] = bal;
@@ -555,7 +555,7 @@ struct LaneVit {
 	}
 	/* d[j] for butterflies j = 0..7, from the (G1,G2) classes of viterbi_cch.c:35-40:
 	 * j: 0 1 2 3 4 5 6 7 -> (G1,G2) of out(j,0): 00 10 01 11 01 11 00 10 */
-	__device__ __forceinline__ uint32_t step(const int dA, const int dB, const int dC, const int dD)
+	__device__ __forceinline__ uint32_t step(const int dA, const int dB, const int dC, const int dD, const bool tie_hi)
 	{
 		/* dA: class 00, dB: class 10, dC: class 01, dD: class 11 */
 		const int dj[8] = { dA, dB, dC, dD, dC, dD, dA, dB };
@@ -565,7 +565,7 @@ struct LaneVit {
 		for (int j = 0; j < 8; ++j) {
 			const int a0 = pm[j] + dj[j], a1 = pm[j + 8] - dj[j];
 			const int b0 = pm[j] - dj[j], b1 = pm[j + 8] + dj[j];
-			const bool e = a1 < a0, f = b1 < b0;
+			const bool e = tie_hi ? a1 <= a0 : a1 < a0, f = tie_hi ? b1 <= b0 : b1 < b0;
 			nm[2 * j] = e ? a1 : a0;
 			nm[2 * j + 1] = f ? b1 : b0;
 			dec |= (e ? 1u : 0u) << (2 * j);
@@ -579,7 +579,7 @@ struct LaneVit {
 
 /* t3: packed type-3 bits (own copy, any memory), dec: N/2+2 words, out: packed type-2 bits */
 template <int N>
-__device__ inline void viterbi_lane(const uint32_t *t3, uint32_t *dec, uint32_t *out)
+__device__ inline void viterbi_lane(const uint32_t *t3, uint32_t *dec, uint32_t *out, bool tie_hi)
 {
 	LaneVit v;
 	v.init();
@@ -589,15 +589,15 @@ __device__ inline void viterbi_lane(const uint32_t *t3, uint32_t *dec, uint32_t 
 		const int r1 = r & 1, r2 = (r >> 1) & 1, r3 = (r >> 2) & 1;
 		/* even step: d = m(out) - m(~out) = 2*m(out) - 2 over (G1,G2) */
 		const int m00 = r1 + r2, m10 = (1 - r1) + r2, m01 = r1 + (1 - r2), m11 = 2 - m00;
-		uint32_t d0 = v.step(2 * m00 - 2, 2 * m10 - 2, 2 * m01 - 2, 2 * m11 - 2);
+		uint32_t d0 = v.step(2 * m00 - 2, 2 * m10 - 2, 2 * m01 - 2, 2 * m11 - 2, tie_hi);
 		/* odd step: only G1: d = 2*m - 1 */
 		const int n0 = r3, n1 = 1 - r3;
-		uint32_t d1 = v.step(2 * n0 - 1, 2 * n1 - 1, 2 * n0 - 1, 2 * n1 - 1);
+		uint32_t d1 = v.step(2 * n0 - 1, 2 * n1 - 1, 2 * n0 - 1, 2 * n1 - 1, tie_hi);
 		dec[q] = d0 | (d1 << 16);
 	}
 	for (int q = N / 2; q < N / 2 + 2; ++q) {
-		uint32_t d0 = v.step(0, 0, 0, 0);
-		uint32_t d1 = v.step(0, 0, 0, 0);
+		uint32_t d0 = v.step(0, 0, 0, 0, tie_hi);
+		uint32_t d1 = v.step(0, 0, 0, 0, tie_hi);
 		dec[q] = d0 | (d1 << 16);
 	}
 	unsigned st = 0;
@@ -684,6 +684,7 @@ struct RxGeom {
 	uint32_t chunk;            /* bits per modelled call (tetra-rx.c:83: 64) */
 	uint32_t n_slots;
 	int fmt;                   /* IN_BYTES / IN_PACKED / IN_F32SYM: how `bits` encodes the stream (base_bit % 128 == 0 unless bytes) */
+	int tie_hi;                /* Viterbi tie rule (include/tetra_tie_rule.h), used by the warp-form SB1 decode */
 };
 
 /* bits the search sees for slot k: bits_in_buf when the slot is processed
@@ -740,7 +741,7 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
 			if (lane < 4) S.bw[16 + lane] = 0;
 			__syncwarp();
 			gather_type3<0, PL_SB1>(S.bw, S.lf, S.t3[0], lane);
-			viterbi_warp<80>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
+			viterbi_warp<80>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0], g.tie_hi != 0);
 			const uint32_t crc = crc16_half(S.t2[0], 76, 0, tab);
 			good = (crc == 0x1d0f);
 			sb1_crc = crc;
@@ -936,6 +937,7 @@ struct DecodeArgs {
 	const uint32_t *kind_list;    /* [4][list_stride] their indices */
 	uint32_t list_stride;
 	uint32_t *crc;                /* optional: CRC-16 registers per slot, block A (SB1 / SCH-F / BLK1) | block B (SB2 / BLK2) << 16 */
+	int tie_hi;                   /* Viterbi tie rule (warp form; the lane kernels are templates) */
 };
 
 /* Pass 2 (warp-shuffle Viterbi form), one warp per slot: everything of tp_sap_udata_ind
@@ -974,7 +976,7 @@ k_decode_warp(DecodeArgs a)
 				S.bbk[0] = (extract_bits(S.bw, 252, 14) ^ S.lf[0]) & 0x3fff; S.bbk[1] = 0;
 			}
 			gather_type3<1, PL_BLK2>(S.bw, S.lf, S.t3[0], lane);
-			viterbi_warp<144>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
+			viterbi_warp<144>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0], a.tie_hi != 0);
 			const uint32_t crc = crc16_half(S.t2[0], 140, 1, tab);
 			if (crc == 0x1d0f) flags |= F_CRC_B;
 			crcs = (w.sb1_crc & 0xffffu) | (crc << 16);
@@ -988,7 +990,7 @@ k_decode_warp(DecodeArgs a)
 				S.bbk[0] = (extract_bits(S.bw, 230, 14) ^ S.lf[0]) & 0x3fff; S.bbk[1] = 0;
 			}
 			gather_type3<5, PL_SCHF>(S.bw, S.lf, S.t3[0], lane);
-			viterbi_warp<288>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0]);
+			viterbi_warp<288>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0], a.tie_hi != 0);
 			const uint32_t crc = crc16_half(S.t2[0], 284, 2, tab);
 			if (crc == 0x1d0f) flags |= F_CRC_A;
 			crcs = crc & 0xffffu;
@@ -1001,7 +1003,7 @@ k_decode_warp(DecodeArgs a)
 			}
 			gather_type3<1, PL_BLK1>(S.bw, S.lf, S.t3[0], lane);
 			gather_type3<1, PL_BLK2>(S.bw, S.lf, S.t3[1], lane);
-			viterbi_warp<144>(S.t3[0], S.t3[1], true, S.dec, S.t2[0], S.t2[1]);
+			viterbi_warp<144>(S.t3[0], S.t3[1], true, S.dec, S.t2[0], S.t2[1], a.tie_hi != 0);
 			const uint32_t crc = crc16_half(S.t2[lane >> 4], 140, 1, tab);
 			const uint32_t okA = __shfl_sync(FULL, crc == 0x1d0f, 0), okB = __shfl_sync(FULL, crc == 0x1d0f, 16);
 			if (okA) flags |= F_CRC_A;

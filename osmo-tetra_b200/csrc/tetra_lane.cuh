@@ -118,14 +118,22 @@ __device__ __forceinline__ uint32_t sub_opaque(uint32_t a, uint32_t b)
  * earlier (bit-reversed), and also the four decoded bits of the previous group.
  * M0[c] = 16 * mismatches of output class c (per half); the complementary branch has class c ^ 3.
  * Cost: one add + one VIADDMNMX.U16x2 per state and step for two trellises. */
+/* TIE_HI (include/tetra_tie_rule.h, the other tie rule): the tag goes on the candidate from s>>1 instead, ties
+ * then go to (s>>1)|8 and the history bits come out complemented (take_history* flips them back). */
+template <bool TIE_HI>
 __device__ __forceinline__ void acs2_step(uint32_t (&pm)[16], const uint32_t (&M0)[4], const uint32_t (&M1)[4])
 {
 	uint32_t nm[16];
 #pragma unroll
 	for (int s = 0; s < 16; ++s) {
 		const unsigned c = branch_class(s >> 1) ^ ((s & 1) ? 3u : 0u);
-		const uint32_t c1 = pm[(s >> 1) | 8] + M1[c ^ 3];
-		nm[s] = __viaddmin_u16x2(pm[s >> 1], M0[c], c1);
+		if (TIE_HI) {
+			const uint32_t c1 = pm[(s >> 1) | 8] + M0[c ^ 3];
+			nm[s] = __viaddmin_u16x2(pm[s >> 1], M1[c], c1);
+		} else {
+			const uint32_t c1 = pm[(s >> 1) | 8] + M1[c ^ 3];
+			nm[s] = __viaddmin_u16x2(pm[s >> 1], M0[c], c1);
+		}
 	}
 #pragma unroll
 	for (int s = 0; s < 16; ++s) pm[s] = nm[s];
@@ -134,6 +142,7 @@ __device__ __forceinline__ void acs2_step(uint32_t (&pm)[16], const uint32_t (&M
 /* After the fourth step of a group: strip the history nibbles off the 16 metrics and pack them.
  * The nibble of state s goes to position rev4(s), so that the trace back can index it with the
  * previous group's decoded nibble directly.  Result: x,y = trellis X positions 0-7, 8-15; z,w = Y. */
+template <bool TIE_HI>
 __device__ __forceinline__ uint4 take_history(uint32_t (&pm)[16])
 {
 	uint32_t W[4];
@@ -147,7 +156,7 @@ __device__ __forceinline__ uint4 take_history(uint32_t (&pm)[16])
 			pm[s] = sub_opaque(pm[s], h);
 			acc = i == 3 ? h : mad16_opaque(acc, h);
 		}
-		W[j] = acc;
+		W[j] = TIE_HI ? ~acc : acc;
 	}
 	return make_uint4(__byte_perm(W[0], W[1], 0x5410), __byte_perm(W[2], W[3], 0x5410),
 	                  __byte_perm(W[0], W[1], 0x7632), __byte_perm(W[2], W[3], 0x7632));
@@ -164,7 +173,7 @@ __device__ __forceinline__ uint32_t nibble64(uint32_t lo, uint32_t hi, uint32_t 
  * (columns of this thread).  nx, ny: type-2 lengths (0 = no block); nmax: warp-wide maximum so
  * the loop is uniform.  Leaves the decoded type-2 bits in the same columns.
  * dec: this thread's column of the history scratch, one uint4 per group of four steps. */
-template <bool MASKED>
+template <bool MASKED, bool TIE_HI>
 __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	uint32_t pm[16];
@@ -197,12 +206,12 @@ __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *
 			M0[3] = mad_k<-16>(t, two);         M1[3] = mad_k<-16>(t, two + te);
 			M0[2] = mad_k<16>(u, 0u);           M1[2] = mad_k<16>(u, te);
 			M0[1] = mad_k<-16>(u, two);         M1[1] = mad_k<-16>(u, two + te);
-			acs2_step(pm, M0, M1);
+			acs2_step<TIE_HI>(pm, M0, M1);
 			M0[0] = mad_k<16>(r3, 0u);          M1[0] = mad_k<16>(r3, to);   /* odd step: only G1 was sent */
 			M0[2] = mad_k<-16>(r3, one);        M1[2] = mad_k<-16>(r3, one + to);
 			M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
-			acs2_step(pm, M0, M1);
-			if (p & 1) dec[(2 * g + (p >> 1)) * nt] = take_history(pm);
+			acs2_step<TIE_HI>(pm, M0, M1);
+			if (p & 1) dec[(2 * g + (p >> 1)) * nt] = take_history<TIE_HI>(pm);
 		}
 	}
 	{
@@ -213,9 +222,9 @@ __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *
 		for (int q = 0; q < 4; ++q) {
 			const uint32_t tq = 0x00010001u << q;
 			const uint32_t Z1[4] = { tq, tq, tq, tq };
-			acs2_step(pm, Z0, Z1);
+			acs2_step<TIE_HI>(pm, Z0, Z1);
 		}
-		dec[(nmax >> 2) * nt] = take_history(pm);
+		dec[(nmax >> 2) * nt] = take_history<TIE_HI>(pm);
 	}
 	/* Trace back, one group (= one decoded nibble) per step.  f = decoded nibble of group g = bit-reversed
 	 * state after the group; the history nibble at position f of group g is the decoded nibble of group
@@ -263,6 +272,7 @@ __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *
 /* strip the history bytes; word i of the result holds positions 4i..4i+3 (position = rev4(state)).
  * One PRMT pulls the two history bytes (trellis X, trellis Y) of two states into one word, one AND per
  * state clears them. */
+template <bool TIE_HI>
 __device__ __forceinline__ void take_history8(uint32_t (&pm)[16], uint4 &hx, uint4 &hy)
 {
 	uint32_t W[8];          /* W[j]: positions 2j, 2j+1; low half = trellis X, high half = trellis Y */
@@ -270,6 +280,7 @@ __device__ __forceinline__ void take_history8(uint32_t (&pm)[16], uint4 &hx, uin
 	for (int j = 0; j < 8; ++j) {
 		const unsigned s1 = rev4(2 * j + 1), s0 = rev4(2 * j);
 		W[j] = __byte_perm(pm[s0], pm[s1], 0x6240);     /* s0.b0, s1.b0, s0.b2, s1.b2 */
+		if (TIE_HI) W[j] = ~W[j];
 		pm[s1] &= 0xff00ff00u;
 		pm[s0] &= 0xff00ff00u;
 	}
@@ -289,7 +300,7 @@ __device__ __forceinline__ uint32_t byte128(const uint4 &h, uint32_t f)
 
 /* two trellis steps (an even one with two received symbols, an odd one with one) of the eight-step form.
  * t, u, r3: mismatch counts per half, scaled so that count * K = 256 per mismatch; p = pair index in the group. */
-template <int K>
+template <int K, bool TIE_HI>
 __device__ __forceinline__ void step_pair_u8(uint32_t (&pm)[16], uint32_t t, uint32_t u, uint32_t r3, int p)
 {
 	const uint32_t te = 0x00010001u << (2 * p), to = 0x00020002u << (2 * p);
@@ -298,13 +309,14 @@ __device__ __forceinline__ void step_pair_u8(uint32_t (&pm)[16], uint32_t t, uin
 	M0[3] = mad_k<-K>(t, 0x02000200u);      M1[3] = mad_k<-K>(t, 0x02000200u + te);
 	M0[2] = mad_k<K>(u, 0u);                M1[2] = mad_k<K>(u, te);
 	M0[1] = mad_k<-K>(u, 0x02000200u);      M1[1] = mad_k<-K>(u, 0x02000200u + te);
-	acs2_step(pm, M0, M1);
+	acs2_step<TIE_HI>(pm, M0, M1);
 	M0[0] = mad_k<K>(r3, 0u);               M1[0] = mad_k<K>(r3, to);        /* odd step: only G1 was sent */
 	M0[2] = mad_k<-K>(r3, 0x01000100u);     M1[2] = mad_k<-K>(r3, 0x01000100u + to);
 	M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
-	acs2_step(pm, M0, M1);
+	acs2_step<TIE_HI>(pm, M0, M1);
 }
 
+template <bool TIE_HI>
 __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t *cy, int n)
 {
 	uint32_t pm[16];
@@ -326,11 +338,11 @@ __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t 
 			const uint32_t A = zz & 0x00090009u, B = (zz >> 1) & 0x00090009u, C3 = (zz >> 2) & 0x00090009u;
 			const uint32_t T = A + B;                         /* mismatches if 00 was sent: 0..2 per field */
 			const uint32_t U = (A ^ 0x00090009u) + B;         /* mismatches if G1=1, G2=0 was sent */
-			step_pair_u8<256>(pm, T & 0x00030003u, U & 0x00030003u, C3 & 0x00010001u, 2 * h);
-			step_pair_u8<32>(pm, T & 0x00180018u, U & 0x00180018u, C3 & 0x00080008u, 2 * h + 1);
+			step_pair_u8<256, TIE_HI>(pm, T & 0x00030003u, U & 0x00030003u, C3 & 0x00010001u, 2 * h);
+			step_pair_u8<32, TIE_HI>(pm, T & 0x00180018u, U & 0x00180018u, C3 & 0x00080008u, 2 * h + 1);
 		}
 		uint4 hx, hy;
-		take_history8(pm, hx, hy);
+		take_history8<TIE_HI>(pm, hx, hy);
 		dec[(2 * g) * nt] = hx;
 		dec[(2 * g + 1) * nt] = hy;
 		if ((g & 7) == 7) {            /* keep the metrics small: subtract the per-trellis minimum */
@@ -351,9 +363,9 @@ __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t 
 		for (int q = 0; q < 4; ++q) {
 			const uint32_t tq = 0x00010001u << q;
 			const uint32_t Z1[4] = { tq, tq, tq, tq };
-			acs2_step(pm, Z0, Z1);
+			acs2_step<TIE_HI>(pm, Z0, Z1);
 		}
-		hf = take_history(pm);
+		hf = take_history<TIE_HI>(pm);
 	}
 	/* Trace back.  The flush group gives the last four decoded bits (= index into the last eight-step
 	 * group); the byte at position f of group g holds decoded bits [8g-4, 8g+4), its low nibble is the index
@@ -383,12 +395,13 @@ __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t 
 	}
 }
 
+template <bool TIE_HI>
 __device__ __forceinline__ void viterbi_pair(uint4 *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	/* warp-uniform choice: no masking work when every lane carries two full-length blocks */
 	const bool uniform = __all_sync(FULL, nx == nmax && ny == nmax);
-	if (uniform) viterbi_pair_u8(dec, cx, cy, nmax);
-	else         viterbi_pair_t<true>(dec, cx, cy, nx, ny, nmax);
+	if (uniform) viterbi_pair_u8<TIE_HI>(dec, cx, cy, nmax);
+	else         viterbi_pair_t<true, TIE_HI>(dec, cx, cy, nx, ny, nmax);
 }
 
 /* CRC-16-CCITT of the first L type-2 bits of a column, reflected byte-table form of
@@ -552,6 +565,7 @@ __device__ __forceinline__ void load_slot_bits(const uint32_t *__restrict__ slot
 /* =============================================================== SB1 pass ==
  * SYNC bursts only: SB1 always uses scrambling code 3 (tetra_lower_mac.c:181-183), so it can be
  * decoded before the cell state is known.  Fills the SYNC-PDU part of SlotWs. */
+template <bool TIE_HI>
 __global__ void __launch_bounds__(32)
 k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
            const uint32_t *__restrict__ sb_list, const uint32_t *__restrict__ sb_count,
@@ -584,7 +598,7 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
 			}
 		}
 		if (!__ballot_sync(FULL, n[0] != 0)) continue;
-		viterbi_pair(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], 80);
+		viterbi_pair<TIE_HI>(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], 80);
 #pragma unroll
 		for (int h = 0; h < 2; ++h) {
 			if (n[h]) {
@@ -618,6 +632,7 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
  * one length: 288 steps for two SCH/F slots, 144 for the two halves BLK1 / BLK2 of ONE two-block slot or
  * for the SB2 blocks of two SYNC bursts; dropped slots only get their record.  Units are handed out
  * longest first.  Warps that straddle two lists run the masked form of the trellis loop. */
+template <bool TIE_HI>
 __global__ void __launch_bounds__(32, 16)
 k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 {
@@ -695,7 +710,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			const int o = __shfl_xor_sync(FULL, nmax, d);
 			nmax = o > nmax ? o : nmax;
 		}
-		if (nmax) viterbi_pair(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], nmax);
+		if (nmax) viterbi_pair<TIE_HI>(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], nmax);
 		uint32_t crcs[2] = { 0, 0 };            /* block A | block B << 16 of each slot */
 		if (kind[0] == KIND_NDB_2) {
 			const uint32_t ca = crc_col(sm, sm.t3col(0, tid), 140), cb = crc_col(sm, sm.t3col(1, tid), 140);

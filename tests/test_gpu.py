@@ -63,6 +63,27 @@ def test_stream_config2_shape(gpu, orc, variant, ber):
         assert rec["crc_ok"].mean() > 0.999
 
 
+@pytest.mark.parametrize("variant", [T.VITERBI_WARP, T.VITERBI_LANE])
+def test_other_tie_rule(gpu, orc, ref, variant):
+    """include/tetra_tie_rule.h: the switch flipped in kernels, oracle and the stand-in behind the reference build"""
+    try:
+        orc.set_tie(T.TIE_HIGH_PRED); ref.set_tie(T.TIE_HIGH_PRED)
+        for kw in (dict(n=6000, random_cell=1, ber_per_65536=2000),
+                   dict(n=6000, sb_period=64, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=0)):
+            bits, _ = _stream(orc, **kw)
+            slots, got = _check(gpu, orc, bits, viterbi=variant, pipeline_slots=0, viterbi_tie=T.TIE_HIGH_PRED)
+            ref.reset(); ref.feed(bits, 64)
+            T.check_stream_against(ref.records(), ref.events(), slots, got)
+            gpu.set_options(viterbi_tie=T.TIE_LOW_PRED)
+            _, t1_low, _ = gpu.rx_stream_host(bits)
+            gpu.set_options(viterbi_tie=T.TIE_HIGH_PRED)
+            _, t1_high, _ = gpu.rx_stream_host(bits)
+            assert not np.array_equal(t1_low, t1_high)
+    finally:
+        orc.set_tie(T.TIE_LOW_PRED); ref.set_tie(T.TIE_LOW_PRED)
+        gpu.set_options(viterbi_tie=T.TIE_LOW_PRED)
+
+
 def test_stream_config3_shape(gpu, orc):
     """mixed SB / NDB one- and two-channel bursts, lead-in, accidental training sequences left in"""
     bits, _ = _stream(orc, n=30000, random_cell=1)

@@ -327,3 +327,50 @@ def test_uplink_and_bbk_rows(ref, orc):
         ref.tp_sap(T.T_BBK, 0, bb); orc.tp_sap(T.T_BBK, 0, bb)
         ok, msg = T.records_equal(ref.records(), orc.records())
         assert ok, (i, msg)
+
+
+@pytest.mark.parametrize("tie", [T.TIE_LOW_PRED, T.TIE_HIGH_PRED])
+def test_viterbi_tie_switch(ref, orc, tie):
+    """include/tetra_tie_rule.h: the one switch moves the oracle port and both restatements of osmo_conv_decode
+    together (the reference wrapper runs on the acc-style stand-in); the two settings really differ on noisy blocks"""
+    rng = np.random.default_rng(99 + tie)
+    lib = ref.lib
+    differ = 0
+    try:
+        for n in (80, 144, 288):
+            K = n * 3 // 2
+            for _ in range(60):
+                t2 = np.zeros(n, np.uint8)
+                t2[:n - 4] = rng.integers(0, 2, n - 4)
+                t3 = orc.punct_2_3(orc.conv_encode(t2), K)
+                t3 ^= (rng.random(K) < 0.03).astype(np.uint8)
+                mother = orc.depunct_2_3(t3, 4 * n)
+                orc.set_tie(tie); ref.set_tie(tie)
+                a = orc.viterbi(mother, n)
+                b = ref.viterbi(mother, n)
+                soft = np.zeros(4 * (n + 4), np.int8)
+                soft[:4 * n] = np.where(mother == 0, 127, np.where(mother == 0xff, 0, -127))
+                c = np.zeros(n, np.uint8)
+                d = np.zeros(n, np.uint8)
+                lib.oracle_tetra_cch_decode(0, soft.ctypes.data_as(C.c_void_p), n, c.ctypes.data_as(C.c_void_p))
+                lib.oracle_tetra_cch_decode(1, soft.ctypes.data_as(C.c_void_p), n, d.ctypes.data_as(C.c_void_p))
+                assert np.array_equal(a, b) and np.array_equal(a, c) and np.array_equal(a, d), (tie, n)
+                orc.set_tie(1 - tie)
+                differ += int(not np.array_equal(a, orc.viterbi(mother, n)))
+    finally:
+        orc.set_tie(T.TIE_LOW_PRED); ref.set_tie(T.TIE_LOW_PRED)
+    assert differ > 20          # SURVEY 8(c): the rule changes 70 % of the blocks at 3 % BER
+
+
+def test_pin_conv_program_selfcheck(tmp_path):
+    """oracle/pin_conv.c (`make -C oracle pin-libosmocore`) compiles and, linked against the stand-in in the role of
+    the library, reports the compiled-in tie rule as matching and the other rule as differing"""
+    import subprocess
+    exe = str(tmp_path / "pin_self")
+    subprocess.check_call(["gcc", "-O2", "-I" + os.path.join(T.ORACLE_DIR, "stubs"), "-o", exe,
+                           os.path.join(T.ORACLE_DIR, "pin_conv.c"), os.path.join(T.ORACLE_DIR, "osmo_standin.c")])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "PINNED" in r.stdout and " on 0 (ties keep s>>1)" in r.stdout and "/ 0 (ties" not in r.stdout, r.stdout
+    r = subprocess.run(["make", "-s", "-C", T.ORACLE_DIR, "pin-libosmocore"], capture_output=True, text=True)
+    assert r.returncode == 0 and ("UNPINNED" in r.stdout or "PINNED" in r.stdout), r.stdout + r.stderr

@@ -109,6 +109,27 @@ def test_stream_mixed(emu, orc, variant):
     assert slots.size == 119
 
 
+@pytest.mark.parametrize("variant", [T.VITERBI_WARP, T.VITERBI_LANE])
+def test_stream_other_tie_rule(emu, orc, variant):
+    """include/tetra_tie_rule.h: with the switch flipped on both sides the kernels still equal the oracle (masked
+    four-step form, uniform eight-step form, SB1 pass and warp form all carry the rule)"""
+    try:
+        orc.set_tie(T.TIE_HIGH_PRED)
+        bits, _ = _stream(orc, n=100, random_cell=1, ber_per_65536=2000)
+        _check(emu, orc, bits, viterbi=variant, pipeline_slots=0, viterbi_tie=T.TIE_HIGH_PRED)
+        bits, _ = _stream(orc, n=140, sb_period=0, ndb2_per_256=0, ber_per_65536=2000, lead_in_bits=5)
+        slots = _check(emu, orc, bits, viterbi=variant, pipeline_slots=0, viterbi_tie=T.TIE_HIGH_PRED)
+        # and the rule matters on this input: the default setting gives other bits
+        emu.set_options(viterbi_tie=T.TIE_LOW_PRED)
+        s2, t1b, _ = emu.rx_stream_host(bits)
+        emu.set_options(viterbi_tie=T.TIE_HIGH_PRED)
+        s1, t1a, _ = emu.rx_stream_host(bits)
+        assert not np.array_equal(t1a, t1b)
+    finally:
+        orc.set_tie(T.TIE_LOW_PRED)
+        emu.set_options(viterbi_tie=T.TIE_LOW_PRED)
+
+
 def test_stream_uniform_schf(emu, orc):
     """only SCH/F bursts after the two leading SBs: whole warps of the lane kernel take the unmasked path"""
     bits, _ = _stream(orc, n=200, sb_period=0, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=5)

@@ -142,6 +142,10 @@ class Ref(_Recorder):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
         self.lib.ref_tp_sap(typ, blk_num, _ptr(bits), bits.size, 1)
 
+    def set_tie(self, tie):
+        """tie rule of the osmo_conv_decode stand-in the reference code is linked against (libosmocore is absent)"""
+        self.lib.oracle_conv_set_tie(int(tie))
+
     def find_train_seq(self, window, end, mask):
         """window must have >= end+21 readable bytes"""
         off = C.c_uint(0)
@@ -263,6 +267,10 @@ class Oracle(_Recorder):
     def set_cell(self, scramb_init):
         self.lib.orc_set_cell(C.c_uint32(scramb_init))
 
+    def set_tie(self, tie):
+        """Viterbi tie rule of the restatement (include/tetra_tie_rule.h); the default is the compile-time switch"""
+        self.lib.orc_set_tie(int(tie))
+
     def find_train_seq(self, window, end, mask):
         off = C.c_uint(0)
         w = np.ascontiguousarray(window, dtype=np.uint8)
@@ -379,6 +387,7 @@ RECORD_DTYPE, SLOT_DTYPE, GenCfg, Options, Timing, Carry, ShardSummary, Stats = 
     _B.RECORD_DTYPE, _B.SLOT_DTYPE, _B.GenCfg, _B.Options, _B.Timing, _B.Carry, _B.ShardSummary, _B.Stats)
 TB200_FRESH, TB200_FINAL, OUT_UNPACKED, OUT_PACKED = _B.TB200_FRESH, _B.TB200_FINAL, _B.OUT_UNPACKED, _B.OUT_PACKED
 IN_BYTES, IN_PACKED, IN_F32SYM, VITERBI_WARP, VITERBI_LANE = _B.IN_BYTES, _B.IN_PACKED, _B.IN_F32SYM, _B.VITERBI_WARP, _B.VITERBI_LANE
+TIE_LOW_PRED, TIE_HIGH_PRED = _B.TIE_LOW_PRED, _B.TIE_HIGH_PRED
 shard_plan, SHARD_HALO, DevBuffer, peer_pointer, sharded_decode, pack_bits = (
     _B.shard_plan, _B.SHARD_HALO, _B.DevBuffer, _B.peer_pointer, _B.sharded_decode, _B.pack_bits)
 
