@@ -74,7 +74,7 @@ struct tb200_rx_carry {
 	uint8_t  tn, fn, mn;       /* t_phy_state.time */
 };
 
-struct tb200_stats {
+struct tb200_stats {             /* since the last TB200_FRESH call, except kernel_launches */
 	uint64_t slots;            /* slots consumed while LOCKED */
 	uint64_t bursts_decoded;   /* slots handed to the lower MAC (kind != NONE) */
 	uint64_t blocks;           /* TMV-SAP primitives produced */

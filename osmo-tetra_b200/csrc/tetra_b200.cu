@@ -156,6 +156,8 @@ struct tb200_ctx {
 	uint32_t *d_flags = nullptr;     /* first unlocking slot per piece */
 	uint32_t *h_flags = nullptr;     /* pinned mirror */
 	size_t flags_cap = 0;
+	unsigned long long *d_pstats = nullptr;   /* [flags_cap][3] per-piece counters of the decode pass (tb200_stats) */
+	unsigned long long *h_pstats = nullptr;   /* pinned mirror */
 	/* host path staging */
 	uint8_t *d_in[NBUF] = {nullptr, nullptr, nullptr};
 	size_t in_cap = 0;
@@ -186,6 +188,10 @@ struct tb200_ctx {
 	/* sharded decode: what pass 1 left for pass 2 */
 	uint64_t shard_a0 = 0;
 	uint32_t shard_slots = 0;
+	/* grow-only device scratch of the leaf operators: no cudaMalloc / cudaFree per call, nothing to leak on an error path */
+	void *leaf_mem[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+	size_t leaf_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	cudaEvent_t leaf_ev[2] = {nullptr, nullptr};
 	/* profiling (options.profile) */
 	std::vector<cudaEvent_t> prof_ev;    /* 6 per piece: start, after classify, after scan, after decode, after carry, after the search kernel */
 	size_t prof_used = 0;
@@ -402,6 +408,10 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry); cudaFree(ctx->d_ws); cudaFree(ctx->d_slot_bits);
 	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev); cudaFree(ctx->d_sb_list); cudaFree(ctx->d_kind_list);
 	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch);
+	cudaFree(ctx->d_pstats); cudaFreeHost(ctx->h_pstats);
+	for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
+	for (int i = 0; i < 8; i++) cudaFree(ctx->leaf_mem[i]);
+	for (int i = 0; i < 2; i++) if (ctx->leaf_ev[i]) cudaEventDestroy(ctx->leaf_ev[i]);
 	for (int i = 0; i < NBUF; i++) {
 		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]); cudaFree(ctx->d_ocrc[i]);
 		cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]);
@@ -466,6 +476,9 @@ static int ensure_pieces(tb200_ctx *ctx, size_t npieces)
 		if ((rc = grow(ctx, &ctx->d_flags, cap))) return rc;
 		if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
 		CU(cudaHostAlloc((void **)&ctx->h_flags, cap * sizeof(uint32_t), cudaHostAllocDefault));
+		if ((rc = grow(ctx, &ctx->d_pstats, 3 * cap))) return rc;
+		if (ctx->h_pstats) cudaFreeHost(ctx->h_pstats);
+		CU(cudaHostAlloc((void **)&ctx->h_pstats, 3 * cap * sizeof(unsigned long long), cudaHostAllocDefault));
 		ctx->flags_cap = cap;
 	}
 	return 0;
@@ -620,44 +633,53 @@ static int scan_more_hits(tb200_ctx *ctx, const Source &src, uint64_t from, uint
 	const uint64_t first_bit = src.on_device ? src.new_base : ctx->tail_base;
 	while (ctx->hits_hi < upto && ctx->hits_hi < confirmable) {
 		const uint64_t lo = ctx->hits_hi;
-		const uint64_t hi = std::min<uint64_t>(lo + REGION_BITS, confirmable);
-		const uint8_t *dbits;
-		uint64_t dbase, davail;
-		if (src.on_device) {
-			dbits = src.data; dbase = src.new_base; davail = src.end - src.new_base;
-		} else {
-			const uint64_t rd_lo = (lo > first_bit) ? lo - 1 : lo;      /* one bit back for the blind-spot rule */
-			const uint64_t rd_hi = std::min<uint64_t>(hi + 64, src.end);
-			const size_t nb = (size_t)(rd_hi - rd_lo);
-			const size_t need = fmt_bytes(IN_F32SYM, (uint64_t)REGION_BITS + 512);
-			if (need > ctx->region_cap) {
-				CU(cudaDeviceSynchronize());
-				int rc = grow(ctx, &ctx->d_region, need);
+		uint64_t hi = std::min<uint64_t>(lo + REGION_BITS, confirmable);
+		uint32_t n = 0;
+		/* A region that holds more matches than the list (the SYNC sequence overlaps itself at shift 24: a
+		 * period-24 stream gives 10 923 hits per 2^18 bits) is scanned again at half the length; 8192 bits
+		 * can never overflow a list of 8192. */
+		for (;;) {
+			const uint8_t *dbits;
+			uint64_t dbase, davail;
+			if (src.on_device) {
+				dbits = src.data; dbase = src.new_base; davail = src.end - src.new_base;
+			} else {
+				const uint64_t rd_lo = (lo > first_bit) ? lo - 1 : lo;      /* one bit back for the blind-spot rule */
+				const uint64_t rd_hi = std::min<uint64_t>(hi + 64, src.end);
+				const size_t need = fmt_bytes(IN_F32SYM, (uint64_t)REGION_BITS + 512);
+				if (need > ctx->region_cap) {
+					CU(cudaDeviceSynchronize());
+					int rc = grow(ctx, &ctx->d_region, need);
+					if (rc) return rc;
+					ctx->region_cap = need;
+				}
+				int rc = stage_bits(ctx, src, rd_lo, rd_hi, ctx->d_region, ctx->s_compute, &dbase);
 				if (rc) return rc;
-				ctx->region_cap = need;
+				dbits = ctx->d_region; davail = rd_hi - dbase;
 			}
-			(void)nb;
-			int rc = stage_bits(ctx, src, rd_lo, rd_hi, ctx->d_region, ctx->s_compute, &dbase);
-			if (rc) return rc;
-			dbits = ctx->d_region; davail = rd_hi - dbase;
-		}
-		CU(cudaMemsetAsync(ctx->d_hits, 0, sizeof(uint32_t) * (2 + 2 * 64), ctx->s_compute));
-		const unsigned blocks = (unsigned)std::min<uint64_t>((hi - lo + 8191) / 8192, (uint64_t)ctx->sm_count * 4);
-		TB_LAUNCH(k_scan_sync, blocks, 256, ctx->s_compute, dbits, src.fmt, dbase, davail, lo, hi, ctx->d_tab, ctx->d_hits, HIT_CAP);
-		ctx->stats.kernel_launches++;
-		CU(cudaGetLastError());
-		/* the list is short (a SYNC sequence per 18-odd bursts): fetch the count and the first entries, the rest only if needed */
-		const uint32_t first = 64;
-		CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(uint32_t) * (2 + 2 * first), cudaMemcpyDeviceToHost, ctx->s_compute));
-		CU(cudaStreamSynchronize(ctx->s_compute));
-		TB_TRACE("sync-hit list on host");
-		const uint32_t n = ctx->h_hits[0];
-		if (n > HIT_CAP)
-			return fail(ctx, TB200_E_STATE, "SYNC hit list overflow (%u hits in %u bits)", n, REGION_BITS);
-		if (n > first) {
-			CU(cudaMemcpyAsync(ctx->h_hits + 2 + 2 * first, ctx->d_hits + 2 + 2 * first, sizeof(uint32_t) * 2 * (n - first),
-			                   cudaMemcpyDeviceToHost, ctx->s_compute));
+			CU(cudaMemsetAsync(ctx->d_hits, 0, sizeof(uint32_t) * (2 + 2 * 64), ctx->s_compute));
+			const unsigned blocks = (unsigned)std::min<uint64_t>((hi - lo + 8191) / 8192, (uint64_t)ctx->sm_count * 4);
+			TB_LAUNCH(k_scan_sync, blocks, 256, ctx->s_compute, dbits, src.fmt, dbase, davail, lo, hi, ctx->d_tab, ctx->d_hits, HIT_CAP);
+			ctx->stats.kernel_launches++;
+			CU(cudaGetLastError());
+			/* the list is short (a SYNC sequence per 18-odd bursts): fetch the count and the first entries, the rest only if needed */
+			const uint32_t first = 64;
+			CU(cudaMemcpyAsync(ctx->h_hits, ctx->d_hits, sizeof(uint32_t) * (2 + 2 * first), cudaMemcpyDeviceToHost, ctx->s_compute));
 			CU(cudaStreamSynchronize(ctx->s_compute));
+			TB_TRACE("sync-hit list on host");
+			n = ctx->h_hits[0];
+			if (n > HIT_CAP) {
+				if (hi - lo <= HIT_CAP)
+					return fail(ctx, TB200_E_STATE, "SYNC hit list overflow (%u hits in %llu bits)", n, (unsigned long long)(hi - lo));
+				hi = lo + std::max<uint64_t>((hi - lo) / 2, HIT_CAP);
+				continue;
+			}
+			if (n > first) {
+				CU(cudaMemcpyAsync(ctx->h_hits + 2 + 2 * first, ctx->d_hits + 2 + 2 * first, sizeof(uint32_t) * 2 * (n - first),
+				                   cudaMemcpyDeviceToHost, ctx->s_compute));
+				CU(cudaStreamSynchronize(ctx->s_compute));
+			}
+			break;
 		}
 		const size_t old = ctx->hits.size();
 		for (uint32_t i = 0; i < n; i++) {
@@ -799,6 +821,8 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	a.kind_count = ctx->d_kind_list + 4 * ctx->ws_slots; a.kind_list = ctx->d_kind_list; a.list_stride = (uint32_t)ctx->ws_slots;
 	a.crc = o_crc;
 	a.tie_hi = (int)ctx->opt.viterbi_tie;
+	a.stats = ctx->d_pstats + 3 * piece_idx;
+	CU(cudaMemsetAsync(a.stats, 0, 3 * sizeof(unsigned long long), st));
 	if (lane && ctx->opt.viterbi_tie) TB_LAUNCH_SMEM(k_decode_lane<true>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else if (lane)                    TB_LAUNCH_SMEM(k_decode_lane<false>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else                              TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
@@ -921,6 +945,7 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 				CU(cudaMemcpyAsync(out.crc + o0, oc, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		}
 		CU(cudaMemcpyAsync(ctx->h_flags + i, ctx->d_flags + i, sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
+		CU(cudaMemcpyAsync(ctx->h_pstats + 3 * i, ctx->d_pstats + 3 * i, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, so));
 		CU(cudaEventRecord(ctx->ev_d2h[b], so));
 		return 0;
 	};
@@ -972,6 +997,12 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 	}
 	ctx->h_carry = ctx->h_carry_pin[1];
 	out.n += *valid;
+	/* counters of the pieces that count (a piece enqueued behind the one that lost lock does not) */
+	for (size_t i = 0; i < npieces && i <= bad_piece; i++) {
+		ctx->stats.bursts_decoded += ctx->h_pstats[3 * i];
+		ctx->stats.blocks += ctx->h_pstats[3 * i + 1];
+		ctx->stats.crc_ok_blocks += ctx->h_pstats[3 * i + 2];
+	}
 	return 0;
 }
 
@@ -1147,8 +1178,7 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	if (flags & TB200_FRESH) reset_stream(ctx);
 	int rc = push_carry(ctx);
 	if (rc) return rc;
-	const uint64_t kernels_before = ctx->stats.kernel_launches;
-	(void)kernels_before;
+	ctx->stats.kernel_launches = 0;          /* "by the last call" */
 	Source src; src.on_device = false; src.data = bits; src.new_base = ctx->fed_end; src.end = ctx->fed_end + n_bits;
 	src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = false; out.slots = slots; out.type1 = type1; out.packed = type1_packed;
@@ -1406,6 +1436,27 @@ k_descramble_deinterleave(const uint8_t *__restrict__ type5, uint8_t *__restrict
 	}
 }
 
+template <typename T>
+static int leaf_buf(tb200_ctx *ctx, int i, size_t n, T **p)
+{
+	const size_t bytes = n * sizeof(T) + 64;
+	if (bytes > ctx->leaf_cap[i]) {
+		if (ctx->leaf_mem[i]) { CU(cudaDeviceSynchronize()); cudaFree(ctx->leaf_mem[i]); }
+		ctx->leaf_mem[i] = nullptr; ctx->leaf_cap[i] = 0;
+		CU(cudaMalloc(&ctx->leaf_mem[i], bytes + bytes / 4));
+		ctx->leaf_cap[i] = bytes + bytes / 4;
+	}
+	*p = reinterpret_cast<T *>(ctx->leaf_mem[i]);
+	return 0;
+}
+
+static int leaf_events(tb200_ctx *ctx)
+{
+	for (int i = 0; i < 2; i++)
+		if (!ctx->leaf_ev[i]) CU(cudaEventCreateWithFlags(&ctx->leaf_ev[i], 0));
+	return 0;
+}
+
 static int leaf_common(tb200_ctx *ctx)
 {
 	if (!ctx) return TB200_E_ARG;
@@ -1423,19 +1474,18 @@ extern "C" int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_
 	if (r) return r;
 	if (n == 0) return 0;
 	uint8_t *d_bits = nullptr; uint64_t *d_st = nullptr; uint32_t *d_len = nullptr, *d_off = nullptr; int32_t *d_rc = nullptr;
-	CU(cudaMalloc((void **)&d_bits, n_bits + 64));
-	CU(cudaMalloc((void **)&d_st, n * 8)); CU(cudaMalloc((void **)&d_len, n * 4));
-	CU(cudaMalloc((void **)&d_off, n * 4)); CU(cudaMalloc((void **)&d_rc, n * 4));
-	CU(cudaMemcpy(d_bits, bits, n_bits, cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(d_st, starts, n * 8, cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(d_len, lens, n * 4, cudaMemcpyHostToDevice));
+	if ((r = leaf_buf(ctx, 0, n_bits + 64, &d_bits)) || (r = leaf_buf(ctx, 1, n, &d_st)) || (r = leaf_buf(ctx, 2, n, &d_len)) ||
+	    (r = leaf_buf(ctx, 3, n, &d_off)) || (r = leaf_buf(ctx, 4, n, &d_rc))) return r;
+	cudaStream_t st = ctx->s_compute;
+	CU(cudaMemcpyAsync(d_bits, bits, n_bits, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(d_st, starts, n * 8, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(d_len, lens, n * 4, cudaMemcpyHostToDevice, st));
 	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, 4096);
-	TB_LAUNCH(k_leaf_find, blocks, 256, ctx->s_compute, d_bits, n_bits, d_st, d_len, n, mask, ctx->d_tab, d_rc, d_off);
+	TB_LAUNCH(k_leaf_find, blocks, 256, st, d_bits, n_bits, d_st, d_len, n, mask, ctx->d_tab, d_rc, d_off);
 	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(ctx->s_compute));
-	CU(cudaMemcpy(rc, d_rc, n * 4, cudaMemcpyDeviceToHost));
-	CU(cudaMemcpy(offset, d_off, n * 4, cudaMemcpyDeviceToHost));
-	cudaFree(d_bits); cudaFree(d_st); cudaFree(d_len); cudaFree(d_off); cudaFree(d_rc);
+	CU(cudaMemcpyAsync(rc, d_rc, n * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(offset, d_off, n * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
 	return 0;
 }
 
@@ -1455,17 +1505,17 @@ extern "C" int tb200_decode_blocks(tb200_ctx *ctx, int blk_type, const uint8_t *
 	}
 	if (n == 0) return 0;
 	uint8_t *d5 = nullptr, *d1 = nullptr, *dc = nullptr; uint32_t *dcode = nullptr;
-	CU(cudaMalloc((void **)&d5, n * K + 64)); CU(cudaMalloc((void **)&d1, n * T1)); CU(cudaMalloc((void **)&dc, n));
-	CU(cudaMalloc((void **)&dcode, n * 4));
-	CU(cudaMemcpy(d5, type5, n * K, cudaMemcpyHostToDevice));
-	CU(cudaMemcpy(dcode, codes, n * 4, cudaMemcpyHostToDevice));
+	if ((r = leaf_buf(ctx, 0, n * K + 64, &d5)) || (r = leaf_buf(ctx, 1, n * T1, &d1)) || (r = leaf_buf(ctx, 2, n, &dc)) ||
+	    (r = leaf_buf(ctx, 3, n, &dcode))) return r;
+	cudaStream_t st = ctx->s_compute;
+	CU(cudaMemcpyAsync(d5, type5, n * K, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(dcode, codes, n * 4, cudaMemcpyHostToDevice, st));
 	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, 4096);
-	TB_LAUNCH(k_leaf_decode, blocks, 256, ctx->s_compute, blk_type, d5, dcode, n, ctx->d_tab, d1, dc, (int)ctx->opt.viterbi, (int)ctx->opt.viterbi_tie);
+	TB_LAUNCH(k_leaf_decode, blocks, 256, st, blk_type, d5, dcode, n, ctx->d_tab, d1, dc, (int)ctx->opt.viterbi, (int)ctx->opt.viterbi_tie);
 	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(ctx->s_compute));
-	CU(cudaMemcpy(type1, d1, n * T1, cudaMemcpyDeviceToHost));
-	CU(cudaMemcpy(crc_ok, dc, n, cudaMemcpyDeviceToHost));
-	cudaFree(d5); cudaFree(d1); cudaFree(dc); cudaFree(dcode);
+	CU(cudaMemcpyAsync(type1, d1, n * T1, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(crc_ok, dc, n, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
 	return 0;
 }
 
@@ -1478,36 +1528,30 @@ extern "C" int tb200_descramble_deinterleave(tb200_ctx *ctx, const uint8_t *type
 	if (n == 0) return 0;
 	const uint8_t *d5 = type5; uint8_t *d3 = type3; const uint32_t *dcode = codes;
 	uint8_t *a5 = nullptr, *a3 = nullptr; uint32_t *ac = nullptr;
+	cudaStream_t st = ctx->s_compute;
 	if (!is_device) {
-		CU(cudaMalloc((void **)&a5, n * K + 64)); CU(cudaMalloc((void **)&a3, n * K)); CU(cudaMalloc((void **)&ac, n * 4));
-		CU(cudaMemcpy(a5, type5, n * K, cudaMemcpyHostToDevice));
-		CU(cudaMemcpy(ac, codes, n * 4, cudaMemcpyHostToDevice));
+		if ((r = leaf_buf(ctx, 0, n * K + 64, &a5)) || (r = leaf_buf(ctx, 1, n * K, &a3)) || (r = leaf_buf(ctx, 2, n, &ac))) return r;
+		CU(cudaMemcpyAsync(a5, type5, n * K, cudaMemcpyHostToDevice, st));
+		CU(cudaMemcpyAsync(ac, codes, n * 4, cudaMemcpyHostToDevice, st));
 		d5 = a5; d3 = a3; dcode = ac;
 	}
 	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)ctx->sm_count * 8);
-	cudaEvent_t e0 = nullptr, e1 = nullptr;
 	if (ctx->opt.profile) {
-		CU(cudaEventCreateWithFlags(&e0, 0)); CU(cudaEventCreateWithFlags(&e1, 0));
-		CU(cudaEventRecord(e0, ctx->s_compute));
+		if ((r = leaf_events(ctx))) return r;
+		CU(cudaEventRecord(ctx->leaf_ev[0], st));
 	}
 	if (K == ST_K && a == ST_A && (((uintptr_t)d5 | (uintptr_t)d3) & 15) == 0) {
 		const uint64_t groups = (n + 31) / 32;
 		const unsigned sb = (unsigned)std::min<uint64_t>((groups + ST_WARPS - 1) / ST_WARPS, (uint64_t)ctx->sm_count);
-		TB_LAUNCH_SMEM(k_stage_tma, sb, ST_WARPS * 32, ST_SMEM, ctx->s_compute, d5, d3, dcode, n, ctx->d_tab);
+		TB_LAUNCH_SMEM(k_stage_tma, sb, ST_WARPS * 32, ST_SMEM, st, d5, d3, dcode, n, ctx->d_tab);
 	} else {
-		TB_LAUNCH(k_descramble_deinterleave, blocks, 256, ctx->s_compute, d5, d3, dcode, n, K, a, ctx->d_tab);
+		TB_LAUNCH(k_descramble_deinterleave, blocks, 256, st, d5, d3, dcode, n, K, a, ctx->d_tab);
 	}
-	if (ctx->opt.profile) CU(cudaEventRecord(e1, ctx->s_compute));
+	if (ctx->opt.profile) CU(cudaEventRecord(ctx->leaf_ev[1], st));
 	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(ctx->s_compute));
-	if (ctx->opt.profile) {
-		CU(cudaEventElapsedTime(&ctx->timing.leaf_ms, e0, e1));
-		cudaEventDestroy(e0); cudaEventDestroy(e1);
-	}
-	if (!is_device) {
-		CU(cudaMemcpy(type3, a3, n * K, cudaMemcpyDeviceToHost));
-		cudaFree(a5); cudaFree(a3); cudaFree(ac);
-	}
+	if (!is_device) CU(cudaMemcpyAsync(type3, a3, n * K, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (ctx->opt.profile) CU(cudaEventElapsedTime(&ctx->timing.leaf_ms, ctx->leaf_ev[0], ctx->leaf_ev[1]));
 	return 0;
 }
 
@@ -1556,21 +1600,19 @@ extern "C" int tb200_rcpc_depunct(tb200_ctx *ctx, int puncturer, const uint8_t *
 	if (n == 0) return 0;
 	const uint8_t *d3 = type3; uint8_t *dm = mother;
 	uint8_t *a3 = nullptr, *am = nullptr;
+	cudaStream_t st = ctx->s_compute;
 	if (!is_device) {
-		CU(cudaMalloc((void **)&a3, n * len)); CU(cudaMalloc((void **)&am, n * mother_len));
-		CU(cudaMemcpy(a3, type3, n * len, cudaMemcpyHostToDevice));
+		if ((r = leaf_buf(ctx, 0, n * len, &a3)) || (r = leaf_buf(ctx, 1, n * mother_len, &am))) return r;
+		CU(cudaMemcpyAsync(a3, type3, n * len, cudaMemcpyHostToDevice, st));
 		d3 = a3; dm = am;
 	}
 	/* the caller of the reference function fills the mother buffer with 0xff first (tetra_lower_mac.c:249) */
-	CU(cudaMemsetAsync(dm, 0xff, n * mother_len, ctx->s_compute));
+	CU(cudaMemsetAsync(dm, 0xff, n * mother_len, st));
 	const unsigned blocks = (unsigned)std::min<uint64_t>((n * len + 255) / 256, (uint64_t)ctx->sm_count * 16);
-	TB_LAUNCH(k_rcpc_depunct, blocks, 256, ctx->s_compute, d3, len, n, dm, mother_len, k_punct_defs[puncturer]);
+	TB_LAUNCH(k_rcpc_depunct, blocks, 256, st, d3, len, n, dm, mother_len, k_punct_defs[puncturer]);
 	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(ctx->s_compute));
-	if (!is_device) {
-		CU(cudaMemcpy(mother, am, n * mother_len, cudaMemcpyDeviceToHost));
-		cudaFree(a3); cudaFree(am);
-	}
+	if (!is_device) CU(cudaMemcpyAsync(mother, am, n * mother_len, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
 	return 0;
 }
 
@@ -1794,6 +1836,12 @@ extern "C" long tb200_shard_pass2(tb200_ctx *ctx, const tb200_rx_carry *carry_in
 		if (rc) return rc;
 	}
 	CU(cudaMemcpyAsync(&ctx->h_carry, ctx->d_carry + (ctx->shard_slots ? 1 : 0), sizeof(DevCarry), cudaMemcpyDeviceToHost, ctx->s_compute));
+	if (ctx->shard_slots)
+		CU(cudaMemcpyAsync(ctx->h_pstats, ctx->d_pstats, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->s_compute));
 	CU(cudaStreamSynchronize(ctx->s_compute));
+	if (ctx->shard_slots) {
+		ctx->stats.slots += ctx->shard_slots;
+		ctx->stats.bursts_decoded += ctx->h_pstats[0]; ctx->stats.blocks += ctx->h_pstats[1]; ctx->stats.crc_ok_blocks += ctx->h_pstats[2];
+	}
 	return (long)ctx->shard_slots;
 }

@@ -278,6 +278,15 @@ __device__ __forceinline__ uint32_t slice_symbol(float fl)
 	return 1u;                         /* sym -1 -> bits 1,0 (also NaN, like the reference's comparisons) */
 }
 
+/* 32-bit word i of a bit-packed buffer of nbytes bytes (4-byte aligned base); bytes past the end read as zero */
+__device__ __forceinline__ uint32_t packed_word(const uint8_t *base, uint64_t i, uint64_t nbytes)
+{
+	if (4 * (i + 1) <= nbytes) return reinterpret_cast<const uint32_t *>(base)[i];
+	uint32_t v = 0;
+	for (uint64_t b = 4 * i; b < nbytes; ++b) v |= (uint32_t)base[b] << (8 * (b - 4 * i));
+	return v;
+}
+
 /* 32 stream bits [pos, pos+32) of a PACKED / F32SYM buffer that starts at stream bit 0 of `base`
  * and holds `avail` bits; bits at or beyond avail read as zero.  Any pos; base 4-byte aligned. */
 __device__ __forceinline__ uint32_t fetch32(const uint8_t *base, int fmt, uint64_t pos, uint64_t avail)
@@ -285,9 +294,10 @@ __device__ __forceinline__ uint32_t fetch32(const uint8_t *base, int fmt, uint64
 	if (pos >= avail) return 0;
 	uint32_t v;
 	if (fmt == IN_PACKED) {
-		const uint32_t *w = reinterpret_cast<const uint32_t *>(base);
-		const uint64_t i = pos >> 5, nw = (avail + 31) >> 5;
-		const uint32_t lo = w[i], hi = (i + 1 < nw) ? w[i + 1] : 0u;
+		/* the caller's buffer ends with the byte that holds bit avail-1: a word that reaches past it is put
+		 * together from its bytes (sub-allocated buffers, compute-sanitizer) */
+		const uint64_t i = pos >> 5, nbytes = (avail + 7) >> 3;
+		const uint32_t lo = packed_word(base, i, nbytes), hi = packed_word(base, i + 1, nbytes);
 		v = __funnelshift_r(lo, hi, (uint32_t)(pos & 31));
 	} else {
 		const float *f = reinterpret_cast<const float *>(base);
@@ -938,7 +948,32 @@ struct DecodeArgs {
 	uint32_t list_stride;
 	uint32_t *crc;                /* optional: CRC-16 registers per slot, block A (SB1 / SCH-F / BLK1) | block B (SB2 / BLK2) << 16 */
 	int tie_hi;                   /* Viterbi tie rule (warp form; the lane kernels are templates) */
+	unsigned long long *stats;    /* [3] counters of this piece: slots handed to the lower MAC, primitives, CRC-good blocks */
 };
+
+/* what a slot adds to the counters (tb200_stats): packed as bursts | primitives << 8 | CRC-good blocks << 16 */
+__device__ __forceinline__ uint32_t slot_counts(int kind, uint32_t flags)
+{
+	if (kind == KIND_NONE) return 0;
+	return 1u | ((kind == KIND_NDB_F ? 2u : 3u) << 8) | ((uint32_t)__popc(flags & (F_CRC_A | F_CRC_B)) << 16);
+}
+
+/* warp-wide sum of the packed per-lane counts (each field stays below 256: at most two slots per lane), one
+ * atomic per field and warp */
+__device__ __forceinline__ void add_counts(unsigned long long *stats, uint32_t v)
+{
+#ifdef TB_SIMT_EMULATION
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(FULL, v, d);
+#else
+	v = __reduce_add_sync(FULL, v);
+#endif
+	if ((threadIdx.x & 31) == 0 && v) {
+		atomicAdd(&stats[0], (unsigned long long)(v & 0xffu));
+		atomicAdd(&stats[1], (unsigned long long)((v >> 8) & 0xffu));
+		atomicAdd(&stats[2], (unsigned long long)(v >> 16));
+	}
+}
 
 /* Pass 2 (warp-shuffle Viterbi form), one warp per slot: everything of tp_sap_udata_ind
  * (tetra_lower_mac.c:143-357) that depends on the cell state: BBK, SB2, SCH/F, BLK1+BLK2. */
@@ -1026,6 +1061,7 @@ k_decode_warp(DecodeArgs a)
 			a.slots[ko] = o;
 			if (a.crc) a.crc[ko] = crcs;
 		}
+		if (a.stats) add_counts(a.stats, lane == 0 ? slot_counts(kind, flags) : 0u);
 		__syncwarp();
 	}
 }

@@ -778,6 +778,9 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			a.slots[ko] = o;
 			if (a.crc) a.crc[ko] = crcs[h] | (kind[h] == KIND_SB ? (w.sb1_crc & 0xffffu) : 0u);
 		}
+		if (a.stats)
+			add_counts(a.stats, (k[0] != ~0ull ? slot_counts(kind[0], flags[0]) : 0u) +
+			                    (k[1] != ~0ull && kind[0] != KIND_NDB_2 ? slot_counts(kind[1], flags[1]) : 0u));
 		__syncwarp();
 	}
 }

@@ -22,6 +22,9 @@ def _check(gpu, orc, bits, chunk=64, **opts):
     assert np.array_equal(unp[:, :282], t1[:, :282])
     c = gpu.carry()
     assert c.state == orc.rx_state() and c.scramb_init == orc.scramb_init()
+    st = gpu.stats()             # the counters of tb200_stats against the records
+    assert st.slots == slots.size and st.bursts_decoded == int(((slots["flags"] & 3) != 0).sum())
+    assert st.blocks == got.size and st.crc_ok_blocks == int(got["crc_ok"][got["lchan"] != T.LC_AACH].sum())
     return slots, got
 
 

@@ -97,6 +97,9 @@ def _check(emu, orc, bits, chunk=64, **opts):
     assert np.array_equal(unp[:, :282], t1[:, :282])
     c = emu.carry()
     assert c.state == orc.rx_state() and c.scramb_init == orc.scramb_init()
+    st = emu.stats()             # the counters of tb200_stats against the records
+    assert st.slots == slots.size and st.bursts_decoded == int(((slots["flags"] & 3) != 0).sum())
+    assert st.blocks == got.size and st.crc_ok_blocks == int(got["crc_ok"][got["lchan"] != T.LC_AACH].sum())
     if slots.size:
         assert (c.tn, c.fn, c.mn) == orc.get_time()
     return slots
@@ -155,6 +158,25 @@ def test_stream_lock_loss_and_pieces(emu, orc):
     _check(emu, orc, b3, viterbi=T.VITERBI_WARP, pipeline_slots=16)
     b4 = bits.copy(); b4[o(51) + 30:o(51) + 52] = B(SEQS[T.TS_NORM_2])
     _check(emu, orc, b4, viterbi=T.VITERBI_WARP, pipeline_slots=16)
+
+
+def test_stream_of_sync_patterns_degrades_like_the_reference(emu, orc, ref):
+    """the SYNC sequence overlaps itself at shift 24, so y[0:24] repeated gives ~10 900 SYNC matches per
+    2^18 bits - more than the UNLOCKED search's hit list.  The reference cycles lock / unlock and delivers nothing;
+    the library must do the same instead of failing the call."""
+    y = B(SEQS[T.TS_SYNC])
+    bits = np.tile(y[:24], 20000)
+    ref.reset(); ref.feed(bits, 64)
+    orc.reset(); orc.feed(bits, 64)
+    assert ref.records().size == orc.records().size
+    assert np.array_equal(ref.events(), orc.events())
+    emu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0)
+    slots, t1, _ = emu.rx_stream_host(bits)
+    got = emu.expand_records(slots, t1)
+    T.check_stream_against(ref.records(), ref.events(), slots, got)
+    c = emu.carry()
+    assert c.state == ref.rx_state()
+    assert emu.stats().lock_acquisitions == (ref.events()["mask"] == 0b1000).sum() - (ref.events()[ref.events()["mask"] == 0b1000]["rc"] < 0).sum()
 
 
 def test_stream_edge_inputs(emu, orc):
