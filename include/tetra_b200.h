@@ -316,8 +316,10 @@ struct tb200_shard_summary {
 /* lock acquisition on the head of the stream (UNLOCKED / KNOW_FSTART of tetra_burst_sync.c:67-106):
  * returns 1 and the absolute bit of the first LOCKED slot + the call that may process it, 0 if no lock */
 int  tb200_find_lock(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint64_t *a0, uint64_t *cmin);
-/* d_bits holds stream bits [base_bit, base_bit + n_bytes); the shard's slots start at absolute bit a0
- * (= lock a0 + 510 * first slot index), cmin = lock cmin + first slot index, n_end = stream length */
+/* d_bits holds stream bits [base_bit, base_bit + n_bytes) encoded as options.input says (n_bytes counts stream
+ * BITS; bit-packed shards start on a 128-bit boundary of the stream: base_bit % 128 == 0); the shard's slots
+ * start at absolute bit a0 (= lock a0 + 510 * first slot index), cmin = lock cmin + first slot index,
+ * n_end = stream length */
 int  tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t base_bit, uint64_t n_bytes,
                        uint64_t a0, uint64_t cmin, uint64_t n_end, uint32_t n_slots,
                        struct tb200_shard_summary *summary);
@@ -337,6 +339,78 @@ void  tb200_dev_free(tb200_ctx *ctx, void *p);
 int   tb200_ipc_export(tb200_ctx *ctx, const void *d_ptr, uint8_t handle[64]);
 int   tb200_ipc_import(tb200_ctx *ctx, const uint8_t handle[64], void **d_ptr);
 int   tb200_ipc_close(tb200_ctx *ctx, void *d_ptr);
+
+/* ---- one stream decoded by several GPUs: the driver (C, NCCL) ---------------------------------
+ * The calls above are the building blocks; this is the whole job, all ranks calling collectively (one process
+ * or thread per GPU): rank 0 holds the stream (device memory, encoded as options.input says), acquires lock
+ * (tetra_burst_sync.c:67-106), the slot range is cut into contiguous shards, every rank gets at its shard
+ * (TB200_DIST_SCATTER: one grouped ncclSend / ncclRecv from rank 0; TB200_DIST_PEER: nothing is copied, the search
+ * kernels read the shard out of rank 0's memory over NVLink - the stream must then live in tb200_dev_alloc memory),
+ * runs pass 1, the 32-byte summaries are all-gathered (the one exchange step of the path: the cell state of
+ * tetra_lower_mac.c:291-302), every rank derives its carry-in and runs pass 2.  A lock loss inside a shard
+ * (tetra_burst_sync.c:123-142) ends the segment right after the losing slot: the ranks behind it discard their
+ * speculative work, rank 0 runs the UNLOCKED search from there exactly like the single-GPU receiver, and the rest of
+ * the stream is sharded again as a new segment.  Results stay rank-local: `runs` says which global slot range
+ * (in the order a single receiver would deliver them) each local run of slots is.
+ *
+ * TB200_DIST_PACK: the stream on rank 0 is one bit per byte (TB200_IN_BYTES); rank 0 first packs it to eight
+ * bits per byte on the device (inside the call, it is part of the timed work), so that 8x fewer bytes travel.
+ *
+ * Plumbing: NCCL (libnccl.so.2, loaded at run time) - tb200_dist_create; or callbacks supplied by the caller
+ * (the CPU tests drive the same code with gloo) - tb200_dist_create_with_ops. */
+typedef struct tb200_dist tb200_dist;
+#define TB200_DIST_ID_BYTES 128                 /* ncclUniqueId */
+#define TB200_DIST_SCATTER  0u
+#define TB200_DIST_PEER     1u
+#define TB200_DIST_PACK     0x100u
+
+struct tb200_dist_ops {
+	void *user;
+	/* `bytes` of host memory from rank `root` to everyone */
+	int (*bcast)(void *user, void *host_buf, size_t bytes, int root);
+	/* bytes_each of host memory from every rank, concatenated in rank order, to everyone */
+	int (*allgather)(void *user, const void *host_send, void *host_recv, size_t bytes_each);
+	/* device memory: bytes [offsets[r], offsets[r] + sizes[r]) of dev_src on rank `root` to dev_dst on rank r */
+	int (*scatter)(void *user, const void *dev_src, const uint64_t *offsets, const uint64_t *sizes, void *dev_dst, int root);
+};
+
+struct tb200_dist_run {
+	uint64_t global_slot;      /* index of the run's first slot in single-receiver delivery order */
+	uint64_t local_slot;       /* where the run starts in this rank's output arrays */
+	uint64_t n_slots;
+};
+
+struct tb200_dist_timing {       /* wall-clock of this rank's last tb200_dist_rx_stream, milliseconds */
+	float total_ms, pack_ms, lock_ms, transfer_ms, pass1_ms, exchange_ms, pass2_ms;
+	uint64_t bytes_sent;       /* bytes this rank shipped to other ranks (scatter), or served to them (peer: what they pulled) */
+	uint32_t segments;         /* 1 + lock losses handled */
+	uint32_t pad;
+};
+
+int  tb200_dist_get_id(uint8_t id[TB200_DIST_ID_BYTES]);     /* rank 0; hand the id to the other ranks out of band */
+int  tb200_dist_create(tb200_dist **out, tb200_ctx *ctx, int rank, int world, const uint8_t id[TB200_DIST_ID_BYTES]);
+int  tb200_dist_create_with_ops(tb200_dist **out, tb200_ctx *ctx, int rank, int world, const struct tb200_dist_ops *ops);
+void tb200_dist_destroy(tb200_dist *d);
+const char *tb200_dist_last_error(const tb200_dist *d);
+/* d_bits / n_bits: the stream, rank 0 only (ignored elsewhere).  Outputs as for tb200_rx_stream_dev, rank-local;
+ * max_slots >= tb200_dist_max_local_slots(n_bits, world).  Returns the slots written on this rank or TB200_E_*. */
+long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint64_t n_bits, uint32_t mode,
+                          struct tb200_slot *d_slots, uint8_t *d_type1, uint32_t *d_type1_packed, uint64_t max_slots,
+                          struct tb200_dist_run *runs, uint32_t max_runs, uint32_t *n_runs);
+uint64_t tb200_dist_max_local_slots(uint64_t n_bits, int world);
+int  tb200_dist_get_timing(const tb200_dist *d, struct tb200_dist_timing *out);
+
+/* ---- helpers around the chain ------------------------------------------------------------------ */
+
+/* Order-independent 64-bit digest of n slot records + their packed type-1 words (may be NULL).  Slot i counts as
+ * global slot k_base + i, so the digests of the shards of a sharded run add up (mod 2^64) to the digest of a
+ * single-GPU run of the same stream: a whole-run parity check that moves 8 bytes.  Host or device pointers. */
+int tb200_slots_digest(tb200_ctx *ctx, const struct tb200_slot *slots, const uint32_t *type1_packed, uint64_t n,
+                       uint64_t k_base, int is_device, uint64_t *digest);
+
+/* TB200_IN_BYTES -> TB200_IN_PACKED on the device: n_bits bytes holding 0/1 (tetra-rx.c:82-95) to (n_bits+7)/8 bytes,
+ * stream bit i = byte i>>3 bit i&7.  d_packed: 4-byte aligned, room for 4 * ((n_bits + 31) / 32) bytes. */
+int tb200_pack_bits_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint8_t *d_packed);
 
 /* ---- introspection used by the tests ------------------------------------------------ */
 

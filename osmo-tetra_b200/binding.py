@@ -77,6 +77,28 @@ class ShardSummary(C.Structure):
 assert C.sizeof(ShardSummary) == 32
 
 
+class DistRun(C.Structure):
+    _fields_ = [("global_slot", C.c_uint64), ("local_slot", C.c_uint64), ("n_slots", C.c_uint64)]
+
+
+class DistTiming(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("total_ms", "pack_ms", "lock_ms", "transfer_ms", "pass1_ms", "exchange_ms", "pass2_ms")] + \
+               [("bytes_sent", C.c_uint64), ("segments", C.c_uint32), ("pad", C.c_uint32)]
+
+
+BCAST_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+SCATTER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p, C.c_int)
+
+
+class DistOps(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("bcast", BCAST_FN), ("allgather", ALLGATHER_FN), ("scatter", SCATTER_FN)]
+
+
+DIST_SCATTER, DIST_PEER, DIST_PACK = 0, 1, 0x100
+DIST_ID_BYTES = 128
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("slots", "bursts_decoded", "blocks", "crc_ok_blocks",
                                            "lock_losses", "lock_acquisitions", "kernel_launches")]
@@ -134,6 +156,21 @@ class B200:
             lib.tb200_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
         lib.tb200_shard_pass2.restype = C.c_long
         lib.tb200_shard_pass2.argtypes = [C.c_void_p, C.POINTER(Carry), C.c_void_p, C.c_void_p, C.c_void_p]
+        if hasattr(lib, "tb200_dist_create"):
+            lib.tb200_dist_get_id.argtypes = [C.c_void_p]
+            lib.tb200_dist_create.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+            lib.tb200_dist_create_with_ops.argtypes = [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.c_int, C.POINTER(DistOps)]
+            lib.tb200_dist_destroy.argtypes = [C.c_void_p]
+            lib.tb200_dist_last_error.restype = C.c_char_p
+            lib.tb200_dist_last_error.argtypes = [C.c_void_p]
+            lib.tb200_dist_rx_stream.restype = C.c_long
+            lib.tb200_dist_rx_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_uint64, C.POINTER(DistRun), C.c_uint32, C.POINTER(C.c_uint32)]
+            lib.tb200_dist_max_local_slots.restype = C.c_uint64
+            lib.tb200_dist_max_local_slots.argtypes = [C.c_uint64, C.c_int]
+            lib.tb200_dist_get_timing.argtypes = [C.c_void_p, C.POINTER(DistTiming)]
+            lib.tb200_slots_digest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]
+            lib.tb200_pack_bits_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
         lib.tb200_host_alloc.restype = C.c_void_p
         lib.tb200_host_alloc.argtypes = [C.c_size_t]
         lib.tb200_host_free.argtypes = [C.c_void_p]
@@ -246,6 +283,18 @@ class B200:
             raise RuntimeError(self.err())
         return n
 
+    def slots_digest(self, slots, packed, k_base=0, is_device=False, n=None):
+        """tb200_slots_digest: numpy arrays (host) or raw device pointers + n (is_device)"""
+        out = C.c_uint64(0)
+        if is_device:
+            r = self.lib.tb200_slots_digest(self.h, C.c_void_p(slots), C.c_void_p(packed) if packed else None, n, k_base, 1, C.byref(out))
+        else:
+            slots = np.ascontiguousarray(slots); packed = np.ascontiguousarray(packed, dtype=np.uint32)
+            r = self.lib.tb200_slots_digest(self.h, _ptr(slots), _ptr(packed), slots.size, k_base, 0, C.byref(out))
+        if r:
+            raise RuntimeError(self.err())
+        return out.value
+
     def find_train_seq(self, bits, starts, lens, mask):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
         starts = np.ascontiguousarray(starts, dtype=np.uint64); lens = np.ascontiguousarray(lens, dtype=np.uint32)
@@ -299,6 +348,77 @@ class B200:
         if got != need:
             raise RuntimeError(f"tb200_gsmtap_pack: {got} != {need}: {self.err()}")
         return frames[:need], off, nf.value
+
+
+def slots_digest_host(slots, packed, k_base=0):
+    """numpy twin of tb200_slots_digest (csrc/tetra_util.cuh: slot_digest), for checking the device digest"""
+    M = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        k = np.arange(slots.size, dtype=np.uint64) + np.uint64(k_base)
+        h = (k + np.uint64(1)) * np.uint64(0xD6E8FEB86659FD93)
+        h ^= h >> np.uint64(29)
+
+        def mix(h, w):
+            h = (h ^ w.astype(np.uint64)) * M
+            return h ^ (h >> np.uint64(32))
+        h = mix(h, slots["slot_bit"])
+        h = mix(h, slots["scrambling_code"])
+        h = mix(h, slots["find_off"].astype(np.uint32) | (slots["window"].astype(np.uint32) << np.uint32(16)))
+        h = mix(h, slots["time"].astype(np.uint32) | (slots["find_rc"].view(np.uint8).astype(np.uint32) << np.uint32(16)) |
+                (slots["flags"].astype(np.uint32) << np.uint32(24)))
+        for i in range(9):
+            h = mix(h, packed[:, i])
+        return int(h.sum(dtype=np.uint64))
+
+
+class Dist:
+    """tb200_dist_*: one stream decoded by `world` ranks.  nccl_id: 128 bytes from Dist.get_id() on rank 0 (handed to the
+    other ranks by the caller); or ops: a DistOps with the caller's own plumbing (the CPU tests use gloo)."""
+
+    def __init__(self, g, rank, world, nccl_id=None, ops=None):
+        self.g, self.rank, self.world = g, rank, world
+        self.h = C.c_void_p()
+        self._ops = ops
+        if ops is not None:
+            rc = g.lib.tb200_dist_create_with_ops(C.byref(self.h), g.h, rank, world, C.byref(ops))
+        else:
+            buf = (C.c_uint8 * DIST_ID_BYTES).from_buffer_copy(nccl_id)
+            rc = g.lib.tb200_dist_create(C.byref(self.h), g.h, rank, world, buf)
+        if rc:
+            raise RuntimeError(f"tb200_dist_create failed ({rc}): {g.err()}")
+
+    @staticmethod
+    def get_id(g):
+        buf = (C.c_uint8 * DIST_ID_BYTES)()
+        if g.lib.tb200_dist_get_id(buf):
+            raise RuntimeError("tb200_dist_get_id failed (libnccl.so.2 missing?)")
+        return bytes(buf)
+
+    def err(self):
+        return self.g.lib.tb200_dist_last_error(self.h).decode()
+
+    def max_local_slots(self, n_bits):
+        return int(self.g.lib.tb200_dist_max_local_slots(n_bits, self.world))
+
+    def rx_stream(self, bits_ptr, n_bits, mode, slots_ptr, type1_ptr, packed_ptr, max_slots, max_runs=64):
+        runs = (DistRun * max_runs)()
+        nr = C.c_uint32(0)
+        n = self.g.lib.tb200_dist_rx_stream(self.h, C.c_void_p(bits_ptr) if bits_ptr else None, n_bits, mode, C.c_void_p(slots_ptr),
+                                            C.c_void_p(type1_ptr) if type1_ptr else None, C.c_void_p(packed_ptr) if packed_ptr else None,
+                                            max_slots, runs, max_runs, C.byref(nr))
+        if n < 0:
+            raise RuntimeError(f"tb200_dist_rx_stream: {n}: {self.err()}")
+        return n, [(r.global_slot, r.local_slot, r.n_slots) for r in runs[:nr.value]]
+
+    def timing(self):
+        t = DistTiming()
+        self.g.lib.tb200_dist_get_timing(self.h, C.byref(t))
+        return t
+
+    def close(self):
+        if self.h:
+            self.g.lib.tb200_dist_destroy(self.h)
+            self.h = None
 
 
 # --------------------------------------------------------------------------- golden fixtures

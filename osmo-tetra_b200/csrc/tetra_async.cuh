@@ -14,6 +14,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *, unsigned) {}
 __device__ __forceinline__ void mbar_arrive(uint64_t *) {}
 __device__ __forceinline__ void mbar_wait(uint64_t *, unsigned) { __syncwarp(); }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *) { memcpy(dst, src, bytes); }
+__device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, unsigned bytes, uint64_t *) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
 {
 	for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
@@ -47,6 +48,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 {
 	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 	             :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+/* the same with an L2 evict-first hint: stream data that is read exactly once should not push the decode pass's
+ * survivor histories (written once, read once ~100 us later) out of L2 */
+__device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, unsigned bytes, uint64_t *bar)
+{
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+	             :: "r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c) { return __dp4a(a, b, c); }
 #endif

@@ -14,6 +14,7 @@
 #include "tetra_stage_tma.cuh"
 #include "tetra_gen.cuh"
 #include "tetra_gsmtap.cuh"
+#include "tetra_util.cuh"
 #include "../../include/tetra_b200.h"
 
 #include <algorithm>
@@ -144,14 +145,22 @@ struct tb200_ctx {
 	Tables *d_tab = nullptr;
 	DevCarry *d_carry = nullptr;     /* chain of carries, one per piece (+1) */
 	size_t carry_cap = 0;
-	/* per-launch workspace, shared by all pieces (the compute stream serialises them) */
-	SlotWs *d_ws = nullptr;
-	uint32_t *d_slot_bits = nullptr;
-	int32_t *d_last_good = nullptr, *d_blk_last = nullptr, *d_blk_prev = nullptr;
-	uint32_t *d_sb_list = nullptr;   /* slots classified as SYNC bursts; [ws_slots] + counter at the end */
-	uint32_t *d_kind_list = nullptr; /* [4][ws_slots] slots grouped by kind + [4] counters at the end (k_scan_blocks) */
+	/* per-piece workspace: what pass 1 (search, SB1, scans; stream s_front) leaves for pass 2 (decode; stream
+	 * s_compute).  Two sets, so that pass 1 of piece i+1 runs while pass 2 of piece i does: the search is HBM
+	 * bound, the decode pass integer-issue bound. */
+	struct WorkSet {
+		SlotWs *ws = nullptr;
+		uint32_t *slot_bits = nullptr;
+		int32_t *last_good = nullptr, *blk_last = nullptr, *blk_prev = nullptr;
+		uint32_t *sb_list = nullptr;     /* slots classified as SYNC bursts; [ws_slots] + counter at the end */
+		uint32_t *kind_list = nullptr;   /* [4][ws_slots] slots grouped by kind + [4] counters at the end (k_scan_blocks) */
+	} wset[2];
 	size_t ws_slots = 0;
-	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the lane kernels, one area per resident CTA */
+	cudaStream_t s_front = nullptr;
+	cudaEvent_t ev_front[2] = {nullptr, nullptr}, ev_back[2] = {nullptr, nullptr};   /* pass 1 / pass 2 of the set's last piece done */
+	bool back_pending[2] = {false, false};
+	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the decode pass, one area per resident CTA */
+	uint32_t *d_sb1_scratch = nullptr;    /* the same for the SB1 pass (it runs next to the decode pass of the previous piece) */
 	unsigned lane_ctas = 0;               /* resident CTAs of the lane kernels (grid size) */
 	uint32_t *d_flags = nullptr;     /* first unlocking slot per piece */
 	uint32_t *h_flags = nullptr;     /* pinned mirror */
@@ -193,7 +202,7 @@ struct tb200_ctx {
 	size_t leaf_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 	cudaEvent_t leaf_ev[2] = {nullptr, nullptr};
 	/* profiling (options.profile) */
-	std::vector<cudaEvent_t> prof_ev;    /* 6 per piece: start, after classify, after scan, after decode, after carry, after the search kernel */
+	std::vector<cudaEvent_t> prof_ev;    /* PE_COUNT per piece (enum PE_*) */
 	size_t prof_used = 0;
 	tb200_timing timing;
 };
@@ -345,6 +354,11 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 	if (cudaMalloc((void **)&ctx->d_tab, sizeof(Tables)) != cudaSuccess) return bail("cudaMalloc");
 	if (cudaMemcpy(ctx->d_tab, &ctx->h_tab, sizeof(Tables), cudaMemcpyHostToDevice) != cudaSuccess) return bail("cudaMemcpy");
 	if (cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+	if (cudaStreamCreateWithFlags(&ctx->s_front, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+	for (int i = 0; i < 2; i++) {
+		cudaEventCreateWithFlags(&ctx->ev_front[i], cudaEventDisableTiming);
+		cudaEventCreateWithFlags(&ctx->ev_back[i], cudaEventDisableTiming);
+	}
 	if (cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
 	if (cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
 	for (int i = 0; i < NBUF; i++) {
@@ -362,7 +376,8 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 		if (const char *e = getenv("TB200_LANE_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
 		ctx->lane_ctas = (unsigned)(ctx->sm_count * per_sm);
 		const size_t scratch_bytes = (size_t)ctx->lane_ctas * lane_scratch_words_per_cta(LANE_NT) * sizeof(uint32_t);
-		if (cudaMalloc((void **)&ctx->d_lane_scratch, scratch_bytes) != cudaSuccess)
+		if (cudaMalloc((void **)&ctx->d_lane_scratch, scratch_bytes) != cudaSuccess ||
+		    cudaMalloc((void **)&ctx->d_sb1_scratch, scratch_bytes) != cudaSuccess)
 			return bail("cudaMalloc");
 #ifndef TB_SIMT_EMULATION
 		/* Optional (TB200_L2_PERSIST=1): pin the survivor histories (written once, read once ~100 us later by the
@@ -405,9 +420,14 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry); cudaFree(ctx->d_ws); cudaFree(ctx->d_slot_bits);
-	cudaFree(ctx->d_last_good); cudaFree(ctx->d_blk_last); cudaFree(ctx->d_blk_prev); cudaFree(ctx->d_sb_list); cudaFree(ctx->d_kind_list);
-	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch);
+	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry);
+	for (int i = 0; i < 2; i++) {
+		tb200_ctx::WorkSet &w = ctx->wset[i];
+		cudaFree(w.ws); cudaFree(w.slot_bits); cudaFree(w.last_good); cudaFree(w.blk_last); cudaFree(w.blk_prev);
+		cudaFree(w.sb_list); cudaFree(w.kind_list);
+		cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_back[i]);
+	}
+	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch); cudaFree(ctx->d_sb1_scratch);
 	cudaFree(ctx->d_pstats); cudaFreeHost(ctx->h_pstats);
 	for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) cudaFree(ctx->leaf_mem[i]);
@@ -417,7 +437,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 		cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]);
 	}
 	cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_hits); cudaFreeHost(ctx->h_carry_pin); cudaFree(ctx->d_region);
-	cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
+	cudaStreamDestroy(ctx->s_compute); cudaStreamDestroy(ctx->s_front); cudaStreamDestroy(ctx->s_h2d); cudaStreamDestroy(ctx->s_d2h);
 	delete ctx;
 }
 
@@ -447,13 +467,17 @@ static int ensure_workspace(tb200_ctx *ctx, size_t slots)
 	if (slots <= ctx->ws_slots) return 0;
 	CU(cudaDeviceSynchronize());
 	int rc;
-	if ((rc = grow(ctx, &ctx->d_ws, slots))) return rc;
-	if ((rc = grow(ctx, &ctx->d_slot_bits, slots * 16))) return rc;
-	if ((rc = grow(ctx, &ctx->d_last_good, slots))) return rc;
-	if ((rc = grow(ctx, &ctx->d_blk_last, slots / 1024 + 2))) return rc;
-	if ((rc = grow(ctx, &ctx->d_blk_prev, slots / 1024 + 2))) return rc;
-	if ((rc = grow(ctx, &ctx->d_sb_list, slots + 4))) return rc;
-	if ((rc = grow(ctx, &ctx->d_kind_list, 4 * slots + 4))) return rc;
+	for (int i = 0; i < 2; i++) {
+		tb200_ctx::WorkSet &w = ctx->wset[i];
+		if ((rc = grow(ctx, &w.ws, slots))) return rc;
+		if ((rc = grow(ctx, &w.slot_bits, slots * 16))) return rc;
+		if ((rc = grow(ctx, &w.last_good, slots))) return rc;
+		if ((rc = grow(ctx, &w.blk_last, slots / 1024 + 2))) return rc;
+		if ((rc = grow(ctx, &w.blk_prev, slots / 1024 + 2))) return rc;
+		if ((rc = grow(ctx, &w.sb_list, slots + 4))) return rc;
+		if ((rc = grow(ctx, &w.kind_list, 4 * slots + 4))) return rc;
+	}
+	ctx->back_pending[0] = ctx->back_pending[1] = false;
 	ctx->ws_slots = slots;
 	return 0;
 }
@@ -473,9 +497,9 @@ static int ensure_pieces(tb200_ctx *ctx, size_t npieces)
 		CU(cudaDeviceSynchronize());
 		size_t cap = npieces + 64;
 		int rc;
-		if ((rc = grow(ctx, &ctx->d_flags, cap))) return rc;
+		if ((rc = grow(ctx, &ctx->d_flags, 2 * cap))) return rc;
 		if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
-		CU(cudaHostAlloc((void **)&ctx->h_flags, cap * sizeof(uint32_t), cudaHostAllocDefault));
+		CU(cudaHostAlloc((void **)&ctx->h_flags, 2 * cap * sizeof(uint32_t), cudaHostAllocDefault));
 		if ((rc = grow(ctx, &ctx->d_pstats, 3 * cap))) return rc;
 		if (ctx->h_pstats) cudaFreeHost(ctx->h_pstats);
 		CU(cudaHostAlloc((void **)&ctx->h_pstats, 3 * cap * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -531,6 +555,10 @@ struct Source {
 	uint64_t new_base;
 	uint64_t end;
 	int fmt;               /* IN_BYTES / IN_PACKED / IN_F32SYM; the packed formats start at stream bit 0 (no tail) */
+	/* device-resident data that is still arriving (sharded decode: chunks received or packed on other streams):
+	 * stream bits below ready[i].first are in place once event ready[i].second has fired; ascending */
+	const std::vector<std::pair<uint64_t, cudaEvent_t>> *ready = nullptr;
+	bool skip_dependent = false;     /* sharded decode, first pass (DecodeArgs::skip_dependent) */
 };
 
 /* bytes that hold `nbits` stream bits in format fmt */
@@ -743,68 +771,89 @@ static inline uint64_t slot_call(const Segment &s, uint64_t k)   /* call index t
 	return std::max(need, s.cmin + k);
 }
 
-/* pass 1 of a piece: classify (+ SB1) and the scan over "last CRC-good SB1"; needs no cell state */
-static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, cudaEvent_t *pe)
+/* events per piece when options.profile is on */
+enum { PE_START = 0, PE_SB1 = 1, PE_SCAN = 2, PE_DECODE_END = 3, PE_DECODE_START = 4, PE_SEARCH = 5, PE_COUNT = 6 };
+
+/* pass 1 of a piece on stream s_front: search + classification, SB1, the scan over "last CRC-good SB1" and - unless
+ * the cell state in front of the piece is not known yet (sharded decode) - the carry for the next piece: the state
+ * after a piece follows from pass 1 alone (tetra_lower_mac.c:291-302: only SB1 results change it), so the carry
+ * chain runs ahead of the decode pass. */
+static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, int set, cudaEvent_t *pe, bool with_carry, uint64_t k_base = 0)
 {
-	cudaStream_t st = ctx->s_compute;
+	static const bool serial = getenv("TB200_SERIAL") != nullptr;      /* A/B: pass 1 on the decode stream, nothing overlaps */
+	cudaStream_t st = serial ? ctx->s_compute : ctx->s_front;
+	tb200_ctx::WorkSet &w = ctx->wset[set];
 	const uint32_t nb = g.n_slots;
 	const unsigned wpb = 8;
 	const unsigned blocks = (unsigned)std::min<uint64_t>((nb + wpb - 1) / wpb, (uint64_t)ctx->sm_count * 16);
-	CU(cudaMemsetAsync(ctx->d_flags + piece_idx, 0xff, sizeof(uint32_t), st));
-	if (pe) CU(cudaEventRecord(pe[0], st));
+	if (ctx->back_pending[set]) CU(cudaStreamWaitEvent(st, ctx->ev_back[set], 0));     /* the set's previous piece has been decoded */
+	CU(cudaMemsetAsync(ctx->d_flags + 2 * piece_idx, 0xff, 2 * sizeof(uint32_t), st));      /* first lock loss, first CRC-good SB1 */
+	if (pe) CU(cudaEventRecord(pe[PE_START], st));
 	const bool lane = ctx->opt.viterbi == TB200_VITERBI_LANE;
 	const unsigned lane_nt = LANE_NT;
 	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
-	const uint64_t npairs = ((uint64_t)nb + 1) / 2;
-	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->lane_ctas);
 	if (lane) {
 		WinGeom wg;
 		wg.chunk = g.chunk; wg.rel0 = (uint32_t)(g.a0 % g.chunk); wg.c00 = g.a0 / g.chunk;
 		wg.cmin = g.cmin; wg.n_end = g.n_end; wg.a0 = g.a0;
-		uint32_t *sb_count = ctx->d_sb_list + ctx->ws_slots;
+		uint32_t *sb_count = w.sb_list + ctx->ws_slots;
 		CU(cudaMemsetAsync(sb_count, 0, sizeof(uint32_t), st));
 		const unsigned per_tile = g.fmt == IN_F32SYM ? TileFmt<IN_F32SYM>::SLOTS : CT_SLOTS;
 		const unsigned tiles = (nb + per_tile - 1) / per_tile;
-		const unsigned cls_blocks = std::min<unsigned>(tiles, (unsigned)ctx->sm_count * (g.fmt == IN_PACKED ? 8 : 3));
+		unsigned cls_per_sm = g.fmt == IN_PACKED ? 8 : 3;
+		if (const char *e = getenv("TB200_CLS_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v <= 8) cls_per_sm = (unsigned)v; }
+		const unsigned cls_blocks = std::min<unsigned>(tiles, (unsigned)ctx->sm_count * cls_per_sm);
 		if (g.fmt == IN_BYTES)
-			TB_LAUNCH_SMEM(k_classify_tile<IN_BYTES>, cls_blocks, CT_THREADS, ct_smem<IN_BYTES>(), st, g, wg, ctx->d_tab, ctx->d_ws,
-			               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
+			TB_LAUNCH_SMEM(k_classify_tile<IN_BYTES>, cls_blocks, CT_THREADS, ct_smem<IN_BYTES>(), st, g, wg, ctx->d_tab, w.ws,
+			               w.slot_bits, w.sb_list, sb_count);
 		else if (g.fmt == IN_PACKED)
-			TB_LAUNCH_SMEM(k_classify_tile<IN_PACKED>, cls_blocks, CT_THREADS, ct_smem<IN_PACKED>(), st, g, wg, ctx->d_tab, ctx->d_ws,
-			               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
+			TB_LAUNCH_SMEM(k_classify_tile<IN_PACKED>, cls_blocks, CT_THREADS, ct_smem<IN_PACKED>(), st, g, wg, ctx->d_tab, w.ws,
+			               w.slot_bits, w.sb_list, sb_count);
 		else
-			TB_LAUNCH_SMEM(k_classify_tile<IN_F32SYM>, cls_blocks, CT_THREADS, ct_smem<IN_F32SYM>(), st, g, wg, ctx->d_tab, ctx->d_ws,
-			               ctx->d_slot_bits, ctx->d_sb_list, sb_count);
-		if (pe) CU(cudaEventRecord(pe[5], st));
+			TB_LAUNCH_SMEM(k_classify_tile<IN_F32SYM>, cls_blocks, CT_THREADS, ct_smem<IN_F32SYM>(), st, g, wg, ctx->d_tab, w.ws,
+			               w.slot_bits, w.sb_list, sb_count);
+		if (pe) CU(cudaEventRecord(pe[PE_SEARCH], st));
+		/* at most one SYNC burst per slot, two per thread; the kernel reads the real count from sb_count */
+		const uint64_t npairs = ((uint64_t)nb + 1) / 2;
+		const unsigned sb1_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->lane_ctas);
 		if (ctx->opt.viterbi_tie)
-			TB_LAUNCH_SMEM(k_sb1_lane<true>, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
-			               ctx->d_tab, ctx->d_lane_scratch);
+			TB_LAUNCH_SMEM(k_sb1_lane<true>, sb1_blocks, lane_nt, lane_smem, st, w.ws, w.slot_bits, w.sb_list, sb_count,
+			               ctx->d_tab, ctx->d_sb1_scratch);
 		else
-			TB_LAUNCH_SMEM(k_sb1_lane<false>, lane_blocks, lane_nt, lane_smem, st, ctx->d_ws, ctx->d_slot_bits, ctx->d_sb_list, sb_count,
-			               ctx->d_tab, ctx->d_lane_scratch);
+			TB_LAUNCH_SMEM(k_sb1_lane<false>, sb1_blocks, lane_nt, lane_smem, st, w.ws, w.slot_bits, w.sb_list, sb_count,
+			               ctx->d_tab, ctx->d_sb1_scratch);
 		ctx->stats.kernel_launches++;
 	} else {
-		TB_LAUNCH(k_classify<true>, blocks, 256, st, g, ctx->d_tab, ctx->d_ws, ctx->d_slot_bits);
-		if (pe) CU(cudaEventRecord(pe[5], st));
+		TB_LAUNCH(k_classify<true>, blocks, 256, st, g, ctx->d_tab, w.ws, w.slot_bits);
+		if (pe) CU(cudaEventRecord(pe[PE_SEARCH], st));
 	}
-	if (pe) CU(cudaEventRecord(pe[1], st));
+	if (pe) CU(cudaEventRecord(pe[PE_SB1], st));
 	const unsigned nblk = (nb + 1023) / 1024;
-	uint32_t *kind_count = ctx->d_kind_list + 4 * ctx->ws_slots;
+	uint32_t *kind_count = w.kind_list + 4 * ctx->ws_slots;
 	CU(cudaMemsetAsync(kind_count, 0, 4 * sizeof(uint32_t), st));
-	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, ctx->d_ws, nb, ctx->d_last_good, ctx->d_blk_last, ctx->d_flags + piece_idx,
-	          kind_count, ctx->d_kind_list, (uint32_t)ctx->ws_slots);
-	TB_LAUNCH(k_scan_prefix, 1, 1024, st, ctx->d_blk_last, nblk, ctx->d_blk_prev);
-	if (pe) CU(cudaEventRecord(pe[2], st));
+	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, w.ws, nb, w.last_good, w.blk_last, ctx->d_flags + 2 * piece_idx, ctx->d_flags + 2 * piece_idx + 1,
+	          kind_count, w.kind_list, (uint32_t)ctx->ws_slots);
+	TB_LAUNCH(k_scan_prefix, 1, 1024, st, w.blk_last, nblk, w.blk_prev);
 	ctx->stats.kernel_launches += 3;
+	if (with_carry) {
+		CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
+		TB_LAUNCH(k_finalize_carry, 1, 32, st, w.ws, w.last_good, w.blk_prev, nb, ctx->d_carry + piece_idx + 1,
+		          ctx->d_flags + 2 * piece_idx + 1, k_base);
+		ctx->stats.kernel_launches++;
+	}
+	if (pe) CU(cudaEventRecord(pe[PE_SCAN], st));
+	CU(cudaEventRecord(ctx->ev_front[set], st));
 	CU(cudaGetLastError());
 	return 0;
 }
 
-/* pass 2 of a piece: everything that needs the cell state carried in d_carry[piece_idx] */
-static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_idx, cudaEvent_t *pe,
-                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc = nullptr)
+/* pass 2 of a piece on stream s_compute: everything that needs the cell state carried in d_carry[piece_idx] */
+static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_idx, int set, cudaEvent_t *pe, bool with_carry,
+                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc = nullptr,
+                         bool skip_dependent = false)
 {
 	cudaStream_t st = ctx->s_compute;
+	tb200_ctx::WorkSet &w = ctx->wset[set];
 	const bool lane = ctx->opt.viterbi == TB200_VITERBI_LANE;
 	const unsigned lane_nt = LANE_NT;
 	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
@@ -812,33 +861,42 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->lane_ctas);
 	const unsigned blocks = (unsigned)std::min<uint64_t>((nb + 7) / 8, (uint64_t)ctx->sm_count * 16);
 	DecodeArgs a;
-	a.ws = ctx->d_ws; a.slot_bits = ctx->d_slot_bits; a.last_good = ctx->d_last_good; a.blk_prev = ctx->d_blk_prev;
+	a.ws = w.ws; a.slot_bits = w.slot_bits; a.last_good = w.last_good; a.blk_prev = w.blk_prev;
 	a.carry = ctx->d_carry + piece_idx; a.tab = ctx->d_tab;
 	a.slots = o_slots;
 	a.type1 = (ctx->opt.output & TB200_OUT_UNPACKED) ? o_type1 : nullptr;
 	a.type1_packed = (ctx->opt.output & TB200_OUT_PACKED) ? o_packed : nullptr;
 	a.a0 = a0; a.out_base = out_base; a.n_slots = nb;
-	a.kind_count = ctx->d_kind_list + 4 * ctx->ws_slots; a.kind_list = ctx->d_kind_list; a.list_stride = (uint32_t)ctx->ws_slots;
+	a.kind_count = w.kind_list + 4 * ctx->ws_slots; a.kind_list = w.kind_list; a.list_stride = (uint32_t)ctx->ws_slots;
 	a.crc = o_crc;
 	a.tie_hi = (int)ctx->opt.viterbi_tie;
 	a.stats = ctx->d_pstats + 3 * piece_idx;
+	a.skip_dependent = skip_dependent ? 1 : 0;
+	CU(cudaStreamWaitEvent(st, ctx->ev_front[set], 0));
 	CU(cudaMemsetAsync(a.stats, 0, 3 * sizeof(unsigned long long), st));
+	if (pe) CU(cudaEventRecord(pe[PE_DECODE_START], st));
 	if (lane && ctx->opt.viterbi_tie) TB_LAUNCH_SMEM(k_decode_lane<true>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else if (lane)                    TB_LAUNCH_SMEM(k_decode_lane<false>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
 	else                              TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
-	if (pe) CU(cudaEventRecord(pe[3], st));
-	CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
-	TB_LAUNCH(k_finalize_carry, 1, 32, st, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, nb, ctx->d_carry + piece_idx + 1);
-	if (pe) CU(cudaEventRecord(pe[4], st));
-	ctx->stats.kernel_launches += 2;
+	ctx->stats.kernel_launches++;
+	if (pe) CU(cudaEventRecord(pe[PE_DECODE_END], st));
+	if (!with_carry) {
+		CU(cudaMemcpyAsync(ctx->d_carry + piece_idx + 1, ctx->d_carry + piece_idx, sizeof(DevCarry), cudaMemcpyDeviceToDevice, st));
+		TB_LAUNCH(k_finalize_carry, 1, 32, st, w.ws, w.last_good, w.blk_prev, nb, ctx->d_carry + piece_idx + 1,
+		          ctx->d_flags + 2 * piece_idx + 1, (uint64_t)0);
+		ctx->stats.kernel_launches++;
+	}
+	CU(cudaEventRecord(ctx->ev_back[set], st));
+	ctx->back_pending[set] = true;
 	CU(cudaGetLastError());
 	return 0;
 }
 
-/* enqueue classify + scan + decode + carry for slots [k0, k0+nb) of the segment */
+/* enqueue classify + scan + carry (s_front) and decode (s_compute) for slots [k0, k0+nb) of the segment */
 static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32_t nb, const uint8_t *d_bits,
                          uint64_t d_base, uint64_t d_avail, int fmt, size_t piece_idx,
-                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc)
+                         SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc,
+                         bool skip_dependent)
 {
 	RxGeom g;
 	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base; g.fmt = fmt;
@@ -846,19 +904,20 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	g.chunk = seg.chunk; g.n_slots = nb; g.tie_hi = (int)ctx->opt.viterbi_tie;
 	cudaEvent_t *pe = nullptr;
 	if (ctx->opt.profile) {
-		while (ctx->prof_ev.size() < ctx->prof_used + 6) {
+		while (ctx->prof_ev.size() < ctx->prof_used + PE_COUNT) {
 			cudaEvent_t e;
 			CU(cudaEventCreateWithFlags(&e, 0));
 			ctx->prof_ev.push_back(e);
 		}
 		pe = &ctx->prof_ev[ctx->prof_used];
-		ctx->prof_used += 6;
+		ctx->prof_used += PE_COUNT;
 		ctx->timing.pieces++;
 		ctx->timing.slots += nb;
 	}
-	int rc = enqueue_pass1(ctx, g, piece_idx, pe);
+	const int set = (int)(piece_idx & 1);
+	int rc = enqueue_pass1(ctx, g, piece_idx, set, pe, true, k0);
 	if (rc) return rc;
-	return enqueue_pass2(ctx, g.a0, nb, piece_idx, pe, o_slots, o_type1, o_packed, out_base, o_crc);
+	return enqueue_pass2(ctx, g.a0, nb, piece_idx, set, pe, true, o_slots, o_type1, o_packed, out_base, o_crc, skip_dependent);
 }
 
 /* Process slots [0, n_slots) of a LOCKED segment, optimistically assuming lock is kept;
@@ -872,11 +931,17 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 	if (out.n + n_slots > out.max_slots)
 		return fail(ctx, TB200_E_ARG, "output arrays too small: need %llu slots, have %llu",
 		            (unsigned long long)(out.n + n_slots), (unsigned long long)out.max_slots);
-	/* slots per piece: device-resident input 2^20; host input 2^17 with a ramp (below), bit-packed host input 2^18
-	 * without one: its copies are 8x smaller, so the per-piece launch and synchronisation cost weighs more (measured:
-	 * 10^6 bursts packed in and out 2.36 -> 2.00 ms) */
+	/* slots per piece.  Device-resident input 2^21: pass 1 of piece i+1 (stream s_front) fills the SMs that the last
+	 * round of piece i's decode pass (stream s_compute) leaves idle; the two passes do not share an SM well (the
+	 * decode grid holds every register, and the search pushes the survivor histories out of L2), so smaller pieces
+	 * only add round-quantisation loss (measured at 8*10^6 SCH/F bursts: 303 104 slots 1.50, 2^20 1.69, 2^21 1.74 *10^9
+	 * bursts/s; everything on one stream 1.64).  Host input 2^17 with a ramp (below), bit-packed host input 2^18 without
+	 * one: its copies are 8x smaller, so the per-piece launch and synchronisation cost weighs more (measured: 10^6 bursts
+	 * packed in and out 2.36 -> 2.00 ms) */
 	const bool packed_host = !src.on_device && src.fmt == IN_PACKED;
-	uint32_t P = ctx->opt.pipeline_slots ? ctx->opt.pipeline_slots : (src.on_device ? (1u << 20) : packed_host ? (1u << 18) : (1u << 17));
+	uint32_t dev_piece = 1u << 21;
+	if (const char *e = getenv("TB200_PIECE_SLOTS")) { const long v = atol(e); if (v >= 1024 && v <= (1 << 24)) dev_piece = (uint32_t)v; }
+	uint32_t P = ctx->opt.pipeline_slots ? ctx->opt.pipeline_slots : (src.on_device ? dev_piece : packed_host ? (1u << 18) : (1u << 17));
 	if (P > n_slots) P = (uint32_t)n_slots;
 	/* piece boundaries; the host path ramps the first pieces up (P/16, P/8, ...) so that the first
 	 * copy is short and compute / copy-back start early */
@@ -915,12 +980,16 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		const uint64_t hi = std::min<uint64_t>(seg.n_end, lo + (uint64_t)SLOT_BITS * nb + 4096);
 		const uint8_t *dbits; uint64_t dbase, davail;
 		if (src.on_device) {
-			dbits = src.data; dbase = src.new_base; davail = seg.n_end - src.new_base;
+			dbits = src.data; dbase = src.new_base; davail = std::min<uint64_t>(seg.n_end, src.end) - src.new_base;
+			if (src.ready) {
+				for (const auto &rv : *src.ready)
+					if (rv.first >= hi || &rv == &src.ready->back()) { CU(cudaStreamWaitEvent(ctx->s_front, rv.second, 0)); break; }
+			}
 		} else {
 			int r = stage_bits(ctx, src, lo, hi, ctx->d_in[b], ctx->s_h2d, &dbase);
 			if (r) return r;
 			CU(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
-			CU(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_h2d[b], 0));
+			CU(cudaStreamWaitEvent(ctx->s_front, ctx->ev_h2d[b], 0));
 			dbits = ctx->d_in[b]; davail = hi - dbase;
 		}
 		SlotOut *os; uint8_t *ot; uint32_t *op; uint64_t ob; uint32_t *oc;
@@ -929,7 +998,7 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		} else {
 			os = ctx->d_oslots[b]; ot = ctx->d_otype1[b]; op = ctx->d_opacked[b]; ob = 0; oc = out.crc ? ctx->d_ocrc[b] : nullptr;
 		}
-		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob, oc);
+		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob, oc, src.skip_dependent);
 		if (r) return r;
 		CU(cudaEventRecord(ctx->ev_comp[b], ctx->s_compute));
 		cudaStream_t so = host_out ? ctx->s_d2h : ctx->s_compute;
@@ -944,7 +1013,7 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 			if (out.crc)
 				CU(cudaMemcpyAsync(out.crc + o0, oc, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		}
-		CU(cudaMemcpyAsync(ctx->h_flags + i, ctx->d_flags + i, sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
+		CU(cudaMemcpyAsync(ctx->h_flags + 2 * i, ctx->d_flags + 2 * i, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		CU(cudaMemcpyAsync(ctx->h_pstats + 3 * i, ctx->d_pstats + 3 * i, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, so));
 		CU(cudaEventRecord(ctx->ev_d2h[b], so));
 		return 0;
@@ -956,12 +1025,14 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		if ((rc = issue(i, 0))) return rc;
 		if (i >= 1) {
 			CU(cudaEventSynchronize(ctx->ev_d2h[(i - 1) % NBUF]));
-			if (ctx->h_flags[i - 1] != 0xffffffffu) { bad_piece = i - 1; break; }
+			if (ctx->h_flags[2 * (i - 1)] != 0xffffffffu) { bad_piece = i - 1; break; }
 		}
 	}
 	/* the state after the last valid slot becomes the start of the chain again: optimistically from the last
 	 * piece, enqueued behind its kernels so that it costs no extra round trip */
 	auto carry_over = [&](size_t last) -> int {
+		/* on s_compute: behind the decode pass of the last piece, which still reads the head of the chain when the
+		 * call has a single piece (and which waited for the front stream, where the chain is written) */
 		CU(cudaMemcpyAsync(&ctx->h_carry_pin[1], ctx->d_carry + last + 1, sizeof(DevCarry), cudaMemcpyDeviceToHost, ctx->s_compute));
 		CU(cudaMemcpyAsync(ctx->d_carry, ctx->d_carry + last + 1, sizeof(DevCarry), cudaMemcpyDeviceToDevice, ctx->s_compute));
 		return 0;
@@ -969,25 +1040,27 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 	if (bad_piece == npieces && (rc = carry_over(npieces - 1))) return rc;
 	TB_TRACE("pieces enqueued");
 	CU(cudaStreamSynchronize(ctx->s_h2d));
+	CU(cudaStreamSynchronize(ctx->s_front));
 	CU(cudaStreamSynchronize(ctx->s_compute));
 	CU(cudaStreamSynchronize(ctx->s_d2h));
 	TB_TRACE("pieces done");
-	if (bad_piece == npieces && ctx->h_flags[npieces - 1] != 0xffffffffu) bad_piece = npieces - 1;
+	if (bad_piece == npieces && ctx->h_flags[2 * (npieces - 1)] != 0xffffffffu) bad_piece = npieces - 1;
 
 	if (bad_piece < npieces) {
 		/* redo the piece that lost lock, cut right after the losing slot, so that outputs and
 		 * the carried cell state stop exactly where the reference's LOCKED state stops */
-		const uint32_t u = ctx->h_flags[bad_piece];
+		const uint32_t u = ctx->h_flags[2 * bad_piece];
 		uint64_t k0; uint32_t nb;
 		piece_range(bad_piece, &k0, &nb);
 		if (bad_piece == 0) {
 			/* the chain start was overwritten by the optimistic carry-over: put it back */
 			ctx->h_carry_pin[0] = ctx->h_carry;
-			CU(cudaMemcpyAsync(ctx->d_carry, &ctx->h_carry_pin[0], sizeof(DevCarry), cudaMemcpyHostToDevice, ctx->s_compute));
+			CU(cudaMemcpyAsync(ctx->d_carry, &ctx->h_carry_pin[0], sizeof(DevCarry), cudaMemcpyHostToDevice, ctx->s_front));
 		}
 		if ((rc = issue(bad_piece, u + 1))) return rc;
 		if ((rc = carry_over(bad_piece))) return rc;
 		CU(cudaStreamSynchronize(ctx->s_h2d));
+		CU(cudaStreamSynchronize(ctx->s_front));
 		CU(cudaStreamSynchronize(ctx->s_compute));
 		CU(cudaStreamSynchronize(ctx->s_d2h));
 		*valid = k0 + u + 1;
@@ -1008,6 +1081,33 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 
 /* ------------------------------------------------------- the state machine -- */
 
+/* the LOCKED run that starts at the receiver's present position: where its slots sit and how many the modelled
+ * calls up to c_max can process (tetra_burst_sync.c:107-150, one slot per call) */
+static uint64_t locked_extent(const RxHost &rx, uint32_t C, uint64_t n_end, uint64_t c_max, Segment *seg)
+{
+	seg->a0 = rx.buf_start; seg->cmin = rx.calls + 1; seg->n_end = n_end; seg->chunk = C;
+	if (n_end < seg->a0 + SLOT_BITS || c_max < seg->cmin) return 0;
+	const uint64_t by_bits = (n_end - SLOT_BITS - seg->a0) / SLOT_BITS + 1;
+	const uint64_t by_calls = c_max - seg->cmin + 1;
+	return std::min(by_bits, by_calls);
+}
+
+/* receiver state after `valid` slots of that run were consumed, the last of which lost lock if `lost` */
+static void locked_advance(tb200_ctx *ctx, const Segment &seg, uint64_t valid, bool lost)
+{
+	RxHost &rx = ctx->rx;
+	ctx->stats.slots += valid;
+	const uint64_t c_last = slot_call(seg, valid - 1);
+	rx.calls = c_last;
+	rx.buf_start = seg.a0 + (uint64_t)SLOT_BITS * valid;
+	rx.bits_in_buf = (uint32_t)(std::min<uint64_t>(c_last * seg.chunk, seg.n_end) - rx.buf_start);
+	rx.next_frame_start += (uint64_t)SLOT_BITS * valid;
+	if (lost) {
+		rx.state = TB200_RX_UNLOCKED;
+		ctx->stats.lock_losses++;
+	}
+}
+
 static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
 {
 	const uint32_t C = ctx->opt.chunk_bits;
@@ -1022,13 +1122,7 @@ static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
 		if (rx.state == TB200_RX_LOCKED) {
 			if (ctx->stop_at_lock) return 0;
 			Segment seg;
-			seg.a0 = rx.buf_start; seg.cmin = rx.calls + 1; seg.n_end = n_end; seg.chunk = C;
-			uint64_t n_slots = 0;
-			if (n_end >= seg.a0 + SLOT_BITS) {
-				uint64_t by_bits = (n_end - SLOT_BITS - seg.a0) / SLOT_BITS + 1;
-				uint64_t by_calls = c_max - seg.cmin + 1;
-				n_slots = std::min(by_bits, by_calls);
-			}
+			const uint64_t n_slots = locked_extent(rx, C, n_end, c_max, &seg);
 			if (n_slots == 0) {
 				rx.calls = c_max;
 				rx.bits_in_buf = (uint32_t)(T(c_max) - rx.buf_start);
@@ -1036,16 +1130,7 @@ static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
 			}
 			uint64_t valid = 0; bool lost = false;
 			if ((rc = run_locked(ctx, src, seg, n_slots, out, &valid, &lost))) return rc;
-			ctx->stats.slots += valid;
-			const uint64_t c_last = slot_call(seg, valid - 1);
-			rx.calls = c_last;
-			rx.buf_start = seg.a0 + (uint64_t)SLOT_BITS * valid;
-			rx.bits_in_buf = (uint32_t)(T(c_last) - rx.buf_start);
-			rx.next_frame_start += (uint64_t)SLOT_BITS * valid;
-			if (lost) {
-				rx.state = TB200_RX_UNLOCKED;
-				ctx->stats.lock_losses++;
-			}
+			locked_advance(ctx, seg, valid, lost);
 			continue;
 		}
 		/* UNLOCKED / KNOW_FSTART: one modelled call at a time (tetra_burst_sync.c:60-106) */
@@ -1097,15 +1182,15 @@ static int profile_end(tb200_ctx *ctx)
 	if (!ctx->opt.profile || ctx->prof_used == 0) return 0;
 	CU(cudaStreamSynchronize(ctx->s_compute));
 	float ms = 0.f;
-	for (size_t i = 0; i + 6 <= ctx->prof_used; i += 6) {
+	for (size_t i = 0; i + PE_COUNT <= ctx->prof_used; i += PE_COUNT) {
 		cudaEvent_t *e = &ctx->prof_ev[i];
-		CU(cudaEventElapsedTime(&ms, e[0], e[1])); ctx->timing.classify_ms += ms; ctx->timing.launches_classify++;
-		CU(cudaEventElapsedTime(&ms, e[0], e[5])); ctx->timing.search_ms += ms;
-		CU(cudaEventElapsedTime(&ms, e[1], e[2])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan += 2;
-		CU(cudaEventElapsedTime(&ms, e[2], e[3])); ctx->timing.decode_ms += ms; ctx->timing.launches_decode++;
-		CU(cudaEventElapsedTime(&ms, e[3], e[4])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan++;
+		CU(cudaEventElapsedTime(&ms, e[PE_START], e[PE_SB1])); ctx->timing.classify_ms += ms; ctx->timing.launches_classify++;
+		CU(cudaEventElapsedTime(&ms, e[PE_START], e[PE_SEARCH])); ctx->timing.search_ms += ms;
+		CU(cudaEventElapsedTime(&ms, e[PE_SB1], e[PE_SCAN])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan += 3;
+		CU(cudaEventElapsedTime(&ms, e[PE_DECODE_START], e[PE_DECODE_END])); ctx->timing.decode_ms += ms; ctx->timing.launches_decode++;
 	}
-	CU(cudaEventElapsedTime(&ms, ctx->prof_ev[0], ctx->prof_ev[ctx->prof_used - 2]));
+	/* first launch of the call (pass 1 of the first piece) to the end of the last decode pass */
+	CU(cudaEventElapsedTime(&ms, ctx->prof_ev[PE_START], ctx->prof_ev[ctx->prof_used - PE_COUNT + PE_DECODE_END]));
 	ctx->timing.total_ms = ms;
 	return 0;
 }
@@ -1129,8 +1214,10 @@ static int push_carry(tb200_ctx *ctx)
 	/* ordered with the kernels: async copy on the compute stream from pinned staging (a plain cudaMemcpy from
 	 * pageable memory runs on the legacy stream, which our non-blocking streams do not wait for) */
 	CU(cudaStreamSynchronize(ctx->s_compute));
+	CU(cudaStreamSynchronize(ctx->s_front));
 	ctx->h_carry_pin[0] = ctx->h_carry;
-	CU(cudaMemcpyAsync(ctx->d_carry, &ctx->h_carry_pin[0], sizeof(DevCarry), cudaMemcpyHostToDevice, ctx->s_compute));
+	/* on s_front: pass 1 of the first piece reads it there, the decode pass waits for pass 1 */
+	CU(cudaMemcpyAsync(ctx->d_carry, &ctx->h_carry_pin[0], sizeof(DevCarry), cudaMemcpyHostToDevice, ctx->s_front));
 	return 0;
 }
 
@@ -1726,6 +1813,64 @@ extern "C" void tb200_debug_time_advance(uint32_t *tn, uint32_t *fn, uint32_t *m
 	*tn = t.tn; *fn = t.fn; *mn = t.mn;
 }
 
+/* ---------------------------------------------------------- digest, packing -- */
+
+extern "C" int tb200_slots_digest(tb200_ctx *ctx, const tb200_slot *slots, const uint32_t *type1_packed, uint64_t n,
+                                  uint64_t k_base, int is_device, uint64_t *digest)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (!digest || (n && !slots)) return fail(ctx, TB200_E_ARG, "null argument");
+	*digest = 0;
+	if (n == 0) return 0;
+	const SlotOut *d_slots = reinterpret_cast<const SlotOut *>(slots);
+	const uint32_t *d_packed = type1_packed;
+	cudaStream_t st = ctx->s_compute;
+	if (!is_device) {
+		SlotOut *a = nullptr; uint32_t *b = nullptr;
+		if ((r = leaf_buf(ctx, 0, n, &a))) return r;
+		CU(cudaMemcpyAsync(a, slots, n * sizeof(SlotOut), cudaMemcpyHostToDevice, st));
+		d_slots = a;
+		if (type1_packed) {
+			if ((r = leaf_buf(ctx, 1, n * TYPE1_WORDS, &b))) return r;
+			CU(cudaMemcpyAsync(b, type1_packed, n * TYPE1_WORDS * 4, cudaMemcpyHostToDevice, st));
+			d_packed = b;
+		}
+	}
+	unsigned long long *d_out = nullptr;
+	if ((r = leaf_buf(ctx, 2, 1, &d_out))) return r;
+	CU(cudaMemsetAsync(d_out, 0, sizeof(*d_out), st));
+	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+	TB_LAUNCH(k_slots_digest, blocks, 256, st, d_slots, d_packed, n, k_base, d_out);
+	CU(cudaGetLastError());
+	unsigned long long h = 0;
+	CU(cudaMemcpyAsync(&h, d_out, sizeof(h), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	*digest = h;
+	return 0;
+}
+
+static int pack_bits_async(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint8_t *d_packed, cudaStream_t st)
+{
+	if (n_bits == 0) return 0;
+	const uint64_t words = (n_bits + 31) / 32;
+	const unsigned blocks = (unsigned)std::min<uint64_t>((words + 255) / 256, (uint64_t)ctx->sm_count * 16);
+	TB_LAUNCH(k_pack_bits, blocks, 256, st, d_bits, n_bits, reinterpret_cast<uint32_t *>(d_packed));
+	CU(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int tb200_pack_bits_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint8_t *d_packed)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (n_bits && (!d_bits || !d_packed)) return fail(ctx, TB200_E_ARG, "null argument");
+	if ((uintptr_t)d_packed & 3) return fail(ctx, TB200_E_ARG, "d_packed must be 4-byte aligned");
+	if ((r = pack_bits_async(ctx, d_bits, n_bits, d_packed, ctx->s_compute))) return r;
+	CU(cudaStreamSynchronize(ctx->s_compute));
+	return 0;
+}
+
 /* ------------------------------------------------- sharded decode (multi-GPU) -- */
 
 static_assert(sizeof(tb200_shard_summary) == 32, "shard summary ABI");
@@ -1759,7 +1904,7 @@ extern "C" int tb200_find_lock(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	CU(cudaDeviceSynchronize());
 	reset_stream(ctx);
-	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = IN_BYTES;
+	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = true; out.slots = nullptr; out.type1 = nullptr; out.packed = nullptr; out.crc = nullptr; out.max_slots = 0; out.n = 0;
 	ctx->fed_end = n_bits;
 	ctx->stop_at_lock = true;
@@ -1784,16 +1929,19 @@ extern "C" int tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t
 	if ((rc = ensure_workspace(ctx, n_slots ? n_slots : 1))) return rc;
 	if ((rc = ensure_pieces(ctx, 1))) return rc;
 	RxGeom g;
-	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.n_end = n_end; g.fmt = IN_BYTES;
+	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.n_end = n_end; g.fmt = (int)ctx->opt.input;
+	if (g.fmt != IN_BYTES && ((base_bit & 127) || ((uintptr_t)d_bits & 3)))
+		return fail(ctx, TB200_E_ARG, "bit-packed / symbol shards start on a 128-bit boundary of the stream, in a 4-byte aligned buffer");
 	g.chunk = ctx->opt.chunk_bits; g.n_slots = n_slots; g.tie_hi = (int)ctx->opt.viterbi_tie;
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
-	if (n_slots && (rc = enqueue_pass1(ctx, g, 0, nullptr))) return rc;
+	if (n_slots && (rc = enqueue_pass1(ctx, g, 0, 0, nullptr, false))) return rc;
 	tb200_shard_summary *d_sum = reinterpret_cast<tb200_shard_summary *>(ctx->d_hits);    /* small scratch */
-	if (!n_slots) CU(cudaMemsetAsync(ctx->d_flags, 0xff, sizeof(uint32_t), ctx->s_compute));
-	TB_LAUNCH(k_shard_summary, 1, 32, ctx->s_compute, ctx->d_ws, ctx->d_last_good, ctx->d_blk_prev, ctx->d_flags, n_slots, d_sum);
+	cudaStream_t st = ctx->s_front;
+	if (!n_slots) CU(cudaMemsetAsync(ctx->d_flags, 0xff, 2 * sizeof(uint32_t), st));
+	TB_LAUNCH(k_shard_summary, 1, 32, st, ctx->wset[0].ws, ctx->wset[0].last_good, ctx->wset[0].blk_prev, ctx->d_flags, n_slots, d_sum);
 	ctx->stats.kernel_launches++;
-	CU(cudaMemcpyAsync(summary, d_sum, sizeof(*summary), cudaMemcpyDeviceToHost, ctx->s_compute));
-	CU(cudaStreamSynchronize(ctx->s_compute));
+	CU(cudaMemcpyAsync(summary, d_sum, sizeof(*summary), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
 	ctx->shard_a0 = a0;
 	ctx->shard_slots = n_slots;
 	return 0;
@@ -1832,7 +1980,7 @@ extern "C" long tb200_shard_pass2(tb200_ctx *ctx, const tb200_rx_carry *carry_in
 	dc.mcc = carry_in->mcc; dc.mnc = carry_in->mnc; dc.cc = carry_in->colour_code;
 	CU(cudaMemcpyAsync(ctx->d_carry, &dc, sizeof(dc), cudaMemcpyHostToDevice, ctx->s_compute));
 	if (ctx->shard_slots) {
-		int rc = enqueue_pass2(ctx, ctx->shard_a0, ctx->shard_slots, 0, nullptr, (SlotOut *)d_slots, d_type1, d_type1_packed, 0);
+		int rc = enqueue_pass2(ctx, ctx->shard_a0, ctx->shard_slots, 0, 0, nullptr, false, (SlotOut *)d_slots, d_type1, d_type1_packed, 0);
 		if (rc) return rc;
 	}
 	CU(cudaMemcpyAsync(&ctx->h_carry, ctx->d_carry + (ctx->shard_slots ? 1 : 0), sizeof(DevCarry), cudaMemcpyDeviceToHost, ctx->s_compute));
@@ -1845,3 +1993,5 @@ extern "C" long tb200_shard_pass2(tb200_ctx *ctx, const tb200_rx_carry *carry_in
 	}
 	return (long)ctx->shard_slots;
 }
+
+#include "tetra_dist.cuh"

@@ -116,8 +116,11 @@ __device__ __forceinline__ TileGeom tile_geom(const RxGeom &g, uint32_t tile, ui
 	return t;
 }
 
+#ifndef TB_CT_MIN_CTAS
+#define TB_CT_MIN_CTAS 3      /* resident CTAs per SM the register budget is cut for (A/B builds: -DTB_CT_MIN_CTAS=4 -> 64 registers) */
+#endif
 template <int FMT>
-__global__ void __launch_bounds__(CT_THREADS, 3)
+__global__ void __launch_bounds__(CT_THREADS, TB_CT_MIN_CTAS)
 k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__restrict__ ws,
                 uint32_t *__restrict__ slot_bits, uint32_t *__restrict__ sb_list, uint32_t *__restrict__ sb_count)
 {
@@ -147,7 +150,11 @@ k_classify_tile(RxGeom g, WinGeom wg, const Tables *__restrict__ tab, SlotWs *__
 		const TileGeom t = tile_geom<FMT>(g, tile, buf_lo, buf_hi);
 		if (!t.staged) return;
 		mbar_expect_tx(&bars[b], t.bytes);
+#ifdef TB_CT_EVICT_FIRST
+		bulk_g2s_stream(raw + (size_t)b * BUF, t.src, t.bytes, &bars[b]);
+#else
 		bulk_g2s(raw + (size_t)b * BUF, t.src, t.bytes, &bars[b]);
+#endif
 	};
 	if (tid == 0) issue(blockIdx.x, 0);
 	__syncthreads();

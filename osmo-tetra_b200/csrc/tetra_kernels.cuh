@@ -173,7 +173,8 @@ struct DevCarry {
 	uint32_t scramb_init;
 	uint32_t tn, fn, mn;
 	uint32_t mcc, mnc, cc;
-	uint32_t pad;
+	uint32_t seen_good;        /* a CRC-good SB1 has been seen since the chain started (sharded decode: the state no longer depends on the carry-in) */
+	uint64_t first_good;       /* slot index (relative to the chain start) of that first SB1, ~0 if none yet */
 };
 
 constexpr int KIND_NONE = 0, KIND_SB = 1, KIND_NDB_F = 2, KIND_NDB_2 = 3;
@@ -784,7 +785,7 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
  * before me" (or -1), the block's last one, and the first slot that loses lock. */
 __global__ void __launch_bounds__(1024)
 k_scan_blocks(const SlotWs *__restrict__ ws, uint32_t n_slots, int32_t *__restrict__ last_good,
-              int32_t *__restrict__ blk_last, uint32_t *__restrict__ first_unlock,
+              int32_t *__restrict__ blk_last, uint32_t *__restrict__ first_unlock, uint32_t *__restrict__ first_good,
               uint32_t *__restrict__ kind_count, uint32_t *__restrict__ kind_list, uint32_t list_stride)
 {
 	__shared__ int32_t warp_last[32];
@@ -845,6 +846,11 @@ k_scan_blocks(const SlotWs *__restrict__ ws, uint32_t n_slots, int32_t *__restri
 	if (w > 0) { const int32_t o = warp_last[w - 1]; if (o > v) v = o; }
 	if (k < n_slots) last_good[k] = v;
 	if (tid == 1023) blk_last[blockIdx.x] = v;
+	/* first CRC-good SB1 of the piece: the first slot whose running maximum is itself */
+	if (k < n_slots && v == (int32_t)k && (tid == 0 ? true : true)) {
+		const SlotWs s = ws[k];
+		if (s.good_sb) atomicMin(first_good, (uint32_t)k);
+	}
 	if (kind_count && kind >= 0)
 		kind_list[(size_t)kind * list_stride + kbase[kind] + kcnt[kind][w] + my_rank] = (uint32_t)k;
 }
@@ -895,7 +901,8 @@ k_scan_prefix(const int32_t *__restrict__ blk_last, uint32_t n_blocks, int32_t *
 /* cell state in force for slot k (tetra_lower_mac.c:167,283-302 + tetra_burst_sync.c:113):
  * X_k = PDU time of a CRC-good SB in this slot, else one slot after X_{k-1}; the scrambling
  * code is the one announced by the latest CRC-good SB1 at or before k. */
-__device__ __forceinline__ void cell_state(uint64_t k, const SlotWs *__restrict__ ws,
+/* returns true when the state came from the carry (no CRC-good SB1 in this launch at or before k) */
+__device__ __forceinline__ bool cell_state(uint64_t k, const SlotWs *__restrict__ ws,
                                            const int32_t *__restrict__ last_good,
                                            const int32_t *__restrict__ blk_prev,
                                            const DevCarry *__restrict__ carry, Tm *tm, uint32_t *code)
@@ -907,16 +914,18 @@ __device__ __forceinline__ void cell_state(uint64_t k, const SlotWs *__restrict_
 		Tm t = { s.tn, s.fn, s.mn };
 		*tm = tm_advance(t, k - (uint64_t)j);
 		*code = s.sb_code;
-	} else {
-		Tm t = { carry->tn, carry->fn, carry->mn };
-		*tm = tm_advance(t, k + 1);
-		*code = carry->scramb_init;
+		return false;
 	}
+	Tm t = { carry->tn, carry->fn, carry->mn };
+	*tm = tm_advance(t, k + 1);
+	*code = carry->scramb_init;
+	return true;
 }
 
 /* after the launch's last valid slot: the state the next launch starts from */
 __global__ void k_finalize_carry(const SlotWs *__restrict__ ws, const int32_t *__restrict__ last_good,
-                                 const int32_t *__restrict__ blk_prev, uint32_t n_valid, DevCarry *carry)
+                                 const int32_t *__restrict__ blk_prev, uint32_t n_valid, DevCarry *carry,
+                                 const uint32_t *__restrict__ first_good, uint64_t k_base)
 {
 	if (threadIdx.x != 0 || blockIdx.x != 0 || n_valid == 0) return;
 	const uint64_t k = n_valid - 1;
@@ -927,6 +936,12 @@ __global__ void k_finalize_carry(const SlotWs *__restrict__ ws, const int32_t *_
 	DevCarry c = *carry;
 	c.scramb_init = code; c.tn = tm.tn; c.fn = tm.fn; c.mn = tm.mn;
 	if (j >= 0) { c.mcc = ws[j].mcc; c.mnc = ws[j].mnc; c.cc = ws[j].cc; }
+	if (j >= 0 && !c.seen_good) {
+		/* first_good may name a slot behind n_valid when the piece was cut at a lock loss and issued whole before;
+		 * it is recomputed by the scan of the cut piece, so it is below n_valid here */
+		c.seen_good = 1;
+		c.first_good = k_base + (first_good ? (uint64_t)*first_good : (uint64_t)j);
+	}
 	*carry = c;
 }
 
@@ -949,6 +964,8 @@ struct DecodeArgs {
 	uint32_t *crc;                /* optional: CRC-16 registers per slot, block A (SB1 / SCH-F / BLK1) | block B (SB2 / BLK2) << 16 */
 	int tie_hi;                   /* Viterbi tie rule (warp form; the lane kernels are templates) */
 	unsigned long long *stats;    /* [3] counters of this piece: slots handed to the lower MAC, primitives, CRC-good blocks */
+	int skip_dependent;           /* sharded decode, first pass: leave out the slots whose cell state would come from a carry-in that
+	                               * is not known yet (no CRC-good SB1 since the shard began); they are decoded once it is */
 };
 
 /* what a slot adds to the counters (tb200_stats): packed as bursts | primitives << 8 | CRC-good blocks << 16 */
@@ -989,7 +1006,8 @@ k_decode_warp(DecodeArgs a)
 	for (uint64_t k = (uint64_t)blockIdx.x * (blockDim.x >> 5) + wib; k < a.n_slots; k += nwarps) {
 		const SlotWs w = a.ws[k];
 		Tm tm; uint32_t code;
-		cell_state(k, a.ws, a.last_good, a.blk_prev, a.carry, &tm, &code);
+		const bool dep = cell_state(k, a.ws, a.last_good, a.blk_prev, a.carry, &tm, &code);
+		if (a.skip_dependent && dep && !a.carry->seen_good) continue;          /* warp-uniform */
 		const int kind = w.kind;
 		uint32_t flags = (uint32_t)kind | (w.unlock ? F_UNLOCK : 0);
 		uint32_t crcs = 0;

@@ -672,7 +672,10 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			if (have) {
 				const SlotWs w = a.ws[k[h]];
 				kind[h] = w.kind; good_sb = w.good_sb; unlock = w.unlock;
-				cell_state(k[h], a.ws, a.last_good, a.blk_prev, a.carry, &tm[h], &code[h]);
+				const bool dep = cell_state(k[h], a.ws, a.last_good, a.blk_prev, a.carry, &tm[h], &code[h]);
+				if (a.skip_dependent && dep && !a.carry->seen_good) {     /* sharded decode: decoded later, with the real carry-in */
+					k[h] = ~0ull; kind[h] = KIND_NONE; good_sb = unlock = false;
+				}
 			}
 			flags[h] = (uint32_t)kind[h] | (unlock ? F_UNLOCK : 0) | ((kind[h] == KIND_SB && good_sb) ? F_CRC_A : 0);
 			uint32_t lf[LANE_T3_ROWS];

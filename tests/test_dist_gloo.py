@@ -135,3 +135,93 @@ def test_one_stream_sharded_over_two_ranks():
     for rank, ok, msg, n, want_total, got in res:
         assert ok, (rank, msg)
     assert sum(r[5] for r in res) == res[0][4]       # the shards together give every record of the stream
+
+
+# ---------------------------------------------------------------- the C driver (tb200_dist_*) over gloo
+
+def _dist_streams(orc):
+    """(name, bits, mode) cases for the C driver: plain, packed on rank 0, and a training sequence wiped in every shard"""
+    cfg = T.GenCfg(seed=78, sb_period=7, lead_sb=2, ndb2_per_256=64, ber_per_65536=655, random_cell=1, lead_in_bits=333)
+    nb = 170
+    bits = np.ascontiguousarray(orc.gen_stream(cfg, 0, nb))
+    wiped = bits.copy()
+    for k in (40, 120):                      # normal bursts in the first and in the second rank's shard: lock is lost twice
+        while orc.gen_kind(cfg, k) == 1:
+            k += 1
+        wiped[333 + 510 * k + 244:333 + 510 * k + 266] = 0
+    sparse = T.GenCfg(seed=79, sb_period=120, lead_sb=2, ndb2_per_256=64, ber_per_65536=655, random_cell=1, lead_in_bits=17)
+    far = np.ascontiguousarray(orc.gen_stream(sparse, 0, nb))     # the second shard holds no SYNC burst at all
+    return [("plain", bits, T.DIST_SCATTER), ("packed", bits, T.DIST_SCATTER | T.DIST_PACK),
+            ("lock lost in both shards", wiped, T.DIST_SCATTER), ("lock lost, packed", wiped, T.DIST_SCATTER | T.DIST_PACK),
+            ("no SB in the second shard", far, T.DIST_SCATTER)]
+
+
+def _dist_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = T.B200(emulate=True)
+    g.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, output=T.OUT_UNPACKED | T.OUT_PACKED, pipeline_slots=0)
+    ops = T.gloo_dist_ops(dist)
+    dd = T.Dist(g, rank, world, ops=ops)
+    orc = T.Oracle()
+    out = []
+    for name, bits, mode in _dist_streams(orc):
+        ms = bits.size // 510 + 16
+        slots = np.zeros(ms, dtype=T.SLOT_DTYPE)
+        t1 = np.zeros((ms, 288), dtype=np.uint8)
+        pk = np.zeros((ms, 9), dtype=np.uint32)
+        n, runs = dd.rx_stream(bits.ctypes.data if rank == 0 else None, bits.size, mode, slots.ctypes.data, t1.ctypes.data,
+                               pk.ctypes.data, ms)
+        dig = sum(g.slots_digest(slots[l:l + c], pk[l:l + c], k_base=gs) for gs, l, c in runs) & (2 ** 64 - 1)
+        cy = g.carry()
+        out.append((name, n, runs, slots[:n].copy(), t1[:n].copy(), pk[:n].copy(), dig, (cy.state, cy.scramb_init, cy.tn, cy.fn, cy.mn),
+                    dd.timing().segments))
+    q.put((rank, out))
+    dist.barrier()
+    dd.close()
+    dist.destroy_process_group()
+
+
+def test_c_driver_two_ranks(orc):
+    """tb200_dist_rx_stream (the C sharding driver) with gloo plumbing on two CPU ranks: the runs of both ranks, put
+    in global slot order, are exactly what ONE receiver delivers - records and search log against the oracle -
+    also when lock is lost inside a shard, and the per-rank digests add up to the digest of the single run"""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    emu = T.B200(emulate=True)
+    emu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, output=T.OUT_UNPACKED | T.OUT_PACKED, pipeline_slots=0)
+    for ci, (name, bits, mode) in enumerate(_dist_streams(orc)):
+        orc.reset(); orc.feed(bits, 64)
+        want, ev = orc.records(), orc.events()
+        pieces = []
+        for rank in range(world):
+            _, n, runs, slots, t1, pk, dig, cy, segs = res[rank][ci]
+            assert sum(c for _, _, c in runs) == n, name
+            for gs, l, c in runs:
+                pieces.append((gs, slots[l:l + c], t1[l:l + c], pk[l:l + c]))
+        pieces.sort(key=lambda x: x[0])
+        pos = 0
+        for gs, s, _, _ in pieces:               # the runs tile the global slot order without gaps
+            assert gs == pos, (name, gs, pos)
+            pos += s.size
+        slots = np.concatenate([p[1] for p in pieces]); t1 = np.concatenate([p[2] for p in pieces]); pk = np.concatenate([p[3] for p in pieces])
+        T.check_stream_against(want, ev, slots, emu.expand_records(slots, t1))
+        one_s, one_t1, one_pk = emu.rx_stream_host(bits)
+        assert np.array_equal(one_s, slots) and np.array_equal(one_pk, pk), name
+        total = sum(res[r][ci][6] for r in range(world)) & (2 ** 64 - 1)
+        assert total == emu.slots_digest(one_s, one_pk) == T.slots_digest_host(one_s, one_pk), name
+        # rank 0 holds the receiver state a single receiver ends with
+        c = emu.carry()
+        assert res[0][ci][7] == (c.state, c.scramb_init, c.tn, c.fn, c.mn), name
+        if "lock lost" in name:
+            assert res[0][ci][8] >= 3, name          # 1 + two losses

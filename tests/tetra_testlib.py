@@ -392,6 +392,45 @@ shard_plan, SHARD_HALO, DevBuffer, peer_pointer, sharded_decode, pack_bits = (
     _B.shard_plan, _B.SHARD_HALO, _B.DevBuffer, _B.peer_pointer, _B.sharded_decode, _B.pack_bits)
 
 
+Dist, DistOps, DIST_SCATTER, DIST_PEER, DIST_PACK, slots_digest_host = (
+    _B.Dist, _B.DistOps, _B.DIST_SCATTER, _B.DIST_PEER, _B.DIST_PACK, _B.slots_digest_host)
+
+
+def gloo_dist_ops(dist):
+    """tb200_dist_ops over torch.distributed (gloo, host memory): the plumbing the CPU tests hand to the C driver
+    (under the SIMT emulation "device" pointers are host pointers).  Keep the returned object alive."""
+    import torch
+
+    def view(ptr, n):
+        return torch.from_numpy(np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n,)))
+
+    def bcast(user, buf, n, root):
+        dist.broadcast(view(buf, n), root)
+        return 0
+
+    def allgather(user, send, recv, each):
+        world = dist.get_world_size()
+        out = [torch.zeros(each, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(out, view(send, each).clone())
+        view(recv, each * world).copy_(torch.cat(out))
+        return 0
+
+    def scatter(user, src, offs, sizes, dst, root):
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if rank == root:
+            for r in range(world):
+                if r != root and sizes[r]:
+                    dist.send(view(src + offs[r], sizes[r]).clone(), r)
+        elif sizes[rank]:
+            t = torch.zeros(sizes[rank], dtype=torch.uint8)
+            dist.recv(t, root)
+            view(dst, sizes[rank]).copy_(t)
+        return 0
+
+    ops = _B.DistOps(None, _B.BCAST_FN(bcast), _B.ALLGATHER_FN(allgather), _B.SCATTER_FN(scatter))
+    return ops
+
+
 def B200(emulate=False, device=0):
     """the product binding; emulate=True: on the SIMT-emulation build of the CUDA sources (CPU tests)"""
     return _B.B200(device=device, lib_path=build_simt() if emulate else None)
