@@ -186,6 +186,12 @@ struct tb200_lock_event {
 	uint32_t pad;
 };
 int    tb200_set_crc_buffer(tb200_ctx *ctx, uint32_t *crc);
+/* RM(30,14) decoding of the AACH, which the reference leaves out: its lower MAC hands the first 14 descrambled bits of
+ * the broadcast block up unchecked (tetra_lower_mac.c:268-274 "FIXME: RM3014-decode", tetra_rm3014.c:92-96 returns
+ * inp >> 16).  The type-1 bits of the slot stay what the reference delivers; this is an opt-in side output at the same
+ * index as the slot record (residency as for tb200_set_crc_buffer; NULL switches it off): the result of
+ * tb200_rm3014_decode() for the slot's 30 descrambled broadcast bits, 0xffffffff for slots handed to nobody. */
+int    tb200_set_aach_buffer(tb200_ctx *ctx, uint32_t *aach);
 size_t tb200_get_lock_events(const tb200_ctx *ctx, struct tb200_lock_event *ev, size_t max_events);
 
 int tb200_get_carry(const tb200_ctx *ctx, struct tb200_rx_carry *out);
@@ -264,6 +270,14 @@ int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits,
  * checkpoint.  TB200_E_ARG for an unknown puncturer (-EINVAL in the reference). */
 int tb200_rcpc_depunct(tb200_ctx *ctx, int puncturer, const uint8_t *type3, uint32_t len, uint64_t n,
                        uint8_t *mother, uint32_t mother_len, int is_device);
+
+/* Maximum-likelihood decoding of the (30,14) Reed-Muller code of the AACH (generator: tetra_rm3014.c:28-43) for n
+ * received 30-bit words laid out like tetra_rm3014_compute's result (bit 29 = first bit on air, information = word >> 16,
+ * the argument of the reference's tetra_rm3014_decode(inp, out), tetra_rm3014.c:92-96).  The code has minimum distance 8:
+ * up to three bit errors are always corrected.  out[i] = the 14 information bits of the nearest code word (what
+ * tetra_rm3014_decode's *out would be for it) | distance to it << 16 | (received word is not a code word) << 24; among
+ * equally near code words the one with the numerically smallest error pattern wins.  Host or device pointers. */
+int tb200_rm3014_decode(tb200_ctx *ctx, const uint32_t *words, uint64_t n, uint32_t *out, int is_device);
 
 /* GSMTAP framing of the decoded blocks: what tetra_gsmtap_makemsg (tetra_gsmtap.c:31-63) builds
  * when rx_tmv_unitdata_ind hands it a CRC-good block (tetra_upper_mac.c:480-488), for every block of n_slots slots:

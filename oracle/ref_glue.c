@@ -179,6 +179,31 @@ long ref_feed(const uint8_t *bits, size_t n, unsigned int chunk, int quiet)
 	return (long)g_nrec;
 }
 
+/* The same with a read() size per call and the reference's return value of every call
+ * (tetra_burst_sync.c:66-106: len, 0 while KNOW_FSTART waits, -1 when the UNLOCKED search fails). */
+long ref_feed_calls(const uint8_t *bits, const uint32_t *lens, size_t n_calls, int32_t *rc_out, int quiet)
+{
+	uint8_t buf[4096];
+	size_t pos = 0;
+	if (!g_trs)
+		ref_reset();
+	if (quiet)
+		silence();
+	for (size_t i = 0; i < n_calls; i++) {
+		if (lens[i] > sizeof(buf))
+			break;
+		memcpy(buf, bits + pos, lens[i]);
+		pos += lens[i];
+		g_call_index++;
+		const int rc = tetra_burst_sync_in(g_trs, buf, lens[i]);
+		if (rc_out)
+			rc_out[i] = rc;
+	}
+	if (quiet)
+		unsilence();
+	return (long)g_nrec;
+}
+
 /* Drive the lower MAC directly at the TP-SAP seam (drop-in depth C of SURVEY 8b). */
 void ref_tp_sap(int type, int blk_num, const uint8_t *bits, unsigned int len, int quiet)
 {

@@ -234,6 +234,35 @@ uint32_t orc_rm3014_compute(uint16_t info)
 	return v;
 }
 
+/* Maximum-likelihood decoding of a received 30-bit word (bit 29 = first bit on air, as tetra_rm3014_compute
+ * returns it) by brute force over all 2^14 code words: the nearest code word wins, among equally near ones the
+ * one whose error pattern word ^ cw is numerically smallest.  The reference has no RM decoder to compare with
+ * (tetra_rm3014.c:92-96 returns inp >> 16, tetra_lower_mac.c:268-274 "FIXME: RM3014-decode"): the code itself is
+ * pinned through orc_rm3014_compute == tetra_rm3014_compute, the decoder by this exhaustive search.
+ * Returns the distance; *info = the 14 information bits of the winner (as tetra_rm3014_decode's *out). */
+int orc_rm3014_decode_ml(uint32_t word, uint16_t *info)
+{
+	static uint32_t cw[1 << 14];
+	static int have;
+	if (!have) {
+		for (uint32_t i = 0; i < (1u << 14); i++)
+			cw[i] = orc_rm3014_compute((uint16_t)i);
+		have = 1;
+	}
+	word &= 0x3fffffffu;
+	int best_d = 31;
+	uint32_t best_e = 0xffffffffu, best_i = 0;
+	for (uint32_t i = 0; i < (1u << 14); i++) {
+		const uint32_t e = word ^ cw[i];
+		const int d = __builtin_popcount(e);
+		if (d < best_d || (d == best_d && e < best_e)) {
+			best_d = d; best_e = e; best_i = i;
+		}
+	}
+	*info = (uint16_t)best_i;
+	return best_d;
+}
+
 /* ------------------------------------------------------ leaf: TDMA time -- */
 
 struct orc_time { uint32_t tn, fn, mn; };

@@ -295,6 +295,29 @@ class B200:
             raise RuntimeError(self.err())
         return out.value
 
+    def rm3014_decode(self, words):
+        """tb200_rm3014_decode on a host array of 30-bit words -> (info14, distance, not_a_code_word)"""
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        out = np.zeros(words.size, dtype=np.uint32)
+        self.lib.tb200_rm3014_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_int]
+        if self.lib.tb200_rm3014_decode(self.h, _ptr(words), words.size, _ptr(out), 0):
+            raise RuntimeError(self.err())
+        return out & 0x3fff, (out >> 16) & 0xff, (out >> 24) & 1
+
+    def rx_stream_host_aach(self, bits):
+        """rx_stream_host with the RM(30,14)-decoded AACH side output switched on for this call"""
+        bits = np.ascontiguousarray(bits, dtype=np.uint8)
+        ms = int(self.lib.tb200_max_slots(bits.size)) + 16
+        aach = np.zeros(ms, dtype=np.uint32)
+        self.lib.tb200_set_aach_buffer.argtypes = [C.c_void_p, C.c_void_p]
+        if self.lib.tb200_set_aach_buffer(self.h, _ptr(aach)):
+            raise RuntimeError(self.err())
+        try:
+            slots, t1, pk = self.rx_stream_host(bits, max_slots=ms)
+        finally:
+            self.lib.tb200_set_aach_buffer(self.h, None)
+        return slots, t1, pk, aach[:slots.size]
+
     def find_train_seq(self, bits, starts, lens, mask):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
         starts = np.ascontiguousarray(starts, dtype=np.uint64); lens = np.ascontiguousarray(lens, dtype=np.uint32)

@@ -89,6 +89,18 @@ static void build_tables(Tables *t)
 		t->crc_tab_r[256 + x] = r;
 	}
 
+	/* RM(30,14): parity halves of the systematic generator matrix (tetra_rm3014.c:28-43; rows as tetra_rm3014_init
+	 * builds them, :59-72: information bit i of the 14 sits at word bit 29 - i) */
+	static const uint16_t rm_parity[14] = { 0x9b60, 0x2de0, 0xfc20, 0xe03c, 0x983a, 0x5436, 0x2c2e,
+	                                        0xffdf, 0x8339, 0x42b5, 0x21ad, 0x1273, 0x096b, 0x04e7 };
+	for (unsigned half = 0; half < 2; half++)
+		for (unsigned v = 0; v < 128; v++) {
+			uint16_t p = 0;
+			for (unsigned b = 0; b < 7; b++)
+				if ((v >> b) & 1) p ^= rm_parity[13 - (7 * half + b)];     /* info bit j (LSB = last on air) <-> row 13 - j */
+			t->rm_par[half][v] = p;
+		}
+
 	/* pre-filter blind spot, by running the filter of tetra_burst.c:286-303 on a buffer
 	 * that carries the sequence at offset k with the bit before it set to `prev` */
 	const uint64_t seqs[3] = {SEQ_Y, SEQ_N, SEQ_P};
@@ -131,6 +143,9 @@ struct RxHost {
 	uint64_t buf_start = 0;      /* bitbuf_start_bitnum (64-bit here) */
 	uint32_t bits_in_buf = 0;
 	uint64_t next_frame_start = 0;
+	/* the current run of equal-length reads (CallGeom): calls and bits before it */
+	uint64_t c_base = 0, t_base = 0;
+	uint64_t delivered = 0;      /* bits the modelled calls have delivered so far (the end of the last run) */
 };
 
 struct SyncHit { uint64_t pos; uint32_t prev; };
@@ -175,6 +190,9 @@ struct tb200_ctx {
 	uint32_t *d_opacked[NBUF] = {nullptr, nullptr, nullptr};
 	uint32_t *d_ocrc[NBUF] = {nullptr, nullptr, nullptr};
 	uint32_t *user_crc = nullptr;    /* optional CRC-register output (tb200_set_crc_buffer), same residency as the slots */
+	uint32_t *user_aach = nullptr;   /* optional RM(30,14)-decoded AACH output (tb200_set_aach_buffer) */
+	uint32_t *d_oaach[NBUF] = {nullptr, nullptr, nullptr};
+	uint32_t *d_rm_leader = nullptr; /* [2^16] coset leaders, built on first use */
 	std::vector<tb200_lock_event> lock_events;   /* lock acquisitions of the last rx call */
 	size_t out_cap = 0;
 	/* UNLOCKED search */
@@ -206,6 +224,24 @@ struct tb200_ctx {
 	size_t prof_used = 0;
 	tb200_timing timing;
 };
+
+/* coset leaders of the RM(30,14) code: for every 16-bit syndrome the lightest error pattern that has it, the
+ * numerically smallest among equally light ones (patterns visited by weight, then value: Gosper's hack) */
+static void build_rm_leaders(const Tables *t, std::vector<uint32_t> &leader)
+{
+	leader.assign(1u << 16, 0xffffffffu);
+	size_t left = leader.size();
+	leader[0] = 0; left--;
+	for (int w = 1; w <= 30 && left; w++) {
+		uint32_t e = (1u << w) - 1;
+		while (e < (1u << 30)) {
+			const uint32_t syn = rm3014_syndrome(t, e);
+			if (leader[syn] == 0xffffffffu) { leader[syn] = e; left--; }
+			const uint32_t c = e & (0u - e), r = e + c;
+			e = (((r ^ e) >> 2) / c) | r;
+		}
+	}
+}
 
 static int fail(tb200_ctx *c, int code, const char *fmt, ...)
 {
@@ -323,6 +359,25 @@ extern "C" int tb200_set_crc_buffer(tb200_ctx *ctx, uint32_t *crc)
 	return 0;
 }
 
+static int ensure_rm_leaders(tb200_ctx *ctx)
+{
+	if (ctx->d_rm_leader) return 0;
+	std::vector<uint32_t> leader;
+	build_rm_leaders(&ctx->h_tab, leader);
+	CU(cudaMalloc((void **)&ctx->d_rm_leader, leader.size() * sizeof(uint32_t)));
+	CU(cudaMemcpy(ctx->d_rm_leader, leader.data(), leader.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+extern "C" int tb200_set_aach_buffer(tb200_ctx *ctx, uint32_t *aach)
+{
+	if (!ctx) return TB200_E_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	if (aach) { int rc = ensure_rm_leaders(ctx); if (rc) return rc; }
+	ctx->user_aach = aach;
+	return 0;
+}
+
 extern "C" size_t tb200_get_lock_events(const tb200_ctx *ctx, tb200_lock_event *ev, size_t max_events)
 {
 	if (!ctx) return 0;
@@ -428,7 +483,8 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 		cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_back[i]);
 	}
 	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch); cudaFree(ctx->d_sb1_scratch);
-	cudaFree(ctx->d_pstats); cudaFreeHost(ctx->h_pstats);
+	cudaFree(ctx->d_pstats); cudaFreeHost(ctx->h_pstats); cudaFree(ctx->d_rm_leader);
+	for (int i = 0; i < NBUF; i++) cudaFree(ctx->d_oaach[i]);
 	for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) cudaFree(ctx->leaf_mem[i]);
 	for (int i = 0; i < 2; i++) if (ctx->leaf_ev[i]) cudaEventDestroy(ctx->leaf_ev[i]);
@@ -523,6 +579,7 @@ static int ensure_staging(tb200_ctx *ctx, size_t in_bytes, size_t slots)
 			if ((rc = grow(ctx, &ctx->d_otype1[i], slots * TYPE1_STRIDE))) return rc;
 			if ((rc = grow(ctx, &ctx->d_opacked[i], slots * TYPE1_WORDS))) return rc;
 			if ((rc = grow(ctx, &ctx->d_ocrc[i], slots))) return rc;
+			if ((rc = grow(ctx, &ctx->d_oaach[i], slots))) return rc;
 		}
 		ctx->out_cap = slots;
 	}
@@ -754,6 +811,7 @@ struct Outputs {
 	uint8_t *type1;
 	uint32_t *packed;
 	uint32_t *crc;               /* optional (tb200_set_crc_buffer) */
+	uint32_t *aach = nullptr;    /* optional (tb200_set_aach_buffer) */
 	uint64_t max_slots;
 	uint64_t n;                  /* slots written so far */
 };
@@ -761,14 +819,12 @@ struct Outputs {
 struct Segment {
 	uint64_t a0;                 /* absolute bit of slot 0 */
 	uint64_t cmin;               /* first call that may process slot 0 */
-	uint64_t n_end;
-	uint32_t chunk;
+	CallGeom cg;                 /* the modelled calls: run of equal-length reads */
 };
 
 static inline uint64_t slot_call(const Segment &s, uint64_t k)   /* call index that processes slot k */
 {
-	uint64_t need = (s.a0 + (uint64_t)SLOT_BITS * k + SLOT_BITS + s.chunk - 1) / s.chunk;
-	return std::max(need, s.cmin + k);
+	return call_for(s.cg, s.a0 + (uint64_t)SLOT_BITS * k + SLOT_BITS, s.cmin + k);
 }
 
 /* events per piece when options.profile is on */
@@ -794,8 +850,7 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, int 
 	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
 	if (lane) {
 		WinGeom wg;
-		wg.chunk = g.chunk; wg.rel0 = (uint32_t)(g.a0 % g.chunk); wg.c00 = g.a0 / g.chunk;
-		wg.cmin = g.cmin; wg.n_end = g.n_end; wg.a0 = g.a0;
+		wg.cg = g.cg; wg.cmin = g.cmin; wg.a0 = g.a0;
 		uint32_t *sb_count = w.sb_list + ctx->ws_slots;
 		CU(cudaMemsetAsync(sb_count, 0, sizeof(uint32_t), st));
 		const unsigned per_tile = g.fmt == IN_F32SYM ? TileFmt<IN_F32SYM>::SLOTS : CT_SLOTS;
@@ -850,7 +905,7 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, int 
 /* pass 2 of a piece on stream s_compute: everything that needs the cell state carried in d_carry[piece_idx] */
 static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_idx, int set, cudaEvent_t *pe, bool with_carry,
                          SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc = nullptr,
-                         bool skip_dependent = false)
+                         bool skip_dependent = false, uint32_t *o_aach = nullptr)
 {
 	cudaStream_t st = ctx->s_compute;
 	tb200_ctx::WorkSet &w = ctx->wset[set];
@@ -872,6 +927,7 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	a.tie_hi = (int)ctx->opt.viterbi_tie;
 	a.stats = ctx->d_pstats + 3 * piece_idx;
 	a.skip_dependent = skip_dependent ? 1 : 0;
+	a.aach = o_aach; a.rm_leader = ctx->d_rm_leader;
 	CU(cudaStreamWaitEvent(st, ctx->ev_front[set], 0));
 	CU(cudaMemsetAsync(a.stats, 0, 3 * sizeof(unsigned long long), st));
 	if (pe) CU(cudaEventRecord(pe[PE_DECODE_START], st));
@@ -896,12 +952,12 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32_t nb, const uint8_t *d_bits,
                          uint64_t d_base, uint64_t d_avail, int fmt, size_t piece_idx,
                          SlotOut *o_slots, uint8_t *o_type1, uint32_t *o_packed, uint64_t out_base, uint32_t *o_crc,
-                         bool skip_dependent)
+                         bool skip_dependent, uint32_t *o_aach)
 {
 	RxGeom g;
 	g.bits = d_bits; g.n_bytes = d_avail; g.base_bit = d_base; g.fmt = fmt;
-	g.a0 = seg.a0 + (uint64_t)SLOT_BITS * k0; g.cmin = seg.cmin + k0; g.n_end = seg.n_end;
-	g.chunk = seg.chunk; g.n_slots = nb; g.tie_hi = (int)ctx->opt.viterbi_tie;
+	g.a0 = seg.a0 + (uint64_t)SLOT_BITS * k0; g.cmin = seg.cmin + k0; g.cg = seg.cg;
+	g.n_slots = nb; g.tie_hi = (int)ctx->opt.viterbi_tie;
 	cudaEvent_t *pe = nullptr;
 	if (ctx->opt.profile) {
 		while (ctx->prof_ev.size() < ctx->prof_used + PE_COUNT) {
@@ -917,7 +973,7 @@ static int enqueue_piece(tb200_ctx *ctx, const Segment &seg, uint64_t k0, uint32
 	const int set = (int)(piece_idx & 1);
 	int rc = enqueue_pass1(ctx, g, piece_idx, set, pe, true, k0);
 	if (rc) return rc;
-	return enqueue_pass2(ctx, g.a0, nb, piece_idx, set, pe, true, o_slots, o_type1, o_packed, out_base, o_crc, skip_dependent);
+	return enqueue_pass2(ctx, g.a0, nb, piece_idx, set, pe, true, o_slots, o_type1, o_packed, out_base, o_crc, skip_dependent, o_aach);
 }
 
 /* Process slots [0, n_slots) of a LOCKED segment, optimistically assuming lock is kept;
@@ -977,10 +1033,10 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		if (nb_override) nb = nb_override;
 		const int b = (int)(i % NBUF);
 		const uint64_t lo = seg.a0 + (uint64_t)SLOT_BITS * k0;
-		const uint64_t hi = std::min<uint64_t>(seg.n_end, lo + (uint64_t)SLOT_BITS * nb + 4096);
+		const uint64_t hi = std::min<uint64_t>(seg.cg.n_end, lo + (uint64_t)SLOT_BITS * nb + 4096);
 		const uint8_t *dbits; uint64_t dbase, davail;
 		if (src.on_device) {
-			dbits = src.data; dbase = src.new_base; davail = std::min<uint64_t>(seg.n_end, src.end) - src.new_base;
+			dbits = src.data; dbase = src.new_base; davail = std::min<uint64_t>(seg.cg.n_end, src.end) - src.new_base;
 			if (src.ready) {
 				for (const auto &rv : *src.ready)
 					if (rv.first >= hi || &rv == &src.ready->back()) { CU(cudaStreamWaitEvent(ctx->s_front, rv.second, 0)); break; }
@@ -992,13 +1048,14 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 			CU(cudaStreamWaitEvent(ctx->s_front, ctx->ev_h2d[b], 0));
 			dbits = ctx->d_in[b]; davail = hi - dbase;
 		}
-		SlotOut *os; uint8_t *ot; uint32_t *op; uint64_t ob; uint32_t *oc;
+		SlotOut *os; uint8_t *ot; uint32_t *op; uint64_t ob; uint32_t *oc, *oa;
 		if (out.on_device) {
-			os = (SlotOut *)out.slots; ot = out.type1; op = out.packed; ob = out.n + k0; oc = out.crc;
+			os = (SlotOut *)out.slots; ot = out.type1; op = out.packed; ob = out.n + k0; oc = out.crc; oa = out.aach;
 		} else {
 			os = ctx->d_oslots[b]; ot = ctx->d_otype1[b]; op = ctx->d_opacked[b]; ob = 0; oc = out.crc ? ctx->d_ocrc[b] : nullptr;
+			oa = out.aach ? ctx->d_oaach[b] : nullptr;
 		}
-		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob, oc, src.skip_dependent);
+		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob, oc, src.skip_dependent, oa);
 		if (r) return r;
 		CU(cudaEventRecord(ctx->ev_comp[b], ctx->s_compute));
 		cudaStream_t so = host_out ? ctx->s_d2h : ctx->s_compute;
@@ -1012,6 +1069,8 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 				CU(cudaMemcpyAsync(out.packed + o0 * TYPE1_WORDS, op, (size_t)nb * TYPE1_WORDS * 4, cudaMemcpyDeviceToHost, so));
 			if (out.crc)
 				CU(cudaMemcpyAsync(out.crc + o0, oc, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
+			if (out.aach)
+				CU(cudaMemcpyAsync(out.aach + o0, oa, (size_t)nb * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		}
 		CU(cudaMemcpyAsync(ctx->h_flags + 2 * i, ctx->d_flags + 2 * i, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		CU(cudaMemcpyAsync(ctx->h_pstats + 3 * i, ctx->d_pstats + 3 * i, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, so));
@@ -1083,11 +1142,11 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 
 /* the LOCKED run that starts at the receiver's present position: where its slots sit and how many the modelled
  * calls up to c_max can process (tetra_burst_sync.c:107-150, one slot per call) */
-static uint64_t locked_extent(const RxHost &rx, uint32_t C, uint64_t n_end, uint64_t c_max, Segment *seg)
+static uint64_t locked_extent(const RxHost &rx, const CallGeom &cg, uint64_t c_max, Segment *seg)
 {
-	seg->a0 = rx.buf_start; seg->cmin = rx.calls + 1; seg->n_end = n_end; seg->chunk = C;
-	if (n_end < seg->a0 + SLOT_BITS || c_max < seg->cmin) return 0;
-	const uint64_t by_bits = (n_end - SLOT_BITS - seg->a0) / SLOT_BITS + 1;
+	seg->a0 = rx.buf_start; seg->cmin = rx.calls + 1; seg->cg = cg;
+	if (cg.n_end < seg->a0 + SLOT_BITS || c_max < seg->cmin) return 0;
+	const uint64_t by_bits = (cg.n_end - SLOT_BITS - seg->a0) / SLOT_BITS + 1;
 	const uint64_t by_calls = c_max - seg->cmin + 1;
 	return std::min(by_bits, by_calls);
 }
@@ -1100,7 +1159,7 @@ static void locked_advance(tb200_ctx *ctx, const Segment &seg, uint64_t valid, b
 	const uint64_t c_last = slot_call(seg, valid - 1);
 	rx.calls = c_last;
 	rx.buf_start = seg.a0 + (uint64_t)SLOT_BITS * valid;
-	rx.bits_in_buf = (uint32_t)(std::min<uint64_t>(c_last * seg.chunk, seg.n_end) - rx.buf_start);
+	rx.bits_in_buf = (uint32_t)(bits_at_call(seg.cg, c_last) - rx.buf_start);
 	rx.next_frame_start += (uint64_t)SLOT_BITS * valid;
 	if (lost) {
 		rx.state = TB200_RX_UNLOCKED;
@@ -1108,21 +1167,40 @@ static void locked_advance(tb200_ctx *ctx, const Segment &seg, uint64_t valid, b
 	}
 }
 
-static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out)
+/* the calls of this run: everything the stream holds beyond what earlier runs delivered, `chunk` bits per call; the
+ * last call of a FINAL run may be short (read() at EOF), a non-final run ends on a call boundary */
+static CallGeom run_geometry(const tb200_ctx *ctx, uint64_t total, bool final, uint64_t *c_max)
 {
-	const uint32_t C = ctx->opt.chunk_bits;
+	const RxHost &rx = ctx->rx;
+	CallGeom cg;
+	cg.chunk = ctx->opt.chunk_bits; cg.pad = 0;
+	cg.c_base = rx.c_base; cg.t_base = rx.t_base;
+	const uint64_t fresh = total - rx.t_base;
+	const uint64_t ncalls = final ? (fresh + cg.chunk - 1) / cg.chunk : fresh / cg.chunk;
+	*c_max = rx.c_base + ncalls;
+	cg.n_end = final ? total : rx.t_base + ncalls * cg.chunk;
+	return cg;
+}
+
+static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out, bool same_run = false)
+{
 	const uint64_t total = src.end;
-	const uint64_t c_max = final ? (total + C - 1) / C : total / C;
-	const uint64_t n_end = final ? total : c_max * C;
 	RxHost &rx = ctx->rx;
-	auto T = [&](uint64_t c) { return std::min<uint64_t>(c * C, n_end); };
+	/* a new run starts where the calls modelled so far ended (same_run: the caller comes back into the run it left
+	 * with stop_at_lock) */
+	if (!same_run) { rx.c_base = rx.calls; rx.t_base = rx.delivered; }
+	uint64_t c_max = 0;
+	const CallGeom cg = run_geometry(ctx, total, final, &c_max);
+	const uint64_t n_end = cg.n_end;
+	auto T = [&](uint64_t c) { return bits_at_call(cg, c); };
 	int rc;
+	struct Delivered { RxHost &rx; uint64_t n_end; ~Delivered() { rx.delivered = n_end; } } mark_delivered{rx, n_end};
 
 	while (rx.calls < c_max) {
 		if (rx.state == TB200_RX_LOCKED) {
 			if (ctx->stop_at_lock) return 0;
 			Segment seg;
-			const uint64_t n_slots = locked_extent(rx, C, n_end, c_max, &seg);
+			const uint64_t n_slots = locked_extent(rx, cg, c_max, &seg);
 			if (n_slots == 0) {
 				rx.calls = c_max;
 				rx.bits_in_buf = (uint32_t)(T(c_max) - rx.buf_start);
@@ -1242,7 +1320,7 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 	TB_TRACE("carry pushed");
 	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
-	out.crc = ctx->user_crc; out.max_slots = max_slots; out.n = 0;
+	out.crc = ctx->user_crc; out.aach = ctx->user_aach; out.max_slots = max_slots; out.n = 0;
 	ctx->lock_events.clear();
 	ctx->fed_end = n_bits;
 	profile_begin(ctx);
@@ -1269,7 +1347,7 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	Source src; src.on_device = false; src.data = bits; src.new_base = ctx->fed_end; src.end = ctx->fed_end + n_bits;
 	src.fmt = (int)ctx->opt.input;
 	Outputs out; out.on_device = false; out.slots = slots; out.type1 = type1; out.packed = type1_packed;
-	out.crc = ctx->user_crc; out.max_slots = max_slots; out.n = 0;
+	out.crc = ctx->user_crc; out.aach = ctx->user_aach; out.max_slots = max_slots; out.n = 0;
 	ctx->lock_events.clear();
 	ctx->fed_end += n_bits;
 	profile_begin(ctx);
@@ -1813,6 +1891,40 @@ extern "C" void tb200_debug_time_advance(uint32_t *tn, uint32_t *fn, uint32_t *m
 	*tn = t.tn; *fn = t.fn; *mn = t.mn;
 }
 
+/* ------------------------------------------------------------ RM(30,14) leaf -- */
+
+__global__ void __launch_bounds__(256)
+k_rm3014_decode(const uint32_t *__restrict__ words, uint64_t n, const Tables *__restrict__ tab,
+                const uint32_t *__restrict__ leader, uint32_t *__restrict__ out)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+		out[i] = rm3014_decode(tab, leader, words[i]);
+}
+
+extern "C" int tb200_rm3014_decode(tb200_ctx *ctx, const uint32_t *words, uint64_t n, uint32_t *out, int is_device)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (n && (!words || !out)) return fail(ctx, TB200_E_ARG, "null argument");
+	if (n == 0) return 0;
+	if ((r = ensure_rm_leaders(ctx))) return r;
+	const uint32_t *dw = words; uint32_t *dout = out;
+	cudaStream_t st = ctx->s_compute;
+	if (!is_device) {
+		uint32_t *a = nullptr, *b = nullptr;
+		if ((r = leaf_buf(ctx, 0, n, &a)) || (r = leaf_buf(ctx, 1, n, &b))) return r;
+		CU(cudaMemcpyAsync(a, words, n * 4, cudaMemcpyHostToDevice, st));
+		dw = a; dout = b;
+	}
+	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sm_count * 8);
+	TB_LAUNCH(k_rm3014_decode, blocks, 256, st, dw, n, ctx->d_tab, ctx->d_rm_leader, dout);
+	CU(cudaGetLastError());
+	if (!is_device) CU(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return 0;
+}
+
 /* ---------------------------------------------------------- digest, packing -- */
 
 extern "C" int tb200_slots_digest(tb200_ctx *ctx, const tb200_slot *slots, const uint32_t *type1_packed, uint64_t n,
@@ -1929,10 +2041,11 @@ extern "C" int tb200_shard_pass1(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t
 	if ((rc = ensure_workspace(ctx, n_slots ? n_slots : 1))) return rc;
 	if ((rc = ensure_pieces(ctx, 1))) return rc;
 	RxGeom g;
-	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.n_end = n_end; g.fmt = (int)ctx->opt.input;
+	g.bits = d_bits; g.n_bytes = n_bytes; g.base_bit = base_bit; g.a0 = a0; g.cmin = cmin; g.fmt = (int)ctx->opt.input;
 	if (g.fmt != IN_BYTES && ((base_bit & 127) || ((uintptr_t)d_bits & 3)))
 		return fail(ctx, TB200_E_ARG, "bit-packed / symbol shards start on a 128-bit boundary of the stream, in a 4-byte aligned buffer");
-	g.chunk = ctx->opt.chunk_bits; g.n_slots = n_slots; g.tie_hi = (int)ctx->opt.viterbi_tie;
+	g.cg.c_base = 0; g.cg.t_base = 0; g.cg.n_end = n_end; g.cg.chunk = ctx->opt.chunk_bits; g.cg.pad = 0;
+	g.n_slots = n_slots; g.tie_hi = (int)ctx->opt.viterbi_tie;
 	memset(&ctx->stats, 0, sizeof(ctx->stats));
 	if (n_slots && (rc = enqueue_pass1(ctx, g, 0, 0, nullptr, false))) return rc;
 	tb200_shard_summary *d_sum = reinterpret_cast<tb200_shard_summary *>(ctx->d_hits);    /* small scratch */

@@ -29,25 +29,17 @@
 
 namespace tb {
 
-/* bits_in_buf when slot k is processed, in 32-bit arithmetic relative to the launch
- * (same value as slot_window(); rel = first slot's offset inside its read() chunk) */
+/* bits_in_buf when slot k of the launch is processed (same value as slot_window()) */
 struct WinGeom {
-	uint32_t chunk, rel0;        /* rel0 = a0 mod chunk */
-	uint64_t c00;                /* a0 div chunk */
-	uint64_t cmin, n_end, a0;
+	CallGeom cg;
+	uint64_t cmin, a0;
 };
 
 __device__ __forceinline__ unsigned slot_window32(const WinGeom &g, uint32_t k)
 {
 	/* 64-bit: a shard of the sharded path can hold more than 2^32 / 510 slots in one launch */
-	const uint64_t num = (uint64_t)g.rel0 + 510ull * k + 510u + g.chunk - 1;
-	const uint64_t q = g.chunk == 64 ? num >> 6 : (num <= 0xffffffffull ? (uint64_t)((uint32_t)num / g.chunk) : num / g.chunk);
-	uint64_t c = g.c00 + q;
-	const uint64_t lo = g.cmin + k;
-	if (c < lo) c = lo;
-	uint64_t t = c * g.chunk;
-	if (t > g.n_end) t = g.n_end;
-	return (unsigned)(t - (g.a0 + 510ull * k));
+	const uint64_t ak = g.a0 + 510ull * k;
+	return (unsigned)(bits_at_call(g.cg, call_for(g.cg, ak + 510u, g.cmin + k)) - ak);
 }
 
 constexpr int CT_THREADS = 256;

@@ -113,6 +113,9 @@ static int dfail(tb200_dist *d, int code, const char *fmt, ...)
 	va_end(ap);
 	return code;
 }
+/* TB200_DIST_TRACE=1: progress of every rank on stderr (hunting a rank that waits for another) */
+#define DTRACE(...) do { static const bool on_ = getenv("TB200_DIST_TRACE") != nullptr; \
+	if (on_) { fprintf(stderr, "[tb200 dist r%d] ", d->rank); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } } while (0)
 #define DCU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
 	return dfail(d, TB200_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 
@@ -319,6 +322,7 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 	memset(&d->timing, 0, sizeof(d->timing));
 	*n_runs = 0;
 	uint64_t n_local = 0;
+	bool first_segment = true;
 	const tb200_options saved_opt = ctx->opt;
 	auto restore = [&]() { ctx->opt = saved_opt; };
 
@@ -352,15 +356,18 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 		uint64_t c_max = 0;
 		if (rank == 0) {
 			const uint32_t C = ctx->opt.chunk_bits;
-			c_max = (n_bits + C - 1) / C;
 			Outputs none; none.on_device = true; none.slots = nullptr; none.type1 = nullptr; none.packed = nullptr; none.crc = nullptr; none.max_slots = 0; none.n = 0;
 			ctx->stop_at_lock = true;
 			ctx->opt.input = (uint32_t)src_fmt;
-			int rc = rx_run(ctx, fsm_src, true, none);
+			int rc = rx_run(ctx, fsm_src, true, none, !first_segment);
+			first_segment = false;
 			ctx->stop_at_lock = false;
 			if (rc) { restore(); return dfail(d, rc, "%s", ctx->err); }
+			CallGeom cg;
+			cg.c_base = 0; cg.t_base = 0; cg.n_end = n_bits; cg.chunk = C; cg.pad = 0;      /* one run: the whole stream, C bits per call */
+			c_max = (n_bits + C - 1) / C;
 			if (ctx->rx.state == TB200_RX_LOCKED) {
-				m.n_slots = locked_extent(ctx->rx, C, n_bits, c_max, &seg);
+				m.n_slots = locked_extent(ctx->rx, cg, c_max, &seg);
 				m.ok = m.n_slots > 0;
 			}
 			m.chunk = C; m.fmt = (uint32_t)xfer_fmt; m.tie = ctx->opt.viterbi_tie;
@@ -380,9 +387,11 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 			if (rc) { restore(); return rc; }
 		}
 		d->timing.lock_ms += ms_since(t0);
+		DTRACE("segment meta: ok %u a0 %llu slots %llu fmt %u", m.ok, (unsigned long long)m.a0, (unsigned long long)m.n_slots, m.fmt);
 		if (!m.ok) break;
 		d->timing.segments++;
-		seg.a0 = m.a0; seg.cmin = m.cmin; seg.n_end = m.n_end; seg.chunk = m.chunk;
+		seg.a0 = m.a0; seg.cmin = m.cmin;
+		seg.cg.c_base = 0; seg.cg.t_base = 0; seg.cg.n_end = m.n_end; seg.cg.chunk = m.chunk; seg.cg.pad = 0;
 		ctx->opt.chunk_bits = m.chunk; ctx->opt.viterbi_tie = m.tie; ctx->opt.input = m.fmt;
 
 		const DistPlan me = dist_plan(m, world, rank);
@@ -527,6 +536,7 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 			}
 		}
 		d->timing.transfer_ms += ms_since(t0);
+		DTRACE("data queued: %llu slots, %zu ready events", (unsigned long long)n_mine, ready.size());
 
 		/* ---- speculative pass over the shard */
 		t0 = clk::now();
@@ -535,7 +545,7 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 		mine.first_good = ~0ull;
 		const uint64_t local_base = n_local;
 		Segment sseg;                 /* the shard as a LOCKED run of its own */
-		sseg.a0 = me.lo; sseg.cmin = m.cmin + me.k0; sseg.n_end = m.n_end; sseg.chunk = m.chunk;
+		sseg.a0 = me.lo; sseg.cmin = m.cmin + me.k0; sseg.cg = seg.cg;
 		Source ssrc; ssrc.on_device = true; ssrc.data = shard_ptr; ssrc.new_base = me.base; ssrc.end = me.hi; ssrc.fmt = (int)m.fmt;
 		ssrc.ready = ready.empty() ? nullptr : &ready;
 		ssrc.skip_dependent = rank > 0;
@@ -554,6 +564,7 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 			mine.mcc = chain_end.mcc; mine.mnc = chain_end.mnc; mine.cc = chain_end.cc;
 		}
 		d->timing.pass1_ms += ms_since(t0);
+		DTRACE("first pass done: valid %llu lost %u seen_good %u", (unsigned long long)mine.n_valid, mine.lost, mine.seen_good);
 
 		/* ---- the exchange step: everyone's summary to everyone */
 		t0 = clk::now();
@@ -565,6 +576,7 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 			all[0] = mine;
 		}
 		d->timing.exchange_ms += ms_since(t0);
+		DTRACE("summaries exchanged");
 
 		/* the segment ends behind the first lock loss; ranks behind it drop what they decoded */
 		int r_lost = -1;
@@ -633,7 +645,6 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 		if (rank == 0) {
 			/* the run_locked calls above counted rank 0's slots only */
 			ctx->stats.slots = m.k_done;
-			seg.a0 = m.a0; seg.cmin = m.cmin; seg.n_end = m.n_end; seg.chunk = m.chunk;
 			locked_advance(ctx, seg, seg_valid, r_lost >= 0);
 			if (r_lost < 0) {         /* what rx_run does when no further slot fits: the remaining calls only fill the buffer */
 				ctx->rx.calls = c_max;

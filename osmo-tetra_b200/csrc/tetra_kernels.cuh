@@ -53,7 +53,31 @@ struct Tables {
 	/* the same CRC with the register bit-reversed: byte table [0,256) and nibble table [256,272),
 	 * so that LSB-first packed bytes feed it directly (lane kernels) */
 	uint32_t crc_tab_r[272];
+	/* RM(30,14), tetra_rm3014.c:28-43: parity (low 16 bits of the code word) of the low / high 7 information bits */
+	uint16_t rm_par[2][128];
 };
+
+/* ---- RM(30,14) decoding (the AACH, tetra_lower_mac.c:268-274 has a FIXME where this belongs) ----
+ * Words follow tetra_rm3014_compute: 30 bits, bit 29 first on air, information = word >> 16.  The code is linear, so
+ * the nearest code word is word ^ leader[syndrome], leader = the lightest (then numerically smallest) error pattern
+ * with that syndrome: a 2^16-entry table built on the host.  Result: information bits of the nearest code word |
+ * distance << 16 | (syndrome != 0) << 24. */
+TB_HD inline uint32_t rm3014_syndrome(const Tables *tab, uint32_t word)
+{
+	const uint32_t info = (word >> 16) & 0x3fffu;
+	return (uint32_t)(tab->rm_par[0][info & 127] ^ tab->rm_par[1][info >> 7] ^ (word & 0xffffu));
+}
+
+__device__ __forceinline__ uint32_t rm3014_decode(const Tables *__restrict__ tab, const uint32_t *__restrict__ leader, uint32_t word)
+{
+	word &= 0x3fffffffu;
+	const uint32_t syn = rm3014_syndrome(tab, word);
+	const uint32_t e = leader[syn];
+	return ((word ^ e) >> 16) | ((uint32_t)__popc(e) << 16) | (syn ? 1u << 24 : 0u);
+}
+
+/* the slot's 30 descrambled BBK bits, first bit on air in bit 0 -> the word convention above */
+__device__ __forceinline__ uint32_t rm3014_word_from_air(uint32_t bits_lsb_first) { return __brev(bits_lsb_first) >> 2; }
 
 /* training sequences, LSB = first bit on air (values checked against the reference's
  * arrays tetra_burst.c:59-70 by tests/test_oracle.py) */
@@ -685,14 +709,43 @@ __device__ __forceinline__ uint32_t field_msb_first(const uint32_t *w, unsigned 
 
 /* =================================================================== kernels == */
 
+/* The modelled tetra_burst_sync_in() calls of the current RUN of equal-length reads (tetra-rx.c:82-95 reads 64 bytes
+ * at a time, a pipe may hand out less): calls c_base+1, c_base+2, ... deliver `chunk` bits each, so after call c the
+ * receiver has been given T(c) = min(t_base + (c - c_base) * chunk, n_end) bits.  A stream fed with changing read sizes
+ * is a sequence of such runs (one library call per run). */
+struct CallGeom {
+	uint64_t c_base;           /* calls made before the run */
+	uint64_t t_base;           /* bits they delivered */
+	uint64_t n_end;            /* bits delivered when the run's last call is done */
+	uint32_t chunk;            /* bits per call of the run */
+	uint32_t pad;
+};
+
+/* the call that processes a slot ending at stream bit end_bit: the first one that has delivered it, but one slot per
+ * call (tetra_burst_sync.c:107-150), i.e. not before call cfloor */
+TB_HD inline uint64_t call_for(const CallGeom &cg, uint64_t end_bit, uint64_t cfloor)
+{
+	uint64_t need = cg.c_base;
+	if (end_bit > cg.t_base) {
+		const uint64_t x = end_bit - cg.t_base + cg.chunk - 1;
+		need += cg.chunk == 64 ? x >> 6 : (x <= 0xffffffffull ? (uint64_t)((uint32_t)x / cg.chunk) : x / cg.chunk);
+	}
+	return need > cfloor ? need : cfloor;
+}
+
+TB_HD inline uint64_t bits_at_call(const CallGeom &cg, uint64_t c)
+{
+	const uint64_t t = cg.t_base + (c - cg.c_base) * cg.chunk;
+	return t < cg.n_end ? t : cg.n_end;
+}
+
 struct RxGeom {
 	const uint8_t *bits;       /* device buffer holding stream bits [base_bit, base_bit + n_bytes) */
 	uint64_t n_bytes;          /* stream BITS available from base_bit (= bytes in the 1-bit-per-byte format) */
 	uint64_t base_bit;
 	uint64_t a0;               /* absolute bit of slot 0 of this launch */
 	uint64_t cmin;             /* first tetra_burst_sync_in() call that may process slot 0 */
-	uint64_t n_end;            /* bits that the modelled calls deliver in total */
-	uint32_t chunk;            /* bits per modelled call (tetra-rx.c:83: 64) */
+	CallGeom cg;               /* the modelled calls */
 	uint32_t n_slots;
 	int fmt;                   /* IN_BYTES / IN_PACKED / IN_F32SYM: how `bits` encodes the stream (base_bit % 128 == 0 unless bytes) */
 	int tie_hi;                /* Viterbi tie rule (include/tetra_tie_rule.h), used by the warp-form SB1 decode */
@@ -702,11 +755,7 @@ struct RxGeom {
  * (tetra_burst_sync.c:107-120 with one slot per call and `chunk` new bits per call) */
 __device__ __forceinline__ unsigned slot_window(const RxGeom &g, uint64_t k, uint64_t ak)
 {
-	const uint64_t need = (ak + SLOT_BITS + g.chunk - 1) / g.chunk;
-	const uint64_t c = need > g.cmin + k ? need : g.cmin + k;
-	uint64_t t = c * g.chunk;
-	if (t > g.n_end) t = g.n_end;
-	return (unsigned)(t - ak);
+	return (unsigned)(bits_at_call(g.cg, call_for(g.cg, ak + SLOT_BITS, g.cmin + k)) - ak);
 }
 
 /* Pass 1, one warp per slot: load + pack the slot, search the training sequence with the
@@ -964,6 +1013,8 @@ struct DecodeArgs {
 	uint32_t *crc;                /* optional: CRC-16 registers per slot, block A (SB1 / SCH-F / BLK1) | block B (SB2 / BLK2) << 16 */
 	int tie_hi;                   /* Viterbi tie rule (warp form; the lane kernels are templates) */
 	unsigned long long *stats;    /* [3] counters of this piece: slots handed to the lower MAC, primitives, CRC-good blocks */
+	uint32_t *aach;               /* optional: RM(30,14) decoding of the slot's AACH (rm3014_decode), ~0 for slots without one */
+	const uint32_t *rm_leader;    /* its coset-leader table */
 	int skip_dependent;           /* sharded decode, first pass: leave out the slots whose cell state would come from a carry-in that
 	                               * is not known yet (no CRC-good SB1 since the shard began); they are decoded once it is */
 };
@@ -1010,7 +1061,7 @@ k_decode_warp(DecodeArgs a)
 		if (a.skip_dependent && dep && !a.carry->seen_good) continue;          /* warp-uniform */
 		const int kind = w.kind;
 		uint32_t flags = (uint32_t)kind | (w.unlock ? F_UNLOCK : 0);
-		uint32_t crcs = 0;
+		uint32_t crcs = 0, bb30 = 0;
 
 		if (lane < 16) S.bw[lane] = a.slot_bits[k * 16 + lane];
 		if (lane < 4) S.bw[16 + lane] = 0;
@@ -1027,6 +1078,7 @@ k_decode_warp(DecodeArgs a)
 			if (lane == 0) {
 				S.sb1[0] = w.sb1_t1[0]; S.sb1[1] = w.sb1_t1[1]; S.sb1[2] = 0;
 				S.bbk[0] = (extract_bits(S.bw, 252, 14) ^ S.lf[0]) & 0x3fff; S.bbk[1] = 0;
+				bb30 = (extract_bits(S.bw, 252, 30) ^ S.lf[0]) & 0x3fffffffu;
 			}
 			gather_type3<1, PL_BLK2>(S.bw, S.lf, S.t3[0], lane);
 			viterbi_warp<144>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0], a.tie_hi != 0);
@@ -1041,6 +1093,7 @@ k_decode_warp(DecodeArgs a)
 			/* BBK | SCH/F (tetra_burst.c:363-373) */
 			if (lane == 0) {
 				S.bbk[0] = (extract_bits(S.bw, 230, 14) ^ S.lf[0]) & 0x3fff; S.bbk[1] = 0;
+				bb30 = ((extract_bits(S.bw, 230, 14) | (extract_bits(S.bw, 266, 16) << 14)) ^ S.lf[0]) & 0x3fffffffu;
 			}
 			gather_type3<5, PL_SCHF>(S.bw, S.lf, S.t3[0], lane);
 			viterbi_warp<288>(S.t3[0], S.t3[0], false, S.dec, S.t2[0], S.t2[0], a.tie_hi != 0);
@@ -1053,6 +1106,7 @@ k_decode_warp(DecodeArgs a)
 			/* BBK | BLK1 | BLK2 (tetra_burst.c:354-362), the two halves decode side by side */
 			if (lane == 0) {
 				S.bbk[0] = (extract_bits(S.bw, 230, 14) ^ S.lf[0]) & 0x3fff; S.bbk[1] = 0;
+				bb30 = ((extract_bits(S.bw, 230, 14) | (extract_bits(S.bw, 266, 16) << 14)) ^ S.lf[0]) & 0x3fffffffu;
 			}
 			gather_type3<1, PL_BLK1>(S.bw, S.lf, S.t3[0], lane);
 			gather_type3<1, PL_BLK2>(S.bw, S.lf, S.t3[1], lane);
@@ -1078,6 +1132,7 @@ k_decode_warp(DecodeArgs a)
 			o.find_rc = w.find_rc; o.flags = (uint8_t)flags;
 			a.slots[ko] = o;
 			if (a.crc) a.crc[ko] = crcs;
+			if (a.aach) a.aach[ko] = kind == KIND_NONE ? 0xffffffffu : rm3014_decode(tab, a.rm_leader, rm3014_word_from_air(bb30));
 		}
 		if (a.stats) add_counts(a.stats, lane == 0 ? slot_counts(kind, flags) : 0u);
 		__syncwarp();

@@ -658,7 +658,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 		else if (u < uF + u2)           { k[0] = l2[u - uF]; }
 		else if (u < uF + u2 + uS)      { const uint64_t i = u - uF - u2; k[0] = lS[2 * i]; if (2 * i + 1 < cS) k[1] = lS[2 * i + 1]; }
 		else if (u < units)             { const uint64_t i = u - uF - u2 - uS; k[0] = l0[2 * i]; if (2 * i + 1 < c0) k[1] = l0[2 * i + 1]; }
-		uint32_t code[2] = { 0, 0 }, flags[2] = { 0, 0 }, bbk[2] = { 0, 0 };
+		uint32_t code[2] = { 0, 0 }, flags[2] = { 0, 0 }, bbk[2] = { 0, 0 };      /* bbk: the 30 descrambled AACH bits, first on air in bit 0 */
 		int kind[2] = { KIND_NONE, KIND_NONE };
 		int n[2] = { 0, 0 };
 		Tm tm[2];
@@ -687,13 +687,14 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 				if (kind[h] == KIND_SB) {
 					xor_region<252, 0, 30>(bw, lf);
 					xor_region<282, 0, 216>(bw, lf);
-					bbk[h] = extract_bits(bw, 252, 14);
+					bbk[h] = extract_bits(bw, 252, 30);
 					gather_lane<1, PL_BLK2>(bw, col, nt); n[h] = 144;
 				} else if (kind[h] == KIND_NDB_F) {
 					xor_region<14, 0, 216>(bw, lf);
 					xor_region<282, 216, 216>(bw, lf);
 					xor_region<230, 0, 14>(bw, lf);
 					bbk[h] = extract_bits(bw, 230, 14);
+					if (a.aach) bbk[h] |= ((extract_bits(bw, 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;       /* the broadcast block's second part */
 					gather_lane<5, PL_SCHF>(bw, col, nt); n[h] = 288;
 				} else if (h == 0) {
 					/* two-block slot: BLK1 on trellis X, BLK2 on trellis Y of this thread (k[1] is unused) */
@@ -701,6 +702,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 					xor_region<282, 0, 216>(bw, lf);
 					xor_region<230, 0, 14>(bw, lf);
 					bbk[h] = extract_bits(bw, 230, 14);
+					if (a.aach) bbk[h] |= ((extract_bits(bw, 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;
 					gather_lane<1, PL_BLK1>(bw, sm.t3col(0, tid), nt);
 					gather_lane<1, PL_BLK2>(bw, sm.t3col(1, tid), nt);
 					n[0] = n[1] = 144;
@@ -743,7 +745,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 #pragma unroll
 			for (int i = 0; i < 9; ++i) outw[i] = 0;
 			const uint32_t *col = sm.t3col(h, tid);
-			const uint32_t bb = bbk[h];
+			const uint32_t bb = bbk[h] & 0x3fffu;
 			const SlotWs w = a.ws[k[h]];
 			if (kind[h] == KIND_SB) {
 				const uint32_t s0 = w.sb1_t1[0], s1 = w.sb1_t1[1];
@@ -780,6 +782,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			o.find_rc = w.find_rc; o.flags = (uint8_t)flags[h];
 			a.slots[ko] = o;
 			if (a.crc) a.crc[ko] = crcs[h] | (kind[h] == KIND_SB ? (w.sb1_crc & 0xffffu) : 0u);
+			if (a.aach) a.aach[ko] = kind[h] == KIND_NONE ? 0xffffffffu : rm3014_decode(tab, a.rm_leader, rm3014_word_from_air(bbk[h]));
 		}
 		if (a.stats)
 			add_counts(a.stats, (k[0] != ~0ull ? slot_counts(kind[0], flags[0]) : 0u) +

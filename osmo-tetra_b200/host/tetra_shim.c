@@ -10,7 +10,14 @@
  * TMV-SAP primitive the reference builds (tetra_lower_mac.c:129-140,162-167,276-352) to
  *     int upper_mac_prim_recv(struct osmo_prim_hdr *op, void *priv)              tetra_upper_mac.h:22
  *
- * Bits are queued and decoded on the GPU in batches (TETRA_B200_BATCH_BITS, default 8 Mi bits).
+ * Bits are queued and decoded on the GPU in batches: a batch ends when TETRA_B200_BATCH_BITS (default 8 Mi bits) are
+ * queued, when TETRA_B200_FLUSH_MS (default 250) milliseconds have passed since the last one (a demodulator piped into
+ * tetra-rx delivers 36 kbit/s: primitives then reach the upper MAC four times a second instead of every four minutes),
+ * and whenever the length of the reads changes: read() on a pipe returns what is there (tetra-rx.c:82-95), the library
+ * models one run of equal-length reads per call, so any sequence of read sizes gives the reference's search windows.
+ * TETRA_B200_BATCH_BITS=0 decodes on every call and returns the reference's own return value (len, 0 while
+ * KNOW_FSTART waits, -1 when the UNLOCKED search fails, tetra_burst_sync.c:77-78,93-94); batched calls return len
+ * (what the result will be is not known yet; tetra-rx.c:94 ignores it).
  * tetra-rx has no end-of-stream call: it reads until read() returns 0, prints "EOF", frees its state and
  * exits (tetra-rx.c:82-102).  Built with -DTETRA_B200_SHIM_WRAP_READ and linked with -Wl,--wrap=read the
  * shim sees that read() itself: when the descriptor that feeds tetra_burst_sync_in() reports end of file
@@ -33,13 +40,14 @@
  * (tetra_lower_mac.c:190-241) and writes the same <dumpdir>/traffic_*.out / .txt files for SCH/F-shaped
  * traffic slots.  Not reproduced: the dump of a 216-bit second block (the reference fills half of it from
  * uninitialised memory).  The stdout / stderr text of the reference's PHY and lower MAC is printed from
- * tetra_text.h in the reference's order (TETRA_B200_TEXT=0 switches it off).  read() sizes must be constant
- * (64 in tetra-rx.c:83) except for the last one; other call patterns are rejected loudly.
+ * tetra_text.h in the reference's order (TETRA_B200_TEXT=0 switches it off).  Reads of more than 296 bits are rejected
+ * (one slot per call could not keep up with them: the reference then drops bits in make_bitbuf_space).
  */
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <osmocom/core/msgb.h>
 #include <osmocom/core/talloc.h>
@@ -74,9 +82,11 @@ static struct {
 	uint8_t *hist;         /* [SHIM_HIST bits of history][the batch = bits] */
 	size_t n_hist;
 	uint64_t fed_before;   /* stream bits handed to the library before this batch */
-	unsigned int chunk;
-	int short_read_seen;
+	unsigned int chunk;    /* length of the reads of the queued run */
 	int started;
+	int flush_ms;          /* wall-clock flush interval (0: off) */
+	struct timespec last_flush;
+	unsigned int calls_since_clock;
 	int finished;          /* the stream was flushed: a second flush (atexit after an explicit one) does nothing */
 	struct tetra_rx_state *trs;
 	struct tb200_slot *slots;
@@ -193,6 +203,15 @@ static void shim_run(int final)
 	if (final)
 		S.finished = 1;
 	uint32_t flags = (S.started ? 0 : TB200_FRESH) | (final ? TB200_FINAL : 0);
+	if (S.chunk) {                    /* the reads of this run */
+		struct tb200_options opt;
+		tb200_default_options(&opt);
+		opt.chunk_bits = S.chunk;
+		opt.output = TB200_OUT_UNPACKED;
+		if (tb200_set_options(S.ctx, &opt) != 0)
+			shim_die(tb200_last_error(S.ctx));
+	}
+	clock_gettime(CLOCK_MONOTONIC, &S.last_flush);
 	long n = tb200_rx_stream_host(S.ctx, S.bits, S.n_bits, flags, S.slots, S.type1, NULL, S.max_slots);
 	if (n < 0) {
 		fprintf(stderr, "tetra_b200 shim: %s\n", tb200_last_error(S.ctx));
@@ -214,9 +233,12 @@ static void shim_run(int final)
 	size_t nrec = tb200_expand_records(S.slots, S.type1, (size_t)n, S.rec, 3 * S.max_slots);
 	struct tetra_mac_state *tms = priv;
 	/* lock acquisitions of this batch, for the "found SYNC training sequence" lines */
-	struct tb200_lock_event ev[64];
-	size_t n_ev = S.text ? tb200_get_lock_events(S.ctx, ev, 64) : 0, e = 0, ri = 0;
-	if (n_ev > 64) n_ev = 64;
+	size_t n_ev = S.text ? tb200_get_lock_events(S.ctx, NULL, 0) : 0, e = 0, ri = 0;
+	struct tb200_lock_event *ev = n_ev ? malloc(n_ev * sizeof(*ev)) : NULL;      /* a noisy batch can hold any number */
+	if (n_ev && !ev)
+		shim_die("out of memory");
+	if (n_ev)
+		tb200_get_lock_events(S.ctx, ev, n_ev);
 	for (long i = 0; i <= n; i++) {
 		while (e < n_ev && ev[e].next_slot == (uint64_t)i)
 			tb200_text_lock(ev[e++].offset);
@@ -264,6 +286,7 @@ static void shim_run(int final)
 			deliver(r, priv);
 		}
 	}
+	free(ev);
 	if (S.text)
 		fflush(stdout);
 #endif
@@ -316,8 +339,10 @@ static void shim_init(unsigned int first_len)
 {
 	const char *e = getenv("TETRA_B200_BATCH_BITS");
 	const char *d = getenv("TETRA_B200_DEVICE");
-	S.batch_bits = e ? strtoull(e, NULL, 0) : (8u << 20);
-	if (S.batch_bits < 4096) S.batch_bits = 4096;
+	S.batch_bits = e ? strtoull(e, NULL, 0) : (8u << 20);        /* 0: decode on every call */
+	const char *fm = getenv("TETRA_B200_FLUSH_MS");
+	S.flush_ms = fm ? atoi(fm) : 250;
+	clock_gettime(CLOCK_MONOTONIC, &S.last_flush);
 	if (tb200_create(&S.ctx, d ? atoi(d) : 0) != 0)
 		shim_die("no usable CUDA device - this build has no CPU lower MAC");
 	struct tb200_options opt;
@@ -327,7 +352,7 @@ static void shim_init(unsigned int first_len)
 	if (tb200_set_options(S.ctx, &opt) != 0)
 		shim_die(tb200_last_error(S.ctx));
 	S.chunk = first_len;
-	S.cap_bits = S.batch_bits + 4096;
+	S.cap_bits = (S.batch_bits < 4096 ? 4096 : S.batch_bits) + 4096;
 	S.hist = tb200_host_alloc(S.cap_bits + SHIM_HIST);
 	S.bits = S.hist ? S.hist + SHIM_HIST : NULL;
 	S.max_slots = tb200_max_slots(S.cap_bits) + 16;
@@ -352,15 +377,35 @@ int tetra_burst_sync_in(struct tetra_rx_state *trs, uint8_t *bits, unsigned int 
 	if (bits == g_last_read_buf)
 		g_stream_fd = g_last_read_fd;         /* the descriptor whose data reaches the receiver */
 #endif
-	if (S.short_read_seen && len)
-		shim_die("a short read() was followed by more data: only constant read sizes are modelled");
-	if (len != S.chunk)
-		S.short_read_seen = 1;
+	if (len > 296)
+		shim_die("reads of more than 296 bits are not modelled");
+	if (S.n_bits && len != S.chunk)
+		shim_run(0);                          /* the length of the reads changes: a new run */
 	if (len > S.cap_bits - S.n_bits)
 		shim_run(0);
+	S.chunk = len;
 	memcpy(S.bits + S.n_bits, bits, len);
 	S.n_bits += len;
-	if (S.n_bits >= S.batch_bits && S.n_bits % S.chunk == 0)
+	if (S.batch_bits == 0) {
+		/* synchronous: decode now and return what the reference returns (tetra_burst_sync.c:66-106) */
+		struct tb200_rx_carry before, after;
+		tb200_get_carry(S.ctx, &before);
 		shim_run(0);
+		tb200_get_carry(S.ctx, &after);
+		if (before.state == TB200_RX_UNLOCKED && after.state == TB200_RX_UNLOCKED && after.bits_in_buf >= 2 * TB200_BITS_PER_SLOT)
+			return -1;                        /* the SYNC search over the buffer failed */
+		if (before.state == TB200_RX_KNOW_FSTART && after.state == TB200_RX_KNOW_FSTART)
+			return 0;                         /* the frame start is not in the buffer yet */
+		return len;
+	}
+	if (S.n_bits >= S.batch_bits)
+		shim_run(0);
+	else if (S.flush_ms && ++S.calls_since_clock >= 16) {
+		struct timespec now;
+		S.calls_since_clock = 0;
+		clock_gettime(CLOCK_MONOTONIC, &now);
+		if ((now.tv_sec - S.last_flush.tv_sec) * 1000 + (now.tv_nsec - S.last_flush.tv_nsec) / 1000000 >= S.flush_ms)
+			shim_run(0);
+	}
 	return len;
 }

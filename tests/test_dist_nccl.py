@@ -24,6 +24,19 @@ def _free_port():
 
 
 def _worker(rank, world, port, n_bursts, q, mode, wipe):
+    try:
+        _worker_body(rank, world, port, n_bursts, q, mode, wipe)
+    except BaseException:
+        import traceback
+        q.put((rank, "error", traceback.format_exc()))
+        raise
+
+
+def _worker_body(rank, world, port, n_bursts, q, mode, wipe):
+    import faulthandler
+    import sys
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(150, exit=True, file=sys.stderr)      # a rank stuck in a collective says where
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -125,13 +138,23 @@ def test_one_stream_sharded_over_gpus(world, mode, lose_lock):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_bursts, q, mode, wipe)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_bursts, q, mode, wipe), daemon=True) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted(q.get(timeout=600) for _ in range(world))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    try:
+        res = []
+        for _ in range(world):
+            r = q.get(timeout=240)
+            assert r[1] != "error", f"rank {r[0]}:\n{r[2]}"
+            res.append(r)
+        res.sort()
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:              # a rank that died leaves its peers inside a collective
+            if p.is_alive():
+                p.kill()
     digest_sum = 0
     for rank, ok, n, tot, ns, codes, dig, one_digest, oracle_ok, losses, segs in res:
         assert ok, f"rank {rank}: a run differs from the single-GPU decode"

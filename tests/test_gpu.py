@@ -449,3 +449,99 @@ def test_leaf_decode_uplink_and_bbk(gpu, orc, variant):
         orc.reset(); orc.set_cell(int(codes[i])); orc.tp_sap(T.T_BBK, 0, bb[i])
         assert np.array_equal(orc.records()[0]["type1"][:14], out[i]) and ok[i] == 1
     gpu.set_options(viterbi=T.VITERBI_LANE)
+
+
+@pytest.mark.parametrize("mode", [T.DIST_SCATTER, T.DIST_SCATTER | T.DIST_PACK])
+def test_dist_driver_one_rank(gpu, orc, mode):
+    """tb200_dist_rx_stream with a world of one (what a single-GPU box can run of config 5): NCCL communicator of one
+    rank, on-device packing in chunks with per-chunk events, the segment loop with a lock loss; equal to the plain
+    receiver (slots, type-1 bits, digest, final state) and to the oracle"""
+    import torch
+    bits, cfg = _stream(orc, n=6000, random_cell=1, sb_period=11)
+    k = 3000
+    while orc.gen_kind(cfg, k) == 1:
+        k += 1
+    bits = bits.copy()
+    bits[333 + 510 * k + 244:333 + 510 * k + 266] = 0          # a normal burst loses its training sequence
+    orc.reset(); orc.feed(bits, 64)
+    gpu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, output=T.OUT_UNPACKED | T.OUT_PACKED)
+    one_s, one_t1, one_pk = gpu.rx_stream_host(bits)
+    T.check_stream_against(orc.records(), orc.events(), one_s, gpu.expand_records(one_s, one_t1))
+    want_state = gpu.carry()
+    d = torch.from_numpy(np.ascontiguousarray(bits)).cuda()
+    dd = T.Dist(gpu, 0, 1, nccl_id=T.Dist.get_id(gpu))
+    ms = dd.max_local_slots(bits.size)
+    ds = torch.zeros(ms * 16, dtype=torch.uint8, device="cuda")
+    dt = torch.zeros(ms * 288, dtype=torch.uint8, device="cuda")
+    dp = torch.zeros(ms * 9, dtype=torch.int32, device="cuda")
+    n, runs = dd.rx_stream(d.data_ptr(), bits.size, mode, ds.data_ptr(), dt.data_ptr(), dp.data_ptr(), ms)
+    assert n == one_s.size and len(runs) == 2 and dd.timing().segments == 2
+    assert [r[0] for r in runs] == [0, runs[0][2]] and [r[1] for r in runs] == [0, runs[0][2]]
+    assert np.array_equal(ds[:n * 16].cpu().numpy().view(T.SLOT_DTYPE), one_s)
+    assert np.array_equal(dt[:n * 288].cpu().numpy().reshape(n, 288), one_t1)
+    assert np.array_equal(dp[:n * 9].cpu().numpy().view(np.uint32).reshape(n, 9), one_pk)
+    dig = gpu.slots_digest(ds.data_ptr(), dp.data_ptr(), 0, is_device=True, n=n)
+    assert dig == gpu.slots_digest(one_s, one_pk) == T.slots_digest_host(one_s, one_pk)
+    c = gpu.carry()
+    assert (c.state, c.scramb_init, c.tn, c.fn, c.mn) == (want_state.state, want_state.scramb_init, want_state.tn, want_state.fn, want_state.mn)
+    dd.close()
+
+
+def test_pack_bits_leaf(gpu):
+    import torch
+    rng = np.random.default_rng(5)
+    for n, shift in ((1, 0), (31, 3), (4096, 0), (100003, 5), (1 << 20, 16)):
+        bits = rng.integers(0, 2, n).astype(np.uint8)
+        buf = torch.zeros(n + shift + 64, dtype=torch.uint8, device="cuda")
+        buf[shift:shift + n] = torch.from_numpy(bits).cuda()
+        out = torch.full((4 * ((n + 31) // 32) + 16,), 0xAA, dtype=torch.uint8, device="cuda")
+        assert gpu.lib.tb200_pack_bits_dev(gpu.h, C.c_void_p(buf.data_ptr() + shift), n, C.c_void_p(out.data_ptr())) == 0, gpu.err()
+        want = np.packbits(bits, bitorder="little")
+        got = out.cpu().numpy()
+        assert np.array_equal(got[:want.size], want), (n, shift)
+        assert (got[4 * ((n + 31) // 32):] == 0xAA).all()        # nothing written behind the last word
+
+
+def test_rm3014_leaf_gpu(gpu, orc):
+    """real RM(30,14) decoding (the reference has a FIXME there): leaf operator against the exhaustive search"""
+    from test_simt import _rm_words
+    rng = np.random.default_rng(9)
+    words = _rm_words(orc, rng, 3000)
+    info, dist, bad = gpu.rm3014_decode(words)
+    for i, w in enumerate(words):
+        wi, wd = orc.rm3014_decode_ml(int(w))
+        assert (int(info[i]), int(dist[i]), int(bad[i])) == (wi, wd, int(wd != 0)), (i, hex(int(w)))
+    # every pattern of up to three errors is corrected: a million of them on the device
+    import torch
+    n = 1_000_000
+    infos = rng.integers(0, 1 << 14, n).astype(np.uint32)
+    cw = np.array([orc.rm3014(i) for i in range(1 << 14)], dtype=np.uint32)[infos]
+    err = np.zeros(n, dtype=np.uint32)
+    ne = rng.integers(0, 4, n)
+    for r in range(3):
+        bit = rng.integers(0, 30, n)
+        err |= np.where(ne > r, np.uint32(1) << bit.astype(np.uint32), 0).astype(np.uint32)
+    got, dist, _ = gpu.rm3014_decode(cw ^ err)
+    assert np.array_equal(got, infos)
+    assert np.array_equal(dist[:2000], np.array([bin(int(e)).count("1") for e in err[:2000]], dtype=np.uint32))
+
+
+def test_aach_side_output_gpu(gpu, orc):
+    """the RM-decoded AACH next to the chain's reference-exact output: both decoder forms, clean and damaged broadcast blocks"""
+    from test_simt import _check_aach
+    bits, cfg = _stream(orc, n=400, random_cell=1, sb_period=3)
+    gpu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0)
+    slots, aach, n_err = _check_aach(gpu, orc, bits)
+    noisy = bits.copy()
+    rng = np.random.default_rng(6)
+    for k in range(3, 398):
+        for p in rng.choice(np.arange(266, 282), int(rng.integers(1, 4)), replace=False):
+            noisy[333 + 510 * k + p] ^= 1
+    s2, a2, n_err2 = _check_aach(gpu, orc, noisy)
+    assert n_err2 > 300 and np.array_equal(s2["slot_bit"], slots["slot_bit"])
+    ok = (slots["flags"] & 3) != 0
+    assert np.array_equal(a2[ok] & 0x3fff, aach[ok] & 0x3fff)
+    gpu.set_options(viterbi=T.VITERBI_WARP)
+    _, _, _, a3 = gpu.rx_stream_host_aach(noisy)
+    assert np.array_equal(a2, a3)
+    gpu.set_options(viterbi=T.VITERBI_LANE)

@@ -374,3 +374,21 @@ def test_pin_conv_program_selfcheck(tmp_path):
     assert "PINNED" in r.stdout and " on 0 (ties keep s>>1)" in r.stdout and "/ 0 (ties" not in r.stdout, r.stdout
     r = subprocess.run(["make", "-s", "-C", T.ORACLE_DIR, "pin-libosmocore"], capture_output=True, text=True)
     assert r.returncode == 0 and ("UNPINNED" in r.stdout or "PINNED" in r.stdout), r.stdout + r.stderr
+
+
+def test_rm3014_ml_decoder(ref, orc):
+    """the brute-force RM(30,14) decoder of the oracle: the code has minimum distance 8 (checked here over all 2^14 code
+    words of the REFERENCE's tetra_rm3014_compute), so every pattern of up to three errors decodes back"""
+    cws = np.array([ref.rm3014(i) for i in range(1 << 14)], dtype=np.uint32)
+    assert np.array_equal(cws, np.array([orc.rm3014(i) for i in range(1 << 14)], dtype=np.uint32))
+    w = np.array([bin(int(x)).count("1") for x in cws[1:]])
+    assert w.min() == 8                                            # linear code: minimum distance = lightest non-zero word
+    rng = np.random.default_rng(3014)
+    for _ in range(300):
+        info = int(rng.integers(0, 1 << 14))
+        ne = int(rng.integers(0, 4))
+        e = 0
+        for b in rng.choice(30, ne, replace=False):
+            e |= 1 << int(b)
+        got, d = orc.rm3014_decode_ml(int(cws[info]) ^ e)
+        assert (got, d) == (info, ne)

@@ -214,3 +214,65 @@ def test_shim_follows_the_traffic_feedback(orc, tmp_path, ndb2):
     assert ref_files and ref_files == sorted(os.listdir(shim_dir))
     for f in ref_files:
         assert open(os.path.join(ref_dir, f), "rb").read() == open(os.path.join(shim_dir, f), "rb").read(), f
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF_SRC) and T.have_ref()), reason="reference build not present")
+@pytest.mark.parametrize("batch", ["0", "9000"])
+def test_shim_variable_reads_and_return_values(orc, ref, batch):
+    """tetra-rx on a pipe (tetra-rx.c:82-95, src/receiver1udp): read() hands out what is there, so the lengths of the
+    tetra_burst_sync_in() calls change.  The shim must deliver the reference's primitives for the same call lengths, and
+    with TETRA_B200_BATCH_BITS=0 (decode on every call) return the reference's own value from every call
+    (tetra_burst_sync.c:77-78,93-94: len / 0 / -1)."""
+    from test_simt import _random_runs
+    simt = T.build_simt()
+    os.makedirs(BUILD, exist_ok=True)
+    rec_c = os.path.join(BUILD, "shim_recorder.c")
+    open(rec_c, "w").write(RECORDER)
+    so = os.path.join(BUILD, f"libshimtest_var{batch}.so")
+    subprocess.check_call(["gcc", "-O1", "-g", "-fPIC", "-shared", "-I" + REF_SRC, "-I" + os.path.join(T.ROOT, "oracle", "stubs"),
+                           "-I" + os.path.join(T.ROOT, "oracle"), "-I" + os.path.join(T.ROOT, "include"),
+                           os.path.join(T.ROOT, "osmo-tetra_b200", "host", "tetra_shim.c"), rec_c, simt,
+                           "-Wl,-rpath," + os.path.dirname(simt), "-o", so])
+    rng = np.random.default_rng(12)
+    bits, cfg = _stream(orc, n=70, random_cell=1, sb_period=6, lead_in_bits=1500)
+    bits = bits.copy()
+    bits[1500 + 510 * 33 + 200:1500 + 510 * 33 + 300] = 0          # lock is lost once: UNLOCKED searches that fail return -1
+    lens = np.array([ln for m, ln in _random_runs(rng, bits.size) for _ in range(m)], dtype=np.uint32)
+    assert lens.sum() == bits.size
+    want_rc = np.zeros(lens.size, dtype=np.int32)
+    ref.reset()
+    ref.lib.ref_feed_calls.restype = C.c_long
+    ref.lib.ref_feed_calls.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+    b = np.ascontiguousarray(bits)
+    ref.lib.ref_feed_calls(b.ctypes.data, lens.ctypes.data, lens.size, want_rc.ctypes.data, 1)
+    want = ref.records()
+    assert set(np.unique(want_rc)) >= {-1, 0}                       # the stream really exercises all three values
+    os.environ["TETRA_B200_BATCH_BITS"] = batch
+    os.environ["TETRA_B200_FLUSH_MS"] = "0"
+    lib = C.CDLL(so)
+
+    class Trs(C.Structure):
+        _fields_ = [("state", C.c_int), ("bits_in_buf", C.c_uint), ("bitbuf", C.c_uint8 * 4096),
+                    ("start", C.c_uint), ("next", C.c_uint), ("priv", C.c_void_p)]
+    trs = Trs()
+    got_rc = np.zeros(lens.size, dtype=np.int32)
+    pos = 0
+    for i, ln in enumerate(lens):
+        chunk = np.ascontiguousarray(bits[pos:pos + ln])
+        pos += int(ln)
+        got_rc[i] = lib.tetra_burst_sync_in(C.byref(trs), chunk.ctypes.data_as(C.c_void_p), int(ln))
+    lib.tetra_b200_shim_flush()
+    lib.shimtest_n.restype = C.c_size_t
+    lib.shimtest_rec.restype = C.c_void_p
+    n = lib.shimtest_n()
+    got = np.frombuffer(C.string_at(lib.shimtest_rec(), n * 288), dtype=T.RECORD_DTYPE).copy()
+    assert n == want.size
+    got["slot_bit"] = want["slot_bit"]
+    ok, msg = T.records_equal(want, got)
+    assert ok, msg
+    assert trs.state == ref.rx_state()
+    if batch == "0":
+        assert np.array_equal(got_rc, want_rc)
+    else:
+        assert np.array_equal(got_rc, lens.astype(np.int32))
+    del os.environ["TETRA_B200_FLUSH_MS"]

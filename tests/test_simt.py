@@ -179,6 +179,133 @@ def test_stream_of_sync_patterns_degrades_like_the_reference(emu, orc, ref):
     assert emu.stats().lock_acquisitions == (ref.events()["mask"] == 0b1000).sum() - (ref.events()[ref.events()["mask"] == 0b1000]["rc"] < 0).sum()
 
 
+def _feed_runs(rx, lib, bits, runs):
+    """the same sequence of read() sizes into a CPU receiver and into the library: runs = [(calls, length), ...]; the
+    library gets one call per run of equal-length reads (tb200_rx_stream_host continues the stream, flags = 0)"""
+    rx.reset()
+    pos, outs = 0, []
+    for i, (m, ln) in enumerate(runs):
+        part = bits[pos:pos + m * ln]
+        pos += part.size
+        rx.feed(part, ln)
+        lib.set_options(chunk_bits=ln)
+        last = i == len(runs) - 1
+        flags = (T.TB200_FRESH if i == 0 else 0) | (T.TB200_FINAL if last else 0)
+        outs.append(lib.rx_stream_host(part, flags=flags))
+    assert pos == bits.size
+    slots = np.concatenate([o[0] for o in outs]); t1 = np.concatenate([o[1] for o in outs])
+    return slots, t1
+
+
+def _random_runs(rng, n_bits, max_len=64):
+    """reads the way a pipe hands them out: mostly full 64-byte reads, now and then shorter ones of every length"""
+    runs, left = [], n_bits
+    while left:
+        ln = 64 if rng.random() < 0.5 else int(rng.integers(1, max_len + 1))
+        m = int(rng.integers(1, 40)) if ln == 64 else int(rng.integers(1, 4))
+        m = min(m, left // ln)
+        if m == 0:
+            ln, m = left, 1          # the last, short read
+            if ln > 296:
+                ln, m = 64, left // 64
+        runs.append((m, ln))
+        left -= m * ln
+    return runs
+
+
+def test_stream_variable_read_sizes(emu, ref, orc):
+    """tetra-rx on a pipe: read() returns what is there (tetra-rx.c:82-95), so the calls of tetra_burst_sync_in() have
+    changing lengths and with them the search windows (bits_in_buf) and the calls that process a slot.  Records, search
+    log and final state must equal the reference fed with the same read sizes - also across lock losses."""
+    rng = np.random.default_rng(31)
+    emu.set_options(viterbi=T.VITERBI_LANE, pipeline_slots=0)
+    for case in range(4):
+        bits, cfg = _stream(orc, n=90, random_cell=1, sb_period=6, lead_in_bits=int(rng.integers(0, 400)))
+        bits = bits.copy()
+        if case % 2:
+            k = 41
+            while orc.gen_kind(cfg, k) == 1:
+                k += 1
+            o = cfg.lead_in_bits + 510 * k
+            bits[o + 244:o + 266] = 0
+        runs = _random_runs(rng, bits.size)
+        slots, t1 = _feed_runs(ref, emu, bits, runs)
+        T.check_stream_against(ref.records(), ref.events(), slots, emu.expand_records(slots, t1))
+        c = emu.carry()
+        assert c.state == ref.rx_state() and c.scramb_init == ref.scramb_init() and c.calls == sum(m for m, _ in runs)
+        if slots.size:
+            assert (c.tn, c.fn, c.mn) == ref.get_time()
+    emu.set_options(chunk_bits=64)
+
+
+def _rm_words(orc, rng, n):
+    """received words around code words: 0..9 errors, and purely random ones"""
+    words = []
+    for i in range(n):
+        cw = orc.rm3014(int(rng.integers(0, 1 << 14)))
+        e = 0
+        for b in rng.choice(30, int(rng.integers(0, 10)), replace=False):
+            e |= 1 << int(b)
+        words.append(cw ^ e if i % 5 else int(rng.integers(0, 1 << 30)))
+    return np.array(words, dtype=np.uint32)
+
+
+def test_rm3014_leaf(emu, orc):
+    """tb200_rm3014_decode (syndrome -> coset leader table) equals the exhaustive nearest-code-word search, ties included"""
+    rng = np.random.default_rng(8)
+    words = _rm_words(orc, rng, 400)
+    info, dist, bad = emu.rm3014_decode(words)
+    for i, w in enumerate(words):
+        wi, wd = orc.rm3014_decode_ml(int(w))
+        assert (int(info[i]), int(dist[i])) == (wi, wd), (i, hex(int(w)))
+        assert int(bad[i]) == int(wd != 0)
+
+
+def _check_aach(lib, orc, bits):
+    """the AACH side output of the chain: RM-decoded broadcast block of every delivered slot"""
+    slots, t1, pk, aach = lib.rx_stream_host_aach(bits)
+    kinds = slots["flags"] & 3
+    assert (aach[kinds == 0] == 0xffffffff).all()
+    n_err = 0
+    for i in np.nonzero(kinds)[0]:
+        a = int(slots["slot_bit"][i])
+        burst = bits[a:a + 510]
+        raw = np.concatenate([burst[252:282]]) if kinds[i] == 1 else np.concatenate([burst[230:244], burst[266:282]])
+        desc = orc.scramb_bits(int(slots["scrambling_code"][i]), raw)
+        word = int("".join(str(int(b)) for b in desc), 2)              # first bit on air = bit 29
+        wi, wd = orc.rm3014_decode_ml(word)
+        assert (int(aach[i]) & 0x3fff, (int(aach[i]) >> 16) & 0xff, (int(aach[i]) >> 24) & 1) == (wi, wd, int(wd != 0)), i
+        # the reference's own AACH type-1 bits are the uncorrected ones: equal when nothing had to be corrected
+        off = 60 if kinds[i] == 1 else 0
+        uncorrected = int("".join(str(int(b)) for b in t1[i][off:off + 14]), 2)
+        assert (uncorrected == wi) or wd > 0
+        n_err += int(wd > 0)
+    return slots, aach, n_err
+
+
+def test_stream_aach_rm_decoding(emu, orc):
+    bits, cfg = _stream(orc, n=60, random_cell=1, sb_period=3)
+    emu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0)
+    slots, aach, n_err = _check_aach(emu, orc, bits)
+    assert n_err <= 2                       # the generator leaves the broadcast block clean (before the first cell is known it is not)
+    noisy = bits.copy()
+    rng = np.random.default_rng(5)
+    for k in range(3, 58):                  # up to three bit errors in every broadcast block: all corrected
+        o = 333 + 510 * k
+        pos = np.arange(266, 282)            # part of the broadcast block in SYNC and in normal bursts alike
+        for p in rng.choice(pos, int(rng.integers(1, 4)), replace=False):
+            noisy[o + p] ^= 1
+    s2, a2, n_err2 = _check_aach(emu, orc, noisy)
+    assert n_err2 > 20
+    assert np.array_equal(s2["slot_bit"], slots["slot_bit"])
+    ok = (slots["flags"] & 3) != 0
+    assert np.array_equal(a2[ok] & 0x3fff, aach[ok] & 0x3fff)       # every damaged block decodes to what the clean one carried
+    emu.set_options(viterbi=T.VITERBI_WARP)
+    s3, _, _, a3 = emu.rx_stream_host_aach(noisy)
+    assert np.array_equal(a2, a3)
+    emu.set_options(viterbi=T.VITERBI_LANE)
+
+
 def test_stream_edge_inputs(emu, orc):
     bits, _ = _stream(orc, n=12)
     rng = np.random.default_rng(3)

@@ -327,6 +327,12 @@ class Oracle(_Recorder):
     def rm3014(self, info):
         return self.lib.orc_rm3014_compute(C.c_uint16(info))
 
+    def rm3014_decode_ml(self, word):
+        """brute-force nearest code word -> (info14, distance)"""
+        info = C.c_uint16(0)
+        d = self.lib.orc_rm3014_decode_ml(C.c_uint32(int(word)), C.byref(info))
+        return info.value, d
+
     def time_add_slot(self, tn, fn, mn):
         t = (C.c_uint32 * 3)(tn, fn, mn)
         self.lib.orc_time_add_slot(t)
