@@ -125,6 +125,9 @@ struct tb200_options {
 	uint32_t pipeline_slots;    /* slots per pipelined piece in the host-buffer path (0 = default) */
 	uint32_t profile;           /* 1: bracket every kernel with CUDA events on its stream (tb200_get_timing) */
 	uint32_t input;             /* TB200_IN_*; the packed / symbol formats need the lane kernels */
+	uint32_t serial_passes;     /* 1: pass 1 (search, SB1, scans) of a piece on the same CUDA stream as the decode passes, so that no two
+	                             * kernels of the receiver ever run side by side (clean per-kernel timings); 0 (default): pass 1 of
+	                             * piece i+1 on its own stream under the decode pass of piece i */
 	uint32_t viterbi_tie;       /* survivor on equal path metrics (tetra_tie_rule.h): 0 = predecessor s>>1 (libosmocore's
 	                             * osmo_conv_decode as restated, viterbi_cch.c:58-66), 1 = predecessor (s>>1)|8.  The default is
 	                             * TETRA_VITERBI_TIE_DEFAULT, the compile-time switch the CPU oracle shares */
@@ -271,6 +274,14 @@ int tb200_find_train_seq(tb200_ctx *ctx, const uint8_t *bits, uint64_t n_bits,
 int tb200_rcpc_depunct(tb200_ctx *ctx, int puncturer, const uint8_t *type3, uint32_t len, uint64_t n,
                        uint8_t *mother, uint32_t mother_len, int is_device);
 
+/* viterbi_dec_sb1_wrapper (viterbi.c:6-25: byte 0 -> strong 0, 0xff -> erased, anything else -> strong 1, four erased
+ * flush steps) + conv_cch_decode (viterbi_cch.c:58-66, the K = 5 rate-1/4 mother code with all four generators) for n
+ * independent blocks of sym_count type-2 bits: 4 * sym_count mother-code bytes per block in, sym_count bytes (0/1) out.
+ * With tb200_rcpc_depunct in front of it every RCPC rate of tetra_conv_enc.c:128-198 (1/3, 292/432, 148/432 and the
+ * speech rates next to 2/3) decodes end to end; the receive chain itself only ever needs 2/3 and folds de-puncturing
+ * and decoding into one packed trellis loop.  Tie rule: options.viterbi_tie.  Host or device pointers. */
+int tb200_viterbi_decode(tb200_ctx *ctx, const uint8_t *mother, uint64_t n, uint32_t sym_count, uint8_t *out, int is_device);
+
 /* Maximum-likelihood decoding of the (30,14) Reed-Muller code of the AACH (generator: tetra_rm3014.c:28-43) for n
  * received 30-bit words laid out like tetra_rm3014_compute's result (bit 29 = first bit on air, information = word >> 16,
  * the argument of the reference's tetra_rm3014_decode(inp, out), tetra_rm3014.c:92-96).  The code has minimum distance 8:
@@ -350,6 +361,8 @@ long tb200_shard_pass2(tb200_ctx *ctx, const struct tb200_rx_carry *carry_in, st
  * start of a tb200_dev_alloc allocation. */
 void *tb200_dev_alloc(tb200_ctx *ctx, size_t bytes);
 void  tb200_dev_free(tb200_ctx *ctx, void *p);
+/* host <-> device copy for callers that do not link the CUDA runtime themselves (the C programs) */
+int   tb200_dev_copy(tb200_ctx *ctx, void *dst, const void *src, size_t bytes, int to_device);
 int   tb200_ipc_export(tb200_ctx *ctx, const void *d_ptr, uint8_t handle[64]);
 int   tb200_ipc_import(tb200_ctx *ctx, const uint8_t handle[64], void **d_ptr);
 int   tb200_ipc_close(tb200_ctx *ctx, void *d_ptr);
@@ -406,8 +419,10 @@ int  tb200_dist_create(tb200_dist **out, tb200_ctx *ctx, int rank, int world, co
 int  tb200_dist_create_with_ops(tb200_dist **out, tb200_ctx *ctx, int rank, int world, const struct tb200_dist_ops *ops);
 void tb200_dist_destroy(tb200_dist *d);
 const char *tb200_dist_last_error(const tb200_dist *d);
-/* d_bits / n_bits: the stream, rank 0 only (ignored elsewhere).  Outputs as for tb200_rx_stream_dev, rank-local;
- * max_slots >= tb200_dist_max_local_slots(n_bits, world).  Returns the slots written on this rank or TB200_E_*. */
+/* d_bits / n_bits: the stream, rank 0 only (ignored elsewhere).  Outputs as for tb200_rx_stream_dev, rank-local.
+ * A stream that keeps lock gives every rank ceil(slots / world) slots; lock losses skew that towards the first ranks
+ * (see tb200_dist_max_local_slots, the bound that holds for any stream).  Arrays that turn out too small make the
+ * call fail with TB200_E_ARG on that rank.  Returns the slots written on this rank or TB200_E_*. */
 long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint64_t n_bits, uint32_t mode,
                           struct tb200_slot *d_slots, uint8_t *d_type1, uint32_t *d_type1_packed, uint64_t max_slots,
                           struct tb200_dist_run *runs, uint32_t max_runs, uint32_t *n_runs);

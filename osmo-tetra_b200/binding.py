@@ -52,7 +52,7 @@ TIE_LOW_PRED, TIE_HIGH_PRED = 0, 1        # include/tetra_tie_rule.h
 class Options(C.Structure):
     _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
                 ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32), ("input", C.c_uint32),
-                ("viterbi_tie", C.c_uint32)]
+                ("serial_passes", C.c_uint32), ("viterbi_tie", C.c_uint32)]
 
 
 class Timing(C.Structure):
@@ -294,6 +294,15 @@ class B200:
         if r:
             raise RuntimeError(self.err())
         return out.value
+
+    def viterbi_decode(self, mother, sym_count):
+        """tb200_viterbi_decode over the rows of `mother` (n x 4*sym_count bytes: 0 / 1 / 0xff) -> n x sym_count bits"""
+        mother = np.ascontiguousarray(mother, dtype=np.uint8).reshape(-1, 4 * sym_count)
+        out = np.zeros((mother.shape[0], sym_count), dtype=np.uint8)
+        self.lib.tb200_viterbi_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_int]
+        if self.lib.tb200_viterbi_decode(self.h, _ptr(mother), mother.shape[0], sym_count, _ptr(out), 0):
+            raise RuntimeError(self.err())
+        return out
 
     def rm3014_decode(self, words):
         """tb200_rm3014_decode on a host array of 30-bit words -> (info14, distance, not_a_code_word)"""

@@ -272,6 +272,7 @@ extern "C" void tb200_default_options(tb200_options *o)
 	o->pipeline_slots = 0;
 	o->profile = 0;
 	o->input = TB200_IN_BYTES;
+	o->serial_passes = getenv("TB200_SERIAL") ? 1 : 0;
 	o->viterbi_tie = TETRA_VITERBI_TIE_DEFAULT;
 }
 
@@ -308,6 +309,14 @@ extern "C" void tb200_dev_free(tb200_ctx *ctx, void *p)
 {
 	if (ctx) cudaSetDevice(ctx->device);
 	cudaFree(p);
+}
+
+extern "C" int tb200_dev_copy(tb200_ctx *ctx, void *dst, const void *src, size_t bytes, int to_device)
+{
+	if (!ctx || (bytes && (!dst || !src))) return TB200_E_ARG;
+	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
+	CU(cudaMemcpy(dst, src, bytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost));
+	return 0;
 }
 
 extern "C" int tb200_ipc_export(tb200_ctx *ctx, const void *d_ptr, uint8_t handle[64])
@@ -836,8 +845,7 @@ enum { PE_START = 0, PE_SB1 = 1, PE_SCAN = 2, PE_DECODE_END = 3, PE_DECODE_START
  * chain runs ahead of the decode pass. */
 static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, int set, cudaEvent_t *pe, bool with_carry, uint64_t k_base = 0)
 {
-	static const bool serial = getenv("TB200_SERIAL") != nullptr;      /* A/B: pass 1 on the decode stream, nothing overlaps */
-	cudaStream_t st = serial ? ctx->s_compute : ctx->s_front;
+	cudaStream_t st = ctx->opt.serial_passes ? ctx->s_compute : ctx->s_front;
 	tb200_ctx::WorkSet &w = ctx->wset[set];
 	const uint32_t nb = g.n_slots;
 	const unsigned wpb = 8;
@@ -1228,7 +1236,8 @@ static int rx_run(tb200_ctx *ctx, const Source &src, bool final, Outputs &out, b
 			ctx->stats.lock_acquisitions++;
 			{
 				tb200_lock_event le;
-				le.next_slot = out.n; le.call = c; le.offset = (uint32_t)(pos - rx.buf_start); le.pad = 0;
+				le.next_slot = ctx->stop_at_lock ? ctx->stats.slots : out.n;      /* (sharded decode: rank 0 counts the slots of all ranks) */
+				le.call = c; le.offset = (uint32_t)(pos - rx.buf_start); le.pad = 0;
 				ctx->lock_events.push_back(le);
 			}
 			continue;
@@ -1889,6 +1898,80 @@ extern "C" void tb200_debug_time_advance(uint32_t *tn, uint32_t *fn, uint32_t *m
 	Tm t = { *tn, *fn, *mn };
 	t = tm_advance(t, n);
 	*tn = t.tn; *fn = t.fn; *mn = t.mn;
+}
+
+/* ------------------------------------------- Viterbi wrapper as a leaf (any rate) -- */
+
+/* viterbi_dec_sb1_wrapper (viterbi.c:6-25) + conv_cch_decode (viterbi_cch.c:58-66) for independent blocks: the full
+ * rate-1/4 mother trellis with all four generators, any of the 4 * sym_count symbols may be erased, so together with
+ * tb200_rcpc_depunct every RCPC rate of tetra_conv_enc.c:128-198 decodes end to end (the receive chain itself only
+ * uses 2/3 and runs the packed two-symbol form).  One thread per block, decisions in a scratch row. */
+__global__ void __launch_bounds__(128)
+k_viterbi_mother(const uint8_t *__restrict__ mother, uint64_t n, uint32_t sym_count, uint8_t *__restrict__ out,
+                 uint16_t *__restrict__ dec, int tie_hi)
+{
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+	const uint32_t steps = sym_count + 4;
+	for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const uint8_t *in = mother + i * 4ull * sym_count;
+		uint16_t *d = dec + i * steps;
+		uint32_t pm[16];
+#pragma unroll
+		for (int s = 0; s < 16; ++s) pm[s] = s ? (1u << 28) : 0u;          /* start in state 0 (osmo_conv_decode) */
+		for (uint32_t t = 0; t < steps; ++t) {
+			uint32_t known = 0, val = 0;                                    /* bit 3 = G1 (viterbi_cch.c:35-40 output nibbles) */
+			if (t < sym_count) {
+#pragma unroll
+				for (int g = 0; g < 4; ++g) {
+					const uint8_t v = in[4 * t + g];                          /* viterbi.c:13-22: 0 -> +127, 0xff -> 0, else -127 */
+					if (v != 0xff) { known |= 8u >> g; if (v != 0) val |= 8u >> g; }
+				}
+			}
+			uint32_t nm[16], bits = 0;
+#pragma unroll
+			for (unsigned s = 0; s < 16; ++s) {
+				const unsigned b = s & 1, p0 = s >> 1, p1 = p0 | 8;
+				const uint32_t c0 = pm[p0] + __popc((mother_out(p0, b) ^ val) & known);
+				const uint32_t c1 = pm[p1] + __popc((mother_out(p1, b) ^ val) & known);
+				const bool hi = tie_hi ? c1 <= c0 : c1 < c0;                /* include/tetra_tie_rule.h */
+				nm[s] = hi ? c1 : c0;
+				bits |= (hi ? 1u : 0u) << s;
+			}
+#pragma unroll
+			for (int s = 0; s < 16; ++s) pm[s] = nm[s];
+			d[t] = (uint16_t)bits;
+		}
+		unsigned st = 0;
+		for (int t = (int)steps - 1; t >= 0; --t) {
+			if ((uint32_t)t < sym_count) out[i * sym_count + t] = st & 1;
+			st = (st >> 1) | (((d[t] >> st) & 1u) << 3);
+		}
+	}
+}
+
+extern "C" int tb200_viterbi_decode(tb200_ctx *ctx, const uint8_t *mother, uint64_t n, uint32_t sym_count, uint8_t *out, int is_device)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (sym_count == 0 || sym_count > 1024) return fail(ctx, TB200_E_ARG, "sym_count must be 1..1024");
+	if (n && (!mother || !out)) return fail(ctx, TB200_E_ARG, "null argument");
+	if (n == 0) return 0;
+	const uint8_t *dm = mother; uint8_t *dout = out;
+	cudaStream_t st = ctx->s_compute;
+	if (!is_device) {
+		uint8_t *a = nullptr, *b = nullptr;
+		if ((r = leaf_buf(ctx, 0, n * 4 * sym_count, &a)) || (r = leaf_buf(ctx, 1, n * sym_count, &b))) return r;
+		CU(cudaMemcpyAsync(a, mother, n * 4 * sym_count, cudaMemcpyHostToDevice, st));
+		dm = a; dout = b;
+	}
+	uint16_t *dec = nullptr;
+	if ((r = leaf_buf(ctx, 2, n * (sym_count + 4), &dec))) return r;
+	const unsigned blocks = (unsigned)std::min<uint64_t>((n + 127) / 128, (uint64_t)ctx->sm_count * 8);
+	TB_LAUNCH(k_viterbi_mother, blocks, 128, st, dm, n, sym_count, dout, dec, (int)ctx->opt.viterbi_tie);
+	CU(cudaGetLastError());
+	if (!is_device) CU(cudaMemcpyAsync(out, dout, n * sym_count, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	return 0;
 }
 
 /* ------------------------------------------------------------ RM(30,14) leaf -- */

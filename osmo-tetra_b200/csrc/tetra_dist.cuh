@@ -175,8 +175,11 @@ static int dist_common_init(tb200_dist *d)
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return dfail(d, TB200_E_CUDA, "cudaSetDevice");
 	DCU(cudaMalloc((void **)&d->d_stage, 16384));
 	DCU(cudaHostAlloc((void **)&d->h_stage, 16384, cudaHostAllocDefault));
-	DCU(cudaStreamCreateWithFlags(&d->s_pack, cudaStreamNonBlocking));
-	DCU(cudaStreamCreateWithFlags(&d->s_xfer, cudaStreamNonBlocking));
+	/* packing and shipping feed every other rank: their blocks go first whenever an SM has room */
+	int prio_lo = 0, prio_hi = 0;
+	DCU(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+	DCU(cudaStreamCreateWithPriority(&d->s_pack, cudaStreamNonBlocking, prio_hi));
+	DCU(cudaStreamCreateWithPriority(&d->s_xfer, cudaStreamNonBlocking, prio_hi));
 	DCU(cudaEventCreateWithFlags(&d->ev_pack[0], 0));
 	DCU(cudaEventCreateWithFlags(&d->ev_pack[1], 0));
 	memset(&d->timing, 0, sizeof(d->timing));
@@ -237,8 +240,11 @@ extern "C" const char *tb200_dist_last_error(const tb200_dist *d) { return d ? d
 
 extern "C" uint64_t tb200_dist_max_local_slots(uint64_t n_bits, int world)
 {
-	const uint64_t all = n_bits / SLOT_BITS + 1;
-	return std::min<uint64_t>(all, all / (uint64_t)(world > 0 ? world : 1) + 4096);
+	/* Without lock losses a rank gets ceil(slots / world).  Every lock loss starts a new segment that is cut evenly
+	 * again, while what a rank decoded in front of the loss stays with it - a stream that keeps losing lock early in
+	 * its segments piles its slots up on the first ranks.  The bound that holds for every stream is all of them. */
+	(void)world;
+	return n_bits / SLOT_BITS + 1;
 }
 
 extern "C" int tb200_dist_get_timing(const tb200_dist *d, tb200_dist_timing *out)
@@ -390,6 +396,7 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 		DTRACE("segment meta: ok %u a0 %llu slots %llu fmt %u", m.ok, (unsigned long long)m.a0, (unsigned long long)m.n_slots, m.fmt);
 		if (!m.ok) break;
 		d->timing.segments++;
+		xfer_fmt = (int)m.fmt;            /* every rank: how the shards are encoded on the wire */
 		seg.a0 = m.a0; seg.cmin = m.cmin;
 		seg.cg.c_base = 0; seg.cg.t_base = 0; seg.cg.n_end = m.n_end; seg.cg.chunk = m.chunk; seg.cg.pad = 0;
 		ctx->opt.chunk_bits = m.chunk; ctx->opt.viterbi_tie = m.tie; ctx->opt.input = m.fmt;
@@ -550,7 +557,8 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 		ssrc.ready = ready.empty() ? nullptr : &ready;
 		ssrc.skip_dependent = rank > 0;
 		Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
-		out.crc = nullptr; out.max_slots = max_slots; out.n = n_local;
+		out.crc = ctx->user_crc; out.aach = ctx->user_aach;     /* side outputs: rank-local, indexed like the slots */
+		out.max_slots = max_slots; out.n = n_local;
 		DevCarry chain_end = m.carry;
 		if (n_mine) {
 			ctx->h_carry = m.carry;

@@ -88,6 +88,38 @@ def test_cli_text_matches_reference_gpu(gpu, orc):
             assert got == want, (seed, chunk)
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not T.have_ref(), reason="reference build (oracle/_ref) not present")
+def test_cli_multi_gpu_text_matches_reference(gpu, orc):
+    """tetra-rx-b200 -G N: the C program decodes ONE stream on N GPUs (a host thread per GPU around tb200_dist_rx_stream,
+    NCCL inside the library) and prints the reference's text, lock losses inside shards included.  N = 1 on a one-GPU box
+    (a communicator of one rank: the same driver), N = all GPUs of a bigger box as well."""
+    import torch
+    worlds = sorted({1, min(2, torch.cuda.device_count()), torch.cuda.device_count()})
+    with tempfile.TemporaryDirectory() as d:
+        cli = build_cli(T.PRODUCT_SO, os.path.join(d, "tetra-rx-b200"))
+        for seed, bits, chunk in _cases(orc, (5001, 5005), 1600):
+            bits = bits.copy()
+            for k in (400, 1100):                     # wiped training sequences: lock is lost twice
+                bits[510 * k + 150:510 * k + 660] = 0
+            path = os.path.join(d, f"m{seed}.bits")
+            bits.tofile(path)
+            want = reference_stdout(path, chunk)
+            assert want.count(b"found SYNC") >= 3 and want.count(b"CRC COMP") > 1000
+            for w in worlds:
+                got = subprocess.run([cli, "-c", str(chunk), "-G", str(w), path], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                     check=True, timeout=120).stdout
+                assert got == want, (seed, chunk, w)
+        packed = os.path.join(d, "p.bin")
+        bits = bits[:bits.size & ~127]
+        bits.tofile(path)
+        T.pack_bits(bits).tofile(packed)
+        want = reference_stdout(path, chunk)
+        got = subprocess.run([cli, "-f", "packed", "-c", str(chunk), "-G", str(worlds[-1]), packed], stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, check=True, timeout=120).stdout
+        assert got == want
+
+
 def _pcap_payloads(path):
     """(timestamps in us, UDP payloads) of a LINKTYPE_RAW pcap written by tetra-rx-b200 -p; checks the headers"""
     raw = open(path, "rb").read()

@@ -65,3 +65,48 @@ def test_depunct_errors(emu):
 @pytest.mark.parametrize("t2,t3,rate,pu", TUPLES)
 def test_depunct_gpu(gpu, ref, t2, t3, rate, pu):
     _run(gpu, ref, t2, t3, rate, pu, 300)
+
+
+# ---- every rate-1/4 RCPC rate end to end: de-puncture + the Viterbi wrapper as leaves
+
+RATE4 = [t for t in TUPLES if t[2] == 4]
+
+
+def _roundtrip(g, ref, orc, t2, t3, pu, n, ber):
+    """type-2 bits -> reference encoder + puncturer -> noise -> tb200_rcpc_depunct -> tb200_viterbi_decode, against the
+    reference's own tetra_rcpc_depunct + viterbi_dec_sb1_wrapper (on the osmo_conv_decode stand-in) block by block"""
+    rng = np.random.default_rng(77 * pu + t3)
+    type2 = np.zeros((n, t2), dtype=np.uint8)
+    type2[:, :t2 - 4] = rng.integers(0, 2, (n, t2 - 4))            # four tail bits bring the encoder back to state 0
+    type3 = np.zeros((n, t3), dtype=np.uint8)
+    for b in range(n):
+        type3[b] = _ref_punct(ref, pu, ref.conv_encode(type2[b]), t3)
+    type3 ^= (rng.random((n, t3)) < ber).astype(np.uint8)
+    mother = g.rcpc_depunct(pu, type3, 4 * t2)
+    got = g.viterbi_decode(mother, t2)
+    want_m = _ref_depunct(ref, pu, type3, 4 * t2)
+    assert np.array_equal(mother, want_m)
+    for b in range(n):
+        assert np.array_equal(got[b], ref.viterbi(want_m[b], t2)), (pu, b)
+        assert np.array_equal(got[b], orc.viterbi(want_m[b], t2)), (pu, b)
+    if ber == 0:
+        assert np.array_equal(got, type2)
+
+
+@pytest.mark.parametrize("t2,t3,rate,pu", RATE4)
+def test_all_rates_decode_end_to_end_emulated(emu, ref, orc, t2, t3, rate, pu):
+    _roundtrip(emu, ref, orc, t2, t3, pu, 6, 0.0)
+    _roundtrip(emu, ref, orc, t2, t3, pu, 12, 0.04)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("t2,t3,rate,pu", RATE4)
+def test_all_rates_decode_end_to_end_gpu(gpu, ref, orc, t2, t3, rate, pu):
+    _roundtrip(gpu, ref, orc, t2, t3, pu, 40, 0.0)
+    _roundtrip(gpu, ref, orc, t2, t3, pu, 200, 0.04)
+    # the other tie rule moves oracle, stand-in and kernel together here too
+    try:
+        orc.set_tie(T.TIE_HIGH_PRED); ref.set_tie(T.TIE_HIGH_PRED); gpu.set_options(viterbi_tie=T.TIE_HIGH_PRED)
+        _roundtrip(gpu, ref, orc, t2, t3, pu, 60, 0.04)
+    finally:
+        orc.set_tie(T.TIE_LOW_PRED); ref.set_tie(T.TIE_LOW_PRED); gpu.set_options(viterbi_tie=T.TIE_LOW_PRED)

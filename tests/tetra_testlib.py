@@ -425,12 +425,19 @@ def gloo_dist_ops(dist):
         rank, world = dist.get_rank(), dist.get_world_size()
         if rank == root:
             for r in range(world):
-                if r != root and sizes[r]:
-                    dist.send(view(src + offs[r], sizes[r]).clone(), r)
-        elif sizes[rank]:
-            t = torch.zeros(sizes[rank], dtype=torch.uint8)
-            dist.recv(t, root)
-            view(dst, sizes[rank]).copy_(t)
+                if r != root:
+                    dist.send(torch.tensor([sizes[r]], dtype=torch.int64), r)
+                    if sizes[r]:
+                        dist.send(view(src + offs[r], sizes[r]).clone(), r)
+        else:
+            n = torch.zeros(1, dtype=torch.int64)
+            dist.recv(n, root)
+            if int(n[0]) != sizes[rank]:          # sender and receiver must agree on the shard's size on the wire
+                return -2
+            if sizes[rank]:
+                t = torch.zeros(sizes[rank], dtype=torch.uint8)
+                dist.recv(t, root)
+                view(dst, sizes[rank]).copy_(t)
         return 0
 
     ops = _B.DistOps(None, _B.BCAST_FN(bcast), _B.ALLGATHER_FN(allgather), _B.SCATTER_FN(scatter))
