@@ -113,7 +113,8 @@ const char *tb200_version(void);
 
 /* how the bit stream handed to tb200_rx_stream_* is encoded */
 #define TB200_IN_BYTES   0   /* one bit per byte: the file format tetra-rx reads (tetra-rx.c:82-95), float_to_bits' output */
-#define TB200_IN_PACKED  1   /* eight bits per byte, stream bit i = byte i>>3, bit i&7 (4-byte aligned buffer) */
+#define TB200_IN_PACKED  1   /* eight bits per byte, stream bit i = byte i>>3, bit i&7 (4-byte aligned buffer); a stream fed over several
+                              * tb200_rx_stream_host calls continues on 128-bit boundaries (n_bits % 128 == 0 except for the last call) */
 #define TB200_IN_F32SYM  2   /* one float32 per symbol, the demodulator output float_to_bits reads (float_to_bits.c:128-164):
                               * two hard bits per symbol, sliced on the device exactly like process_sym_fl + sym_int2bits
                               * (float_to_bits.c:33-72) without the optional pseudo-AFC (-a); n_bits = 2 * symbols */

@@ -89,6 +89,14 @@ static void build_tables(Tables *t)
 		t->crc_tab_r[256 + x] = r;
 	}
 
+	/* the scrambler 32 steps at a time, one table per byte of the register */
+	for (int byte = 0; byte < 4; byte++)
+		for (uint32_t v = 0; v < 256; v++) {
+			uint32_t st = v << (8 * byte);
+			for (int i = 0; i < 32; i++) lfsr_step_host(&st);
+			t->lfsr_leap[byte][v] = st;
+		}
+
 	/* RM(30,14): parity halves of the systematic generator matrix (tetra_rm3014.c:28-43; rows as tetra_rm3014_init
 	 * builds them, :59-72: information bit i of the 14 sits at word bit 29 - i) */
 	static const uint16_t rm_parity[14] = { 0x9b60, 0x2de0, 0xfc20, 0xe03c, 0x983a, 0x5436, 0x2c2e,
@@ -208,6 +216,7 @@ struct tb200_ctx {
 	RxHost rx;
 	std::vector<uint8_t> tail;       /* bits [tail_base, fed_end) kept from earlier calls (host path) */
 	uint64_t tail_base = 0;
+	int tail_fmt = 0;                /* encoding of the tail = input format of the stream */
 	uint64_t fed_end = 0;            /* absolute bits handed to the ctx so far */
 	DevCarry h_carry;
 	DevCarry *h_carry_pin = nullptr;   /* pinned: [0] upload staging, [1] download staging (ordered on s_compute) */
@@ -620,7 +629,7 @@ struct Source {
 	const uint8_t *data;
 	uint64_t new_base;
 	uint64_t end;
-	int fmt;               /* IN_BYTES / IN_PACKED / IN_F32SYM; the packed formats start at stream bit 0 (no tail) */
+	int fmt;               /* IN_BYTES / IN_PACKED / IN_F32SYM; the packed formats continue on 128-bit boundaries of the stream */
 	/* device-resident data that is still arriving (sharded decode: chunks received or packed on other streams):
 	 * stream bits below ready[i].first are in place once event ready[i].second has fired; ascending */
 	const std::vector<std::pair<uint64_t, cudaEvent_t>> *ready = nullptr;
@@ -640,10 +649,22 @@ static int stage_bits(tb200_ctx *ctx, const Source &src, uint64_t lo, uint64_t h
 	*dbase = lo;
 	if (hi <= lo) return 0;
 	if (src.fmt != IN_BYTES) {
+		/* the packed formats are copied in 128-bit units of the stream; the caller's buffer of this call starts at
+		 * stream bit new_base, what earlier calls left is in the tail (both on 128-bit boundaries) */
 		const uint64_t lo_al = lo & ~(uint64_t)127;
 		*dbase = lo_al;
-		const size_t b0 = fmt_bytes(src.fmt, lo_al), b1 = fmt_bytes(src.fmt, hi);
-		CU(cudaMemcpyAsync(dst, src.data + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+		uint64_t p = lo_al;
+		if (p < src.new_base) {
+			const uint64_t h = std::min(hi, src.new_base);
+			const size_t b0 = fmt_bytes(src.fmt, p - ctx->tail_base), b1 = fmt_bytes(src.fmt, h - ctx->tail_base);
+			CU(cudaMemcpyAsync(dst, ctx->tail.data() + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+			dst += fmt_bytes(src.fmt, src.new_base - p);      /* (h == new_base unless the piece ends inside the tail) */
+			p = src.new_base;
+		}
+		if (hi > p) {
+			const size_t b0 = fmt_bytes(src.fmt, p - src.new_base), b1 = fmt_bytes(src.fmt, hi - src.new_base);
+			CU(cudaMemcpyAsync(dst, src.data + b0, b1 - b0, cudaMemcpyHostToDevice, st));
+		}
 		return 0;
 	}
 	if (lo < src.new_base) {
@@ -1346,10 +1367,12 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 {
 	if (!ctx) return TB200_E_ARG;
 	if ((!bits && n_bits) || !slots) return fail(ctx, TB200_E_ARG, "null buffer");
-	if (ctx->opt.input != TB200_IN_BYTES && (flags & (TB200_FRESH | TB200_FINAL)) != (TB200_FRESH | TB200_FINAL))
-		return fail(ctx, TB200_E_ARG, "packed / symbol input must be given in one call (TB200_FRESH | TB200_FINAL)");
+	if (ctx->opt.input != TB200_IN_BYTES && !(flags & TB200_FINAL) && (n_bits & 127))
+		return fail(ctx, TB200_E_ARG, "a bit-packed / symbol stream continues on 128-bit boundaries: n_bits of every call but the last must be a multiple of 128");
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	if (flags & TB200_FRESH) reset_stream(ctx);
+	if (!(flags & TB200_FRESH) && ctx->tail_fmt != (int)ctx->opt.input && ctx->fed_end)
+		return fail(ctx, TB200_E_ARG, "the input format cannot change inside a stream");
 	int rc = push_carry(ctx);
 	if (rc) return rc;
 	ctx->stats.kernel_launches = 0;          /* "by the last call" */
@@ -1364,13 +1387,25 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	if (rc) return rc;
 	if ((rc = profile_end(ctx))) return rc;
 	/* keep what a later call may still look at: everything from bitbuf[0] on */
-	const uint64_t keep_from = std::min<uint64_t>(ctx->rx.buf_start, ctx->fed_end);
+	uint64_t keep_from = std::min<uint64_t>(ctx->rx.buf_start, ctx->fed_end);
 	std::vector<uint8_t> nt;
-	nt.reserve(ctx->fed_end - keep_from);
-	for (uint64_t i = keep_from; i < ctx->fed_end; i++)
-		nt.push_back(i < src.new_base ? ctx->tail[i - ctx->tail_base] : bits[i - src.new_base]);
+	if (src.fmt == IN_BYTES) {
+		nt.reserve(ctx->fed_end - keep_from);
+		for (uint64_t i = keep_from; i < ctx->fed_end; i++)
+			nt.push_back(i < src.new_base ? ctx->tail[i - ctx->tail_base] : bits[i - src.new_base]);
+	} else if (!(flags & TB200_FINAL)) {
+		keep_from &= ~(uint64_t)127;                     /* whole 128-bit units, as the staging copies them */
+		if (keep_from < src.new_base) {
+			const size_t b0 = fmt_bytes(src.fmt, keep_from - ctx->tail_base), b1 = fmt_bytes(src.fmt, src.new_base - ctx->tail_base);
+			nt.insert(nt.end(), ctx->tail.begin() + b0, ctx->tail.begin() + b1);
+		}
+		const uint64_t from_new = std::max(keep_from, src.new_base);
+		const size_t c0 = fmt_bytes(src.fmt, from_new - src.new_base), c1 = fmt_bytes(src.fmt, ctx->fed_end - src.new_base);
+		nt.insert(nt.end(), bits + c0, bits + c1);
+	}
 	ctx->tail.swap(nt);
 	ctx->tail_base = keep_from;
+	ctx->tail_fmt = src.fmt;
 	/* hits before the kept range are of no further use */
 	return (long)out.n;
 }

@@ -55,7 +55,15 @@ struct Tables {
 	uint32_t crc_tab_r[272];
 	/* RM(30,14), tetra_rm3014.c:28-43: parity (low 16 bits of the code word) of the low / high 7 information bits */
 	uint16_t rm_par[2][128];
+	/* the scrambler 32 steps at a time: the register after 32 steps of tetra_scramb.c:34-50 IS the word of the 32 bits it
+	 * put out, so sequence word i+1 = L(word i), word 0 = L(init), L linear: XOR of one entry per byte of the argument */
+	uint32_t lfsr_leap[4][256];
 };
+
+__device__ __forceinline__ uint32_t lfsr_leap32(const uint32_t *__restrict__ leap, uint32_t x)
+{
+	return leap[x & 255u] ^ leap[256 + ((x >> 8) & 255u)] ^ leap[512 + ((x >> 16) & 255u)] ^ leap[768 + (x >> 24)];
+}
 
 /* ---- RM(30,14) decoding (the AACH, tetra_lower_mac.c:268-274 has a FIXME where this belongs) ----
  * Words follow tetra_rm3014_compute: 30 bits, bit 29 first on air, information = word >> 16.  The code is linear, so
@@ -139,6 +147,30 @@ TB_HD inline Tm tm_advance(Tm t, uint64_t n)
 			if (t.mn == 0) { t.mn = 1; cm--; }
 			uint64_t m = (uint64_t)(t.mn - 1) + cm;
 			t.mn = (uint32_t)(m % 60) + 1;
+		}
+	}
+	return t;
+}
+
+/* the same in 32-bit arithmetic (n < 2^31): what the kernels use - the distance to the last SYNC burst is small, and
+ * 64-bit remainders by 18 and 60 cost a subroutine call each */
+TB_HD inline Tm tm_advance_small(Tm t, uint32_t n)
+{
+	if (n == 0) return t;
+	t = tm_step(t);
+	if (--n == 0) return t;
+	const uint32_t a = (t.tn - 1) + n;
+	t.tn = (a & 3u) + 1;
+	uint32_t cf = a >> 2;
+	if (cf) {
+		if (t.fn == 0) { t.fn = 1; cf--; }
+		const uint32_t f = (t.fn - 1) + cf;
+		t.fn = f % 18u + 1;
+		uint32_t cm = f / 18u;
+		if (cm) {
+			if (t.mn == 0) { t.mn = 1; cm--; }
+			const uint32_t m = (t.mn - 1) + cm;
+			t.mn = m % 60u + 1;
 		}
 	}
 	return t;
@@ -961,12 +993,12 @@ __device__ __forceinline__ bool cell_state(uint64_t k, const SlotWs *__restrict_
 	if (j >= 0) {
 		const SlotWs s = ws[j];
 		Tm t = { s.tn, s.fn, s.mn };
-		*tm = tm_advance(t, k - (uint64_t)j);
+		*tm = tm_advance_small(t, (uint32_t)(k - (uint64_t)j));      /* k indexes the slots of one launch: < 2^32 */
 		*code = s.sb_code;
 		return false;
 	}
 	Tm t = { carry->tn, carry->fn, carry->mn };
-	*tm = tm_advance(t, k + 1);
+	*tm = k + 1 < 0x7fffffffull ? tm_advance_small(t, (uint32_t)(k + 1)) : tm_advance(t, k + 1);
 	*code = carry->scramb_init;
 	return true;
 }

@@ -30,7 +30,7 @@ constexpr int LANE_NT = 32;           /* threads per CTA of the lane kernels: on
  * (written once, read once a few microseconds later, 128-byte coalesced rows). */
 __host__ __device__ constexpr size_t lane_smem_words(int nt)
 {
-	return (size_t)2 * LANE_T3_ROWS * nt + 256 + 16 + (nt / 32) * 16;
+	return (size_t)2 * LANE_T3_ROWS * nt + 256 + 16 + (nt / 32) * 16 + 1024;
 }
 __host__ __device__ constexpr size_t lane_scratch_words_per_cta(int nt) { return (size_t)LANE_DEC_ROWS * nt; }
 
@@ -39,6 +39,7 @@ struct LaneSmem {
 	uint32_t *t3;        /* [2][LANE_T3_ROWS][NT] type-3 bits, later the decoded type-2 bits */
 	uint32_t *crc_tab;   /* [256] reflected CRC-CCITT byte table, then [16] nibble table */
 	uint32_t *lfb;       /* [NT/32][16] per-warp scrambling sequence broadcast */
+	uint32_t *leap;      /* [4][256] the scrambler 32 steps at a time (Tables::lfsr_leap) */
 	static constexpr int nt = LANE_NT;
 	__device__ __forceinline__ LaneSmem(uint8_t *base, uint32_t *scratch)
 	{
@@ -46,7 +47,8 @@ struct LaneSmem {
 		dec = reinterpret_cast<uint4 *>(scratch + (size_t)blockIdx.x * lane_scratch_words_per_cta(nt));
 		t3 = p; p += 2 * LANE_T3_ROWS * nt;
 		crc_tab = p; p += 256 + 16;
-		lfb = p;
+		lfb = p; p += (nt / 32) * 16;
+		leap = p;
 	}
 	__device__ __forceinline__ uint32_t *t3col(int tr, int tid) const { return t3 + (size_t)tr * LANE_T3_ROWS * nt + tid; }
 };
@@ -522,33 +524,46 @@ __device__ __forceinline__ void put_lane(uint32_t (&outw)[9], int dst, int len, 
 	}
 }
 
-/* scrambling sequence words for `code`, for every lane of the warp: cooperative when the warp
- * shares one code (the normal case: one cell), per distinct code otherwise */
+/* scrambling sequence words for `code`, for every lane of the warp.  One cell per warp (the normal case): cooperative,
+ * 16 lanes build one word each from the column table and broadcast it.  Lanes with different codes (a stream whose
+ * SYNC bursts announce ever new cells, BASELINE config 4): every lane runs its own scrambler 32 steps at a time with
+ * the byte tables in shared memory - 14 dependent look-ups instead of one cooperative round per distinct code. */
 __device__ inline void lane_lfsr(uint32_t code, bool need, uint32_t (&lf)[LANE_T3_ROWS], uint32_t *bcast,
-                                 const Tables *__restrict__ tab)
+                                 const Tables *__restrict__ tab, const uint32_t *__restrict__ leap)
 {
 	const unsigned lane = threadIdx.x & 31;
-	unsigned pending = __ballot_sync(FULL, need);
-	while (pending) {
-		const int leader = __ffs((int)pending) - 1;
-		const uint32_t c = __shfl_sync(FULL, code, leader);
+	const unsigned pending = __ballot_sync(FULL, need);
+	if (!pending) return;
+	const int leader = __ffs((int)pending) - 1;
+	const uint32_t c = __shfl_sync(FULL, code, leader);
+	if (__all_sync(FULL, !need || code == c)) {
 		const uint32_t wv = lfsr_word(c, lane, tab);
 		if (lane < 16) bcast[lane] = wv;
 		__syncwarp();
-		const bool mine = need && code == c;
-		if (mine) {
+		if (need) {
 #pragma unroll
 			for (int i = 0; i < LANE_T3_ROWS; ++i) lf[i] = bcast[i];
 		}
-		pending &= ~__ballot_sync(FULL, mine);
 		__syncwarp();
+		return;
+	}
+	if (need) {
+		uint32_t w = code;
+#pragma unroll
+		for (int i = 0; i < LANE_T3_ROWS; ++i) {
+			w = lfsr_leap32(leap, w);
+			lf[i] = w;
+		}
 	}
 }
 
-__device__ __forceinline__ void lane_load_tables(const LaneSmem &sm, const Tables *__restrict__ tab)
+__device__ __forceinline__ void lane_load_tables(const LaneSmem &sm, const Tables *__restrict__ tab, bool with_leap = false)
 {
 	for (int i = threadIdx.x; i < 256 + 16; i += blockDim.x)
 		sm.crc_tab[i] = tab->crc_tab_r[i];
+	if (with_leap)
+		for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+			sm.leap[i] = (&tab->lfsr_leap[0][0])[i];
 	__syncthreads();
 }
 
@@ -638,7 +653,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 {
 	LaneSmem sm(TB_DYN_SMEM(), scratch);
 	const Tables *__restrict__ tab = a.tab;
-	lane_load_tables(sm, tab);
+	lane_load_tables(sm, tab, true);
 	const int tid = threadIdx.x;
 	constexpr int nt = LANE_NT;
 	uint32_t *bcast = sm.lfb + (tid >> 5) * 16;
@@ -679,7 +694,7 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 			}
 			flags[h] = (uint32_t)kind[h] | (unlock ? F_UNLOCK : 0) | ((kind[h] == KIND_SB && good_sb) ? F_CRC_A : 0);
 			uint32_t lf[LANE_T3_ROWS];
-			lane_lfsr(code[h], kind[h] != KIND_NONE, lf, bcast, tab);
+			lane_lfsr(code[h], kind[h] != KIND_NONE, lf, bcast, tab, sm.leap);
 			if (kind[h] != KIND_NONE) {
 				uint32_t bw[16];
 				load_slot_bits(a.slot_bits, k[h], bw);

@@ -27,6 +27,7 @@
  *           all-gather for the cell state, lock losses handled); the text is the same, line for line
  */
 #include <pthread.h>
+#include <unistd.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -174,12 +175,20 @@ int main(int argc, char **argv)
 		sh.slots = calloc(cap, sizeof(*sh.slots)); sh.type1 = calloc(cap, TB200_TYPE1_STRIDE); sh.crc = calloc(cap, sizeof(uint32_t));
 		pthread_mutex_init(&sh.mu, NULL);
 		if (!sh.slots || !sh.type1 || !sh.crc) { fprintf(stderr, "out of memory\n"); return 1; }
+		/* stdout carries the receiver's text and nothing else: while the GPUs work (NCCL prints its version line to
+		 * stdout when NCCL_DEBUG asks for it) descriptor 1 points at stderr */
+		fflush(stdout);
+		const int saved_stdout = dup(1);
+		dup2(2, 1);
 		if (tb200_dist_get_id(sh.id) != 0) { fprintf(stderr, "NCCL (libnccl.so.2) is not available\n"); return 1; }
 		pthread_t th[64];
 		struct mg_rank rk[64];
 		if (gpus > 64) { fprintf(stderr, "at most 64 GPUs\n"); return 2; }
 		for (int r = 0; r < gpus; r++) { rk[r].sh = &sh; rk[r].rank = r; pthread_create(&th[r], NULL, mg_thread, &rk[r]); }
 		for (int r = 0; r < gpus; r++) pthread_join(th[r], NULL);
+		fflush(stdout);
+		dup2(saved_stdout, 1);
+		close(saved_stdout);
 		if (sh.failed) return 1;
 		slots = sh.slots; type1 = sh.type1; crc = sh.crc; ev = sh.ev; n_ev = sh.n_ev; n = sh.n_total;
 	} else {

@@ -78,11 +78,45 @@ def test_symbol_input_emulated(emu, orc, lead_in):
         emu.set_options(input=T.IN_BYTES, pipeline_slots=0)
 
 
+def _continued(lib, orc, fmt, n_bursts, seed):
+    """a packed / symbol stream handed over in several calls (128-bit boundaries) equals the reference chain on the whole stream"""
+    rng = np.random.default_rng(seed)
+    bits, cfg = _stream(orc, n=n_bursts, random_cell=1, sb_period=8, lead_in_bits=int(rng.integers(0, 300)))
+    bits = bits[:bits.size & ~1].copy()
+    k = n_bursts // 2
+    while orc.gen_kind(cfg, k) == 1:
+        k += 1
+    bits[cfg.lead_in_bits + 510 * k + 244:cfg.lead_in_bits + 510 * k + 266] = 0        # and lock is lost on the way
+    want, ev = _ref_records(orc, bits)
+    buf = T.pack_bits(bits) if fmt == T.IN_PACKED else T.bits_to_symbols(bits, rng)
+    per_bit = 1 / 8 if fmt == T.IN_PACKED else 2                              # buffer elements (bytes / floats) per 1 stream bit... floats: 1 per 2 bits
+    lib.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, input=fmt)
+    try:
+        pos, outs = 0, []
+        while pos < bits.size:
+            n = min(bits.size - pos, 128 * int(rng.integers(1, 60)))
+            last = pos + n >= bits.size
+            part = buf[pos // 8:(pos + n + 7) // 8] if fmt == T.IN_PACKED else buf[pos // 2:(pos + n + 1) // 2]
+            flags = (T.TB200_FRESH if pos == 0 else 0) | (T.TB200_FINAL if last else 0)
+            outs.append(lib.rx_stream_host_raw(np.ascontiguousarray(part), n, flags=flags))
+            pos += n
+        slots = np.concatenate([o[0] for o in outs]); t1 = np.concatenate([o[1] for o in outs])
+        T.check_stream_against(want, ev, slots, lib.expand_records(slots, t1))
+        assert len(outs) > 5
+    finally:
+        lib.set_options(input=T.IN_BYTES, pipeline_slots=0)
+
+
+@pytest.mark.parametrize("fmt", [T.IN_PACKED, T.IN_F32SYM])
+def test_packed_and_symbol_streams_continue(emu, orc, fmt):
+    _continued(emu, orc, fmt, 60, 41 + fmt)
+
+
 def test_format_rules(emu):
     emu.set_options(input=T.IN_PACKED, viterbi=T.VITERBI_LANE)
     try:
-        with pytest.raises(RuntimeError):          # continuation is only defined for the byte format
-            emu.rx_stream_host_raw(np.zeros(64, np.uint8), 512, flags=T.TB200_FRESH)
+        with pytest.raises(RuntimeError):          # a packed stream continues on 128-bit boundaries only
+            emu.rx_stream_host_raw(np.zeros(64, np.uint8), 500, flags=T.TB200_FRESH)
         with pytest.raises(ValueError):
             emu.set_options(viterbi=T.VITERBI_WARP)
     finally:
