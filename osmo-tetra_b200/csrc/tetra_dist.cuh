@@ -82,7 +82,8 @@ struct DistMeta {              /* rank 0 -> all, per segment */
 	DevCarry carry;
 	uint64_t src_ptr;          /* PEER: the (packed or original) stream on rank 0 */
 	int64_t pid;
-	int32_t src_device, pad;
+	int32_t src_device;
+	uint32_t feeder_ppm;       /* share of the whole segment that rank 0 gives up because it also packs the stream (parts per million) */
 	uint8_t ipc[64];
 };
 
@@ -274,12 +275,29 @@ struct DistPlan {
 	uint64_t lo, hi, base;     /* stream bits: first slot, end of the data the shard needs, start of the data it holds */
 };
 
+/* Contiguous slot ranges.  Even, unless rank 0 also has to turn the whole one-bit-per-byte stream into packed bits
+ * (TB200_DIST_PACK): that costs it rho = feeder_ppm / 10^6 of the time one GPU needs to decode the whole segment (it
+ * reads 510 bytes per slot at HBM speed, decoding runs at ~1.6 * 10^9 slots/s), so the other ranks get
+ * n (1 + rho) / world slots each and rank 0 what is left - with enough ranks nothing: it then only feeds the others. */
+static void dist_bounds(const DistMeta &m, int world, int r, uint64_t *k0, uint64_t *k1)
+{
+	const uint64_t n = m.n_slots;
+	if (world == 1) { *k0 = 0; *k1 = n; return; }
+	const double rho = m.feeder_ppm * 1e-6;
+	double others = (double)n * (1.0 + rho) / world;
+	double first = others - rho * (double)n;
+	if (first < 0) { first = 0; others = (double)n / (world - 1); }
+	const uint64_t n0 = std::min<uint64_t>(n, (uint64_t)first);
+	const uint64_t per = (n - n0 + world - 2) / (world - 1);
+	if (r == 0) { *k0 = 0; *k1 = n0; return; }
+	*k0 = std::min<uint64_t>(n, n0 + (uint64_t)(r - 1) * per);
+	*k1 = std::min<uint64_t>(n, n0 + (uint64_t)r * per);
+}
+
 static DistPlan dist_plan(const DistMeta &m, int world, int r)
 {
 	DistPlan p;
-	const uint64_t per = (m.n_slots + world - 1) / world;
-	p.k0 = std::min<uint64_t>((uint64_t)r * per, m.n_slots);
-	p.k1 = std::min<uint64_t>((uint64_t)(r + 1) * per, m.n_slots);
+	dist_bounds(m, world, r, &p.k0, &p.k1);
 	p.lo = m.a0 + SLOT_BITS * p.k0;
 	p.hi = std::max(p.lo, std::min<uint64_t>(m.n_end, m.a0 + SLOT_BITS * p.k1 + DIST_HALO));
 	p.base = m.fmt == IN_BYTES ? p.lo : (p.lo & ~(uint64_t)127);
@@ -380,6 +398,11 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 			m.a0 = seg.a0; m.cmin = seg.cmin; m.n_end = n_bits; m.k_done = ctx->stats.slots;
 			m.carry = ctx->h_carry; m.carry.seen_good = 0; m.carry.first_good = ~0ull;
 			m.src_ptr = (uint64_t)(uintptr_t)xfer_src; m.pid = (int64_t)getpid(); m.src_device = ctx->device;
+			if (pack && world > 1) {
+				/* packing reads 510 B per slot at ~6 TB/s = 1.2e10 slots/s, decoding runs at ~1.6e9 slots/s */
+				m.feeder_ppm = 130000;
+				if (const char *e = getenv("TB200_DIST_FEEDER_PPM")) m.feeder_ppm = (uint32_t)atoi(e);
+			}
 #ifndef TB_SIMT_EMULATION
 			if (peer && world > 1 && m.ok) {
 				cudaIpcMemHandle_t h;
@@ -423,9 +446,12 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 			/* packing runs front to back over the stream, so the order of the chunks is also the order of the bits as
 			 * long as chunk c of rank r+1 lies behind chunk c of rank r - it does not (rank-minor order jumps back and
 			 * forth), so every chunk packs exactly its own bit range [start, end) */
+			/* two sweeps over the chunk indices: first the chunks of the other ranks (every rank's first chunk leaves
+			 * first, so all of them start early), then rank 0's own - it decodes once it has fed everybody */
+			for (int sweep = 0; sweep < 2; sweep++)
 			for (size_t c = 0; c < max_chunks; c++) {
 				bool group_open = false;
-				for (int r = 0; r < world; r++) {
+				for (int r = sweep == 0 ? 1 : 0; r < (sweep == 0 ? world : 1); r++) {
 					if (c >= ends[r].size()) continue;
 					const uint64_t b0 = c == 0 ? plans[r].base : ends[r][c - 1];
 					const uint64_t b1 = ends[r][c];
@@ -433,7 +459,10 @@ extern "C" long tb200_dist_rx_stream(tb200_dist *d, const uint8_t *d_bits, uint6
 					if (pack) {
 						/* [b0, b1) of the byte stream -> packed words; b0 is a multiple of 128 */
 						if (!packed_any) { DCU(cudaEventRecord(d->ev_pack[0], d->s_pack)); packed_any = true; }
-						int rc = pack_bits_async(ctx, d_bits + b0, b1 - b0, d->d_packed + (b0 >> 3), d->s_pack);
+						/* whole words, also the last one: the ranges of neighbouring ranks overlap by the halo, and whoever
+						 * packs a word must write all of it */
+						const uint64_t b1w = std::min<uint64_t>((b1 + 31) & ~(uint64_t)31, n_bits);
+						int rc = pack_bits_async(ctx, d_bits + b0, b1w - b0, d->d_packed + (b0 >> 3), d->s_pack);
 						if (rc) { restore(); return dfail(d, rc, "%s", ctx->err); }
 						int er = dist_event(d, &ev_packed);
 						if (er) { restore(); return er; }

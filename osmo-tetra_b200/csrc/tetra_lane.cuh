@@ -141,6 +141,40 @@ __device__ __forceinline__ void acs2_step(uint32_t (&pm)[16], const uint32_t (&M
 	for (int s = 0; s < 16; ++s) pm[s] = nm[s];
 }
 
+/* The odd trellis steps (only G1 was sent, rate 2/3) with the metrics taken relative to the branches whose G1 is 0:
+ * those cost nothing, the others d = U * (1 - 2 r) (U = metric unit, r = received bit), i.e. +U or -U.  Every path
+ * collects the same offset per step, so nothing changes for the comparisons, but half of the candidates need no add at all:
+ *   G1(lo branch) = 0:  new = min(pm[hi] + (d + tag), pm[lo])            one VIADDMNMX
+ *   G1(lo branch) = 1:  new = min(pm[lo] + d, pm[hi] + tag)              one add with a constant + one VIADDMNMX
+ * 24 instead of 32 instructions per step for two trellises.  d can be negative; VIADDMNMX.U16x2 adds half by half, so d
+ * and d + tag come in two's complement PER HALF (mad with U * 254 instead of -2 U: the 2^16 of a negative low half lands
+ * where it cancels the borrow), and the metrics carry a floor that the -U steps cannot eat up (callers).
+ * TIE_HI mirrors it: the tag sits on the lo candidate, the free candidates are the ones whose hi branch has G1 = 0. */
+template <bool TIE_HI>
+__device__ __forceinline__ void acs2_odd_step(uint32_t (&pm)[16], const uint32_t d, const uint32_t dT, const uint32_t tagw)
+{
+	uint32_t nm[16];
+#pragma unroll
+	for (int s = 0; s < 16; ++s) {
+		const unsigned c = branch_class(s >> 1) ^ ((s & 1) ? 3u : 0u);
+		const bool g1_lo = (c >> 1) & 1;                      /* G1 of the branch from s>>1; the one from (s>>1)|8 has the complement */
+		const uint32_t lo = pm[s >> 1], hi = pm[(s >> 1) | 8];
+		if (!TIE_HI) {
+			if (!g1_lo) nm[s] = __viaddmin_u16x2(hi, dT, lo);
+			else        nm[s] = __viaddmin_u16x2(lo, d, hi + tagw);
+		} else {
+			if (g1_lo)  nm[s] = __viaddmin_u16x2(lo, dT, hi);
+			else        nm[s] = __viaddmin_u16x2(hi, d, lo + tagw);
+		}
+	}
+#pragma unroll
+	for (int s = 0; s < 16; ++s) pm[s] = nm[s];
+}
+
+/* multiplier that turns the received bit r (per half, carried with weight W) into -2 U r in two's complement per half:
+ * (2^16 - 2 U) / W; added to U that is U (1 - 2 r), and nothing carries from the low half into the high one */
+__host__ __device__ constexpr int odd_mult(int unit, int weight) { return (65536 - 2 * unit) / weight; }
+
 /* After the fourth step of a group: strip the history nibbles off the 16 metrics and pack them.
  * The nibble of state s goes to position rev4(s), so that the trace back can index it with the
  * previous group's decoded nibble directly.  Result: x,y = trellis X positions 0-7, 8-15; z,w = Y. */
@@ -179,8 +213,9 @@ template <bool MASKED, bool TIE_HI>
 __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *cy, int nx, int ny, int nmax)
 {
 	uint32_t pm[16];
+	/* start in state 0 (osmo_conv_decode); the floor 0x1000 is what the odd steps may take off (at most 16 each, 146 of them) */
 #pragma unroll
-	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x40004000u : 0u;     /* start in state 0 (osmo_conv_decode) */
+	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x50005000u : 0x10001000u;
 	constexpr int nt = LANE_NT;
 	const int groups = nmax / 8;                       /* 4 step pairs = 12 type-3 bits per group */
 	for (int g = 0; g < groups; ++g) {
@@ -209,10 +244,8 @@ __device__ __noinline__ void viterbi_pair_t(uint4 *dec, uint32_t *cx, uint32_t *
 			M0[2] = mad_k<16>(u, 0u);           M1[2] = mad_k<16>(u, te);
 			M0[1] = mad_k<-16>(u, two);         M1[1] = mad_k<-16>(u, two + te);
 			acs2_step<TIE_HI>(pm, M0, M1);
-			M0[0] = mad_k<16>(r3, 0u);          M1[0] = mad_k<16>(r3, to);   /* odd step: only G1 was sent */
-			M0[2] = mad_k<-16>(r3, one);        M1[2] = mad_k<-16>(r3, one + to);
-			M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
-			acs2_step<TIE_HI>(pm, M0, M1);
+			/* odd step: only G1 was sent; 16 * (1 - 2 r3) per half, two's complement per half (16 * 254 = 65536 / 16 - 32) */
+			acs2_odd_step<TIE_HI>(pm, mad_k<odd_mult(16, 1)>(r3, one), mad_k<odd_mult(16, 1)>(r3, one + to), to);
 			if (p & 1) dec[(2 * g + (p >> 1)) * nt] = take_history<TIE_HI>(pm);
 		}
 	}
@@ -312,18 +345,18 @@ __device__ __forceinline__ void step_pair_u8(uint32_t (&pm)[16], uint32_t t, uin
 	M0[2] = mad_k<K>(u, 0u);                M1[2] = mad_k<K>(u, te);
 	M0[1] = mad_k<-K>(u, 0x02000200u);      M1[1] = mad_k<-K>(u, 0x02000200u + te);
 	acs2_step<TIE_HI>(pm, M0, M1);
-	M0[0] = mad_k<K>(r3, 0u);               M1[0] = mad_k<K>(r3, to);        /* odd step: only G1 was sent */
-	M0[2] = mad_k<-K>(r3, 0x01000100u);     M1[2] = mad_k<-K>(r3, 0x01000100u + to);
-	M0[1] = M0[0]; M0[3] = M0[2]; M1[1] = M1[0]; M1[3] = M1[2];
-	acs2_step<TIE_HI>(pm, M0, M1);
+	/* odd step: only G1 was sent; 256 * (1 - 2 r3) per half (r3 carries weight 256 / K) */
+	acs2_odd_step<TIE_HI>(pm, mad_k<odd_mult(256, 256 / K)>(r3, 0x01000100u), mad_k<odd_mult(256, 256 / K)>(r3, 0x01000100u + to), to);
 }
 
 template <bool TIE_HI>
 __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t *cy, int n)
 {
 	uint32_t pm[16];
+	/* start in state 0 (osmo_conv_decode); the floor 0x2400 covers what the odd steps take off between two re-centrings
+	 * (at most 256 each, 32 of them) */
 #pragma unroll
-	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x40004000u : 0u;     /* start in state 0 (osmo_conv_decode) */
+	for (int i = 0; i < 16; ++i) pm[i] = i ? 0x64006400u : 0x24002400u;
 	constexpr int nt = LANE_NT;
 	const int groups = n / 8;                          /* 4 step pairs = 12 type-3 bits per group */
 	for (int g = 0; g < groups; ++g) {
@@ -347,10 +380,11 @@ __device__ __noinline__ void viterbi_pair_u8(uint4 *dec, uint32_t *cx, uint32_t 
 		take_history8<TIE_HI>(pm, hx, hy);
 		dec[(2 * g) * nt] = hx;
 		dec[(2 * g + 1) * nt] = hy;
-		if ((g & 7) == 7) {            /* keep the metrics small: subtract the per-trellis minimum */
+		if ((g & 7) == 7) {            /* keep the metrics small: bring the per-trellis minimum back to the floor */
 			uint32_t m = pm[0];
 #pragma unroll
 			for (int i = 1; i < 16; ++i) m = __viaddmin_u16x2(pm[i], 0u, m);
+			m = sub_opaque(m, 0x24002400u);
 #pragma unroll
 			for (int i = 0; i < 16; ++i) pm[i] = sub_opaque(pm[i], m);
 		}
