@@ -117,7 +117,7 @@ const char *tb200_version(void);
                               * tb200_rx_stream_host calls continues on 128-bit boundaries (n_bits % 128 == 0 except for the last call) */
 #define TB200_IN_F32SYM  2   /* one float32 per symbol, the demodulator output float_to_bits reads (float_to_bits.c:128-164):
                               * two hard bits per symbol, sliced on the device exactly like process_sym_fl + sym_int2bits
-                              * (float_to_bits.c:33-72) without the optional pseudo-AFC (-a); n_bits = 2 * symbols */
+                              * (float_to_bits.c:33-72), with its pseudo-AFC (-a) when options.afc is set; n_bits = 2 * symbols */
 
 struct tb200_options {
 	uint32_t chunk_bits;        /* read() size the caller models; tetra-rx.c:83 uses 64. 1..296 */
@@ -129,6 +129,10 @@ struct tb200_options {
 	uint32_t serial_passes;     /* 1: pass 1 (search, SB1, scans) of a piece on the same CUDA stream as the decode passes, so that no two
 	                             * kernels of the receiver ever run side by side (clean per-kernel timings); 0 (default): pass 1 of
 	                             * piece i+1 on its own stream under the decode pass of piece i */
+	uint32_t afc;               /* TB200_IN_F32SYM only: 1 = slice like `float_to_bits -a`, i.e. with its pseudo-AFC (float_to_bits.c:140-147;
+	                             * what the reference's live pipeline runs, src/receiver1udp:62), exactly (tb200_float_to_bits) */
+	float    afc_filter_val;    /* float_to_bits -f (default 0.0001) */
+	float    afc_filter_goal;   /* float_to_bits -F (default 0) */
 	uint32_t viterbi_tie;       /* survivor on equal path metrics (tetra_tie_rule.h): 0 = predecessor s>>1 (libosmocore's
 	                             * osmo_conv_decode as restated, viterbi_cch.c:58-66), 1 = predecessor (s>>1)|8.  The default is
 	                             * TETRA_VITERBI_TIE_DEFAULT, the compile-time switch the CPU oracle shares */
@@ -441,6 +445,16 @@ int tb200_slots_digest(tb200_ctx *ctx, const struct tb200_slot *slots, const uin
 /* TB200_IN_BYTES -> TB200_IN_PACKED on the device: n_bits bytes holding 0/1 (tetra-rx.c:82-95) to (n_bits+7)/8 bytes,
  * stream bit i = byte i>>3 bit i&7.  d_packed: 4-byte aligned, room for 4 * ((n_bits + 31) / 32) bytes. */
 int tb200_pack_bits_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint8_t *d_packed);
+
+/* float_to_bits (float_to_bits.c:128-164) on the device: n_sym float32 symbols -> 2 * n_sym hard bits, packed eight per
+ * byte (TB200_IN_PACKED: bit i of the stream = byte i>>3 bit i&7; room for 4 * ceil(n_sym / 16) bytes).  afc = 1 is the
+ * program's -a, its pseudo-AFC (:140-147) with -f filter_val (default 0.0001) and -F filter_goal (default 0): a serial
+ * float recurrence, reproduced bit for bit (speculative chunks + verification, csrc/tetra_afc.cuh).  *state (may be NULL):
+ * the tracker's value in front of the first symbol (0 at the start of a stream), replaced by its value behind the last, so
+ * a stream can be sliced piece by piece.  Returns the number of chunks that had to be redone (>= 0) or TB200_E_*.
+ * The receive calls do this themselves for TB200_IN_F32SYM input when options.afc is set. */
+int tb200_float_to_bits(tb200_ctx *ctx, const float *sym, uint64_t n_sym, int afc, float filter_val, float filter_goal,
+                        float *state, uint8_t *packed_bits, int is_device);
 
 /* ---- introspection used by the tests ------------------------------------------------ */
 

@@ -793,8 +793,7 @@ void orc_gen_stream(const struct orc_gen_cfg *c, uint64_t k0, uint64_t n, uint8_
  * one float per pi/4-DQPSK symbol (phase step in units of pi/4) -> two unpacked bits.
  * process_sym_fl (float_to_bits.c:33-50): strict comparisons, > 2 -> 3, > 0 -> 1, < -2 -> -3, else -1
  * (so 2.0 -> 1, 0.0 -> -1, -2.0 -> -1, NaN -> -1); sym_int2bits (:52-76): 3 -> 0,1   1 -> 0,0
- * -3 -> 1,1   -1 -> 1,0.  The optional pseudo-AFC (-a, :138-147) is a serial float IIR and is
- * not restated: it is off by default in the reference and out of scope for the GPU path. */
+ * -3 -> 1,1   -1 -> 1,0.  The pseudo-AFC (-a, :138-147) follows below. */
 void orc_float_to_bits(const float *sym, size_t n, uint8_t *bits)
 {
 	for (size_t i = 0; i < n; i++) {
@@ -811,6 +810,26 @@ void orc_float_to_bits(const float *sym, size_t n, uint8_t *bits)
 		default: bits[2 * i] = 1; bits[2 * i + 1] = 0; break;
 		}
 	}
+}
+
+/* float_to_bits -a (float_to_bits.c:140-147): a one-pole tracker of the symbols' mean, subtracted before slicing.
+ *     if (-5 < fl < 5) filter = filter * (1.0 - filter_val) + (fl - filter_goal) * filter_val;     slice(fl - filter)
+ * filter, filter_val, filter_goal are floats; `1.0` is a double, so the first product and the sum are formed in double
+ * and rounded to float once per symbol, the second product in float (C's usual arithmetic conversions; no fused
+ * multiply-add: plain x86-64 code).  *filter is the tracker's state: zero at the start of the program. */
+void orc_float_to_bits_afc(const float *sym, size_t n, float filter_val, float filter_goal, float *filter, uint8_t *bits)
+{
+	volatile float f = *filter;            /* volatile: every step is rounded to float, whatever the compiler would like */
+	for (size_t i = 0; i < n; i++) {
+		const float fl = sym[i];
+		if ((fl > -5.0) && (fl < 5.0)) {
+			volatile double a = (double)f * (1.0 - (double)filter_val);
+			volatile float b = (fl - filter_goal) * filter_val;
+			f = (float)(a + (double)b);
+		}
+		orc_float_to_bits(&(float){ fl - f }, 1, bits + 2 * i);
+	}
+	*filter = f;
 }
 
 /* ----------------------------------------------------------- GSMTAP framing --

@@ -52,7 +52,8 @@ TIE_LOW_PRED, TIE_HIGH_PRED = 0, 1        # include/tetra_tie_rule.h
 class Options(C.Structure):
     _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
                 ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32), ("input", C.c_uint32),
-                ("serial_passes", C.c_uint32), ("viterbi_tie", C.c_uint32)]
+                ("serial_passes", C.c_uint32), ("afc", C.c_uint32), ("afc_filter_val", C.c_float), ("afc_filter_goal", C.c_float),
+                ("viterbi_tie", C.c_uint32)]
 
 
 class Timing(C.Structure):
@@ -303,6 +304,18 @@ class B200:
         if self.lib.tb200_viterbi_decode(self.h, _ptr(mother), mother.shape[0], sym_count, _ptr(out), 0):
             raise RuntimeError(self.err())
         return out
+
+    def float_to_bits(self, sym, afc=False, filter_val=0.0001, filter_goal=0.0, state=0.0):
+        """tb200_float_to_bits on a host array -> (unpacked bits, tracker state afterwards, chunks redone)"""
+        sym = np.ascontiguousarray(sym, dtype=np.float32)
+        out = np.zeros(4 * ((sym.size + 15) // 16) + 4, dtype=np.uint8)
+        st = C.c_float(state)
+        self.lib.tb200_float_to_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_float, C.c_float,
+                                                 C.POINTER(C.c_float), C.c_void_p, C.c_int]
+        rc = self.lib.tb200_float_to_bits(self.h, _ptr(sym), sym.size, int(afc), filter_val, filter_goal, C.byref(st), _ptr(out), 0)
+        if rc < 0:
+            raise RuntimeError(self.err())
+        return np.unpackbits(out, bitorder="little")[:2 * sym.size], st.value, rc
 
     def rm3014_decode(self, words):
         """tb200_rm3014_decode on a host array of 30-bit words -> (info14, distance, not_a_code_word)"""

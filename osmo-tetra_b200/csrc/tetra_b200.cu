@@ -15,6 +15,7 @@
 #include "tetra_gen.cuh"
 #include "tetra_gsmtap.cuh"
 #include "tetra_util.cuh"
+#include "tetra_afc.cuh"
 #include "../../include/tetra_b200.h"
 
 #include <algorithm>
@@ -224,6 +225,14 @@ struct tb200_ctx {
 	/* sharded decode: what pass 1 left for pass 2 */
 	uint64_t shard_a0 = 0;
 	uint32_t shard_slots = 0;
+	/* float_to_bits -a (options.afc): the tracker's state between calls, scratch of the pre-pass */
+	float afc_state = 0.f;
+	float *d_afc_sym = nullptr; size_t afc_sym_cap = 0;
+	uint8_t *d_afc_bits = nullptr; size_t afc_bits_cap = 0;
+	float *d_afc_f = nullptr; size_t afc_f_cap = 0;
+	std::vector<float> h_afc_f;
+	std::vector<uint8_t> h_afc_bits;
+	uint64_t afc_repairs = 0;        /* chunks of the last pre-pass whose speculative start state was wrong */
 	/* grow-only device scratch of the leaf operators: no cudaMalloc / cudaFree per call, nothing to leak on an error path */
 	void *leaf_mem[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	size_t leaf_cap[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -282,6 +291,7 @@ extern "C" void tb200_default_options(tb200_options *o)
 	o->profile = 0;
 	o->input = TB200_IN_BYTES;
 	o->serial_passes = getenv("TB200_SERIAL") ? 1 : 0;
+	o->afc = 0; o->afc_filter_val = 0.0001f; o->afc_filter_goal = 0.f;      /* float_to_bits.c:83-86 */
 	o->viterbi_tie = TETRA_VITERBI_TIE_DEFAULT;
 }
 
@@ -296,6 +306,8 @@ extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
 		return fail(ctx, TB200_E_ARG, "unknown input format");
 	if (o->viterbi_tie > 1)
 		return fail(ctx, TB200_E_ARG, "viterbi_tie must be 0 or 1");
+	if (o->afc > 1 || (o->afc && (!(o->afc_filter_val > 0.f) || !(o->afc_filter_val <= 1.f))))
+		return fail(ctx, TB200_E_ARG, "afc must be 0 or 1 with afc_filter_val in (0, 1]");
 	if (o->input != TB200_IN_BYTES && o->viterbi != TB200_VITERBI_LANE)
 		return fail(ctx, TB200_E_ARG, "packed / symbol input needs the lane kernels (TB200_VITERBI_LANE)");
 	ctx->opt = *o;
@@ -502,6 +514,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	}
 	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch); cudaFree(ctx->d_sb1_scratch);
 	cudaFree(ctx->d_pstats); cudaFreeHost(ctx->h_pstats); cudaFree(ctx->d_rm_leader);
+	cudaFree(ctx->d_afc_sym); cudaFree(ctx->d_afc_bits); cudaFree(ctx->d_afc_f);
 	for (int i = 0; i < NBUF; i++) cudaFree(ctx->d_oaach[i]);
 	for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) cudaFree(ctx->leaf_mem[i]);
@@ -618,6 +631,9 @@ struct HostTrace {
 };
 static HostTrace *g_trace = nullptr;
 #define TB_TRACE(what) do { if (g_trace) g_trace->mark(what); } while (0)
+
+static int float_to_bits_dev(tb200_ctx *ctx, const float *d_sym, uint64_t n_sym, int afc, float filter_val, float filter_goal,
+                             float *state, uint32_t *d_out);
 
 /* ------------------------------------------------------------ the source -- */
 
@@ -1349,6 +1365,19 @@ extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint6
 	if (rc) return rc;
 	TB_TRACE("carry pushed");
 	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = (int)ctx->opt.input;
+	if (ctx->opt.input == TB200_IN_F32SYM && ctx->opt.afc) {
+		/* float_to_bits -a first (the tracker is a recurrence over the whole stream), then the chain on packed bits */
+		const size_t need = 4 * (size_t)((n_bits / 2 + 15) / 16) + 256;
+		if (need > ctx->afc_bits_cap) {
+			cudaFree(ctx->d_afc_bits); ctx->d_afc_bits = nullptr; ctx->afc_bits_cap = 0;
+			CU(cudaMalloc((void **)&ctx->d_afc_bits, need));
+			ctx->afc_bits_cap = need;
+		}
+		ctx->afc_state = 0.f;
+		if ((rc = float_to_bits_dev(ctx, reinterpret_cast<const float *>(d_bits), n_bits / 2, 1, ctx->opt.afc_filter_val,
+		                            ctx->opt.afc_filter_goal, &ctx->afc_state, reinterpret_cast<uint32_t *>(ctx->d_afc_bits)))) return rc;
+		src.data = ctx->d_afc_bits; src.fmt = IN_PACKED;
+	}
 	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
 	out.crc = ctx->user_crc; out.aach = ctx->user_aach; out.max_slots = max_slots; out.n = 0;
 	ctx->lock_events.clear();
@@ -1370,14 +1399,39 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	if (ctx->opt.input != TB200_IN_BYTES && !(flags & TB200_FINAL) && (n_bits & 127))
 		return fail(ctx, TB200_E_ARG, "a bit-packed / symbol stream continues on 128-bit boundaries: n_bits of every call but the last must be a multiple of 128");
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
-	if (flags & TB200_FRESH) reset_stream(ctx);
-	if (!(flags & TB200_FRESH) && ctx->tail_fmt != (int)ctx->opt.input && ctx->fed_end)
+	if (flags & TB200_FRESH) { reset_stream(ctx); ctx->afc_state = 0.f; }
+	const bool afc = ctx->opt.input == TB200_IN_F32SYM && ctx->opt.afc;
+	const int eff_fmt = afc ? IN_PACKED : (int)ctx->opt.input;          /* how the chain sees this call's bits */
+	if (!(flags & TB200_FRESH) && ctx->tail_fmt != eff_fmt && ctx->fed_end)
 		return fail(ctx, TB200_E_ARG, "the input format cannot change inside a stream");
+	if (afc && n_bits) {
+		/* float_to_bits -a over this call's symbols, from the tracker state the last call left: symbols up, packed bits back */
+		const uint64_t n_sym = n_bits / 2;
+		const size_t out_bytes = 4 * (size_t)((n_sym + 15) / 16);
+		if (n_sym > ctx->afc_sym_cap) {
+			cudaFree(ctx->d_afc_sym); ctx->d_afc_sym = nullptr; ctx->afc_sym_cap = 0;
+			CU(cudaMalloc((void **)&ctx->d_afc_sym, n_sym * sizeof(float) + 64));
+			ctx->afc_sym_cap = n_sym;
+		}
+		if (out_bytes + 256 > ctx->afc_bits_cap) {
+			cudaFree(ctx->d_afc_bits); ctx->d_afc_bits = nullptr; ctx->afc_bits_cap = 0;
+			CU(cudaMalloc((void **)&ctx->d_afc_bits, out_bytes + 256));
+			ctx->afc_bits_cap = out_bytes + 256;
+		}
+		CU(cudaMemcpyAsync(ctx->d_afc_sym, bits, n_sym * sizeof(float), cudaMemcpyHostToDevice, ctx->s_compute));
+		int rc0 = float_to_bits_dev(ctx, ctx->d_afc_sym, n_sym, 1, ctx->opt.afc_filter_val, ctx->opt.afc_filter_goal, &ctx->afc_state,
+		                            reinterpret_cast<uint32_t *>(ctx->d_afc_bits));
+		if (rc0) return rc0;
+		ctx->h_afc_bits.resize(out_bytes + 64);
+		CU(cudaMemcpyAsync(ctx->h_afc_bits.data(), ctx->d_afc_bits, out_bytes, cudaMemcpyDeviceToHost, ctx->s_compute));
+		CU(cudaStreamSynchronize(ctx->s_compute));
+		bits = ctx->h_afc_bits.data();
+	}
 	int rc = push_carry(ctx);
 	if (rc) return rc;
 	ctx->stats.kernel_launches = 0;          /* "by the last call" */
 	Source src; src.on_device = false; src.data = bits; src.new_base = ctx->fed_end; src.end = ctx->fed_end + n_bits;
-	src.fmt = (int)ctx->opt.input;
+	src.fmt = eff_fmt;
 	Outputs out; out.on_device = false; out.slots = slots; out.type1 = type1; out.packed = type1_packed;
 	out.crc = ctx->user_crc; out.aach = ctx->user_aach; out.max_slots = max_slots; out.n = 0;
 	ctx->lock_events.clear();
@@ -2041,6 +2095,89 @@ extern "C" int tb200_rm3014_decode(tb200_ctx *ctx, const uint32_t *words, uint64
 	if (!is_device) CU(cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
 	return 0;
+}
+
+/* ------------------------------------------------- float_to_bits (with -a) -- */
+
+/* d_sym[0..n_sym) -> packed hard bits d_out (4 * ceil(n_sym / 16) bytes), on stream s_compute; *state: the tracker's
+ * state in front of symbol 0, updated to the state behind the last one.  Synchronous (the verification walks on the host). */
+static int float_to_bits_dev(tb200_ctx *ctx, const float *d_sym, uint64_t n_sym, int afc, float filter_val, float filter_goal,
+                             float *state, uint32_t *d_out)
+{
+	cudaStream_t st = ctx->s_compute;
+	ctx->afc_repairs = 0;
+	if (n_sym == 0) return 0;
+	if (!afc) {
+		const uint64_t words = (n_sym + 15) / 16;
+		const unsigned blocks = (unsigned)std::min<uint64_t>((words + 255) / 256, (uint64_t)ctx->sm_count * 16);
+		TB_LAUNCH(k_slice_symbols, blocks, 256, st, d_sym, n_sym, d_out);
+		CU(cudaGetLastError());
+		CU(cudaStreamSynchronize(st));
+		return 0;
+	}
+	if (!(filter_val > 0.f) || !(filter_val <= 1.f)) return fail(ctx, TB200_E_ARG, "afc_filter_val must be in (0, 1]");
+	AfcParams p;
+	p.filter_val = filter_val; p.filter_goal = filter_goal; p.keep = 1.0 - (double)filter_val;
+	/* warm-up: the start value has decayed by e^-24 < 2^-34; chunks as long as the warm-up (twice the serial work),
+	 * but short enough to give every SM a few hundred threads when the stream is long */
+	uint64_t W = (uint64_t)std::min<double>(24.0 / (double)filter_val + 64.0, 4e9);
+	uint64_t L = std::max<uint64_t>(4096, std::min<uint64_t>(W, n_sym / ((uint64_t)ctx->sm_count * 256) + 1));
+	L = (L + 15) & ~(uint64_t)15;
+	if (L > 0x7ffffff0ull) L = 0x7ffffff0ull;
+	const uint64_t n_chunks = (n_sym + L - 1) / L;
+	if (2 * n_chunks > ctx->afc_f_cap) {
+		if (ctx->d_afc_f) { CU(cudaDeviceSynchronize()); cudaFree(ctx->d_afc_f); ctx->d_afc_f = nullptr; ctx->afc_f_cap = 0; }
+		CU(cudaMalloc((void **)&ctx->d_afc_f, 2 * n_chunks * sizeof(float) + 64));
+		ctx->afc_f_cap = 2 * n_chunks;
+	}
+	float *d_fs = ctx->d_afc_f, *d_fe = ctx->d_afc_f + n_chunks;
+	const unsigned blocks = (unsigned)((n_chunks + 127) / 128);
+	TB_LAUNCH(k_afc_chunks, blocks, 128, st, d_sym, n_sym, p, *state, (uint32_t)L, W, d_out, d_fs, d_fe, (long long)-1, 0.f);
+	CU(cudaGetLastError());
+	ctx->h_afc_f.resize(2 * n_chunks);
+	CU(cudaMemcpyAsync(ctx->h_afc_f.data(), ctx->d_afc_f, 2 * n_chunks * sizeof(float), cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	/* verify: chunk c assumed h_fs[c] at its start; the truth is what chunk c-1 ended with */
+	float *h_fs = ctx->h_afc_f.data(), *h_fe = h_fs + n_chunks;
+	for (uint64_t c = 1; c < n_chunks; c++) {
+		uint32_t a, b;
+		memcpy(&a, &h_fs[c], 4); memcpy(&b, &h_fe[c - 1], 4);
+		if (a == b) continue;
+		TB_LAUNCH(k_afc_chunks, 1, 128, st, d_sym, n_sym, p, 0.f, (uint32_t)L, W, d_out, d_fs, d_fe, (long long)c, h_fe[c - 1]);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(&h_fe[c], d_fe + c, sizeof(float), cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		ctx->afc_repairs++;
+	}
+	*state = h_fe[n_chunks - 1];
+	return 0;
+}
+
+extern "C" int tb200_float_to_bits(tb200_ctx *ctx, const float *sym, uint64_t n_sym, int afc, float filter_val, float filter_goal,
+                                   float *state, uint8_t *packed_bits, int is_device)
+{
+	int r = leaf_common(ctx);
+	if (r) return r;
+	if (n_sym && (!sym || !packed_bits)) return fail(ctx, TB200_E_ARG, "null argument");
+	if (n_sym == 0) return 0;
+	float st0 = state ? *state : 0.f;
+	const float *d_sym = sym; uint32_t *d_out = reinterpret_cast<uint32_t *>(packed_bits);
+	const size_t out_bytes = 4 * (size_t)((n_sym + 15) / 16);
+	if (!is_device) {
+		float *a = nullptr; uint32_t *b = nullptr;
+		if ((r = leaf_buf(ctx, 0, n_sym, &a)) || (r = leaf_buf(ctx, 1, out_bytes / 4, &b))) return r;
+		CU(cudaMemcpyAsync(a, sym, n_sym * sizeof(float), cudaMemcpyHostToDevice, ctx->s_compute));
+		d_sym = a; d_out = b;
+	} else if ((uintptr_t)packed_bits & 3) {
+		return fail(ctx, TB200_E_ARG, "packed_bits must be 4-byte aligned");
+	}
+	if ((r = float_to_bits_dev(ctx, d_sym, n_sym, afc, filter_val, filter_goal, &st0, d_out))) return r;
+	if (!is_device) {
+		CU(cudaMemcpyAsync(packed_bits, d_out, (size_t)((2 * n_sym + 7) / 8), cudaMemcpyDeviceToHost, ctx->s_compute));
+		CU(cudaStreamSynchronize(ctx->s_compute));
+	}
+	if (state) *state = st0;
+	return (int)std::min<uint64_t>(ctx->afc_repairs, 0x7fffffff);
 }
 
 /* ---------------------------------------------------------- digest, packing -- */

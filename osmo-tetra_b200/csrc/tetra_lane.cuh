@@ -151,8 +151,14 @@ __device__ __forceinline__ void acs2_step(uint32_t (&pm)[16], const uint32_t (&M
  * where it cancels the borrow), and the metrics carry a floor that the -U steps cannot eat up (callers).
  * TIE_HI mirrors it: the tag sits on the lo candidate, the free candidates are the ones whose hi branch has G1 = 0. */
 template <bool TIE_HI>
-__device__ __forceinline__ void acs2_odd_step(uint32_t (&pm)[16], const uint32_t d, const uint32_t dT, const uint32_t tagw)
+__device__ __forceinline__ void acs2_odd_step(uint32_t (&pm)[16], const uint32_t d, const uint32_t dT, uint32_t tagw)
 {
+#if !defined(TB_SIMT_EMULATION) && !defined(TB_ODD_TAG_IMMEDIATE)
+	/* the tag as a register the optimiser cannot see through (threadIdx.y is 0, but only at run time): register + register
+	 * adds go to the multiply-add pipe (IMAD.IADD), register + immediate ones to the ALU pipe (VIADD), and that is the
+	 * pipe the VIADDMNMX already saturate */
+	tagw += threadIdx.y;
+#endif
 	uint32_t nm[16];
 #pragma unroll
 	for (int s = 0; s < 16; ++s) {

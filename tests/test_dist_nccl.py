@@ -159,7 +159,7 @@ def test_one_stream_sharded_over_gpus(world, mode, lose_lock):
     for rank, ok, n, tot, ns, codes, dig, one_digest, oracle_ok, losses, segs in res:
         assert ok, f"rank {rank}: a run differs from the single-GPU decode"
         assert tot == ns                       # the runs together are every slot of the single-GPU run
-        assert codes > 1000 or n == 0          # random cells: the carried cell state really mattered
+        assert codes > min(1000, n // 8) or n == 0          # random cells: the carried cell state really mattered
         assert oracle_ok is None or oracle_ok, f"rank {rank}: window at the shard edge differs from the oracle"
         digest_sum = (digest_sum + dig) & (2 ** 64 - 1)
         if lose_lock:

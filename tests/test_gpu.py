@@ -545,3 +545,23 @@ def test_aach_side_output_gpu(gpu, orc):
     _, _, _, a3 = gpu.rx_stream_host_aach(noisy)
     assert np.array_equal(a2, a3)
     gpu.set_options(viterbi=T.VITERBI_LANE)
+
+
+def test_config2_whole_run_against_reference(gpu, ref):
+    """BASELINE config 2 at FULL size against a CPU run of the reference's own code, record for record: 10^6 SCH/F bursts
+    at BER 1e-2 through tetra_burst_sync_in + lower MAC compiled in place (about 25 s on one core), no sampling"""
+    import torch
+    n = 1_000_000
+    cfg = T.GenCfg(seed=0x7E7A0002, sb_period=64, lead_sb=2, ndb2_per_256=0, ber_per_65536=655, random_cell=0, lead_in_bits=0)
+    d, nbits = _gen_on_gpu(gpu, cfg, n, lead_in=False)
+    bits = d[:nbits].cpu().numpy()
+    gpu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, output=T.OUT_UNPACKED | T.OUT_PACKED)
+    slots, t1, pk = _dev_decode(gpu, d, nbits, n + 16, want_type1=True, want_packed=True)
+    ref.reset(); ref.feed(bits, 64)
+    want = ref.records()
+    got = gpu.expand_records(slots, t1)
+    ok, msg = T.records_equal(want, got)
+    assert ok, msg
+    lev = T.locked_events(ref.events())
+    assert lev.size == slots.size and np.array_equal(lev["rc"], slots["find_rc"]) and np.array_equal(lev["window"], slots["window"])
+    assert gpu.slots_digest(slots, pk) == T.slots_digest_host(slots, pk)

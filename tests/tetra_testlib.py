@@ -260,6 +260,15 @@ class Oracle(_Recorder):
         self.lib.orc_float_to_bits(_ptr(sym), sym.size, _ptr(out))
         return out
 
+    def float_to_bits_afc(self, sym, filter_val=0.0001, filter_goal=0.0, state=0.0):
+        """float_to_bits -a [-f filter_val] [-F filter_goal]: (bits, tracker state afterwards)"""
+        sym = np.ascontiguousarray(sym, dtype=np.float32)
+        out = np.zeros(2 * sym.size, dtype=np.uint8)
+        f = C.c_float(state)
+        self.lib.orc_float_to_bits_afc.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.POINTER(C.c_float), C.c_void_p]
+        self.lib.orc_float_to_bits_afc(_ptr(sym), sym.size, C.c_float(filter_val), C.c_float(filter_goal), C.byref(f), _ptr(out))
+        return out, f.value
+
     def tp_sap(self, typ, blk_num, bits):
         bits = np.ascontiguousarray(bits, dtype=np.uint8)
         self.lib.orc_tp_sap(typ, blk_num, _ptr(bits))
@@ -534,9 +543,9 @@ def bits_to_symbols(bits, rng, edge_share=0.02):
 REF_FLOAT_TO_BITS = os.path.join(ROOT, "oracle", "_ref", "float_to_bits")
 
 
-def ref_float_to_bits(sym, tmpdir):
-    """run the reference's own float_to_bits program (compiled unmodified into oracle/_ref) on a file"""
+def ref_float_to_bits(sym, tmpdir, args=()):
+    """run the reference's own float_to_bits program (compiled unmodified into oracle/_ref) on a file; args: e.g. ("-a",)"""
     fin, fout = os.path.join(tmpdir, "sym.f32"), os.path.join(tmpdir, "sym.bits")
     np.ascontiguousarray(sym, dtype=np.float32).tofile(fin)
-    subprocess.check_call([REF_FLOAT_TO_BITS, fin, fout])
+    subprocess.check_call([REF_FLOAT_TO_BITS, *args, fin, fout])
     return np.fromfile(fout, dtype=np.uint8)

@@ -1,0 +1,105 @@
+"""gpurun_out/{prof_r02_config*.ncu-rep, r02_launches.csv, ncu_r02_*.log} -> profiles/r02_summary.md, profiles/r02_launches.csv,
+profiles/kernel_constants.json (per-slot / per-ACS constants that bench.py quotes), profiles/r02_acs_loop.sass."""
+import csv, json, os, re, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+out, src = os.path.join(ROOT, "profiles"), os.path.join(ROOT, "gpurun_out")
+ACS_SB1, ACS_HALF, ACS_SCHF = 16 * 84, 16 * 148, 16 * 292
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+lines = ["# ncu summary r02", "",
+         "`ncu --set full --clock-control none --import-source on -k regex:'k_decode_lane|k_classify_tile|k_sb1_lane' -s 3 -c 3 python tools/prof_run.py <shape> 2097152 2`",
+         "(one launch each over a piece of 2^21 slots, options.serial_passes = 1; cold-cache serialised replays: compare shares and counts, not absolute times;",
+         "the PROF lines are the same script's CUDA-event times without the profiler)", ""]
+consts = {"source": "profiles/r02_summary.md (ncu --set full, one launch over 2^21 slots of the named shape, tools/prof_run.py)",
+          "k_decode_lane": {}, "k_classify_tile": {}, "k_sb1_lane": {}}
+for shape in ("config4", "config2"):
+    rep = os.path.join(src, f"prof_r02_{shape}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    log = open(os.path.join(src, f"ncu_r02_{shape}.log")).read()
+    m = re.search(r"PROF \S+ slots (\d+) kinds \[(\d+), (\d+), (\d+), (\d+)\]", log)
+    ns, kinds = int(m.group(1)), [int(m.group(i)) for i in range(2, 6)]
+    live = [l for l in open(os.path.join(src, "run_r02n.log")).read().splitlines() if l.startswith(f"PROF {shape}")]
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    lines += [f"## {shape}: {ns} slots, kinds dropped/SB/SCH-F/two-block = {kinds}", ""]
+    if live:
+        lines += ["CUDA-event times of the same launches without the profiler: `" + live[-1] + "`", ""]
+    acs = {"k_decode_lane": kinds[1] * ACS_HALF + kinds[2] * ACS_SCHF + kinds[3] * 2 * ACS_HALF, "k_sb1_lane": kinds[1] * ACS_SB1}
+    for r in rows[2:]:
+        kname = re.sub(r"^void ", "", r[idx["Kernel Name"]]).split("<")[0].split("(")[0]
+        lines += [f"### {kname} ({shape})", "", "| metric | value | unit |", "|---|---|---|"]
+        for k in KEYS:
+            if k in idx and r[idx[k]] != "":
+                lines.append(f"| {k} | {r[idx[k]]} | {units[idx[k]]} |")
+        st = []
+        for k in hdr:
+            if "issue_stalled" in k and k.endswith("per_issue_active.ratio") and r[idx[k]] != "":
+                st.append((float(r[idx[k]]), k))
+        for v, k in sorted(st, reverse=True)[:6]:
+            lines.append(f"| {k} | {v:.2f} | warps/issue |")
+        dram = float(r[idx["dram__bytes_read.sum"]]) * UNIT[units[idx["dram__bytes_read.sum"]]] + \
+            float(r[idx["dram__bytes_write.sum"]]) * UNIT[units[idx["dram__bytes_write.sum"]]]
+        tinst = float(r[idx["smsp__inst_executed.sum"]]) * 32
+        c = {"dram_bytes_per_slot": dram / ns, "thread_inst_per_slot": tinst / ns, "ncu_duration_us": float(r[idx["gpu__time_duration.sum"]]), "slots": ns}
+        if kname in acs and acs[kname]:
+            c["thread_inst_per_acs"] = tinst / acs[kname]
+            lines.append(f"| thread instructions per add-compare-select ({acs[kname]} ACS in the launch) | {c['thread_inst_per_acs']:.3f} | |")
+        lines.append(f"| DRAM traffic per slot (read + write) | {dram / ns:.1f} | byte |")
+        lines.append("")
+        consts.setdefault(kname, {})[shape] = c
+for k in ("k_decode_lane", "k_classify_tile", "k_sb1_lane"):
+    if "config2" in consts[k] and "config3" not in consts[k]:
+        consts[k]["config3"] = dict(consts[k]["config2"], note="config-2 capture (same kernels, mostly SCH/F)")
+json.dump(consts, open(os.path.join(out, "kernel_constants.json"), "w"), indent=1)
+lc = os.path.join(src, "r02_launches.csv")
+if os.path.exists(lc):
+    rows = [r for r in csv.reader(open(lc)) if len(r) > 14 and r[0].isdigit()]
+    tot, cnt = {}, {}
+    for r in rows:
+        name = re.sub(r"^void ", "", r[4]).split("<")[0].split("(")[0]
+        tot[name] = tot.get(name, 0.0) + float(r[-1]); cnt[name] = cnt.get(name, 0) + 1
+    alls = sum(tot.values())
+    lines += ["## launch list of a short bench run", "",
+              "`ncu --metrics gpu__time_duration.sum --clock-control none -c 300 python bench.py --steps 2 --warmup 1 --bursts 8000000 --no-e2e --no-cpu --no-config5 --no-configs --no-parity`",
+              "(first 300 launches; raw list: `profiles/r02_launches.csv`)", "", "| kernel | launches | total ns | share |", "|---|---|---|---|"]
+    for k, v in sorted(tot.items(), key=lambda x: -x[1]):
+        lines.append(f"| {k} | {cnt[k]} | {v:.0f} | {v / alls:.3f} |")
+    open(os.path.join(out, "r02_launches.csv"), "w").write(open(lc).read())
+open(os.path.join(out, "r02_summary.md"), "w").write("\n".join(lines) + "\n")
+# SASS of the ACS loop of the eight-step form (the loop between the two back-edges around the VIADDMNMX run)
+sass = subprocess.run(["cuobjdump", "-sass", os.path.join(ROOT, "osmo-tetra_b200", "libtetra_b200.so")], capture_output=True, text=True).stdout
+m = re.search(r"Function : _ZN2tb13k_decode_laneILb0EEEvNS_10DecodeArgsEPj(.*?)\n\s*\.\.\.\.\.\.\.\.\.\.", sass, re.S)
+body = m.group(1) if m else ""
+ins = [(int(x.group(1), 16), x.group(0)) for x in re.finditer(r"/\*([0-9a-f]{4,5})\*/\s+[^\n]*", body)]
+# the loop: the longest backward branch whose body holds >= 120 VIADDMNMX
+best = None
+for addr, text in ins:
+    b = re.search(r"BRA\s+(?:U\w+,\s*)?0x([0-9a-f]+)", text)
+    if b and int(b.group(1), 16) < addr:
+        lo = int(b.group(1), 16)
+        seg = [t for a, t in ins if lo <= a <= addr]
+        nv = sum("VIADDMNMX" in t for t in seg)
+        if nv >= 120 and (best is None or len(seg) < len(best)):
+            best = seg
+if best:
+    ops = {}
+    for t in best:
+        op = re.search(r"\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", t).group(1)
+        key = op if op.startswith("IMAD") and op.count(".") >= 1 and op.split(".")[1] in ("IADD", "MOV", "SHL", "U32", "WIDE") else op.split(".")[0]
+        if op.startswith("IMAD"): key = ".".join(op.split(".")[:2]) if op.split(".")[1:2] and op.split(".")[1] in ("IADD", "MOV", "SHL", "U32", "WIDE") else "IMAD"
+        ops[key] = ops.get(key, 0) + 1
+    head = ["// k_decode_lane<false>: the ACS loop of viterbi_pair_u8 (eight trellis steps of two packed trellises per iteration)",
+            f"// {len(best)} instructions: " + ", ".join(f"{k} {v}" for k, v in sorted(ops.items(), key=lambda x: -x[1])),
+            "// cuobjdump -sass osmo-tetra_b200/libtetra_b200.so (sm_100a), extracted by tools/summarize_r02.py", ""]
+    open(os.path.join(out, "r02_acs_loop.sass"), "w").write("\n".join(head + best) + "\n")
+    print("ACS loop:", head[1])
+print(json.dumps(consts, indent=1)[:1500])
