@@ -378,8 +378,8 @@ int   tb200_ipc_close(tb200_ctx *ctx, void *d_ptr);
  * (tetra_burst_sync.c:67-106), the slot range is cut into contiguous shards, every rank gets at its shard
  * (TB200_DIST_SCATTER: one grouped ncclSend / ncclRecv from rank 0; TB200_DIST_PEER: nothing is copied, the search
  * kernels read the shard out of rank 0's memory over NVLink - the stream must then live in tb200_dev_alloc memory),
- * runs pass 1, the 32-byte summaries are all-gathered (the one exchange step of the path: the cell state of
- * tetra_lower_mac.c:291-302), every rank derives its carry-in and runs pass 2.  A lock loss inside a shard
+ * runs its piece pipeline speculatively, the 56-byte summaries are all-gathered (the one exchange step of the path: the cell state of
+ * tetra_lower_mac.c:291-302), every rank derives its carry-in and decodes the few slots that depended on it.  A lock loss inside a shard
  * (tetra_burst_sync.c:123-142) ends the segment right after the losing slot: the ranks behind it discard their
  * speculative work, rank 0 runs the UNLOCKED search from there exactly like the single-GPU receiver, and the rest of
  * the stream is sharded again as a new segment.  Results stay rank-local: `runs` says which global slot range
