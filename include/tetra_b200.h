@@ -218,6 +218,8 @@ struct tb200_timing {
 	uint64_t slots;             /* slots those launches covered */
 	float leaf_ms;              /* last tb200_descramble_deinterleave kernel (device pointers) */
 	float search_ms;            /* the training-sequence search kernel alone (classify_ms minus the SB1 pass) */
+	float prepare_ms;           /* split decode pass: k_lane_prepare (cell state, descramble, de-interleave); 0 for the fused kernel */
+	float trellis_ms;           /* split decode pass: k_lane_trellis (ACS loop + trace back [+ finish]); decode_ms - prepare_ms - trellis_ms = k_lane_finish */
 };
 int tb200_get_timing(const tb200_ctx *ctx, struct tb200_timing *out);
 

@@ -59,7 +59,8 @@ class Options(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("classify_ms", C.c_float), ("scan_ms", C.c_float), ("decode_ms", C.c_float),
                 ("launches_classify", C.c_uint32), ("launches_scan", C.c_uint32), ("launches_decode", C.c_uint32),
-                ("pieces", C.c_uint32), ("slots", C.c_uint64), ("leaf_ms", C.c_float), ("search_ms", C.c_float)]
+                ("pieces", C.c_uint32), ("slots", C.c_uint64), ("leaf_ms", C.c_float), ("search_ms", C.c_float),
+                ("prepare_ms", C.c_float), ("trellis_ms", C.c_float)]
 
 
 class Carry(C.Structure):

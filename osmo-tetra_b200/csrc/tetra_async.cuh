@@ -13,6 +13,7 @@ __device__ __forceinline__ void mbar_init(uint64_t *, unsigned) {}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *, unsigned) {}
 __device__ __forceinline__ void mbar_arrive(uint64_t *) {}
 __device__ __forceinline__ void mbar_wait(uint64_t *, unsigned) { __syncwarp(); }
+__device__ __forceinline__ void fence_async_shared() {}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ void bulk_g2s_stream(void *dst, const void *src, unsigned bytes, uint64_t *) { memcpy(dst, src, bytes); }
 __device__ __forceinline__ uint32_t dp4a_u(uint32_t a, uint32_t b, uint32_t c)
@@ -43,6 +44,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
 		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
 		"@!p bra W_%=;\n\t}"
 		:: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+/* generic-proxy accesses to shared memory before this point are ordered before later async-proxy (bulk copy) accesses */
+__device__ __forceinline__ void fence_async_shared()
+{
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, uint64_t *bar)
 {

@@ -186,6 +186,10 @@ struct tb200_ctx {
 	uint32_t *d_lane_scratch = nullptr;   /* survivor decisions of the decode pass, one area per resident CTA */
 	uint32_t *d_sb1_scratch = nullptr;    /* the same for the SB1 pass (it runs next to the decode pass of the previous piece) */
 	unsigned lane_ctas = 0;               /* resident CTAs of the lane kernels (grid size) */
+	uint32_t *d_units = nullptr;          /* split decode pass: the unit blocks between prepare / trellis / finish (lane_unit_blocks(ws_slots)) */
+	int lane_form = 1;                    /* 0 fused kernel, 1 prepare | trellis+finish, 2 prepare | trellis | finish (TB200_LANE_FORM) */
+	unsigned prep_ctas = 0, fin_ctas = 0; /* grids of the prepare / finish kernels */
+	unsigned form_ctas[3] = {0, 0, 0};    /* grid of the trellis-carrying kernel of each form (<= lane_ctas, which sizes the history scratch) */
 	uint32_t *d_flags = nullptr;     /* first unlocking slot per piece */
 	uint32_t *h_flags = nullptr;     /* pinned mirror */
 	size_t flags_cap = 0;
@@ -453,13 +457,34 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 	}
 	{
 		int per_sm = 8;
+		if (const char *e = getenv("TB200_LANE_FORM")) { const int v = atoi(e); if (v >= 0 && v <= 2) ctx->lane_form = v; }
+		int prep_per_sm = 8, fin_per_sm = 8, fused = 8, split = 8, split3 = 8;
 #ifndef TB_SIMT_EMULATION
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_decode_lane<false>, LANE_NT,
-		                                                   lane_smem_words(LANE_NT) * sizeof(uint32_t)) != cudaSuccess || per_sm < 1)
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fused, k_decode_lane<false>, LANE_NT,
+		                                                   lane_smem_words(LANE_NT) * sizeof(uint32_t)) != cudaSuccess || fused < 1 ||
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split, k_lane_trellis<false, true>, LANE_NT,
+		                                                   lane_trellis_smem_words<true>() * sizeof(uint32_t)) != cudaSuccess || split < 1 ||
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&split3, k_lane_trellis<false, false>, LANE_NT,
+		                                                   lane_trellis_smem_words<false>() * sizeof(uint32_t)) != cudaSuccess || split3 < 1 ||
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&prep_per_sm, k_lane_prepare, LANE_NT,
+		                                                   lane_prepare_smem_words() * sizeof(uint32_t)) != cudaSuccess || prep_per_sm < 1 ||
+		    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fin_per_sm, k_lane_finish, LANE_NT,
+		                                                   lane_finish_smem_words() * sizeof(uint32_t)) != cudaSuccess || fin_per_sm < 1)
 			return bail("cudaOccupancyMaxActiveBlocksPerMultiprocessor");
 #endif
-		if (const char *e = getenv("TB200_LANE_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }
+		if (const char *e = getenv("TB200_LANE_CTAS_PER_SM")) {
+			const int v = atoi(e);
+			if (v >= 1) { fused = std::min(fused, v); split = std::min(split, v); split3 = std::min(split3, v); }
+		}
+		if (const char *e = getenv("TB200_PREP_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < prep_per_sm) prep_per_sm = v; }
+		if (const char *e = getenv("TB200_FIN_CTAS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < fin_per_sm) fin_per_sm = v; }
+		per_sm = std::max(fused, std::max(split, split3));      /* the history scratch is sized for the largest grid */
+		ctx->form_ctas[0] = (unsigned)(ctx->sm_count * fused);
+		ctx->form_ctas[1] = (unsigned)(ctx->sm_count * split);
+		ctx->form_ctas[2] = (unsigned)(ctx->sm_count * split3);
 		ctx->lane_ctas = (unsigned)(ctx->sm_count * per_sm);
+		ctx->prep_ctas = (unsigned)(ctx->sm_count * prep_per_sm);
+		ctx->fin_ctas = (unsigned)(ctx->sm_count * fin_per_sm);
 		const size_t scratch_bytes = (size_t)ctx->lane_ctas * lane_scratch_words_per_cta(LANE_NT) * sizeof(uint32_t);
 		if (cudaMalloc((void **)&ctx->d_lane_scratch, scratch_bytes) != cudaSuccess ||
 		    cudaMalloc((void **)&ctx->d_sb1_scratch, scratch_bytes) != cudaSuccess)
@@ -512,7 +537,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 		cudaFree(w.sb_list); cudaFree(w.kind_list);
 		cudaEventDestroy(ctx->ev_front[i]); cudaEventDestroy(ctx->ev_back[i]);
 	}
-	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch); cudaFree(ctx->d_sb1_scratch);
+	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch); cudaFree(ctx->d_sb1_scratch); cudaFree(ctx->d_units);
 	cudaFree(ctx->d_pstats); cudaFreeHost(ctx->h_pstats); cudaFree(ctx->d_rm_leader);
 	cudaFree(ctx->d_afc_sym); cudaFree(ctx->d_afc_bits); cudaFree(ctx->d_afc_f);
 	for (int i = 0; i < NBUF; i++) cudaFree(ctx->d_oaach[i]);
@@ -564,6 +589,7 @@ static int ensure_workspace(tb200_ctx *ctx, size_t slots)
 		if ((rc = grow(ctx, &w.sb_list, slots + 4))) return rc;
 		if ((rc = grow(ctx, &w.kind_list, 4 * slots + 4))) return rc;
 	}
+	if ((rc = grow(ctx, &ctx->d_units, lane_unit_blocks(slots) * LANE_UNIT_WORDS))) return rc;
 	ctx->back_pending[0] = ctx->back_pending[1] = false;
 	ctx->ws_slots = slots;
 	return 0;
@@ -874,7 +900,7 @@ static inline uint64_t slot_call(const Segment &s, uint64_t k)   /* call index t
 }
 
 /* events per piece when options.profile is on */
-enum { PE_START = 0, PE_SB1 = 1, PE_SCAN = 2, PE_DECODE_END = 3, PE_DECODE_START = 4, PE_SEARCH = 5, PE_COUNT = 6 };
+enum { PE_START = 0, PE_SB1 = 1, PE_SCAN = 2, PE_DECODE_END = 3, PE_DECODE_START = 4, PE_SEARCH = 5, PE_PREPARE_END = 6, PE_TRELLIS_END = 7, PE_COUNT = 8 };
 
 /* pass 1 of a piece on stream s_front: search + classification, SB1, the scan over "last CRC-good SB1" and - unless
  * the cell state in front of the piece is not known yet (sharded decode) - the carry for the next piece: the state
@@ -958,7 +984,7 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	const unsigned lane_nt = LANE_NT;
 	const size_t lane_smem = lane_smem_words(lane_nt) * sizeof(uint32_t);
 	const uint64_t npairs = ((uint64_t)nb + 1) / 2;
-	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->lane_ctas);
+	const unsigned lane_blocks = (unsigned)std::min<uint64_t>((npairs + lane_nt - 1) / lane_nt, (uint64_t)ctx->form_ctas[0]);
 	const unsigned blocks = (unsigned)std::min<uint64_t>((nb + 7) / 8, (uint64_t)ctx->sm_count * 16);
 	DecodeArgs a;
 	a.ws = w.ws; a.slot_bits = w.slot_bits; a.last_good = w.last_good; a.blk_prev = w.blk_prev;
@@ -976,9 +1002,36 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 	CU(cudaStreamWaitEvent(st, ctx->ev_front[set], 0));
 	CU(cudaMemsetAsync(a.stats, 0, 3 * sizeof(unsigned long long), st));
 	if (pe) CU(cudaEventRecord(pe[PE_DECODE_START], st));
-	if (lane && ctx->opt.viterbi_tie) TB_LAUNCH_SMEM(k_decode_lane<true>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
-	else if (lane)                    TB_LAUNCH_SMEM(k_decode_lane<false>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
-	else                              TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
+	if (pe && !(lane && ctx->lane_form != 0)) { CU(cudaEventRecord(pe[PE_PREPARE_END], st)); CU(cudaEventRecord(pe[PE_TRELLIS_END], st)); }
+	if (lane && ctx->lane_form == 0) {
+		if (ctx->opt.viterbi_tie) TB_LAUNCH_SMEM(k_decode_lane<true>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
+		else                      TB_LAUNCH_SMEM(k_decode_lane<false>, lane_blocks, lane_nt, lane_smem, st, a, ctx->d_lane_scratch);
+	} else if (lane) {
+		/* split form: the unit count is only known on the device (kind_count), so the grids are sized for the worst case
+		 * (every slot a unit of its own) and capped at what is resident */
+		const uint64_t wmax = lane_unit_blocks(nb);
+		const unsigned pblocks = (unsigned)std::min<uint64_t>(wmax, (uint64_t)ctx->prep_ctas);
+		const unsigned tblocks = (unsigned)std::min<uint64_t>(wmax, (uint64_t)ctx->form_ctas[ctx->lane_form]);
+		const unsigned fblocks = (unsigned)std::min<uint64_t>(wmax, (uint64_t)ctx->fin_ctas);
+		TB_LAUNCH_SMEM(k_lane_prepare, pblocks, lane_nt, lane_prepare_smem_words() * sizeof(uint32_t), st, a, ctx->d_units);
+		if (pe) CU(cudaEventRecord(pe[PE_PREPARE_END], st));
+		if (ctx->lane_form == 1) {
+			const size_t sm_b = lane_trellis_smem_words<true>() * sizeof(uint32_t);
+			if (ctx->opt.viterbi_tie) TB_LAUNCH_SMEM((k_lane_trellis<true, true>), tblocks, lane_nt, sm_b, st, a, ctx->d_lane_scratch, ctx->d_units);
+			else                      TB_LAUNCH_SMEM((k_lane_trellis<false, true>), tblocks, lane_nt, sm_b, st, a, ctx->d_lane_scratch, ctx->d_units);
+			if (pe) CU(cudaEventRecord(pe[PE_TRELLIS_END], st));
+			ctx->stats.kernel_launches += 1;
+		} else {
+			const size_t sm_b = lane_trellis_smem_words<false>() * sizeof(uint32_t);
+			if (ctx->opt.viterbi_tie) TB_LAUNCH_SMEM((k_lane_trellis<true, false>), tblocks, lane_nt, sm_b, st, a, ctx->d_lane_scratch, ctx->d_units);
+			else                      TB_LAUNCH_SMEM((k_lane_trellis<false, false>), tblocks, lane_nt, sm_b, st, a, ctx->d_lane_scratch, ctx->d_units);
+			if (pe) CU(cudaEventRecord(pe[PE_TRELLIS_END], st));
+			TB_LAUNCH_SMEM(k_lane_finish, fblocks, lane_nt, lane_finish_smem_words() * sizeof(uint32_t), st, a, ctx->d_units);
+			ctx->stats.kernel_launches += 2;
+		}
+	} else {
+		TB_LAUNCH(k_decode_warp, blocks, 256, st, a);
+	}
 	ctx->stats.kernel_launches++;
 	if (pe) CU(cudaEventRecord(pe[PE_DECODE_END], st));
 	if (!with_carry) {
@@ -1312,6 +1365,8 @@ static int profile_end(tb200_ctx *ctx)
 		CU(cudaEventElapsedTime(&ms, e[PE_START], e[PE_SEARCH])); ctx->timing.search_ms += ms;
 		CU(cudaEventElapsedTime(&ms, e[PE_SB1], e[PE_SCAN])); ctx->timing.scan_ms += ms; ctx->timing.launches_scan += 3;
 		CU(cudaEventElapsedTime(&ms, e[PE_DECODE_START], e[PE_DECODE_END])); ctx->timing.decode_ms += ms; ctx->timing.launches_decode++;
+		CU(cudaEventElapsedTime(&ms, e[PE_DECODE_START], e[PE_PREPARE_END])); ctx->timing.prepare_ms += ms;
+		CU(cudaEventElapsedTime(&ms, e[PE_PREPARE_END], e[PE_TRELLIS_END])); ctx->timing.trellis_ms += ms;
 	}
 	/* first launch of the call (pass 1 of the first piece) to the end of the last decode pass */
 	CU(cudaEventElapsedTime(&ms, ctx->prof_ev[PE_START], ctx->prof_ev[ctx->prof_used - PE_COUNT + PE_DECODE_END]));

@@ -17,6 +17,7 @@
  */
 #pragma once
 #include "tetra_kernels.cuh"
+#include "tetra_async.cuh"
 
 namespace tb {
 
@@ -344,12 +345,18 @@ __device__ __forceinline__ uint32_t byte128(const uint4 &h, uint32_t f)
 template <int K, bool TIE_HI>
 __device__ __forceinline__ void step_pair_u8(uint32_t (&pm)[16], uint32_t t, uint32_t u, uint32_t r3, int p)
 {
-	const uint32_t te = 0x00010001u << (2 * p), to = 0x00020002u << (2 * p);
+	const uint32_t to = 0x00020002u << (2 * p);
+	uint32_t te = 0x00010001u << (2 * p);
+#if !defined(TB_SIMT_EMULATION) && defined(TB_EVEN_TAG_REG)
+	/* as in acs2_odd_step: a tag the optimiser cannot fold keeps "metric + tag" a register + register add on the
+	 * multiply-add pipe instead of a VIADD with an immediate on the ALU pipe */
+	te += threadIdx.y;
+#endif
 	uint32_t M0[4], M1[4];
-	M0[0] = mad_k<K>(t, 0u);                M1[0] = mad_k<K>(t, te);
-	M0[3] = mad_k<-K>(t, 0x02000200u);      M1[3] = mad_k<-K>(t, 0x02000200u + te);
-	M0[2] = mad_k<K>(u, 0u);                M1[2] = mad_k<K>(u, te);
-	M0[1] = mad_k<-K>(u, 0x02000200u);      M1[1] = mad_k<-K>(u, 0x02000200u + te);
+	M0[0] = mad_k<K>(t, 0u);                M1[0] = M0[0] + te;
+	M0[3] = mad_k<-K>(t, 0x02000200u);      M1[3] = M0[3] + te;
+	M0[2] = mad_k<K>(u, 0u);                M1[2] = M0[2] + te;
+	M0[1] = mad_k<-K>(u, 0x02000200u);      M1[1] = M0[1] + te;
 	acs2_step<TIE_HI>(pm, M0, M1);
 	/* odd step: only G1 was sent; 256 * (1 - 2 r3) per half (r3 carries weight 256 / K) */
 	acs2_odd_step<TIE_HI>(pm, mad_k<odd_mult(256, 256 / K)>(r3, 0x01000100u), mad_k<odd_mult(256, 256 / K)>(r3, 0x01000100u + to), to);
@@ -449,24 +456,20 @@ __device__ __forceinline__ void viterbi_pair(uint4 *dec, uint32_t *cx, uint32_t 
 /* CRC-16-CCITT of the first L type-2 bits of a column, reflected byte-table form of
  * crc_simple.c:65-82 (register bit-reversed, so packed LSB-first bytes feed it directly);
  * returns true when the residue is TETRA_CRC_OK (0x1d0f, tetra_common.h:69). L % 8 == 4. */
-__device__ __forceinline__ uint32_t crc_col(const LaneSmem &sm, const uint32_t *col, int L);
-__device__ __forceinline__ bool crc_ok_col(const LaneSmem &sm, const uint32_t *col, int L)
-{
-	return crc_col(sm, col, L) == 0x1d0f;
-}
+__device__ __forceinline__ uint32_t crc_col(const uint32_t *crc_tab, const uint32_t *col, int L);
 /* the CRC register itself, in the reference's bit order (what tetra-rx prints as "CRC COMP: 0x%04x") */
-__device__ __forceinline__ uint32_t crc_col(const LaneSmem &sm, const uint32_t *col, int L)
+__device__ __forceinline__ uint32_t crc_col(const uint32_t *crc_tab, const uint32_t *col, int L)
 {
 	uint32_t r = 0xffff;
 	constexpr int nt = LANE_NT;
 	const int nbytes = L >> 3;
 	for (int i = 0; i < nbytes; ++i) {
 		const uint32_t b = (col[(i >> 2) * nt] >> (8 * (i & 3))) & 0xff;
-		r = (r >> 8) ^ sm.crc_tab[(r ^ b) & 0xff];
+		r = (r >> 8) ^ crc_tab[(r ^ b) & 0xff];
 	}
 	const int bp = L & ~7;
 	const uint32_t nib = (col[(bp >> 5) * nt] >> (bp & 31)) & 0xf;
-	r = (r >> 4) ^ sm.crc_tab[256 + ((r ^ nib) & 0xf)];
+	r = (r >> 4) ^ crc_tab[256 + ((r ^ nib) & 0xf)];
 	return __brev(r) >> 16;           /* the table form keeps the register bit-reversed (0xf0b8 = good) */
 }
 
@@ -659,7 +662,7 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
 			if (n[h]) {
 				const uint32_t *col = sm.t3col(h, tid);
 				constexpr int nt = LANE_NT;
-				const uint32_t crc1 = crc_col(sm, col, 76);
+				const uint32_t crc1 = crc_col(sm.crc_tab, col, 76);
 				const bool good = crc1 == 0x1d0f;
 				const uint32_t w0 = col[0], w1 = col[nt], w2 = col[2 * nt];
 				const uint32_t t2[4] = { w0, w1, w2, 0 };
@@ -686,7 +689,292 @@ k_sb1_lane(SlotWs *__restrict__ ws, const uint32_t *__restrict__ slot_bits,
  * (the two packed trellises).  The slots were grouped by kind (k_scan_blocks), so a warp gets blocks of
  * one length: 288 steps for two SCH/F slots, 144 for the two halves BLK1 / BLK2 of ONE two-block slot or
  * for the SB2 blocks of two SYNC bursts; dropped slots only get their record.  Units are handed out
- * longest first.  Warps that straddle two lists run the masked form of the trellis loop. */
+ * longest first.  Warps that straddle two lists run the masked form of the trellis loop.
+ *
+ * The pass has three parts with very different needs: PREPARE (cell state, scrambling sequence, descramble,
+ * de-interleave: dependent global loads and ~2000 instructions of straight-line code per unit, few registers),
+ * TRELLIS (the ACS loop + trace back: ~100 live registers, pure integer issue) and FINISH (CRC, type-1 assembly,
+ * stores).  Fused into one kernel (k_decode_lane, kept as the second form) a warp holds the trellis loop's
+ * registers while it waits for the loads of the other two parts: at 16 warps per SM more than half of the warps'
+ * time went there (ncu r02: 53 % of the stall samples in 22 % of the instructions) and the issue slots were half
+ * empty.  Split (k_lane_prepare -> k_lane_trellis [-> k_lane_finish]) every kernel runs at the occupancy its own
+ * registers allow, and the type-3 bits travel between them as one 4.6 KB block per warp of units in global
+ * memory ([row][lane], so that every access is a coalesced 128-byte row and the trellis kernel can pull the next
+ * block into shared memory with one bulk copy while it works on the current one). */
+
+constexpr uint32_t LANE_NO_SLOT = 0xffffffffu;
+constexpr int LANE_META_ROW = 2 * LANE_T3_ROWS;                /* rows 28..35 of a unit block: see lane_unit_store */
+constexpr int LANE_UNIT_ROWS = 2 * LANE_T3_ROWS + 8;
+constexpr int LANE_UNIT_WORDS = LANE_UNIT_ROWS * LANE_NT;      /* 1152 words = 4608 bytes per warp of units */
+__host__ __device__ constexpr size_t lane_unit_blocks(size_t slots) { return (slots + 31) / 32 + 4; }   /* worst case: every slot its own unit, + one partial warp per list */
+
+/* what a thread knows about its unit: two slots, or the two halves of one two-block slot (then k[1] is unused) */
+struct LaneUnit {
+	uint32_t k[2];           /* slot index in the piece, LANE_NO_SLOT = none */
+	uint32_t code[2], flags[2];
+	uint32_t bbk[2];         /* the 30 descrambled AACH bits, first on air in bit 0 */
+	uint32_t tm16[2];        /* tn | fn << 3 | mn << 8, the slot record's encoding */
+	int kind[2], n[2];
+};
+
+__device__ __forceinline__ int lane_ncode(int n) { return n == 288 ? 2 : (n == 144 ? 1 : 0); }
+__device__ __forceinline__ int lane_nsteps(uint32_t mw) { const uint32_t c = (mw >> 28) & 3u; return c == 2 ? 288 : (c == 1 ? 144 : 0); }
+
+/* the unit's part of the block: rows 28/29 tm16 | flags << 16 | kind << 24 | step code << 28 per half, then k, code, bbk */
+__device__ __forceinline__ void lane_unit_store(uint32_t *blk_lane, const LaneUnit &m)
+{
+	constexpr int nt = LANE_NT;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		blk_lane[(LANE_META_ROW + h) * nt] = m.tm16[h] | (m.flags[h] << 16) | ((uint32_t)m.kind[h] << 24) | ((uint32_t)lane_ncode(m.n[h]) << 28);
+		blk_lane[(LANE_META_ROW + 2 + h) * nt] = m.k[h];
+		blk_lane[(LANE_META_ROW + 4 + h) * nt] = m.code[h];
+		blk_lane[(LANE_META_ROW + 6 + h) * nt] = m.bbk[h];
+	}
+}
+__device__ __forceinline__ void lane_unit_load(const uint32_t *blk_lane, LaneUnit &m)
+{
+	constexpr int nt = LANE_NT;
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const uint32_t mw = blk_lane[(LANE_META_ROW + h) * nt];
+		m.tm16[h] = mw & 0xffffu; m.flags[h] = (mw >> 16) & 0xffu; m.kind[h] = (int)((mw >> 24) & 0xfu); m.n[h] = lane_nsteps(mw);
+		m.k[h] = blk_lane[(LANE_META_ROW + 2 + h) * nt];
+		m.code[h] = blk_lane[(LANE_META_ROW + 4 + h) * nt];
+		m.bbk[h] = blk_lane[(LANE_META_ROW + 6 + h) * nt];
+	}
+}
+
+/* units per list: pairs of SCH/F slots, single two-block slots, pairs of SYNC bursts, pairs of dropped slots */
+struct LaneLists {
+	uint32_t cF, c2, cS, c0;
+	uint64_t uF, u2, uS, units;
+	const uint32_t *lF, *l2, *lS, *l0;
+	__device__ __forceinline__ explicit LaneLists(const DecodeArgs &a)
+	{
+		cF = a.kind_count[KIND_NDB_F]; c2 = a.kind_count[KIND_NDB_2]; cS = a.kind_count[KIND_SB]; c0 = a.kind_count[KIND_NONE];
+		uF = (cF + 1) / 2; u2 = c2; uS = (cS + 1) / 2;
+		units = uF + u2 + uS + (c0 + 1) / 2;
+		lF = a.kind_list + (size_t)KIND_NDB_F * a.list_stride; l2 = a.kind_list + (size_t)KIND_NDB_2 * a.list_stride;
+		lS = a.kind_list + (size_t)KIND_SB * a.list_stride; l0 = a.kind_list + (size_t)KIND_NONE * a.list_stride;
+	}
+	__device__ __forceinline__ uint64_t warps() const { return (units + 31) / 32; }
+	__device__ __forceinline__ void slots_of(uint64_t u, uint32_t (&k)[2]) const
+	{
+		k[0] = k[1] = LANE_NO_SLOT;
+		if (u < uF)                { k[0] = lF[2 * u]; if (2 * u + 1 < cF) k[1] = lF[2 * u + 1]; }
+		else if (u < uF + u2)      { k[0] = l2[u - uF]; }
+		else if (u < uF + u2 + uS) { const uint64_t i = u - uF - u2; k[0] = lS[2 * i]; if (2 * i + 1 < cS) k[1] = lS[2 * i + 1]; }
+		else if (u < units)        { const uint64_t i = u - uF - u2 - uS; k[0] = l0[2 * i]; if (2 * i + 1 < c0) k[1] = l0[2 * i + 1]; }
+	}
+};
+
+/* PREPARE: load, descramble and de-interleave every block of the unit's slots; the type-3 bits go to the two columns
+ * (stride LANE_NT words: shared memory in the fused kernel, the unit block in global memory otherwise).
+ * The cell state of a slot hangs on a chain of dependent loads (list -> slot state + index of the last CRC-good SYNC burst ->
+ * that burst's state); the chains of the unit's two slots are walked level by level together and the slots' bits are
+ * requested as soon as their index is known, so a unit waits for three load latencies instead of eight. */
+__device__ __forceinline__ void lane_prepare(const DecodeArgs &a, const Tables *__restrict__ tab, uint32_t *bcast, const uint32_t *leap,
+                                             uint64_t u, const LaneLists &L, uint32_t *col0, uint32_t *col1, LaneUnit &m)
+{
+	constexpr int nt = LANE_NT;
+	L.slots_of(u, m.k);
+	/* level 2: everything addressed by the slot index */
+	SlotWs w[2];
+	int32_t j[2];
+	uint32_t bw[2][16];
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		m.code[h] = 0; m.bbk[h] = 0; m.kind[h] = KIND_NONE; m.n[h] = 0;
+		j[h] = -1;
+		if (m.k[h] != LANE_NO_SLOT) {
+			w[h] = a.ws[m.k[h]];
+			j[h] = a.last_good[m.k[h]];
+			load_slot_bits(a.slot_bits, m.k[h], bw[h]);
+		}
+	}
+	/* level 3: the CRC-good SYNC burst the slot's cell state comes from (cell_state(), spelled out for two slots) */
+	Tm tm[2];
+	bool dep[2];
+#pragma unroll
+	for (int h = 0; h < 2; ++h)
+		if (m.k[h] != LANE_NO_SLOT && j[h] < 0) j[h] = a.blk_prev[m.k[h] >> 10];
+	SlotWs sj[2];
+#pragma unroll
+	for (int h = 0; h < 2; ++h)
+		if (m.k[h] != LANE_NO_SLOT && j[h] >= 0) sj[h] = a.ws[j[h]];
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		tm[h].tn = tm[h].fn = tm[h].mn = 0;
+		dep[h] = false;
+		if (m.k[h] == LANE_NO_SLOT) continue;
+		if (j[h] >= 0) {
+			const Tm t = { sj[h].tn, sj[h].fn, sj[h].mn };
+			tm[h] = tm_advance_small(t, m.k[h] - (uint32_t)j[h]);
+			m.code[h] = sj[h].sb_code;
+		} else {
+			const Tm t = { a.carry->tn, a.carry->fn, a.carry->mn };
+			tm[h] = tm_advance_small(t, m.k[h] + 1);          /* k indexes the slots of one launch: < 2^31 */
+			m.code[h] = a.carry->scramb_init;
+			dep[h] = true;
+		}
+	}
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		bool good_sb = false, unlock = false;
+		if (m.k[h] != LANE_NO_SLOT) {
+			m.kind[h] = w[h].kind; good_sb = w[h].good_sb; unlock = w[h].unlock;
+			if (a.skip_dependent && dep[h] && !a.carry->seen_good) {     /* sharded decode: decoded later, with the real carry-in */
+				m.k[h] = LANE_NO_SLOT; m.kind[h] = KIND_NONE; good_sb = unlock = false;
+			}
+		}
+		m.flags[h] = (uint32_t)m.kind[h] | (unlock ? F_UNLOCK : 0) | ((m.kind[h] == KIND_SB && good_sb) ? F_CRC_A : 0);
+		if (m.kind[h] == KIND_SB && tm_is_bnch(tm[h])) m.flags[h] |= F_BNCH;
+		m.tm16[h] = (tm[h].tn | (tm[h].fn << 3) | (tm[h].mn << 8)) & 0xffffu;
+		uint32_t lf[LANE_T3_ROWS];
+		lane_lfsr(m.code[h], m.kind[h] != KIND_NONE, lf, bcast, tab, leap);
+		if (m.kind[h] != KIND_NONE) {
+			uint32_t *col = h ? col1 : col0;
+			if (m.kind[h] == KIND_SB) {
+				xor_region<252, 0, 30>(bw[h], lf);
+				xor_region<282, 0, 216>(bw[h], lf);
+				m.bbk[h] = extract_bits(bw[h], 252, 30);
+				gather_lane<1, PL_BLK2>(bw[h], col, nt); m.n[h] = 144;
+			} else if (m.kind[h] == KIND_NDB_F) {
+				xor_region<14, 0, 216>(bw[h], lf);
+				xor_region<282, 216, 216>(bw[h], lf);
+				xor_region<230, 0, 14>(bw[h], lf);
+				m.bbk[h] = extract_bits(bw[h], 230, 14);
+				if (a.aach) m.bbk[h] |= ((extract_bits(bw[h], 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;       /* the broadcast block's second part */
+				gather_lane<5, PL_SCHF>(bw[h], col, nt); m.n[h] = 288;
+			} else if (h == 0) {
+				/* two-block slot: BLK1 on trellis X, BLK2 on trellis Y of this thread (k[1] is unused) */
+				xor_region<14, 0, 216>(bw[h], lf);
+				xor_region<282, 0, 216>(bw[h], lf);
+				xor_region<230, 0, 14>(bw[h], lf);
+				m.bbk[h] = extract_bits(bw[h], 230, 14);
+				if (a.aach) m.bbk[h] |= ((extract_bits(bw[h], 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;
+				gather_lane<1, PL_BLK1>(bw[h], col0, nt);
+				gather_lane<1, PL_BLK2>(bw[h], col1, nt);
+				m.n[0] = m.n[1] = 144;
+			}
+		}
+	}
+}
+
+/* FINISH: CRCs of the decoded blocks (columns col0 / col1, stride LANE_NT), the slot's type-1 string in the reference's
+ * delivery order, the slot record and the side outputs.
+ * The type-1 strings leave through `stage` (LANE_STAGE_WORDS words of the warp's shared memory, may overlay the columns):
+ * a thread that stored its own slot's 288 bytes would issue 18 stores whose 32 lanes each hit a different 32-byte sector
+ * half way (32 partial-sector requests per instruction, 18 LSU cycles per slot - this, not HBM, bounded the finish part);
+ * staged, lane l stores chunk (32 i + l) of the warp's 64 x 18 chunks, so an instruction covers 512 contiguous bytes. */
+constexpr int LANE_STAGE_STRIDE = 10;                          /* 9 type-1 words + the output index of the slot */
+constexpr int LANE_STAGE_WORDS = 64 * LANE_STAGE_STRIDE;
+__device__ __forceinline__ void lane_finish(const DecodeArgs &a, const Tables *__restrict__ tab, const uint32_t *crc_tab,
+                                            const uint32_t *col0, const uint32_t *col1, LaneUnit &m, uint32_t *stage)
+{
+	constexpr int nt = LANE_NT;
+	const int tid = threadIdx.x & 31;
+	uint32_t crcs[2] = { 0, 0 };            /* block A | block B << 16 of each slot */
+	if (m.kind[0] == KIND_NDB_2) {
+		const uint32_t ca = crc_col(crc_tab, col0, 140), cb = crc_col(crc_tab, col1, 140);
+		if (ca == 0x1d0f) m.flags[0] |= F_CRC_A;
+		if (cb == 0x1d0f) m.flags[0] |= F_CRC_B;
+		crcs[0] = ca | (cb << 16);
+	}
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const uint32_t *col = h ? col1 : col0;
+		if (m.kind[h] == KIND_SB) {
+			const uint32_t cb = crc_col(crc_tab, col, 140);
+			if (cb == 0x1d0f) m.flags[h] |= F_CRC_B;
+			crcs[h] = cb << 16;             /* SB1's half is added from the slot state below */
+		} else if (m.kind[h] == KIND_NDB_F) {
+			const uint32_t ca = crc_col(crc_tab, col, 284);
+			if (ca == 0x1d0f) m.flags[h] |= F_CRC_A;
+			crcs[h] = ca;
+		}
+	}
+	/* assemble the slots' type-1 strings in the reference's delivery order; records and side outputs straight from here */
+	uint32_t outw[2][9];
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+#pragma unroll
+		for (int i = 0; i < 9; ++i) outw[h][i] = 0;
+		if (m.k[h] == LANE_NO_SLOT) continue;
+		const uint32_t *col = h ? col1 : col0;
+		const uint32_t bb = m.bbk[h] & 0x3fffu;
+		const SlotWs w = a.ws[m.k[h]];
+		if (m.kind[h] == KIND_SB) {
+			const uint32_t s0 = w.sb1_t1[0], s1 = w.sb1_t1[1];
+			put_lane(outw[h], 0, 60, [&](int i) { return i == 0 ? s0 : (i == 1 ? s1 : 0u); });
+			put_lane(outw[h], 60, 14, [&](int i) { return i == 0 ? bb : 0u; });
+			put_lane(outw[h], 74, 124, [&](int i) { return col[i * nt]; });
+		} else if (m.kind[h] == KIND_NDB_F) {
+			put_lane(outw[h], 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
+			put_lane(outw[h], 14, 268, [&](int i) { return col[i * nt]; });
+		} else if (m.kind[h] == KIND_NDB_2) {
+			put_lane(outw[h], 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
+			put_lane(outw[h], 14, 124, [&](int i) { return col0[i * nt]; });
+			put_lane(outw[h], 138, 124, [&](int i) { return col1[i * nt]; });
+		}
+		const uint64_t ko = a.out_base + m.k[h];
+		SlotOut o;
+		o.slot_bit = (uint32_t)(a.a0 + (uint64_t)SLOT_BITS * m.k[h]);
+		o.scrambling_code = m.code[h];
+		o.find_off = w.find_off; o.window = w.window;
+		o.time = (uint16_t)m.tm16[h];
+		o.find_rc = w.find_rc; o.flags = (uint8_t)m.flags[h];
+		a.slots[ko] = o;
+		if (a.crc) a.crc[ko] = crcs[h] | (m.kind[h] == KIND_SB ? (w.sb1_crc & 0xffffu) : 0u);
+		if (a.aach) a.aach[ko] = m.kind[h] == KIND_NONE ? 0xffffffffu : rm3014_decode(tab, a.rm_leader, rm3014_word_from_air(m.bbk[h]));
+	}
+	if (a.stats)
+		add_counts(a.stats, (m.k[0] != LANE_NO_SLOT ? slot_counts(m.kind[0], m.flags[0]) : 0u) +
+		                    (m.k[1] != LANE_NO_SLOT && m.kind[0] != KIND_NDB_2 ? slot_counts(m.kind[1], m.flags[1]) : 0u));
+	if (!a.type1 && !a.type1_packed) return;
+	__syncwarp();                             /* every lane is done with the columns: the stage may overlay them */
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		uint32_t *rec = stage + (2 * tid + h) * LANE_STAGE_STRIDE;
+#pragma unroll
+		for (int i = 0; i < 9; ++i) rec[i] = outw[h][i];
+		rec[9] = m.k[h];
+	}
+	__syncwarp();
+	if (a.type1) {
+		for (int q = tid; q < 64 * 18; q += 32) {
+			const int sl = q / 18, c = q - 18 * sl;
+			const uint32_t *rec = stage + sl * LANE_STAGE_STRIDE;
+			const uint32_t k = rec[9];
+			if (k == LANE_NO_SLOT) continue;
+			const uint32_t hbits = (rec[c >> 1] >> (16 * (c & 1))) & 0xffff;
+			__stcs(reinterpret_cast<uint4 *>(a.type1 + (a.out_base + k) * TYPE1_STRIDE) + c,
+			       make_uint4(unpack4(hbits), unpack4(hbits >> 4), unpack4(hbits >> 8), unpack4(hbits >> 12)));
+		}
+	}
+	if (a.type1_packed) {
+		for (int q = tid; q < 64 * 9; q += 32) {
+			const int sl = q / 9, i = q - 9 * sl;
+			const uint32_t *rec = stage + sl * LANE_STAGE_STRIDE;
+			const uint32_t k = rec[9];
+			if (k == LANE_NO_SLOT) continue;
+			__stcs(a.type1_packed + (a.out_base + k) * TYPE1_WORDS + i, rec[i]);
+		}
+	}
+}
+
+__device__ __forceinline__ int lane_warp_max(int v)
+{
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) {
+		const int o = __shfl_xor_sync(FULL, v, d);
+		v = o > v ? o : v;
+	}
+	return v;
+}
+
+/* the fused form: one kernel, the type-3 bits never leave shared memory */
 template <bool TIE_HI>
 __global__ void __launch_bounds__(32, 16)
 k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
@@ -695,153 +983,128 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 	const Tables *__restrict__ tab = a.tab;
 	lane_load_tables(sm, tab, true);
 	const int tid = threadIdx.x;
-	constexpr int nt = LANE_NT;
 	uint32_t *bcast = sm.lfb + (tid >> 5) * 16;
-	const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
-	/* units per list: pairs of SCH/F slots, single two-block slots, pairs of SYNC bursts, pairs of dropped slots */
-	const uint32_t cF = a.kind_count[KIND_NDB_F], c2 = a.kind_count[KIND_NDB_2], cS = a.kind_count[KIND_SB], c0 = a.kind_count[KIND_NONE];
-	const uint64_t uF = (cF + 1) / 2, u2 = c2, uS = (cS + 1) / 2, u0 = (c0 + 1) / 2;
-	const uint64_t units = uF + u2 + uS + u0;
-	const uint64_t rounds = (units + nthreads - 1) / nthreads;
-	const uint32_t *lF = a.kind_list + (size_t)KIND_NDB_F * a.list_stride, *l2 = a.kind_list + (size_t)KIND_NDB_2 * a.list_stride;
-	const uint32_t *lS = a.kind_list + (size_t)KIND_SB * a.list_stride, *l0 = a.kind_list + (size_t)KIND_NONE * a.list_stride;
+	const LaneLists L(a);
+	const uint64_t nw = L.warps();
+	for (uint64_t wu = blockIdx.x; wu < nw; wu += gridDim.x) {
+		LaneUnit m;
+		lane_prepare(a, tab, bcast, sm.leap, wu * 32 + tid, L, sm.t3col(0, tid), sm.t3col(1, tid), m);
+		const int nmax = lane_warp_max(m.n[0] > m.n[1] ? m.n[0] : m.n[1]);
+		if (nmax) viterbi_pair<TIE_HI>(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), m.n[0], m.n[1], nmax);
+		lane_finish(a, tab, sm.crc_tab, sm.t3col(0, tid), sm.t3col(1, tid), m, sm.t3);
+		__syncwarp();
+	}
+}
 
-	for (uint64_t r = 0; r < rounds; ++r) {
-		const uint64_t u = r * nthreads + (uint64_t)blockIdx.x * blockDim.x + tid;
-		uint64_t k[2] = { ~0ull, ~0ull };
-		if (u < uF)                     { k[0] = lF[2 * u]; if (2 * u + 1 < cF) k[1] = lF[2 * u + 1]; }
-		else if (u < uF + u2)           { k[0] = l2[u - uF]; }
-		else if (u < uF + u2 + uS)      { const uint64_t i = u - uF - u2; k[0] = lS[2 * i]; if (2 * i + 1 < cS) k[1] = lS[2 * i + 1]; }
-		else if (u < units)             { const uint64_t i = u - uF - u2 - uS; k[0] = l0[2 * i]; if (2 * i + 1 < c0) k[1] = l0[2 * i + 1]; }
-		uint32_t code[2] = { 0, 0 }, flags[2] = { 0, 0 }, bbk[2] = { 0, 0 };      /* bbk: the 30 descrambled AACH bits, first on air in bit 0 */
-		int kind[2] = { KIND_NONE, KIND_NONE };
-		int n[2] = { 0, 0 };
-		Tm tm[2];
-		/* load, descramble and de-interleave every block of the slots; the packed slot words
-		 * only live inside this loop body, so the ACS loop below runs with a small register set */
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			const bool have = k[h] != ~0ull;
-			tm[h].tn = tm[h].fn = tm[h].mn = 0;
-			bool good_sb = false, unlock = false;
-			if (have) {
-				const SlotWs w = a.ws[k[h]];
-				kind[h] = w.kind; good_sb = w.good_sb; unlock = w.unlock;
-				const bool dep = cell_state(k[h], a.ws, a.last_good, a.blk_prev, a.carry, &tm[h], &code[h]);
-				if (a.skip_dependent && dep && !a.carry->seen_good) {     /* sharded decode: decoded later, with the real carry-in */
-					k[h] = ~0ull; kind[h] = KIND_NONE; good_sb = unlock = false;
+/* ---- the split form ---- */
+
+/* PREPARE as its own kernel: one warp per CTA, no trellis registers, so an SM holds 24+ of them and the dependent
+ * loads of the cell state hide behind each other.  Shared memory: the scrambler's leap tables + one broadcast row. */
+__host__ __device__ constexpr size_t lane_prepare_smem_words() { return 1024 + 16; }
+#ifndef TB_PREP_MIN_CTAS
+#define TB_PREP_MIN_CTAS 16       /* 128 registers, no spills; measured: 20 (96 registers, ~60 words spilled) 8 % slower, 24 12 % */
+#endif
+__global__ void __launch_bounds__(32, TB_PREP_MIN_CTAS)
+k_lane_prepare(DecodeArgs a, uint32_t *__restrict__ units)
+{
+	uint32_t *leap = reinterpret_cast<uint32_t *>(TB_DYN_SMEM());
+	uint32_t *bcast = leap + 1024;
+	const Tables *__restrict__ tab = a.tab;
+	const int tid = threadIdx.x;
+	for (int i = tid; i < 1024; i += 32) leap[i] = (&tab->lfsr_leap[0][0])[i];
+	__syncwarp();
+	const LaneLists L(a);
+	const uint64_t nw = L.warps();
+	for (uint64_t wu = blockIdx.x; wu < nw; wu += gridDim.x) {
+		uint32_t *blk = units + wu * LANE_UNIT_WORDS + tid;
+		LaneUnit m;
+		lane_prepare(a, tab, bcast, leap, wu * 32 + tid, L, blk, blk + LANE_T3_ROWS * LANE_NT, m);
+		lane_unit_store(blk, m);
+		__syncwarp();
+	}
+}
+
+/* TRELLIS: the ACS loop and the trace back over the prepared blocks.  One warp per CTA, 16 CTAs per SM (registers); the
+ * block of the CTA's next unit arrives by bulk copy while the current one is decoded.  FINISH = true runs the finish part
+ * right here out of shared memory, otherwise the decoded bits go back into the block (rows 0..8 and 14..22) for
+ * k_lane_finish. */
+template <bool FINISH>
+__host__ __device__ constexpr size_t lane_trellis_smem_words() { return 2 * LANE_UNIT_WORDS + 4 + (FINISH ? 256 + 16 : 0); }
+
+template <bool TIE_HI, bool FINISH>
+__global__ void __launch_bounds__(32, 16)
+k_lane_trellis(DecodeArgs a, uint32_t *__restrict__ scratch, uint32_t *__restrict__ units)
+{
+	uint32_t *buf = reinterpret_cast<uint32_t *>(TB_DYN_SMEM());
+	uint64_t *bars = reinterpret_cast<uint64_t *>(buf + 2 * LANE_UNIT_WORDS);
+	uint32_t *crc_tab = buf + 2 * LANE_UNIT_WORDS + 4;
+	const Tables *__restrict__ tab = a.tab;
+	const int tid = threadIdx.x;
+	constexpr int nt = LANE_NT;
+	constexpr unsigned BYTES = LANE_UNIT_WORDS * sizeof(uint32_t);
+	uint4 *dec = reinterpret_cast<uint4 *>(scratch + (size_t)blockIdx.x * lane_scratch_words_per_cta(nt)) + tid;
+	if (FINISH)
+		for (int i = tid; i < 256 + 16; i += 32) crc_tab[i] = tab->crc_tab_r[i];
+	if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
+	__syncwarp();
+	const LaneLists L(a);
+	const uint64_t nw = L.warps();
+	if (blockIdx.x < nw && tid == 0) {
+		mbar_expect_tx(&bars[0], BYTES);
+		bulk_g2s(buf, units + (size_t)blockIdx.x * LANE_UNIT_WORDS, BYTES, &bars[0]);
+	}
+	unsigned phase = 0, b = 0;
+	for (uint64_t wu = blockIdx.x; wu < nw; wu += gridDim.x, b ^= 1u) {
+		const uint64_t nxt = wu + gridDim.x;
+		if (nxt < nw && tid == 0) {           /* the other buffer is free: its unit was finished before the __syncwarp below */
+			fence_async_shared();
+			mbar_expect_tx(&bars[b ^ 1u], BYTES);
+			bulk_g2s(buf + (b ^ 1u) * LANE_UNIT_WORDS, units + nxt * LANE_UNIT_WORDS, BYTES, &bars[b ^ 1u]);
+		}
+		mbar_wait(&bars[b], (phase >> b) & 1u);
+		phase ^= 1u << b;
+		uint32_t *cx = buf + b * LANE_UNIT_WORDS + tid, *cy = cx + LANE_T3_ROWS * nt;
+		if (FINISH) {
+			LaneUnit m;
+			lane_unit_load(cx, m);
+			const int nmax = lane_warp_max(m.n[0] > m.n[1] ? m.n[0] : m.n[1]);
+			if (nmax) viterbi_pair<TIE_HI>(dec, cx, cy, m.n[0], m.n[1], nmax);
+			lane_finish(a, tab, crc_tab, cx, cy, m, buf + b * LANE_UNIT_WORDS);
+		} else {
+			const int n0 = lane_nsteps(cx[LANE_META_ROW * nt]), n1 = lane_nsteps(cx[(LANE_META_ROW + 1) * nt]);
+			const int nmax = lane_warp_max(n0 > n1 ? n0 : n1);
+			if (nmax) {
+				viterbi_pair<TIE_HI>(dec, cx, cy, n0, n1, nmax);
+				uint32_t *blk = units + wu * LANE_UNIT_WORDS + tid;
+				const int rows = (nmax + 31) >> 5;
+				for (int i = 0; i < rows; ++i) {
+					if (n0) blk[i * nt] = cx[i * nt];
+					if (n1) blk[(LANE_T3_ROWS + i) * nt] = cy[i * nt];
 				}
 			}
-			flags[h] = (uint32_t)kind[h] | (unlock ? F_UNLOCK : 0) | ((kind[h] == KIND_SB && good_sb) ? F_CRC_A : 0);
-			uint32_t lf[LANE_T3_ROWS];
-			lane_lfsr(code[h], kind[h] != KIND_NONE, lf, bcast, tab, sm.leap);
-			if (kind[h] != KIND_NONE) {
-				uint32_t bw[16];
-				load_slot_bits(a.slot_bits, k[h], bw);
-				uint32_t *col = sm.t3col(h, tid);
-				if (kind[h] == KIND_SB) {
-					xor_region<252, 0, 30>(bw, lf);
-					xor_region<282, 0, 216>(bw, lf);
-					bbk[h] = extract_bits(bw, 252, 30);
-					gather_lane<1, PL_BLK2>(bw, col, nt); n[h] = 144;
-				} else if (kind[h] == KIND_NDB_F) {
-					xor_region<14, 0, 216>(bw, lf);
-					xor_region<282, 216, 216>(bw, lf);
-					xor_region<230, 0, 14>(bw, lf);
-					bbk[h] = extract_bits(bw, 230, 14);
-					if (a.aach) bbk[h] |= ((extract_bits(bw, 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;       /* the broadcast block's second part */
-					gather_lane<5, PL_SCHF>(bw, col, nt); n[h] = 288;
-				} else if (h == 0) {
-					/* two-block slot: BLK1 on trellis X, BLK2 on trellis Y of this thread (k[1] is unused) */
-					xor_region<14, 0, 216>(bw, lf);
-					xor_region<282, 0, 216>(bw, lf);
-					xor_region<230, 0, 14>(bw, lf);
-					bbk[h] = extract_bits(bw, 230, 14);
-					if (a.aach) bbk[h] |= ((extract_bits(bw, 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;
-					gather_lane<1, PL_BLK1>(bw, sm.t3col(0, tid), nt);
-					gather_lane<1, PL_BLK2>(bw, sm.t3col(1, tid), nt);
-					n[0] = n[1] = 144;
-				}
-			}
 		}
-		int nmax = n[0] > n[1] ? n[0] : n[1];
-#pragma unroll
-		for (int d = 16; d > 0; d >>= 1) {
-			const int o = __shfl_xor_sync(FULL, nmax, d);
-			nmax = o > nmax ? o : nmax;
-		}
-		if (nmax) viterbi_pair<TIE_HI>(sm.dec + tid, sm.t3col(0, tid), sm.t3col(1, tid), n[0], n[1], nmax);
-		uint32_t crcs[2] = { 0, 0 };            /* block A | block B << 16 of each slot */
-		if (kind[0] == KIND_NDB_2) {
-			const uint32_t ca = crc_col(sm, sm.t3col(0, tid), 140), cb = crc_col(sm, sm.t3col(1, tid), 140);
-			if (ca == 0x1d0f) flags[0] |= F_CRC_A;
-			if (cb == 0x1d0f) flags[0] |= F_CRC_B;
-			crcs[0] = ca | (cb << 16);
-		}
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			const uint32_t *col = sm.t3col(h, tid);
-			if (kind[h] == KIND_SB) {
-				const uint32_t cb = crc_col(sm, col, 140);
-				if (cb == 0x1d0f) flags[h] |= F_CRC_B;
-				crcs[h] = cb << 16;             /* SB1's half is added from the slot state below */
-				if (tm_is_bnch(tm[h])) flags[h] |= F_BNCH;
-			} else if (kind[h] == KIND_NDB_F) {
-				const uint32_t ca = crc_col(sm, col, 284);
-				if (ca == 0x1d0f) flags[h] |= F_CRC_A;
-				crcs[h] = ca;
-			}
-		}
-		/* assemble the slot's type-1 string in the reference's delivery order and store */
-#pragma unroll
-		for (int h = 0; h < 2; ++h) {
-			if (k[h] == ~0ull) continue;
-			uint32_t outw[9];
-#pragma unroll
-			for (int i = 0; i < 9; ++i) outw[i] = 0;
-			const uint32_t *col = sm.t3col(h, tid);
-			const uint32_t bb = bbk[h] & 0x3fffu;
-			const SlotWs w = a.ws[k[h]];
-			if (kind[h] == KIND_SB) {
-				const uint32_t s0 = w.sb1_t1[0], s1 = w.sb1_t1[1];
-				put_lane(outw, 0, 60, [&](int i) { return i == 0 ? s0 : (i == 1 ? s1 : 0u); });
-				put_lane(outw, 60, 14, [&](int i) { return i == 0 ? bb : 0u; });
-				put_lane(outw, 74, 124, [&](int i) { return col[i * nt]; });
-			} else if (kind[h] == KIND_NDB_F) {
-				put_lane(outw, 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
-				put_lane(outw, 14, 268, [&](int i) { return col[i * nt]; });
-			} else if (kind[h] == KIND_NDB_2) {
-				const uint32_t *colb = sm.t3col(1, tid);
-				put_lane(outw, 0, 14, [&](int i) { return i == 0 ? bb : 0u; });
-				put_lane(outw, 14, 124, [&](int i) { return col[i * nt]; });
-				put_lane(outw, 138, 124, [&](int i) { return colb[i * nt]; });
-			}
-			const uint64_t ko = a.out_base + k[h];
-			if (a.type1) {
-				uint4 *dst = reinterpret_cast<uint4 *>(a.type1 + ko * TYPE1_STRIDE);
-#pragma unroll
-				for (int c = 0; c < 18; ++c) {
-					const uint32_t hbits = (outw[c >> 1] >> (16 * (c & 1))) & 0xffff;
-					__stcs(dst + c, make_uint4(unpack4(hbits), unpack4(hbits >> 4), unpack4(hbits >> 8), unpack4(hbits >> 12)));
-				}
-			}
-			if (a.type1_packed) {
-#pragma unroll
-				for (int i = 0; i < 9; ++i) __stcs(a.type1_packed + ko * TYPE1_WORDS + i, outw[i]);
-			}
-			SlotOut o;
-			o.slot_bit = (uint32_t)(a.a0 + (uint64_t)SLOT_BITS * k[h]);
-			o.scrambling_code = code[h];
-			o.find_off = w.find_off; o.window = w.window;
-			o.time = (uint16_t)(tm[h].tn | (tm[h].fn << 3) | (tm[h].mn << 8));
-			o.find_rc = w.find_rc; o.flags = (uint8_t)flags[h];
-			a.slots[ko] = o;
-			if (a.crc) a.crc[ko] = crcs[h] | (kind[h] == KIND_SB ? (w.sb1_crc & 0xffffu) : 0u);
-			if (a.aach) a.aach[ko] = kind[h] == KIND_NONE ? 0xffffffffu : rm3014_decode(tab, a.rm_leader, rm3014_word_from_air(bbk[h]));
-		}
-		if (a.stats)
-			add_counts(a.stats, (k[0] != ~0ull ? slot_counts(kind[0], flags[0]) : 0u) +
-			                    (k[1] != ~0ull && kind[0] != KIND_NDB_2 ? slot_counts(kind[1], flags[1]) : 0u));
+		__syncwarp();
+	}
+}
+
+/* FINISH as its own kernel: reads the decoded rows and the unit's part of the block */
+__host__ __device__ constexpr size_t lane_finish_smem_words() { return 256 + 16 + LANE_STAGE_WORDS; }
+__global__ void __launch_bounds__(32, 24)
+k_lane_finish(DecodeArgs a, const uint32_t *__restrict__ units)
+{
+	uint32_t *crc_tab = reinterpret_cast<uint32_t *>(TB_DYN_SMEM());
+	uint32_t *stage = crc_tab + 256 + 16;
+	const Tables *__restrict__ tab = a.tab;
+	const int tid = threadIdx.x;
+	for (int i = tid; i < 256 + 16; i += 32) crc_tab[i] = tab->crc_tab_r[i];
+	__syncwarp();
+	const LaneLists L(a);
+	const uint64_t nw = L.warps();
+	for (uint64_t wu = blockIdx.x; wu < nw; wu += gridDim.x) {
+		const uint32_t *blk = units + wu * LANE_UNIT_WORDS + tid;
+		LaneUnit m;
+		lane_unit_load(blk, m);
+		lane_finish(a, tab, crc_tab, blk, blk + LANE_T3_ROWS * LANE_NT, m, stage);
 		__syncwarp();
 	}
 }

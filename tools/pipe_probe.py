@@ -31,6 +31,14 @@ def main():
             ns = step()
         torch.cuda.synchronize(); dt_s = (time.perf_counter() - t0) / k
         res.append("%s %.4g/s (%.3f ms)" % (name, ns / dt_s, dt_s * 1e3))
+        if os.environ.get("PROBE_PROF"):
+            g.set_options(profile=1, serial_passes=1)
+            step(); step()
+            t = g.timing(); per = 1e6 / ns
+            res.append("[per 1e6: search %.4f sb1 %.4f scan %.4f decode %.4f = prep %.4f + trellis %.4f + fin %.4f]" % (
+                t.search_ms * per, (t.classify_ms - t.search_ms) * per, t.scan_ms * per, t.decode_ms * per,
+                t.prepare_ms * per, t.trellis_ms * per, (t.decode_ms - t.prepare_ms - t.trellis_ms) * per))
+            g.set_options(profile=0, serial_passes=0)
         del d, ds, dt
     print("  ".join(res))
 

@@ -24,5 +24,5 @@ for _ in range(steps):
     assert ns > 0.99 * n, (ns, g.err())
 t = g.timing()
 kinds = bench.kinds_of(torch, ds, ns)
-print("PROF %s slots %d kinds %s decode_ms %.4f search_ms %.4f classify_ms %.4f scan_ms %.4f total_ms %.4f" %
-      (shape, ns, kinds, t.decode_ms, t.search_ms, t.classify_ms, t.scan_ms, t.total_ms))
+print("PROF %s slots %d kinds %s decode_ms %.4f prepare_ms %.4f trellis_ms %.4f search_ms %.4f classify_ms %.4f scan_ms %.4f total_ms %.4f" %
+      (shape, ns, kinds, t.decode_ms, t.prepare_ms, t.trellis_ms, t.search_ms, t.classify_ms, t.scan_ms, t.total_ms))
