@@ -230,15 +230,23 @@ def kernel_constants():
         return {}
 
 
+TIM_KEYS = ("total", "classify", "scan", "decode", "search", "prepare", "trellis")
+
+
+def add_timing(tim, t):
+    tim["total"] += t.total_ms; tim["classify"] += t.classify_ms; tim["scan"] += t.scan_ms; tim["decode"] += t.decode_ms
+    tim["search"] += t.search_ms; tim["prepare"] += t.prepare_ms; tim["trellis"] += t.trellis_ms
+
+
 def serial_kernel_times(g, step, steps):
     """per-kernel CUDA-event times of `steps` steps with options.serial_passes = 1, scaled to one step"""
     g.set_options(serial_passes=1, profile=1)
     step()
-    tim = dict.fromkeys(("total", "classify", "scan", "decode", "search"), 0.0)
+    tim = dict.fromkeys(TIM_KEYS, 0.0)
     for _ in range(steps):
         step()
         t = g.timing()
-        tim["total"] += t.total_ms; tim["classify"] += t.classify_ms; tim["scan"] += t.scan_ms; tim["decode"] += t.decode_ms; tim["search"] += t.search_ms
+        add_timing(tim, t)
     g.set_options(serial_passes=0)
     return {k: v / steps for k, v in tim.items()}
 
@@ -252,29 +260,41 @@ def rooflines(kinds, ns, tim, steps, int_peak, peaks, kc, shape):
     """decode pass against the integer-issue peak, search kernel against HBM, from CUDA-event times (sums over the pieces of
     a step; tim holds totals over `steps` steps, taken with serial_passes = 1) and the kind mix of the decoded stream"""
     dec_ms, search_ms, cls_ms, scan_ms, total_ms = (tim[k] / steps for k in ("decode", "search", "classify", "scan", "total"))
+    prep_ms, trel_ms = tim.get("prepare", 0.0) / steps, tim.get("trellis", 0.0) / steps
+    split = trel_ms > 0.05 * dec_ms                     # the split decode pass (k_lane_prepare | k_lane_trellis), the default form
+    kname = "k_lane_trellis" if split else "k_decode_lane"
+    k_ms = trel_ms if split else dec_ms                 # the dominant kernel's own time
     acs_decode = kinds[1] * ACS_HALF + kinds[2] * ACS_SCHF + kinds[3] * 2 * ACS_HALF          # SB2, SCH/F, BLK1 + BLK2
     acs_sb1 = kinds[1] * ACS_SB1
     out_bytes = sum(kinds[k] * T1_BYTES[k] for k in range(4))
-    acs_rate = acs_decode / (dec_ms * 1e-3)
-    kd = kc.get("k_decode_lane", {}).get(shape, {})
+    acs_rate = acs_decode / (k_ms * 1e-3)
+    kd = kc.get(kname, {}).get(shape, {})
     inst_per_acs = kd.get("thread_inst_per_acs")
-    dec = {"kernel": "k_decode_lane", "bound": "int_issue",
+    dec = {"kernel": kname, "bound": "int_issue",
            "achieved": acs_rate / 1e9, "peak": int_peak / 1e9, "unit": "G/s (add-compare-selects against integer thread-instructions)",
            "frac": acs_rate / int_peak if int_peak else None,
            "traffic": kd.get("dram_bytes_per_slot") and kd["dram_bytes_per_slot"] * ns,
-           "ms_per_step": dec_ms, "acs_per_step": acs_decode,
-           "how": "algorithmic ACS of the blocks the pass decodes (16 states x (type-2 bits + 4) per block) / summed CUDA-event time of the pass; "
-                  "the packed form needs one thread instruction per ACS (add + VIADDMNMX.U16x2 per state for two trellises), so frac is the "
-                  "share of the measured integer issue peak (tb200_measure_int_peak: register-only add+min on both pipes) spent on ACS proper",
+           "ms_per_step": k_ms, "acs_per_step": acs_decode,
+           "how": "algorithmic ACS of the blocks the pass decodes (16 states x (type-2 bits + 4) per block) / summed CUDA-event time of the kernel "
+                  "that runs them (k_lane_trellis: ACS loop + trace back + CRC / type-1 output); the packed form needs one thread instruction per "
+                  "ACS (add + VIADDMNMX.U16x2 per state for two trellises), so frac is the share of the measured integer issue peak "
+                  "(tb200_measure_int_peak: register-only add+min on both pipes) spent on ACS proper",
            "thread_inst_per_acs": inst_per_acs,
            "issue_utilisation": (acs_rate * inst_per_acs / int_peak) if (inst_per_acs and int_peak) else None,
+           "decode_pass": {"ms_per_step": dec_ms, "k_lane_prepare_ms": prep_ms if split else None, "k_lane_trellis_ms": trel_ms if split else None,
+                           "frac": acs_decode / (dec_ms * 1e-3) / int_peak if int_peak else None,
+                           "note": "the whole pass 2 (prepare: cell state + descramble + de-interleave, then the trellis kernel) on the same scale"},
            "hbm_view": {"achieved": (BYTES_PER_BURST_IN * ns + out_bytes) / (dec_ms * 1e-3) / 1e9, "peak": peaks.hbm, "unit": "GB/s",
                         "note": "algorithmic bytes of the whole chain (510 B in + type-1 bytes out per slot) over the decode time: the pass is not HBM bound"}}
     dec["hbm_view"]["frac"] = dec["hbm_view"]["achieved"] / peaks.hbm
     search_gbs = BYTES_PER_BURST_IN * ns / (search_ms * 1e-3) / 1e9
     ks = kc.get("k_classify_tile", {}).get(shape, {})
+    own_gbs = (BYTES_PER_BURST_IN + 64 + 32) * ns / (search_ms * 1e-3) / 1e9
     search = {"kernel": "k_classify_tile", "bound": "hbm", "achieved": search_gbs, "peak": peaks.hbm, "unit": "GB/s",
               "frac": search_gbs / peaks.hbm, "ms_per_step": search_ms, "algorithmic_bytes_per_burst": BYTES_PER_BURST_IN,
+              "with_its_outputs": {"bytes_per_burst": BYTES_PER_BURST_IN + 64 + 32, "achieved": own_gbs, "frac": own_gbs / peaks.hbm,
+                                   "note": "510 B of stream read + the 64-byte packed slot record and the 32-byte slot state it has to write "
+                                           "for the later passes; ncu measures 600 B of DRAM traffic per slot"},
               "traffic": ks.get("dram_bytes_per_slot") and ks["dram_bytes_per_slot"] * ns, "peak_source": peaks.src}
     return dec, search, {"search": search_ms / total_ms, "sb1": (cls_ms - search_ms) / total_ms, "scan": scan_ms / total_ms,
                          "decode": dec_ms / total_ms, "sb1_acs_per_step": acs_sb1}
@@ -336,12 +356,12 @@ def run_shape(g, T, torch, shape, n, steps, warmup, seed, int_peak, peaks, kc, r
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
-    tim = dict.fromkeys(("total", "classify", "scan", "decode", "search"), 0.0)
+    tim = dict.fromkeys(TIM_KEYS, 0.0)
     t0 = time.perf_counter()
     for _ in range(steps):
         ns = step()
         t = g.timing()
-        tim["total"] += t.total_ms; tim["classify"] += t.classify_ms; tim["scan"] += t.scan_ms; tim["decode"] += t.decode_ms; tim["search"] += t.search_ms
+        add_timing(tim, t)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     kinds = kinds_of(torch, ds, ns)
@@ -535,12 +555,12 @@ def run_ours(args, rank, world, local_rank):
         time.sleep(0.3)
     barrier()
     t0 = time.perf_counter()
-    tim = dict.fromkeys(("total", "classify", "scan", "decode", "search"), 0.0)
+    tim = dict.fromkeys(TIM_KEYS, 0.0)
     launches = 0
     for _ in range(args.steps):
         ns = step_dev()
         t = g.timing()
-        tim["total"] += t.total_ms; tim["classify"] += t.classify_ms; tim["scan"] += t.scan_ms; tim["decode"] += t.decode_ms; tim["search"] += t.search_ms
+        add_timing(tim, t)
         launches += g.stats().kernel_launches
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0            # this rank's own clock: t0 .. its last kernel done; the max over ranks is the job's
@@ -674,8 +694,8 @@ def run_ours(args, rank, world, local_rank):
                    "config3": run_shape(g, T, torch, "config3", 10_000_000, 10, 3, 0x7E7A0003, int_peak, peaks, kc, rx, rng)}
 
     vals = [wall, tim_serial["total"], tim_serial["classify"], tim_serial["scan"], tim_serial["decode"], tim_serial["search"]] + \
-           ([e2e["wall"]] if e2e else [0.0]) + [tim["total"]] + ([e2e["wall_packed"]] if e2e else [0.0])
-    wall, t_total, t_cls, t_scan, t_dec, t_search, wall_e2e, t_total_overlapped, wall_e2e_packed = reduce_max(dist, vals, "cuda")
+           ([e2e["wall"]] if e2e else [0.0]) + [tim["total"]] + ([e2e["wall_packed"]] if e2e else [0.0]) + [tim_serial["prepare"], tim_serial["trellis"]]
+    wall, t_total, t_cls, t_scan, t_dec, t_search, wall_e2e, t_total_overlapped, wall_e2e_packed, t_prep, t_trel = reduce_max(dist, vals, "cuda")
     tot_slots = torch.tensor([ns, e2e["slots"] if e2e else 0], dtype=torch.int64, device="cuda")
     if dist is not None:
         dist.all_reduce(tot_slots)
@@ -683,7 +703,7 @@ def run_ours(args, rank, world, local_rank):
         if dist is not None:
             dist.destroy_process_group()
         return
-    tim_max = {"total": t_total, "classify": t_cls, "scan": t_scan, "decode": t_dec, "search": t_search}
+    tim_max = {"total": t_total, "classify": t_cls, "scan": t_scan, "decode": t_dec, "search": t_search, "prepare": t_prep, "trellis": t_trel}
     dec, search, share = rooflines(kinds, ns, tim_max, 1, int_peak, peaks, kc, shape)
     dec["timing"] = ("kernel durations: CUDA events on the launching streams over steps run with options.serial_passes = 1 (no two kernels "
                      "side by side); the timed region of `value` overlaps pass 1 of piece i+1 with the decode pass of piece i")

@@ -957,7 +957,7 @@ static int enqueue_pass1(tb200_ctx *ctx, const RxGeom &g, size_t piece_idx, int 
 	const unsigned nblk = (nb + 1023) / 1024;
 	uint32_t *kind_count = w.kind_list + 4 * ctx->ws_slots;
 	CU(cudaMemsetAsync(kind_count, 0, 4 * sizeof(uint32_t), st));
-	TB_LAUNCH(k_scan_blocks, nblk, 1024, st, w.ws, nb, w.last_good, w.blk_last, ctx->d_flags + 2 * piece_idx, ctx->d_flags + 2 * piece_idx + 1,
+	TB_LAUNCH(k_scan_blocks, nblk, SCAN_THREADS, st, w.ws, nb, w.last_good, w.blk_last, ctx->d_flags + 2 * piece_idx, ctx->d_flags + 2 * piece_idx + 1,
 	          kind_count, w.kind_list, (uint32_t)ctx->ws_slots);
 	TB_LAUNCH(k_scan_prefix, 1, 1024, st, w.blk_last, nblk, w.blk_prev);
 	ctx->stats.kernel_launches += 3;

@@ -15,6 +15,7 @@
  * Reference behaviour each routine reproduces is cited as file:line under osmo-tetra/src.
  */
 #pragma once
+#include <cstddef>
 #include <stdint.h>
 
 #ifndef TB_SIMT_EMULATION
@@ -212,6 +213,8 @@ struct SlotWs {
 	uint32_t sb1_crc;        /* CRC-16 register after SB1's 76 bits (0x1d0f = good), for the optional CRC output */
 };
 static_assert(sizeof(SlotWs) == 32, "SlotWs layout");
+static_assert(offsetof(SlotWs, find_rc) == 16 && offsetof(SlotWs, good_sb) == 17 && offsetof(SlotWs, kind) == 18 && offsetof(SlotWs, unlock) == 19,
+              "k_scan_blocks reads these four bytes as one word");
 
 struct SlotOut {                 /* == struct tb200_slot */
 	uint32_t slot_bit;
@@ -863,77 +866,110 @@ k_classify(RxGeom g, const Tables *__restrict__ tab, SlotWs *__restrict__ ws, ui
 }
 
 /* Scan, step a: per block of 1024 slots, running "index of the latest CRC-good SB1 at or
- * before me" (or -1), the block's last one, and the first slot that loses lock. */
-__global__ void __launch_bounds__(1024)
+ * before me" (or -1), the block's last one, and the first slot that loses lock.
+ * 256 threads, four consecutive slots each: the block is one round trip to memory and two barriers, so what counts is how
+ * many blocks an SM has in flight (8 of these; the earlier 1024-thread form had 2 and took 7 waves for a 2^21-slot piece). */
+constexpr int SCAN_BLOCK = 1024, SCAN_THREADS = 256, SCAN_PER = SCAN_BLOCK / SCAN_THREADS;
+__global__ void __launch_bounds__(SCAN_THREADS)
 k_scan_blocks(const SlotWs *__restrict__ ws, uint32_t n_slots, int32_t *__restrict__ last_good,
               int32_t *__restrict__ blk_last, uint32_t *__restrict__ first_unlock, uint32_t *__restrict__ first_good,
               uint32_t *__restrict__ kind_count, uint32_t *__restrict__ kind_list, uint32_t list_stride)
 {
-	__shared__ int32_t warp_last[32];
-	__shared__ uint32_t kcnt[4][32];     /* slots of kind c in warp w, then exclusive offsets */
+	constexpr int NW = SCAN_THREADS / 32;
+	__shared__ int32_t warp_last[NW];
+	__shared__ uint32_t kcnt[4][NW];     /* slots of kind c in warp w, then exclusive offsets */
 	__shared__ uint32_t kbase[4];
 	const unsigned tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-	const uint64_t k = (uint64_t)blockIdx.x * 1024 + tid;
-	int32_t v = -1;
-	int kind = -1;
-	if (k < n_slots) {
-		const SlotWs s = ws[k];
-		if (s.good_sb) v = (int32_t)k;
-		if (s.unlock) atomicMin(first_unlock, (uint32_t)k);
-		kind = s.kind;
-	}
-	/* slots grouped by kind (one list per TB200_KIND_*), so that the lane decode pass can give every warp
-	 * blocks of one length: ranks inside the warp by ballot, warp offsets by a scan, one atomic per kind
-	 * and thread block.  The order inside a list is arbitrary. */
-	uint32_t my_rank = 0;
-	if (kind_count) {
+	const uint64_t k0 = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)SCAN_PER * tid;
+	/* the byte quartet find_rc | good_sb | kind | unlock of every slot (SlotWs bytes 16..19) */
+	uint32_t q[SCAN_PER];
 #pragma unroll
-		for (int c = 0; c < 4; ++c) {
-			const unsigned m = __ballot_sync(FULL, kind == c);
-			if (kind == c) my_rank = __popc(m & ((1u << lane) - 1));
-			if (lane == 0) kcnt[c][w] = __popc(m);
-		}
+	for (int i = 0; i < SCAN_PER; ++i)
+		q[i] = k0 + i < n_slots ? reinterpret_cast<const uint32_t *>(ws + k0 + i)[4] : 0xffffffffu;
+	int32_t incl[SCAN_PER];              /* running maximum inside the thread */
+	int kind[SCAN_PER];
+	uint32_t cnt[4] = { 0, 0, 0, 0 }, rank[SCAN_PER];
+	int32_t run = -1;
+#pragma unroll
+	for (int i = 0; i < SCAN_PER; ++i) {
+		const bool have = k0 + i < n_slots;
+		const bool good = have && ((q[i] >> 8) & 0xffu) != 0;
+		kind[i] = have ? (int)((q[i] >> 16) & 0xffu) : -1;
+		if (have && (q[i] >> 24) != 0) atomicMin(first_unlock, (uint32_t)(k0 + i));
+		if (good) run = (int32_t)(k0 + i);
+		incl[i] = run;
+		rank[i] = 0;
+#pragma unroll
+		for (int c = 0; c < 4; ++c)
+			if (kind[i] == c) { rank[i] = cnt[c]; cnt[c]++; }
 	}
-	/* inclusive max-scan inside the warp */
+	/* inclusive max-scan of the threads' maxima inside the warp */
+	int32_t v = run;
 #pragma unroll
 	for (int d = 1; d < 32; d <<= 1) {
 		const int32_t o = __shfl_up_sync(FULL, v, d);
 		if (lane >= (unsigned)d && o > v) v = o;
 	}
+	int32_t before = __shfl_up_sync(FULL, v, 1);        /* what precedes this thread inside the warp */
+	if (lane == 0) before = -1;
 	if (lane == 31) warp_last[w] = v;
+	/* slots grouped by kind (one list per TB200_KIND_*), so that the lane decode pass can give every warp
+	 * blocks of one length: exclusive sums of the per-thread counts inside the warp, warp offsets by a scan, one atomic
+	 * per kind and thread block.  Lists keep the slots of a block in stream order. */
+	uint32_t pre[4] = { 0, 0, 0, 0 };
+	if (kind_count) {
+#pragma unroll
+		for (int c = 0; c < 4; ++c) {
+			uint32_t x = cnt[c];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t o = __shfl_up_sync(FULL, x, d);
+				if (lane >= (unsigned)d) x += o;
+			}
+			pre[c] = x - cnt[c];
+			if (lane == 31) kcnt[c][w] = x;
+		}
+	}
 	__syncthreads();
 	if (w == 0) {
-		int32_t x = warp_last[lane];
+		int32_t x = lane < NW ? warp_last[lane] : -1;
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
+		for (int d = 1; d < NW; d <<= 1) {
 			const int32_t o = __shfl_up_sync(FULL, x, d);
 			if (lane >= (unsigned)d && o > x) x = o;
 		}
-		warp_last[lane] = x;
+		if (lane < NW) warp_last[lane] = x;
 	} else if (kind_count && w <= 4) {
 		/* warps 1..4: exclusive scan of the per-warp counts of kind w-1, block total -> one atomic */
 		const int c = (int)w - 1;
-		const uint32_t mine = kcnt[c][lane];
+		const uint32_t mine = lane < NW ? kcnt[c][lane] : 0u;
 		uint32_t x = mine;
 #pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
+		for (int d = 1; d < NW; d <<= 1) {
 			const uint32_t o = __shfl_up_sync(FULL, x, d);
 			if (lane >= (unsigned)d) x += o;
 		}
-		kcnt[c][lane] = x - mine;
-		if (lane == 31) kbase[c] = x ? atomicAdd(&kind_count[c], x) : 0u;
+		if (lane < NW) kcnt[c][lane] = x - mine;
+		if (lane == NW - 1) kbase[c] = x ? atomicAdd(&kind_count[c], x) : 0u;
 	}
 	__syncthreads();
-	if (w > 0) { const int32_t o = warp_last[w - 1]; if (o > v) v = o; }
-	if (k < n_slots) last_good[k] = v;
-	if (tid == 1023) blk_last[blockIdx.x] = v;
-	/* first CRC-good SB1 of the piece: the first slot whose running maximum is itself */
-	if (k < n_slots && v == (int32_t)k && (tid == 0 ? true : true)) {
-		const SlotWs s = ws[k];
-		if (s.good_sb) atomicMin(first_good, (uint32_t)k);
+	if (w > 0) { const int32_t o = warp_last[w - 1]; if (o > before) before = o; }
+#pragma unroll
+	for (int i = 0; i < SCAN_PER; ++i) {
+		if (k0 + i >= n_slots) break;
+		const int32_t lg = incl[i] > before ? incl[i] : before;
+		last_good[k0 + i] = lg;
+		/* first CRC-good SB1 of the piece: only a block's first one competes */
+		if (incl[i] == (int32_t)(k0 + i) && before < 0 && (i == 0 || incl[i - 1] < 0)) atomicMin(first_good, (uint32_t)(k0 + i));
+		if (kind_count && kind[i] >= 0) {
+			uint32_t at = rank[i];
+#pragma unroll
+			for (int c = 0; c < 4; ++c)
+				if (kind[i] == c) at += kbase[c] + kcnt[c][w] + pre[c];
+			kind_list[(size_t)kind[i] * list_stride + at] = (uint32_t)(k0 + i);
+		}
 	}
-	if (kind_count && kind >= 0)
-		kind_list[(size_t)kind * list_stride + kbase[kind] + kcnt[kind][w] + my_rank] = (uint32_t)k;
+	if (tid == SCAN_THREADS - 1) blk_last[blockIdx.x] = run > before ? run : before;
 }
 
 /* Scan, step b: exclusive running max over the block results (single thread block). */

@@ -87,6 +87,25 @@ def test_other_tie_rule(gpu, orc, ref, variant):
         gpu.set_options(viterbi_tie=T.TIE_LOW_PRED)
 
 
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_lane_forms_gpu(orc, ref, form, monkeypatch):
+    """every form of the lane decode pass (TB200_LANE_FORM) against the oracle and the reference's own code: mixed kinds with
+    random cells over several pieces, SCH/F-only warps, packed + unpacked output, the AACH side output"""
+    monkeypatch.setenv("TB200_LANE_FORM", str(form))
+    dev = T.B200()
+    try:
+        for kw, opts in ((dict(n=9000, random_cell=1, ber_per_65536=1500), dict(pipeline_slots=2048, output=T.OUT_UNPACKED | T.OUT_PACKED)),
+                         (dict(n=7000, sb_period=64, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=0), dict(pipeline_slots=0))):
+            bits, _ = _stream(orc, **kw)
+            slots, got = _check(dev, orc, bits, viterbi=T.VITERBI_LANE, **opts)
+            ref.reset(); ref.feed(bits, 64)
+            T.check_stream_against(ref.records(), ref.events(), slots, got)
+        s2, t2, p2, aach = dev.rx_stream_host_aach(bits)
+        assert np.array_equal(s2, slots) and ((aach[(s2["flags"] & 3) != 0] >> 25) == 0).all()
+    finally:
+        dev.close()
+
+
 def test_stream_config3_shape(gpu, orc):
     """mixed SB / NDB one- and two-channel bursts, lead-in, accidental training sequences left in"""
     bits, _ = _stream(orc, n=30000, random_cell=1)

@@ -133,6 +133,26 @@ def test_stream_other_tie_rule(emu, orc, variant):
         emu.set_options(viterbi_tie=T.TIE_LOW_PRED)
 
 
+@pytest.mark.parametrize("form", [0, 1, 2])
+def test_stream_lane_forms(orc, form, monkeypatch):
+    """the three forms of the lane decode pass (TB200_LANE_FORM: fused kernel, prepare | trellis+finish, prepare | trellis |
+    finish) give the oracle's records on a mixed stream with random cells, on uniform SCH/F warps, with the AACH side output
+    and with the other tie rule"""
+    monkeypatch.setenv("TB200_LANE_FORM", str(form))
+    dev = T.B200(emulate=True)
+    try:
+        bits, _ = _stream(orc, n=150, random_cell=1, ber_per_65536=1500)
+        _check(dev, orc, bits, viterbi=T.VITERBI_LANE, pipeline_slots=0)
+        _check(dev, orc, bits, viterbi=T.VITERBI_LANE, pipeline_slots=33, output=T.OUT_UNPACKED | T.OUT_PACKED)
+        bits, _ = _stream(orc, n=140, sb_period=0, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=5)
+        _check(dev, orc, bits, viterbi=T.VITERBI_LANE, pipeline_slots=0)
+        orc.set_tie(T.TIE_HIGH_PRED)
+        _check(dev, orc, bits, viterbi=T.VITERBI_LANE, pipeline_slots=0, viterbi_tie=T.TIE_HIGH_PRED)
+    finally:
+        orc.set_tie(T.TIE_LOW_PRED)
+        dev.close()
+
+
 def test_stream_uniform_schf(emu, orc):
     """only SCH/F bursts after the two leading SBs: whole warps of the lane kernel take the unmasked path"""
     bits, _ = _stream(orc, n=200, sb_period=0, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=5)
