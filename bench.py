@@ -755,7 +755,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--bursts", type=int, default=N_BURSTS, help="bursts of the headline stream (profiling runs use less)")
+    ap.add_argument("--bursts", type=lambda v: int(float(v)), default=N_BURSTS, help="bursts of the headline stream (profiling runs use less)")
     ap.add_argument("--e2e-steps", type=int, default=5, help="steps of the host-buffer leg when it runs at full size (1 s per step)")
     ap.add_argument("--config5-steps", type=int, default=5)
     ap.add_argument("--parity-windows", type=int, default=12)
