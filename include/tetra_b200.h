@@ -162,7 +162,10 @@ int  tb200_set_options(tb200_ctx *ctx, const struct tb200_options *opt);
  * be NULL), d_type1_packed (max_slots * TB200_TYPE1_WORDS words, may be NULL) are device
  * buffers owned by the caller.  Returns the number of slots written (>= 0) or TB200_E_*.
  * The call waits for the device on entry (the caller's buffers may still be in flight on other
- * streams) and all its device work is complete when it returns.  Needs TB200_FRESH | TB200_FINAL. */
+ * streams) and all its device work is complete when it returns.  A stream continues across calls like with
+ * tb200_rx_stream_host (flags = 0): the bits the receiver may still look at are kept on the device, a continuing call
+ * copies them and the first 32 Kbit of the new buffer into one piece, works through that and goes on in place in the
+ * caller's buffer.  Host and device calls may alternate inside a stream. */
 long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint32_t flags,
                          struct tb200_slot *d_slots, uint8_t *d_type1, uint32_t *d_type1_packed,
                          uint64_t max_slots);

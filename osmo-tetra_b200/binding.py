@@ -230,6 +230,14 @@ class B200:
             raise RuntimeError(f"tb200_rx_stream_host: {n}: {self.err()}")
         return slots[:n], type1[:n], packed[:n]
 
+    def rx_stream_dev_raw(self, buf_ptr, n_bits, flags, slots_ptr, type1_ptr, packed_ptr, max_slots):
+        """tb200_rx_stream_dev with raw addresses (device pointers; host addresses under the CPU emulation)"""
+        n = self.lib.tb200_rx_stream_dev(self.h, C.c_void_p(buf_ptr), n_bits, flags, C.c_void_p(slots_ptr),
+                                         C.c_void_p(type1_ptr) if type1_ptr else None, C.c_void_p(packed_ptr) if packed_ptr else None, max_slots)
+        if n < 0:
+            raise RuntimeError(f"tb200_rx_stream_dev: {n}: {self.err()}")
+        return n
+
     def expand_records(self, slots, type1):
         slots = np.ascontiguousarray(slots); type1 = np.ascontiguousarray(type1)
         n = self.lib.tb200_expand_records(_ptr(slots), _ptr(type1), slots.size, None, 0)

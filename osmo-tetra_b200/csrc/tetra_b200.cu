@@ -220,6 +220,11 @@ struct tb200_ctx {
 	/* stream state across calls */
 	RxHost rx;
 	std::vector<uint8_t> tail;       /* bits [tail_base, fed_end) kept from earlier calls (host path) */
+	uint8_t *d_tail = nullptr;       /* the same for a stream fed with device buffers; tail_dev says which of the two is current */
+	size_t d_tail_cap = 0, d_tail_bytes = 0;
+	bool tail_dev = false;
+	uint8_t *d_cont = nullptr;       /* device path: kept tail + head of the new buffer, contiguous */
+	size_t d_cont_cap = 0;
 	uint64_t tail_base = 0;
 	int tail_fmt = 0;                /* encoding of the tail = input format of the stream */
 	uint64_t fed_end = 0;            /* absolute bits handed to the ctx so far */
@@ -539,7 +544,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	}
 	cudaFree(ctx->d_flags); cudaFreeHost(ctx->h_flags); cudaFree(ctx->d_lane_scratch); cudaFree(ctx->d_sb1_scratch); cudaFree(ctx->d_units);
 	cudaFree(ctx->d_pstats); cudaFreeHost(ctx->h_pstats); cudaFree(ctx->d_rm_leader);
-	cudaFree(ctx->d_afc_sym); cudaFree(ctx->d_afc_bits); cudaFree(ctx->d_afc_f);
+	cudaFree(ctx->d_afc_sym); cudaFree(ctx->d_afc_bits); cudaFree(ctx->d_afc_f); cudaFree(ctx->d_tail); cudaFree(ctx->d_cont);
 	for (int i = 0; i < NBUF; i++) cudaFree(ctx->d_oaach[i]);
 	for (cudaEvent_t e : ctx->prof_ev) cudaEventDestroy(e);
 	for (int i = 0; i < 8; i++) cudaFree(ctx->leaf_mem[i]);
@@ -1378,6 +1383,7 @@ static void reset_stream(tb200_ctx *ctx)
 {
 	ctx->rx = RxHost();
 	ctx->tail.clear();
+	ctx->d_tail_bytes = 0; ctx->tail_dev = false;
 	ctx->tail_base = 0;
 	ctx->fed_end = 0;
 	ctx->hits.clear();
@@ -1400,49 +1406,125 @@ static int push_carry(tb200_ctx *ctx)
 	return 0;
 }
 
+/* bits of a device-resident stream a continuing call looks at first: what a receiver in any state can still have in its
+ * buffer (4096) plus a slot and the search's look-ahead, generously */
+#define DEV_CONT_HEAD_BITS (1u << 15)
+
+static int dev_reserve(tb200_ctx *ctx, uint8_t **p, size_t *cap, size_t need)
+{
+	if (need <= *cap) return 0;
+	CU(cudaDeviceSynchronize());
+	cudaFree(*p); *p = nullptr; *cap = 0;
+	CU(cudaMalloc((void **)p, need + 256));
+	*cap = need + 256;
+	return 0;
+}
+
 extern "C" long tb200_rx_stream_dev(tb200_ctx *ctx, const uint8_t *d_bits, uint64_t n_bits, uint32_t flags,
                                     tb200_slot *d_slots, uint8_t *d_type1, uint32_t *d_type1_packed, uint64_t max_slots)
 {
 	if (!ctx) return TB200_E_ARG;
-	if ((flags & (TB200_FRESH | TB200_FINAL)) != (TB200_FRESH | TB200_FINAL))
-		return fail(ctx, TB200_E_ARG, "the device-resident call needs TB200_FRESH | TB200_FINAL");
-	if (!d_bits || !d_slots) return fail(ctx, TB200_E_ARG, "null buffer");
+	if ((!d_bits && n_bits) || !d_slots) return fail(ctx, TB200_E_ARG, "null buffer");
 	if (d_type1 && ((uintptr_t)d_type1 & 15)) return fail(ctx, TB200_E_ARG, "d_type1 must be 16-byte aligned");
 	if (ctx->opt.input != TB200_IN_BYTES && ((uintptr_t)d_bits & 3))
 		return fail(ctx, TB200_E_ARG, "packed / symbol input must be 4-byte aligned");
+	const bool fresh = (flags & TB200_FRESH) != 0, fin = (flags & TB200_FINAL) != 0;
+	if (ctx->opt.input != TB200_IN_BYTES && !fin && (n_bits & 127))
+		return fail(ctx, TB200_E_ARG, "a bit-packed / symbol stream continues on 128-bit boundaries: n_bits of every call but the last must be a multiple of 128");
+	const bool afc = ctx->opt.input == TB200_IN_F32SYM && ctx->opt.afc;
+	const int eff_fmt = afc ? IN_PACKED : (int)ctx->opt.input;          /* how the chain sees this call's bits */
+	if (!fresh && ctx->tail_fmt != eff_fmt && ctx->fed_end)
+		return fail(ctx, TB200_E_ARG, "the input format cannot change inside a stream");
 	HostTrace trace;
 	g_trace = trace.on ? &trace : nullptr;
 	if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TB200_E_CUDA, "cudaSetDevice");
 	CU(cudaDeviceSynchronize());        /* the caller's buffers may still be in flight on its own streams */
 	TB_TRACE("entry sync");
-	reset_stream(ctx);
+	if (fresh) { reset_stream(ctx); ctx->afc_state = 0.f; }
 	int rc = push_carry(ctx);
 	if (rc) return rc;
 	TB_TRACE("carry pushed");
-	Source src; src.on_device = true; src.data = d_bits; src.new_base = 0; src.end = n_bits; src.fmt = (int)ctx->opt.input;
-	if (ctx->opt.input == TB200_IN_F32SYM && ctx->opt.afc) {
-		/* float_to_bits -a first (the tracker is a recurrence over the whole stream), then the chain on packed bits */
+	ctx->stats.kernel_launches = 0;          /* "by the last call" */
+	const uint8_t *data = d_bits;
+	if (afc && n_bits) {
+		/* float_to_bits -a first (the tracker is a recurrence over the whole stream, its state carries over between calls),
+		 * then the chain on packed bits */
 		const size_t need = 4 * (size_t)((n_bits / 2 + 15) / 16) + 256;
 		if (need > ctx->afc_bits_cap) {
 			cudaFree(ctx->d_afc_bits); ctx->d_afc_bits = nullptr; ctx->afc_bits_cap = 0;
 			CU(cudaMalloc((void **)&ctx->d_afc_bits, need));
 			ctx->afc_bits_cap = need;
 		}
-		ctx->afc_state = 0.f;
 		if ((rc = float_to_bits_dev(ctx, reinterpret_cast<const float *>(d_bits), n_bits / 2, 1, ctx->opt.afc_filter_val,
 		                            ctx->opt.afc_filter_goal, &ctx->afc_state, reinterpret_cast<uint32_t *>(ctx->d_afc_bits)))) return rc;
-		src.data = ctx->d_afc_bits; src.fmt = IN_PACKED;
+		data = ctx->d_afc_bits;
 	}
 	Outputs out; out.on_device = true; out.slots = d_slots; out.type1 = d_type1; out.packed = d_type1_packed;
 	out.crc = ctx->user_crc; out.aach = ctx->user_aach; out.max_slots = max_slots; out.n = 0;
 	ctx->lock_events.clear();
-	ctx->fed_end = n_bits;
+	const uint64_t base = ctx->fed_end;             /* stream bit of the caller's bit 0 */
+	ctx->fed_end += n_bits;
+	if (base == 0 || ctx->tail_base > base) ctx->tail_base = base;
+	const uint64_t tail_bits = base - ctx->tail_base;
 	profile_begin(ctx);
-	rc = rx_run(ctx, src, true, out);
+	bool whole_staged = false;
+	if (tail_bits == 0) {
+		Source src; src.on_device = true; src.data = data; src.new_base = base; src.end = ctx->fed_end; src.fmt = eff_fmt;
+		rc = rx_run(ctx, src, fin, out);
+	} else {
+		/* a continuing call.  The receiver may still look at bits of earlier calls (its buffer, a slot that straddles
+		 * the calls): those were kept, they go in front of the head of the new buffer into one contiguous piece, and a first
+		 * run works on that.  After DEV_CONT_HEAD_BITS the receiver's buffer lies inside the caller's memory and a second
+		 * run of the same modelled calls goes on in place - nothing else of the new buffer is copied. */
+		const size_t tb = fmt_bytes(eff_fmt, tail_bits);
+		if (!ctx->tail_dev) {                       /* the stream came through host buffers so far */
+			if ((rc = dev_reserve(ctx, &ctx->d_tail, &ctx->d_tail_cap, tb))) return rc;
+			CU(cudaMemcpy(ctx->d_tail, ctx->tail.data(), tb, cudaMemcpyHostToDevice));
+			ctx->d_tail_bytes = tb; ctx->tail_dev = true;
+		}
+		/* (whole modelled reads only count for a run that is not the stream's last: a few of them must fit the head) */
+		const uint64_t head = std::min<uint64_t>(n_bits, (std::max<uint64_t>(DEV_CONT_HEAD_BITS, 4ull * ctx->opt.chunk_bits + 8192) + 127) & ~127ull);
+		whole_staged = head == n_bits;
+		const size_t hb = fmt_bytes(eff_fmt, head);
+		if ((rc = dev_reserve(ctx, &ctx->d_cont, &ctx->d_cont_cap, tb + hb + 64))) return rc;
+		CU(cudaMemcpyAsync(ctx->d_cont, ctx->d_tail, tb, cudaMemcpyDeviceToDevice, ctx->s_compute));
+		if (hb) CU(cudaMemcpyAsync(ctx->d_cont + tb, data, hb, cudaMemcpyDeviceToDevice, ctx->s_compute));
+		CU(cudaMemsetAsync(ctx->d_cont + tb + hb, 0, 64, ctx->s_compute));
+		CU(cudaStreamSynchronize(ctx->s_compute));
+		Source s1; s1.on_device = true; s1.data = ctx->d_cont; s1.new_base = ctx->tail_base; s1.end = base + head; s1.fmt = eff_fmt;
+		rc = rx_run(ctx, s1, fin && whole_staged, out);
+		if (!rc && !whole_staged) {
+			if (ctx->rx.buf_start < base)
+				return fail(ctx, TB200_E_STATE, "device continuation: the receiver still needs bits of the previous call");
+			Source s2; s2.on_device = true; s2.data = data; s2.new_base = base; s2.end = ctx->fed_end; s2.fmt = eff_fmt;
+			rc = rx_run(ctx, s2, fin, out, true);
+		}
+	}
 	TB_TRACE("rx_run done");
 	g_trace = nullptr;
 	if (rc) return rc;
 	if ((rc = profile_end(ctx))) return rc;
+	/* keep what a later call may still look at: everything from bitbuf[0] on (whole 128-bit units of the packed formats) */
+	if (!fin) {
+		uint64_t keep_from = std::min<uint64_t>(ctx->rx.buf_start, ctx->fed_end);
+		if (eff_fmt != IN_BYTES) keep_from &= ~(uint64_t)127;
+		if (keep_from < ctx->tail_base) keep_from = ctx->tail_base;
+		const size_t kb = fmt_bytes(eff_fmt, ctx->fed_end - keep_from);
+		const uint8_t *from;
+		if (keep_from >= base) from = data + fmt_bytes(eff_fmt, keep_from - base);
+		else if (whole_staged) from = ctx->d_cont + fmt_bytes(eff_fmt, keep_from - ctx->tail_base);
+		else return fail(ctx, TB200_E_STATE, "device continuation: tail outside the staged head");
+		/* d_cont / the caller's buffer -> d_tail (never d_tail -> d_tail: the old tail was copied into d_cont) */
+		if ((rc = dev_reserve(ctx, &ctx->d_tail, &ctx->d_tail_cap, kb))) return rc;
+		CU(cudaMemcpyAsync(ctx->d_tail, from, kb, cudaMemcpyDeviceToDevice, ctx->s_compute));
+		CU(cudaStreamSynchronize(ctx->s_compute));
+		ctx->d_tail_bytes = kb; ctx->tail_dev = true;
+		ctx->tail.clear();
+		ctx->tail_base = keep_from;
+	} else {
+		ctx->d_tail_bytes = 0; ctx->tail.clear(); ctx->tail_base = ctx->fed_end;
+	}
+	ctx->tail_fmt = eff_fmt;
 	return (long)out.n;
 }
 
@@ -1459,6 +1541,11 @@ extern "C" long tb200_rx_stream_host(tb200_ctx *ctx, const uint8_t *bits, uint64
 	const int eff_fmt = afc ? IN_PACKED : (int)ctx->opt.input;          /* how the chain sees this call's bits */
 	if (!(flags & TB200_FRESH) && ctx->tail_fmt != eff_fmt && ctx->fed_end)
 		return fail(ctx, TB200_E_ARG, "the input format cannot change inside a stream");
+	if (ctx->tail_dev) {                     /* the stream came through device buffers so far: its kept tail moves to the host */
+		ctx->tail.resize(ctx->d_tail_bytes);
+		if (ctx->d_tail_bytes) CU(cudaMemcpy(ctx->tail.data(), ctx->d_tail, ctx->d_tail_bytes, cudaMemcpyDeviceToHost));
+		ctx->tail_dev = false; ctx->d_tail_bytes = 0;
+	}
 	if (afc && n_bits) {
 		/* float_to_bits -a over this call's symbols, from the tracker state the last call left: symbols up, packed bits back */
 		const uint64_t n_sym = n_bits / 2;

@@ -106,6 +106,71 @@ def test_lane_forms_gpu(orc, ref, form, monkeypatch):
         dev.close()
 
 
+@pytest.mark.parametrize("fmt", ["bytes", "packed"])
+def test_dev_continuation_gpu(gpu, orc, fmt):
+    """a device-resident stream fed in pieces (tb200_rx_stream_dev, flags = 0 in between) decodes like the same stream in one
+    call and like the oracle: pieces of millions of bits (several pipeline pieces each, worked on in place behind the staged
+    head), pieces shorter than the receiver's buffer, a lock loss, a host call in the middle"""
+    import torch
+    rng = np.random.default_rng(5)
+    cfg = T.GenCfg(seed=0x7E7A0044, sb_period=6, lead_sb=2, ndb2_per_256=40, ber_per_65536=800, random_cell=1, lead_in_bits=333)
+    n = 60000
+    d, nbits = _gen_on_gpu(gpu, cfg, n, lead_in=True)
+    bits = d[:nbits].cpu().numpy().copy()
+    a = 333 + 510 * 30000
+    bits[a + 244:a + 244 + 22] ^= 1                       # one normal training sequence wiped: lock lost, found again
+    q = 1
+    if fmt == "packed":
+        q = 128
+        buf = np.packbits(np.concatenate([bits, np.zeros((-nbits) % 128 + 128, np.uint8)]), bitorder="little")
+        per_bit = lambda x: x // 8
+        gpu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=8192, output=T.OUT_UNPACKED | T.OUT_PACKED, input=T.IN_PACKED)
+    else:
+        buf = bits
+        per_bit = lambda x: x
+        gpu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=8192, output=T.OUT_UNPACKED | T.OUT_PACKED, input=T.IN_BYTES)
+    try:
+        dbuf = torch.from_numpy(buf).cuda()
+        ms = n + 16
+        def run(cuts, host_piece=None):
+            ds = torch.zeros(ms * 16, dtype=torch.uint8, device="cuda")
+            dt = torch.zeros(ms * 288, dtype=torch.uint8, device="cuda")
+            dp = torch.zeros(ms * 9, dtype=torch.int32, device="cuda")
+            edges = [0] + cuts + [nbits]
+            got = 0
+            for i in range(len(edges) - 1):
+                lo, hi = edges[i], edges[i + 1]
+                flags = (1 if i == 0 else 0) | (2 if i == len(edges) - 2 else 0)
+                if host_piece == i:
+                    sh, th, ph = gpu.rx_stream_host_raw(buf[per_bit(lo):], hi - lo, flags)
+                    k = sh.size
+                    ds[got * 16:(got + k) * 16] = torch.from_numpy(sh.view(np.uint8).copy()).cuda()
+                    dt[got * 288:(got + k) * 288] = torch.from_numpy(th.reshape(-1).copy()).cuda()
+                    dp[got * 9:(got + k) * 9] = torch.from_numpy(ph.view(np.int32).reshape(-1).copy()).cuda()
+                else:
+                    k = gpu.rx_stream_dev_raw(dbuf.data_ptr() + per_bit(lo), hi - lo, flags, ds.data_ptr() + got * 16,
+                                              dt.data_ptr() + got * 288, dp.data_ptr() + got * 36, ms - got)
+                got += k
+            return (ds[:got * 16].cpu().numpy().view(T.SLOT_DTYPE), dt[:got * 288].cpu().numpy().reshape(got, 288),
+                    dp[:got * 9].cpu().numpy().view(np.uint32).reshape(got, 9))
+        s0, t0, p0 = run([])
+        assert gpu.stats().lock_losses == 1
+        orc.reset(); orc.feed(bits, 64)
+        T.check_stream_against(orc.records(), orc.events(), s0, gpu.expand_records(s0, t0))
+        for trial in range(4):
+            cuts = sorted(set(int(c) // q * q for c in rng.integers(1, nbits, size=[1, 3, 6, 6][trial])))
+            if trial == 2:
+                base = (nbits // 3) // q * q
+                cuts = sorted(set(cuts + [base, base + 1024 // q * q + q, base + 6 * 1024 // q * q]))
+            cuts = [c for c in cuts if 0 < c < nbits]
+            s1, t1, p1 = run(cuts, host_piece=1 if trial == 3 else None)
+            assert np.array_equal(s1, s0) and np.array_equal(t1, t0) and np.array_equal(p1, p0), (trial, cuts)
+            c = gpu.carry()
+            assert c.state == orc.rx_state() and c.scramb_init == orc.scramb_init()
+    finally:
+        gpu.set_options(input=T.IN_BYTES, pipeline_slots=0)
+
+
 def test_stream_config3_shape(gpu, orc):
     """mixed SB / NDB one- and two-channel bursts, lead-in, accidental training sequences left in"""
     bits, _ = _stream(orc, n=30000, random_cell=1)

@@ -153,6 +153,64 @@ def test_stream_lane_forms(orc, form, monkeypatch):
         dev.close()
 
 
+def _dev_pieces(dev, buf, n_bits, cuts, unit_bits, host_first=False):
+    """feed buf (numpy bytes: the stream in the format options.input names, unit_bits stream bits per byte) through
+    tb200_rx_stream_dev in pieces cut at the given bit positions (emulation: host addresses are "device" pointers)"""
+    ms = n_bits // 510 + 16
+    slots = np.zeros(ms, dtype=T.SLOT_DTYPE); t1 = np.zeros((ms, 288), dtype=np.uint8); pk = np.zeros((ms, 9), dtype=np.uint32)
+    got = 0
+    edges = [0] + list(cuts) + [n_bits]
+    for i in range(len(edges) - 1):
+        a, b = edges[i], edges[i + 1]
+        flags = (1 if i == 0 else 0) | (2 if i == len(edges) - 2 else 0)
+        # byte offset of stream bit a: bytes format 1 B per bit, packed 1 B per 8 bits, symbols 4 B per 2 bits
+        boff = {1: a, 8: a // 8, 2: 2 * a}[unit_bits]
+        piece = buf.view(np.uint8)[boff:]
+        if host_first and i == 0:
+            s, t, p = dev.rx_stream_host_raw(piece, b - a, flags)
+            n = s.size; slots[got:got + n] = s; t1[got:got + n] = t; pk[got:got + n] = p
+        else:
+            piece = np.ascontiguousarray(piece)
+            n = dev.rx_stream_dev_raw(piece.ctypes.data, b - a, flags, slots[got:].ctypes.data, t1[got:].ctypes.data, pk[got:].ctypes.data, ms - got)
+        got += n
+    return slots[:got], t1[:got], pk[:got]
+
+
+@pytest.mark.parametrize("fmt", ["bytes", "packed"])
+def test_stream_dev_continuation(emu, orc, fmt):
+    """tb200_rx_stream_dev continues a stream across calls (flags = 0) like tb200_rx_stream_host: pieces shorter than the
+    receiver's buffer, pieces longer than the staged head, a lock loss, a host call followed by device calls"""
+    rng = np.random.default_rng(77)
+    bits, _ = _stream(orc, n=260, random_cell=1, ber_per_65536=900)
+    bits = bits.copy()
+    bits[510 * 120 + 333 + 200:510 * 120 + 333 + 300] ^= 1               # a wiped training sequence: lock loss inside a piece
+    n = bits.size
+    orc.reset(); orc.feed(bits, 64)
+    want, ev = orc.records(), orc.events()
+    if fmt == "packed":
+        buf = np.packbits(np.concatenate([bits, np.zeros((-n) % 128, np.uint8)]), bitorder="little")
+        emu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, input=T.IN_PACKED)
+        q, unit = 128, 8
+    else:
+        buf = bits
+        emu.set_options(chunk_bits=64, viterbi=T.VITERBI_LANE, pipeline_slots=0, input=T.IN_BYTES)
+        q, unit = 1, 1
+    try:
+        for host_first in (False, True):
+            for trial in range(3):
+                k = [2, 5, 9][trial]
+                cuts = sorted(set(int(c) // q * q for c in rng.integers(1, n, size=k)))
+                if trial == 0:
+                    cuts = sorted(set(cuts + [40000 // q * q, (40000 + 1024) // q * q, (40000 + 3072) // q * q]))   # short pieces
+                cuts = [c for c in cuts if 0 < c < n]
+                slots, t1, pk = _dev_pieces(emu, buf, n, cuts, unit, host_first)
+                T.check_stream_against(want, ev, slots, emu.expand_records(slots, t1))
+                c = emu.carry()
+                assert c.state == orc.rx_state() and c.scramb_init == orc.scramb_init()
+    finally:
+        emu.set_options(input=T.IN_BYTES)
+
+
 def test_stream_uniform_schf(emu, orc):
     """only SCH/F bursts after the two leading SBs: whole warps of the lane kernel take the unmasked path"""
     bits, _ = _stream(orc, n=200, sb_period=0, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=5)
