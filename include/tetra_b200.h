@@ -136,6 +136,12 @@ struct tb200_options {
 	uint32_t viterbi_tie;       /* survivor on equal path metrics (tetra_tie_rule.h): 0 = predecessor s>>1 (libosmocore's
 	                             * osmo_conv_decode as restated, viterbi_cch.c:58-66), 1 = predecessor (s>>1)|8.  The default is
 	                             * TETRA_VITERBI_TIE_DEFAULT, the compile-time switch the CPU oracle shares */
+	uint32_t host_pack_threads; /* tb200_rx_stream_host with TB200_IN_BYTES input: 0 (default) = the caller's bytes cross PCIe as they are
+	                             * (510 bytes per burst); n > 0 = n host threads of the library pack them to eight bits per byte first
+	                             * (into pinned staging, piece by piece, under the GPU's work on the previous piece), so that 64 bytes per
+	                             * burst cross the bus.  Pays when the host has cores and memory bandwidth to spare: ~8 threads match
+	                             * PCIe 5 x16, 16 threads on one socket pack ~120 GB/s (tools/microbench/host_pack.c).  Results are
+	                             * identical either way */
 };
 void tb200_default_options(struct tb200_options *opt);
 int  tb200_set_options(tb200_ctx *ctx, const struct tb200_options *opt);

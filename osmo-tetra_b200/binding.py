@@ -53,7 +53,7 @@ class Options(C.Structure):
     _fields_ = [("chunk_bits", C.c_uint32), ("output", C.c_uint32), ("viterbi", C.c_uint32),
                 ("pipeline_slots", C.c_uint32), ("profile", C.c_uint32), ("input", C.c_uint32),
                 ("serial_passes", C.c_uint32), ("afc", C.c_uint32), ("afc_filter_val", C.c_float), ("afc_filter_goal", C.c_float),
-                ("viterbi_tie", C.c_uint32)]
+                ("viterbi_tie", C.c_uint32), ("host_pack_threads", C.c_uint32)]
 
 
 class Timing(C.Structure):

@@ -24,6 +24,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 
 using namespace tb;
 
@@ -159,6 +162,88 @@ struct RxHost {
 
 struct SyncHit { uint64_t pos; uint32_t prev; };
 
+/* ---- host threads that pack the caller's one-bit-per-byte stream before it crosses PCIe (options.host_pack_threads) ----
+ * Eight 0/1 bytes -> one byte with a 64-bit multiply (byte i lands on bit 56 + i, no two partial products share a bit):
+ * stream bit i = byte i >> 3, bit i & 7, the layout of TB200_IN_PACKED.  A persistent pool; the calling thread hands out one
+ * job (a range of bytes) at a time and waits for it, the GPU works on the previous piece meanwhile. */
+static inline uint8_t pack8_bytes(const uint8_t *p)
+{
+	uint64_t x;
+	memcpy(&x, p, 8);
+	return (uint8_t)(((x & 0x0101010101010101ull) * 0x0102040810204080ull) >> 56);
+}
+static void pack_range(const uint8_t *src, size_t n_bits, uint8_t *dst)        /* n_bits bytes -> (n_bits + 7) / 8 bytes */
+{
+	const size_t full = n_bits >> 3;
+	for (size_t i = 0; i < full; i++) dst[i] = pack8_bytes(src + 8 * i);
+	if (n_bits & 7) {
+		uint8_t tmp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		memcpy(tmp, src + 8 * full, n_bits & 7);
+		dst[full] = pack8_bytes(tmp);
+	}
+}
+struct PackPool {
+	std::vector<std::thread> th;
+	std::mutex m;
+	std::condition_variable cv_go, cv_done;
+	uint64_t gen = 0;
+	unsigned pending = 0;
+	bool quit = false;
+	const uint8_t *src = nullptr; uint8_t *dst = nullptr; size_t n_bits = 0;
+	void worker(unsigned id)
+	{
+		uint64_t seen = 0;
+		for (;;) {
+			const uint8_t *s; uint8_t *d; size_t nb; unsigned nth;
+			{
+				std::unique_lock<std::mutex> lk(m);
+				cv_go.wait(lk, [&] { return quit || gen != seen; });
+				if (quit) return;
+				seen = gen; s = src; d = dst; nb = n_bits; nth = (unsigned)th.size();
+			}
+			/* slices of whole 64-byte output lines */
+			const size_t out_bytes = (nb + 7) >> 3, per = ((out_bytes + nth - 1) / nth + 63) & ~(size_t)63;
+			const size_t o0 = std::min(out_bytes, (size_t)id * per), o1 = std::min(out_bytes, o0 + per);
+			if (o1 > o0) pack_range(s + 8 * o0, std::min(nb, 8 * o1) - 8 * o0, d + o0);
+			{
+				std::lock_guard<std::mutex> lk(m);
+				if (--pending == 0) cv_done.notify_one();
+			}
+		}
+	}
+	void resize(unsigned n)
+	{
+		if (n == th.size()) return;
+		stop();
+		quit = false;
+		for (unsigned i = 0; i < n; i++) th.emplace_back([this, i] { worker(i); });
+	}
+	/* start a job and come back; wait() returns when it is done.  One job at a time. */
+	void start(const uint8_t *s, size_t nb, uint8_t *d)
+	{
+		if (th.empty()) { pack_range(s, nb, d); return; }
+		std::lock_guard<std::mutex> lk(m);
+		src = s; dst = d; n_bits = nb; pending = (unsigned)th.size(); ++gen;
+		cv_go.notify_all();
+	}
+	void wait()
+	{
+		if (th.empty()) return;
+		std::unique_lock<std::mutex> lk(m);
+		cv_done.wait(lk, [&] { return pending == 0; });
+	}
+	void run(const uint8_t *s, size_t nb, uint8_t *d) { start(s, nb, d); wait(); }
+	void stop()
+	{
+		{ std::lock_guard<std::mutex> lk(m); quit = true; }
+		cv_go.notify_all();
+		for (auto &t : th) t.join();
+		th.clear();
+	}
+	~PackPool() { stop(); }
+};
+
+
 struct tb200_ctx {
 	int device = 0;
 	int sm_count = 148;
@@ -198,6 +283,11 @@ struct tb200_ctx {
 	/* host path staging */
 	uint8_t *d_in[NBUF] = {nullptr, nullptr, nullptr};
 	size_t in_cap = 0;
+	uint8_t *h_pack[NBUF] = {nullptr, nullptr, nullptr};   /* pinned: a piece of the caller's bytes, packed by the host threads */
+	size_t h_pack_cap = 0;
+	PackPool pack_pool;
+	long pack_inflight = -1;         /* piece whose bytes the pool is packing (or has packed) ahead of its issue */
+	uint64_t pack_inflight_base = 0, pack_inflight_hi = 0;
 	SlotOut *d_oslots[NBUF] = {nullptr, nullptr, nullptr};
 	uint8_t *d_otype1[NBUF] = {nullptr, nullptr, nullptr};
 	uint32_t *d_opacked[NBUF] = {nullptr, nullptr, nullptr};
@@ -302,6 +392,7 @@ extern "C" void tb200_default_options(tb200_options *o)
 	o->serial_passes = getenv("TB200_SERIAL") ? 1 : 0;
 	o->afc = 0; o->afc_filter_val = 0.0001f; o->afc_filter_goal = 0.f;      /* float_to_bits.c:83-86 */
 	o->viterbi_tie = TETRA_VITERBI_TIE_DEFAULT;
+	o->host_pack_threads = 0;
 }
 
 extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
@@ -315,6 +406,8 @@ extern "C" int tb200_set_options(tb200_ctx *ctx, const tb200_options *o)
 		return fail(ctx, TB200_E_ARG, "unknown input format");
 	if (o->viterbi_tie > 1)
 		return fail(ctx, TB200_E_ARG, "viterbi_tie must be 0 or 1");
+	if (o->host_pack_threads > 256)
+		return fail(ctx, TB200_E_ARG, "host_pack_threads must be 0..256");
 	if (o->afc > 1 || (o->afc && (!(o->afc_filter_val > 0.f) || !(o->afc_filter_val <= 1.f))))
 		return fail(ctx, TB200_E_ARG, "afc must be 0 or 1 with afc_filter_val in (0, 1]");
 	if (o->input != TB200_IN_BYTES && o->viterbi != TB200_VITERBI_LANE)
@@ -550,7 +643,7 @@ extern "C" void tb200_destroy(tb200_ctx *ctx)
 	for (int i = 0; i < 8; i++) cudaFree(ctx->leaf_mem[i]);
 	for (int i = 0; i < 2; i++) if (ctx->leaf_ev[i]) cudaEventDestroy(ctx->leaf_ev[i]);
 	for (int i = 0; i < NBUF; i++) {
-		cudaFree(ctx->d_in[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]); cudaFree(ctx->d_ocrc[i]);
+		cudaFree(ctx->d_in[i]); cudaFreeHost(ctx->h_pack[i]); cudaFree(ctx->d_oslots[i]); cudaFree(ctx->d_otype1[i]); cudaFree(ctx->d_opacked[i]); cudaFree(ctx->d_ocrc[i]);
 		cudaEventDestroy(ctx->ev_h2d[i]); cudaEventDestroy(ctx->ev_comp[i]); cudaEventDestroy(ctx->ev_d2h[i]);
 	}
 	cudaFree(ctx->d_hits); cudaFreeHost(ctx->h_hits); cudaFreeHost(ctx->h_carry_pin); cudaFree(ctx->d_region);
@@ -1122,6 +1215,25 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 	/* bits a piece may touch: its slots plus the largest search window (<= 4096) */
 	const size_t piece_in = fmt_bytes(src.fmt, (uint64_t)P * SLOT_BITS + 4096 + 64 + 128) + 64;
 	if (!src.on_device && (rc = ensure_staging(ctx, piece_in, P))) return rc;
+	const bool host_pack = !src.on_device && src.fmt == IN_BYTES && ctx->opt.host_pack_threads > 0;
+	if (host_pack) {
+		const size_t need = ((size_t)P * SLOT_BITS + 4096 + 64 + 256) / 8 + 64;
+		if (need > ctx->h_pack_cap) {
+			CU(cudaDeviceSynchronize());
+			for (int i = 0; i < NBUF; i++) {
+				if (ctx->h_pack[i]) cudaFreeHost(ctx->h_pack[i]);
+				ctx->h_pack[i] = nullptr;
+				CU(cudaHostAlloc((void **)&ctx->h_pack[i], need, cudaHostAllocDefault));
+			}
+			ctx->h_pack_cap = need;
+		}
+		ctx->pack_pool.resize(ctx->opt.host_pack_threads > 1 ? ctx->opt.host_pack_threads : 0);      /* 1: the calling thread packs */
+		if (ctx->pack_inflight >= 0) { ctx->pack_pool.wait(); ctx->pack_inflight = -1; }
+	}
+	/* every TB200_HOST_PACK_EVERY-th piece goes through the host threads, the others cross the bus as bytes (both roads busy) */
+	unsigned pack_every = 1;
+	if (const char *e = getenv("TB200_HOST_PACK_EVERY")) { const int v = atoi(e); if (v >= 1 && v <= 64) pack_every = (unsigned)v; }
+	auto pack_this = [&](size_t i) { return (i % pack_every) == 0; };
 	const bool host_out = !out.on_device;
 	if (src.on_device && host_out)
 		return fail(ctx, TB200_E_ARG, "device input with host output is not supported");
@@ -1138,12 +1250,30 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		const uint64_t lo = seg.a0 + (uint64_t)SLOT_BITS * k0;
 		const uint64_t hi = std::min<uint64_t>(seg.cg.n_end, lo + (uint64_t)SLOT_BITS * nb + 4096);
 		const uint8_t *dbits; uint64_t dbase, davail;
+		int piece_fmt = src.fmt;
 		if (src.on_device) {
 			dbits = src.data; dbase = src.new_base; davail = std::min<uint64_t>(seg.cg.n_end, src.end) - src.new_base;
 			if (src.ready) {
 				for (const auto &rv : *src.ready)
 					if (rv.first >= hi || &rv == &src.ready->back()) { CU(cudaStreamWaitEvent(ctx->s_front, rv.second, 0)); break; }
 			}
+		} else if (host_pack && pack_this(i) && (lo & ~(uint64_t)127) >= src.new_base) {
+			/* the piece lies in this call's buffer: the host threads pack it (from a 128-bit boundary of the stream on, as
+			 * the packed format is staged), 8x fewer bytes cross the bus, the search kernel takes it as TB200_IN_PACKED.
+			 * h_pack[b] is free: the piece that used it last has been copied back (ev_d2h, waited for by the caller's loop) */
+			dbase = lo & ~(uint64_t)127;
+			const size_t nbits_p = (size_t)(hi - dbase);
+			if (ctx->pack_inflight == (long)i && ctx->pack_inflight_base == dbase && ctx->pack_inflight_hi == hi) {
+				ctx->pack_pool.wait();                   /* started when the previous piece was issued */
+			} else {
+				if (ctx->pack_inflight >= 0) ctx->pack_pool.wait();
+				ctx->pack_pool.run(src.data + (dbase - src.new_base), nbits_p, ctx->h_pack[b]);
+			}
+			ctx->pack_inflight = -1;
+			CU(cudaMemcpyAsync(ctx->d_in[b], ctx->h_pack[b], ((nbits_p + 7) >> 3), cudaMemcpyHostToDevice, ctx->s_h2d));
+			CU(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+			CU(cudaStreamWaitEvent(ctx->s_front, ctx->ev_h2d[b], 0));
+			dbits = ctx->d_in[b]; davail = hi - dbase; piece_fmt = IN_PACKED;
 		} else {
 			int r = stage_bits(ctx, src, lo, hi, ctx->d_in[b], ctx->s_h2d, &dbase);
 			if (r) return r;
@@ -1158,7 +1288,7 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 			os = ctx->d_oslots[b]; ot = ctx->d_otype1[b]; op = ctx->d_opacked[b]; ob = 0; oc = out.crc ? ctx->d_ocrc[b] : nullptr;
 			oa = out.aach ? ctx->d_oaach[b] : nullptr;
 		}
-		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, src.fmt, i, os, ot, op, ob, oc, src.skip_dependent, oa);
+		int r = enqueue_piece(ctx, seg, k0, nb, dbits, dbase, davail, piece_fmt, i, os, ot, op, ob, oc, src.skip_dependent, oa);
 		if (r) return r;
 		CU(cudaEventRecord(ctx->ev_comp[b], ctx->s_compute));
 		cudaStream_t so = host_out ? ctx->s_d2h : ctx->s_compute;
@@ -1178,6 +1308,19 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 		CU(cudaMemcpyAsync(ctx->h_flags + 2 * i, ctx->d_flags + 2 * i, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, so));
 		CU(cudaMemcpyAsync(ctx->h_pstats + 3 * i, ctx->d_pstats + 3 * i, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, so));
 		CU(cudaEventRecord(ctx->ev_d2h[b], so));
+		/* the next piece's bytes are packed while this one is copied and decoded (its staging buffer is free: the piece that
+		 * used it last, i + 1 - NBUF, was waited for before this one was issued) */
+		if (host_pack && !nb_override && i + 1 < npieces && pack_this(i + 1)) {
+			uint64_t k1; uint32_t nb1;
+			piece_range(i + 1, &k1, &nb1);
+			const uint64_t lo1 = seg.a0 + (uint64_t)SLOT_BITS * k1;
+			const uint64_t hi1 = std::min<uint64_t>(seg.cg.n_end, lo1 + (uint64_t)SLOT_BITS * nb1 + 4096);
+			const uint64_t base1 = lo1 & ~(uint64_t)127;
+			if (base1 >= src.new_base) {
+				ctx->pack_pool.start(src.data + (base1 - src.new_base), (size_t)(hi1 - base1), ctx->h_pack[(i + 1) % NBUF]);
+				ctx->pack_inflight = (long)(i + 1); ctx->pack_inflight_base = base1; ctx->pack_inflight_hi = hi1;
+			}
+		}
 		return 0;
 	};
 

@@ -18,6 +18,15 @@
 #include <cstring>
 #include <functional>
 #include <vector>
+/* standard headers the host code uses: before the CUDA keywords below become macros (libstdc++ spells attributes like
+ * __noinline__ itself) */
+#include <algorithm>
+#include <chrono>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstddef>
+#include <mutex>
+#include <thread>
 
 #define TB_SIMT_EMULATION 1
 

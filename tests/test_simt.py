@@ -211,6 +211,26 @@ def test_stream_dev_continuation(emu, orc, fmt):
         emu.set_options(input=T.IN_BYTES)
 
 
+@pytest.mark.parametrize("threads", [1, 3])
+def test_stream_host_pack_threads(emu, orc, threads):
+    """options.host_pack_threads: the library's host threads pack the caller's bytes before the copy; same records, same
+    search log, also piece by piece across calls (the piece that holds the kept tail goes the unpacked way)"""
+    bits, _ = _stream(orc, n=180, random_cell=1, ber_per_65536=1200)
+    try:
+        _check(emu, orc, bits, viterbi=T.VITERBI_LANE, pipeline_slots=0, host_pack_threads=threads)
+        _check(emu, orc, bits, viterbi=T.VITERBI_LANE, pipeline_slots=37, host_pack_threads=threads)
+        _check(emu, orc, bits, chunk=23, viterbi=T.VITERBI_LANE, pipeline_slots=16, host_pack_threads=threads)
+        # continuation: three calls
+        orc.reset(); orc.feed(bits, 64)
+        emu.set_options(chunk_bits=64, pipeline_slots=16, host_pack_threads=threads)
+        cuts = [0, 30001, 30001 + 2000, bits.size]
+        parts = [emu.rx_stream_host(bits[cuts[i]:cuts[i + 1]], flags=(1 if i == 0 else 0) | (2 if i == 2 else 0)) for i in range(3)]
+        slots = np.concatenate([p[0] for p in parts]); t1 = np.concatenate([p[1] for p in parts])
+        T.check_stream_against(orc.records(), orc.events(), slots, emu.expand_records(slots, t1))
+    finally:
+        emu.set_options(host_pack_threads=0, pipeline_slots=0, chunk_bits=64)
+
+
 def test_stream_uniform_schf(emu, orc):
     """only SCH/F bursts after the two leading SBs: whole warps of the lane kernel take the unmasked path"""
     bits, _ = _stream(orc, n=200, sb_period=0, ndb2_per_256=0, ber_per_65536=1300, lead_in_bits=5)
