@@ -1108,7 +1108,7 @@ static int enqueue_pass2(tb200_ctx *ctx, uint64_t a0, uint32_t nb, size_t piece_
 		/* split form: the unit count is only known on the device (kind_count), so the grids are sized for the worst case
 		 * (every slot a unit of its own) and capped at what is resident */
 		const uint64_t wmax = lane_unit_blocks(nb);
-		const unsigned pblocks = (unsigned)std::min<uint64_t>(wmax, (uint64_t)ctx->prep_ctas);
+		const unsigned pblocks = (unsigned)std::min<uint64_t>(2 * wmax, (uint64_t)ctx->prep_ctas);      /* a task = one slot of each unit of a block */
 		const unsigned tblocks = (unsigned)std::min<uint64_t>(wmax, (uint64_t)ctx->form_ctas[ctx->lane_form]);
 		const unsigned fblocks = (unsigned)std::min<uint64_t>(wmax, (uint64_t)ctx->fin_ctas);
 		TB_LAUNCH_SMEM(k_lane_prepare, pblocks, lane_nt, lane_prepare_smem_words() * sizeof(uint32_t), st, a, ctx->d_units);

@@ -1001,8 +1001,68 @@ k_decode_lane(DecodeArgs a, uint32_t *__restrict__ scratch)
 /* PREPARE as its own kernel: one warp per CTA, no trellis registers, so an SM holds 24+ of them and the dependent
  * loads of the cell state hide behind each other.  Shared memory: the scrambler's leap tables + one broadcast row. */
 __host__ __device__ constexpr size_t lane_prepare_smem_words() { return 1024 + 16; }
+
+/* one slot's share of PREPARE (k = LANE_NO_SLOT: nothing to do, but the warp collectives of lane_lfsr are still joined).
+ * first: the slot is the unit's first one (only that one can be a two-block slot, which fills both columns). */
+struct LaneSlotPrep { uint32_t k, code, flags, bbk, tm16; int kind, n0, n1; };
+__device__ __forceinline__ LaneSlotPrep lane_prepare_slot(const DecodeArgs &a, const Tables *__restrict__ tab, uint32_t *bcast, const uint32_t *leap,
+                                                          uint32_t k, bool first, uint32_t *col0, uint32_t *col1)
+{
+	constexpr int nt = LANE_NT;
+	LaneSlotPrep r;
+	r.k = k; r.code = 0; r.bbk = 0; r.kind = KIND_NONE; r.n0 = r.n1 = 0;
+	Tm tm; tm.tn = tm.fn = tm.mn = 0;
+	bool good_sb = false, unlock = false;
+	uint32_t bw[16];
+	if (k != LANE_NO_SLOT) {
+		const SlotWs w = a.ws[k];
+		load_slot_bits(a.slot_bits, k, bw);           /* asked for now, needed behind the cell state's chain of loads */
+		r.kind = w.kind; good_sb = w.good_sb; unlock = w.unlock;
+		const bool dep = cell_state(k, a.ws, a.last_good, a.blk_prev, a.carry, &tm, &r.code);
+		if (a.skip_dependent && dep && !a.carry->seen_good) {     /* sharded decode: decoded later, with the real carry-in */
+			r.k = LANE_NO_SLOT; r.kind = KIND_NONE; good_sb = unlock = false;
+		}
+	}
+	r.flags = (uint32_t)r.kind | (unlock ? F_UNLOCK : 0) | ((r.kind == KIND_SB && good_sb) ? F_CRC_A : 0);
+	if (r.kind == KIND_SB && tm_is_bnch(tm)) r.flags |= F_BNCH;
+	r.tm16 = (tm.tn | (tm.fn << 3) | (tm.mn << 8)) & 0xffffu;
+	uint32_t lf[LANE_T3_ROWS];
+	lane_lfsr(r.code, r.kind != KIND_NONE, lf, bcast, tab, leap);
+	if (r.kind != KIND_NONE) {
+		uint32_t *col = first ? col0 : col1;
+		if (r.kind == KIND_SB) {
+			xor_region<252, 0, 30>(bw, lf);
+			xor_region<282, 0, 216>(bw, lf);
+			r.bbk = extract_bits(bw, 252, 30);
+			gather_lane<1, PL_BLK2>(bw, col, nt); r.n0 = 144;
+		} else if (r.kind == KIND_NDB_F) {
+			xor_region<14, 0, 216>(bw, lf);
+			xor_region<282, 216, 216>(bw, lf);
+			xor_region<230, 0, 14>(bw, lf);
+			r.bbk = extract_bits(bw, 230, 14);
+			if (a.aach) r.bbk |= ((extract_bits(bw, 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;       /* the broadcast block's second part */
+			gather_lane<5, PL_SCHF>(bw, col, nt); r.n0 = 288;
+		} else if (first) {
+			/* two-block slot: BLK1 on trellis X, BLK2 on trellis Y of the unit's thread (the unit has no second slot) */
+			xor_region<14, 0, 216>(bw, lf);
+			xor_region<282, 0, 216>(bw, lf);
+			xor_region<230, 0, 14>(bw, lf);
+			r.bbk = extract_bits(bw, 230, 14);
+			if (a.aach) r.bbk |= ((extract_bits(bw, 266, 16) ^ (lf[0] >> 14)) & 0xffffu) << 14;
+			gather_lane<1, PL_BLK1>(bw, col0, nt);
+			gather_lane<1, PL_BLK2>(bw, col1, nt);
+			r.n0 = r.n1 = 144;
+		}
+	}
+	return r;
+}
+
+/* A warp takes ONE slot of each of 32 units (task = 2 * block + half): half the registers of the two-slot form, so an SM
+ * holds twice the warps for the same work, and both the load chains and the ALU-pipe bound gather have more to overlap with.
+ * The halves of a unit block are disjoint (column h, rows 28+h, 30+h, 32+h, 34+h); a two-block slot is the first half's
+ * business alone, it fills both columns and both halves of the unit's state. */
 #ifndef TB_PREP_MIN_CTAS
-#define TB_PREP_MIN_CTAS 16       /* 128 registers, no spills; measured: 20 (96 registers, ~60 words spilled) 8 % slower, 24 12 % */
+#define TB_PREP_MIN_CTAS 24
 #endif
 __global__ void __launch_bounds__(32, TB_PREP_MIN_CTAS)
 k_lane_prepare(DecodeArgs a, uint32_t *__restrict__ units)
@@ -1011,15 +1071,32 @@ k_lane_prepare(DecodeArgs a, uint32_t *__restrict__ units)
 	uint32_t *bcast = leap + 1024;
 	const Tables *__restrict__ tab = a.tab;
 	const int tid = threadIdx.x;
+	constexpr int nt = LANE_NT;
 	for (int i = tid; i < 1024; i += 32) leap[i] = (&tab->lfsr_leap[0][0])[i];
 	__syncwarp();
 	const LaneLists L(a);
-	const uint64_t nw = L.warps();
-	for (uint64_t wu = blockIdx.x; wu < nw; wu += gridDim.x) {
+	const uint64_t ntask = 2 * L.warps();
+	for (uint64_t task = blockIdx.x; task < ntask; task += gridDim.x) {
+		const uint64_t wu = task >> 1, u = wu * 32 + tid;
+		const int h = (int)(task & 1);
 		uint32_t *blk = units + wu * LANE_UNIT_WORDS + tid;
-		LaneUnit m;
-		lane_prepare(a, tab, bcast, leap, wu * 32 + tid, L, blk, blk + LANE_T3_ROWS * LANE_NT, m);
-		lane_unit_store(blk, m);
+		uint32_t k[2];
+		L.slots_of(u, k);
+		const bool two_block_unit = u >= L.uF && u < L.uF + L.u2;
+		const bool mine = !(h == 1 && two_block_unit);
+		const LaneSlotPrep r = lane_prepare_slot(a, tab, bcast, leap, mine ? k[h] : LANE_NO_SLOT, h == 0, blk, blk + LANE_T3_ROWS * nt);
+		if (mine) {
+			blk[(LANE_META_ROW + h) * nt] = r.tm16 | (r.flags << 16) | ((uint32_t)r.kind << 24) | ((uint32_t)lane_ncode(r.n0) << 28);
+			blk[(LANE_META_ROW + 2 + h) * nt] = r.k;
+			blk[(LANE_META_ROW + 4 + h) * nt] = r.code;
+			blk[(LANE_META_ROW + 6 + h) * nt] = r.bbk;
+			if (h == 0 && two_block_unit) {       /* the second trellis carries BLK2 of the same slot; no second slot */
+				blk[(LANE_META_ROW + 1) * nt] = ((uint32_t)KIND_NONE << 24) | ((uint32_t)lane_ncode(r.n1) << 28);
+				blk[(LANE_META_ROW + 3) * nt] = LANE_NO_SLOT;
+				blk[(LANE_META_ROW + 5) * nt] = 0;
+				blk[(LANE_META_ROW + 7) * nt] = 0;
+			}
+		}
 		__syncwarp();
 	}
 }
