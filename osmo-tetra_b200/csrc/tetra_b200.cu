@@ -626,6 +626,7 @@ extern "C" int tb200_create(tb200_ctx **out, int device)
 extern "C" void tb200_destroy(tb200_ctx *ctx)
 {
 	if (!ctx) return;
+	ctx->pack_pool.stop();            /* before its staging buffers go */
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
 	cudaFree(ctx->d_tab); cudaFree(ctx->d_carry);
