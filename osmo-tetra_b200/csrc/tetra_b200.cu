@@ -190,16 +190,16 @@ struct PackPool {
 	unsigned pending = 0;
 	bool quit = false;
 	const uint8_t *src = nullptr; uint8_t *dst = nullptr; size_t n_bits = 0;
-	void worker(unsigned id)
+	unsigned n_workers = 0;          /* workers of the current job (set with it) */
+	void worker(unsigned id, uint64_t seen)       /* seen: the job counter when the thread was made - only later jobs are its own */
 	{
-		uint64_t seen = 0;
 		for (;;) {
 			const uint8_t *s; uint8_t *d; size_t nb; unsigned nth;
 			{
 				std::unique_lock<std::mutex> lk(m);
 				cv_go.wait(lk, [&] { return quit || gen != seen; });
 				if (quit) return;
-				seen = gen; s = src; d = dst; nb = n_bits; nth = (unsigned)th.size();
+				seen = gen; s = src; d = dst; nb = n_bits; nth = n_workers;
 			}
 			/* slices of whole 64-byte output lines */
 			const size_t out_bytes = (nb + 7) >> 3, per = ((out_bytes + nth - 1) / nth + 63) & ~(size_t)63;
@@ -215,15 +215,17 @@ struct PackPool {
 	{
 		if (n == th.size()) return;
 		stop();
-		quit = false;
-		for (unsigned i = 0; i < n; i++) th.emplace_back([this, i] { worker(i); });
+		quit = false; pending = 0;
+		const uint64_t g0 = gen;
+		th.reserve(n);
+		for (unsigned i = 0; i < n; i++) th.emplace_back([this, i, g0] { worker(i, g0); });
 	}
 	/* start a job and come back; wait() returns when it is done.  One job at a time. */
 	void start(const uint8_t *s, size_t nb, uint8_t *d)
 	{
 		if (th.empty()) { pack_range(s, nb, d); return; }
 		std::lock_guard<std::mutex> lk(m);
-		src = s; dst = d; n_bits = nb; pending = (unsigned)th.size(); ++gen;
+		src = s; dst = d; n_bits = nb; pending = n_workers = (unsigned)th.size(); ++gen;
 		cv_go.notify_all();
 	}
 	void wait()
@@ -1228,8 +1230,8 @@ static int run_locked(tb200_ctx *ctx, const Source &src, const Segment &seg, uin
 			}
 			ctx->h_pack_cap = need;
 		}
-		ctx->pack_pool.resize(ctx->opt.host_pack_threads > 1 ? ctx->opt.host_pack_threads : 0);      /* 1: the calling thread packs */
 		if (ctx->pack_inflight >= 0) { ctx->pack_pool.wait(); ctx->pack_inflight = -1; }
+		ctx->pack_pool.resize(ctx->opt.host_pack_threads > 1 ? ctx->opt.host_pack_threads : 0);      /* 1: the calling thread packs */
 	}
 	/* every TB200_HOST_PACK_EVERY-th piece goes through the host threads, the others cross the bus as bytes (both roads busy) */
 	unsigned pack_every = 1;

@@ -227,6 +227,9 @@ def test_stream_host_pack_threads(emu, orc, threads):
         parts = [emu.rx_stream_host(bits[cuts[i]:cuts[i + 1]], flags=(1 if i == 0 else 0) | (2 if i == 2 else 0)) for i in range(3)]
         slots = np.concatenate([p[0] for p in parts]); t1 = np.concatenate([p[1] for p in parts])
         T.check_stream_against(orc.records(), orc.events(), slots, emu.expand_records(slots, t1))
+        # the pool is rebuilt when the thread count changes between calls (new threads must not pick up an old job)
+        for th, ps in ((2, 29), (5, 0), (3, 11)):          # (the staging buffers are re-allocated when the piece size grows)
+            _check(emu, orc, bits, viterbi=T.VITERBI_LANE, pipeline_slots=ps, host_pack_threads=th)
     finally:
         emu.set_options(host_pack_threads=0, pipeline_slots=0, chunk_bits=64)
 
