@@ -207,6 +207,16 @@ def test_stream_dev_continuation(emu, orc, fmt):
                 T.check_stream_against(want, ev, slots, emu.expand_records(slots, t1))
                 c = emu.carry()
                 assert c.state == orc.rx_state() and c.scramb_init == orc.scramb_init()
+        # the stream's end announced by an empty last call (what a caller does that learns of the end afterwards)
+        if fmt == "bytes":
+            cut = 70001
+            ms = n // 510 + 16
+            sl = np.zeros(ms, dtype=T.SLOT_DTYPE); t1 = np.zeros((ms, 288), dtype=np.uint8)
+            a = np.ascontiguousarray(buf[:cut]); b = np.ascontiguousarray(buf[cut:])
+            k0 = emu.rx_stream_dev_raw(a.ctypes.data, cut, 1, sl.ctypes.data, t1.ctypes.data, 0, ms)
+            k1 = emu.rx_stream_dev_raw(b.ctypes.data, n - cut, 0, sl[k0:].ctypes.data, t1[k0:].ctypes.data, 0, ms - k0)
+            k2 = emu.rx_stream_dev_raw(b.ctypes.data, 0, 2, sl[k0 + k1:].ctypes.data, t1[k0 + k1:].ctypes.data, 0, ms - k0 - k1)
+            T.check_stream_against(want, ev, sl[:k0 + k1 + k2], emu.expand_records(sl[:k0 + k1 + k2], t1[:k0 + k1 + k2]))
     finally:
         emu.set_options(input=T.IN_BYTES)
 
