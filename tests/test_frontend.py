@@ -78,7 +78,15 @@ def test_symbol_input_emulated(emu, orc, lead_in):
         emu.set_options(input=T.IN_BYTES, pipeline_slots=0)
 
 
-def _continued(lib, orc, fmt, n_bursts, seed):
+def _dev_call(lib, part, n_bits, flags):
+    """tb200_rx_stream_dev on a numpy buffer (emulation build)"""
+    ms = n_bits // 510 + 16
+    slots = np.zeros(ms, dtype=T.SLOT_DTYPE); t1 = np.zeros((ms, 288), dtype=np.uint8); pk = np.zeros((ms, 9), dtype=np.uint32)
+    k = lib.rx_stream_dev_raw(part.ctypes.data, n_bits, flags, slots.ctypes.data, t1.ctypes.data, pk.ctypes.data, ms)
+    return slots[:k], t1[:k], pk[:k]
+
+
+def _continued(lib, orc, fmt, n_bursts, seed, dev=False):
     """a packed / symbol stream handed over in several calls (128-bit boundaries) equals the reference chain on the whole stream"""
     rng = np.random.default_rng(seed)
     bits, cfg = _stream(orc, n=n_bursts, random_cell=1, sb_period=8, lead_in_bits=int(rng.integers(0, 300)))
@@ -98,7 +106,10 @@ def _continued(lib, orc, fmt, n_bursts, seed):
             last = pos + n >= bits.size
             part = buf[pos // 8:(pos + n + 7) // 8] if fmt == T.IN_PACKED else buf[pos // 2:(pos + n + 1) // 2]
             flags = (T.TB200_FRESH if pos == 0 else 0) | (T.TB200_FINAL if last else 0)
-            outs.append(lib.rx_stream_host_raw(np.ascontiguousarray(part), n, flags=flags))
+            if dev and len(outs) % 3 != 2:            # (emulation: host addresses are the "device" pointers; every third call the host way)
+                outs.append(_dev_call(lib, np.ascontiguousarray(part), n, flags))
+            else:
+                outs.append(lib.rx_stream_host_raw(np.ascontiguousarray(part), n, flags=flags))
             pos += n
         slots = np.concatenate([o[0] for o in outs]); t1 = np.concatenate([o[1] for o in outs])
         T.check_stream_against(want, ev, slots, lib.expand_records(slots, t1))
@@ -110,6 +121,13 @@ def _continued(lib, orc, fmt, n_bursts, seed):
 @pytest.mark.parametrize("fmt", [T.IN_PACKED, T.IN_F32SYM])
 def test_packed_and_symbol_streams_continue(emu, orc, fmt):
     _continued(emu, orc, fmt, 60, 41 + fmt)
+
+
+@pytest.mark.parametrize("fmt", [T.IN_PACKED, T.IN_F32SYM])
+def test_packed_and_symbol_streams_continue_dev(emu, orc, fmt):
+    """the same through tb200_rx_stream_dev (kept bits on the device, staged head), host calls mixed in"""
+    _continued(emu, orc, fmt, 60, 43 + fmt, dev=True)
+    _continued(emu, orc, fmt, 150, 47 + fmt, dev=True)
 
 
 def test_format_rules(emu):
@@ -199,6 +217,14 @@ def test_symbol_stream_with_afc_emulated(emu, orc):
             pos += n
         s3 = np.concatenate([o[0] for o in outs]); t3 = np.concatenate([o[1] for o in outs])
         T.check_stream_against(want, ev, s3, emu.expand_records(s3, t3))
+        # and through the device-resident call
+        outs, pos = [], 0
+        for n in (128 * 40, 128 * 111, bits.size - 128 * 151):
+            flags = (T.TB200_FRESH if pos == 0 else 0) | (T.TB200_FINAL if pos + n == bits.size else 0)
+            outs.append(_dev_call(emu, np.ascontiguousarray(sym[pos // 2:(pos + n) // 2]), n, flags))
+            pos += n
+        s4 = np.concatenate([o[0] for o in outs]); t4 = np.concatenate([o[1] for o in outs])
+        T.check_stream_against(want, ev, s4, emu.expand_records(s4, t4))
     finally:
         emu.set_options(input=T.IN_BYTES, afc=0)
 
