@@ -106,7 +106,11 @@ static void shim_die(const char *msg)
 
 #ifndef TETRA_B200_SHIM_L0_ONLY
 /* what tp_sap_udata_ind does after the arithmetic: allocate the primitive, fill it, hand it up,
- * re-invoke while the upper MAC consumed only part of the block (tetra_lower_mac.c:326-352) */
+ * re-invoke while the upper MAC consumed only part of the block (tetra_lower_mac.c:326-352).
+ * This function and dump_traffic_schf() below follow the reference statement by statement ON PURPOSE: they are the
+ * contract with the untouched upper MAC (which fields of struct tetra_tmvsap_prim it reads, how it walks msg->head /
+ * l1h between re-invocations, the names and the 690-word frame layout of the traffic dump files it appends to) -
+ * host-side glue at the seam, not part of the accelerated path. */
 static void deliver(const struct tb200_record *r, void *priv)
 {
 	struct tetra_tmvsap_prim *ttp = talloc_zero(NULL, struct tetra_tmvsap_prim);
